@@ -1,0 +1,263 @@
+// oracle/harness.cpp — TEST INFRASTRUCTURE ONLY (not product code).
+//
+// Drives the UNMODIFIED reference renderer headlessly. The reference's main.cpp
+// is pulled in textually (its `main` renamed) so that the file-local integrator
+// entry points are reachable exactly as the reference defines them:
+//   render()                      reference src/main.cpp:416-426
+//   TraceContext::raycast()       reference src/main.cpp:63-103
+//   raytrace() / pathtrace()      reference src/main.cpp:105-169
+//   visible()                     reference src/main.cpp:171-190
+//   vfb[][]                       reference src/main.cpp:50
+// The set-up sequence below follows reference src/main.cpp:530-557 and
+// renderThreadEntry/renderStatic (main.cpp:506-527), minus the SDL window.
+//
+// Sub-commands (all write little-endian raw arrays that numpy reads directly):
+//   render  <scene> [--width W --height H --spp N --threads T --repeat R --aa 0|1
+//                    --depth D --out vfb.f32 --bmp out.bmp --exr out.exr]
+//           -> W*H*3 float32 (un-clamped linear, same content as vfb) + one JSON line
+//   primary <scene> [--width W --height H] --out prim.f64
+//           -> per pixel: 6 doubles ray + 24 doubles raycast record (see dump_hit)
+//   rays    <scene> --in rays.f64 --out hits.f64 [--mode raycast|raytrace|visible]
+//           -> raycast/raytrace: in 8 doubles (start, dir, depth, flags), out 24 doubles
+//              visible: in 6 doubles (A, B), out 1 double
+//
+// When built with -DHXR_COUNTING the included main.cpp is a sed-piped stream of the
+// reference file with two counter macros inserted (see oracle/Makefile); that variant
+// is used only to COUNT rays (closest-hit queries past the depth guard + visible()
+// queries), never for timing or parity.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#ifdef HXR_COUNTING
+struct HxrCounterSlot { long long closest = 0, shadow = 0; char pad[48]; };
+static HxrCounterSlot g_hxr_slots[1100];
+static std::atomic<int> g_hxr_next_slot{0};
+static thread_local int g_hxr_slot = -1;
+static inline HxrCounterSlot& hxr_slot()
+{
+    if (g_hxr_slot < 0) g_hxr_slot = g_hxr_next_slot++ % 1100;
+    return g_hxr_slots[g_hxr_slot];
+}
+#define HXR_COUNT_CLOSEST() (hxr_slot().closest++)
+#define HXR_COUNT_SHADOW() (hxr_slot().shadow++)
+#endif
+
+#define main hexray_reference_main
+#include HXR_MAIN_CPP
+#undef main
+
+#include "bitmap.h"
+
+static double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct Args {
+    std::string cmd, scene, out, in, bmp, exr, mode = "raycast";
+    int width = 0, height = 0, spp = 0, threads = 0, repeat = 1, aa = -1, depth = -1;
+};
+
+static Args parse_args(int argc, char** argv)
+{
+    Args a;
+    if (argc < 3) {
+        fprintf(stderr, "usage: %s render|primary|rays <scene.hexray> [options]\n", argv[0]);
+        exit(2);
+    }
+    a.cmd = argv[1];
+    a.scene = argv[2];
+    for (int i = 3; i < argc; i++) {
+        std::string k = argv[i];
+        auto val = [&]() -> const char* {
+            if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", k.c_str()); exit(2); }
+            return argv[++i];
+        };
+        if (k == "--width") a.width = atoi(val());
+        else if (k == "--height") a.height = atoi(val());
+        else if (k == "--spp") a.spp = atoi(val());
+        else if (k == "--threads") a.threads = atoi(val());
+        else if (k == "--repeat") a.repeat = atoi(val());
+        else if (k == "--aa") a.aa = atoi(val());
+        else if (k == "--depth") a.depth = atoi(val());
+        else if (k == "--out") a.out = val();
+        else if (k == "--in") a.in = val();
+        else if (k == "--bmp") a.bmp = val();
+        else if (k == "--exr") a.exr = val();
+        else if (k == "--mode") a.mode = val();
+        else { fprintf(stderr, "unknown option %s\n", k.c_str()); exit(2); }
+    }
+    return a;
+}
+
+// same sequence as reference main.cpp:536-557 + renderThreadEntry/renderStatic, no window
+static bool setup(const Args& a, double& parse_ms, double& begin_render_ms)
+{
+    Color::init_sRGB_cache();
+    double t0 = now_ms();
+    if (!scene.parseScene(a.scene.c_str())) {
+        fprintf(stderr, "Could not parse the scene file (%s)!\n", a.scene.c_str());
+        return false;
+    }
+    parse_ms = now_ms() - t0;
+    if (a.width > 0) scene.settings.frameWidth = a.width;
+    if (a.height > 0) scene.settings.frameHeight = a.height;
+    if (a.aa >= 0) scene.settings.wantAA = a.aa != 0;
+    if (a.depth >= 0) scene.settings.maxTraceDepth = a.depth;
+    if (a.spp > 0) {
+        if (scene.settings.gi) scene.settings.numPaths = a.spp;
+        if (scene.camera->dof) scene.camera->numSamples = a.spp;
+    }
+    scene.settings.numThreads = a.threads > 0 ? a.threads : (int)std::thread::hardware_concurrency();
+    threadPool = std::make_unique<ThreadPool>(scene.settings.numThreads);
+    traceFunction = raytrace;
+    if (scene.settings.gi) traceFunction = [](Ray ray) { return pathtrace(ray); };
+    if (scene.camera->dof)
+        rayGenerator = [](double x, double y, double u, double v, double so) { return scene.camera->getDOFScreenRay(x, y, u, v, so); };
+    else
+        rayGenerator = [](double x, double y, double u, double v, double so) { return scene.camera->getScreenRay(x, y, so); };
+    initGraphics(scene.settings.frameWidth, scene.settings.frameHeight);
+    buckets = getBucketsList(64);
+    t0 = now_ms();
+    scene.beginRender();
+    begin_render_ms = now_ms() - t0;
+    scene.beginFrame();
+    return true;
+}
+
+static void dump_hit(FILE* f, const Ray& ray, int mode /*0 raycast, 1 raytrace*/)
+{
+    double rec[24];
+    for (double& d : rec) d = 0;
+    TraceContext tc;
+    // poison the fields the reference leaves unwritten for some primitives, so the
+    // dump is deterministic (Sphere/Cube never set dNdx/dNdy, geometry.cpp:52-147)
+    tc.closestIntersection.dNdx = Vector(0, 0, 0);
+    tc.closestIntersection.dNdy = Vector(0, 0, 0);
+    tc.closestIntersection.u = tc.closestIntersection.v = 0;
+    auto early = tc.raycast(ray);
+    int nodeIdx = -1;
+    for (int i = 0; i < (int)scene.nodes.size(); i++)
+        if (scene.nodes[i] == tc.closestNode) nodeIdx = i;
+    const IntersectionInfo& ii = tc.closestIntersection;
+    rec[0] = early ? 1 : 0;
+    rec[1] = early ? -1 : nodeIdx;
+    if (!early) {
+        rec[2] = ii.dist;
+        rec[3] = ii.ip.x; rec[4] = ii.ip.y; rec[5] = ii.ip.z;
+        rec[6] = ii.norm.x; rec[7] = ii.norm.y; rec[8] = ii.norm.z;
+        rec[9] = ii.u; rec[10] = ii.v;
+        rec[11] = ii.dNdx.x; rec[12] = ii.dNdx.y; rec[13] = ii.dNdx.z;
+        rec[14] = ii.dNdy.x; rec[15] = ii.dNdy.y; rec[16] = ii.dNdy.z;
+    }
+    Color c(0, 0, 0);
+    if (mode == 1) c = raytrace(ray);
+    else if (early) c = *early;
+    rec[17] = c.r; rec[18] = c.g; rec[19] = c.b;
+    fwrite(rec, sizeof(double), 24, f);
+}
+
+int main(int argc, char** argv)
+{
+    Args a = parse_args(argc, argv);
+    double parse_ms = 0, br_ms = 0;
+    if (!setup(a, parse_ms, br_ms)) return 1;
+    const int W = frameWidth(), H = frameHeight();
+
+    if (a.cmd == "render") {
+        std::string times = "[";
+        double best = 1e300;
+        for (int r = 0; r < a.repeat; r++) {
+            double t0 = now_ms();
+            render(false);
+            double dt = now_ms() - t0;
+            best = dt < best ? dt : best;
+            char b[64];
+            snprintf(b, sizeof b, "%s%.3f", r ? ", " : "", dt);
+            times += b;
+        }
+        times += "]";
+        long long nClosest = -1, nShadow = -1;
+#ifdef HXR_COUNTING
+        nClosest = nShadow = 0;
+        for (auto& s : g_hxr_slots) { nClosest += s.closest; nShadow += s.shadow; }
+        nClosest /= a.repeat; nShadow /= a.repeat;
+#endif
+        if (!a.out.empty()) {
+            FILE* f = fopen(a.out.c_str(), "wb");
+            if (!f) { perror("open --out"); return 1; }
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++) fwrite(vfb[y][x].components, sizeof(float), 3, f);
+            fclose(f);
+        }
+        if (!a.bmp.empty() || !a.exr.empty()) {
+            Bitmap bmp;
+            bmp.generateEmptyImage(W, H);
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++) bmp.setPixel(x, y, vfb[y][x]);
+            if (!a.bmp.empty()) bmp.saveImage(a.bmp.c_str());
+            if (!a.exr.empty()) bmp.saveImage(a.exr.c_str());
+        }
+        int spp = 0;
+        if (scene.camera->dof) spp = scene.camera->numSamples;
+        if (scene.settings.gi) spp = std::max(spp, scene.settings.numPaths);
+        printf("{\"impl\": \"reference\", \"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"gi\": %d, \"dof\": %d, "
+               "\"aa\": %d, \"max_depth\": %d, \"threads\": %d, \"parse_ms\": %.3f, \"begin_render_ms\": %.3f, "
+               "\"render_ms\": %s, \"best_ms\": %.3f, \"rays_closest\": %lld, \"rays_shadow\": %lld}\n",
+               a.scene.c_str(), W, H, spp, (int)scene.settings.gi, (int)scene.camera->dof, (int)scene.settings.wantAA,
+               scene.settings.maxTraceDepth, scene.settings.numThreads, parse_ms, br_ms, times.c_str(), best, nClosest, nShadow);
+        return 0;
+    }
+
+    if (a.cmd == "primary") {
+        FILE* f = fopen(a.out.c_str(), "wb");
+        if (!f) { perror("open --out"); return 1; }
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                Ray ray = scene.camera->getScreenRay(x, y);
+                double r6[6] = {ray.start.x, ray.start.y, ray.start.z, ray.dir.x, ray.dir.y, ray.dir.z};
+                fwrite(r6, sizeof(double), 6, f);
+                dump_hit(f, ray, 0);
+            }
+        fclose(f);
+        printf("{\"width\": %d, \"height\": %d}\n", W, H);
+        return 0;
+    }
+
+    if (a.cmd == "rays") {
+        FILE* fi = fopen(a.in.c_str(), "rb");
+        FILE* fo = fopen(a.out.c_str(), "wb");
+        if (!fi || !fo) { perror("open --in/--out"); return 1; }
+        long n = 0;
+        if (a.mode == "visible") {
+            double ab[6];
+            while (fread(ab, sizeof(double), 6, fi) == 6) {
+                double v = visible(Vector(ab[0], ab[1], ab[2]), Vector(ab[3], ab[4], ab[5])) ? 1.0 : 0.0;
+                fwrite(&v, sizeof(double), 1, fo);
+                n++;
+            }
+        } else {
+            double r8[8];
+            while (fread(r8, sizeof(double), 8, fi) == 8) {
+                Ray ray;
+                ray.start = Vector(r8[0], r8[1], r8[2]);
+                ray.dir = Vector(r8[3], r8[4], r8[5]);
+                ray.depth = (int)r8[6];
+                ray.flags = (unsigned)r8[7];
+                dump_hit(fo, ray, a.mode == "raytrace" ? 1 : 0);
+                n++;
+            }
+        }
+        fclose(fi);
+        fclose(fo);
+        printf("{\"n\": %ld}\n", n);
+        return 0;
+    }
+    fprintf(stderr, "unknown command %s\n", a.cmd.c_str());
+    return 2;
+}
