@@ -1,0 +1,188 @@
+// abi.cpp — extern "C" surface of include/hxr.h. No exception leaves this file.
+#include <cstring>
+#include <memory>
+#include <string>
+#include "../../include/hxr.h"
+#include "host/scene.h"
+#include "renderer.h"
+
+struct hxr_ctx {
+    hxr::Renderer r;
+    std::string err;
+};
+
+struct hxr_scene_file {
+    hxr::host::Scene scene;
+    hxr::host::FlatScene flat;
+    std::string path;
+};
+
+static thread_local std::string g_lastError;
+
+#define HXR_GUARD_BEGIN try {
+#define HXR_GUARD_END(ctxerr)                                         \
+    } catch (const std::bad_alloc&) {                                 \
+        ctxerr = "out of host memory";                                \
+        return HXR_ERR_INVALID;                                       \
+    } catch (const std::exception& e) {                               \
+        ctxerr = std::string("internal error: ") + e.what();          \
+        return HXR_ERR_INVALID;                                       \
+    } catch (...) {                                                   \
+        ctxerr = "internal error";                                    \
+        return HXR_ERR_INVALID;                                       \
+    }
+
+extern "C" {
+
+int hxr_create(const hxr_config* cfg, hxr_ctx** out)
+{
+    if (!out) { g_lastError = "hxr_create: null output"; return HXR_ERR_INVALID; }
+    *out = nullptr;
+    HXR_GUARD_BEGIN
+    hxr_config c;
+    memset(&c, 0, sizeof c);
+    if (cfg) c = *cfg;
+    std::unique_ptr<hxr_ctx> ctx(new hxr_ctx);
+    int rc = ctx->r.create(c);
+    if (rc != HXR_OK) { g_lastError = ctx->r.error(); return rc; }
+    *out = ctx.release();
+    return HXR_OK;
+    HXR_GUARD_END(g_lastError)
+}
+
+void hxr_destroy(hxr_ctx* ctx)
+{
+    try { delete ctx; } catch (...) {}
+}
+
+const char* hxr_last_error(const hxr_ctx* ctx)
+{
+    if (!ctx) return g_lastError.c_str();
+    return ctx->err.empty() ? ctx->r.error().c_str() : ctx->err.c_str();
+}
+
+#define HXR_CTX_CALL(expr)                                   \
+    if (!ctx) { g_lastError = "null context"; return HXR_ERR_INVALID; } \
+    ctx->err.clear();                                        \
+    HXR_GUARD_BEGIN                                          \
+    return (expr);                                           \
+    HXR_GUARD_END(ctx->err)
+
+int hxr_upload_scene(hxr_ctx* ctx, const hxr_scene* scene) { HXR_CTX_CALL(ctx->r.uploadScene(scene)) }
+int hxr_set_camera(hxr_ctx* ctx, const hxr_camera* cam) { HXR_CTX_CALL(ctx->r.setCamera(cam)) }
+
+int hxr_render(hxr_ctx* ctx, const hxr_render_params* p, float* rgb_out, hxr_stats* stats)
+{
+    if (ctx && !p) { ctx->err = "null render params"; return HXR_ERR_INVALID; }
+    if (ctx && !rgb_out) { ctx->err = "null output buffer"; return HXR_ERR_INVALID; }
+    HXR_CTX_CALL(ctx->r.render(*p, rgb_out, nullptr, stats))
+}
+int hxr_render_device(hxr_ctx* ctx, const hxr_render_params* p, void* d_rgb, hxr_stats* stats)
+{
+    if (ctx && !p) { ctx->err = "null render params"; return HXR_ERR_INVALID; }
+    if (ctx && !d_rgb) { ctx->err = "null output buffer"; return HXR_ERR_INVALID; }
+    HXR_CTX_CALL(ctx->r.render(*p, nullptr, d_rgb, stats))
+}
+int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t w, int32_t h, int32_t spp) { HXR_CTX_CALL(ctx->r.resolveDevice(d_rgb, w, h, spp)) }
+int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits) { HXR_CTX_CALL(ctx->r.traceClosest(rays, n, hits)) }
+int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->r.traceVisible(seg, n, vis)) }
+int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { HXR_CTX_CALL(ctx->r.traceColor(rays, n, rgb)) }
+int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out) { HXR_CTX_CALL(ctx->r.accelInfo(mesh, out)) }
+
+// ---------------------------------------------------------------- host front-end
+int hxr_scene_load(const char* path, hxr_scene_file** out)
+{
+    if (!path || !out) { g_lastError = "hxr_scene_load: null argument"; return HXR_ERR_INVALID; }
+    *out = nullptr;
+    HXR_GUARD_BEGIN
+    std::unique_ptr<hxr_scene_file> sf(new hxr_scene_file);
+    sf->path = path;
+    if (!sf->scene.parseScene(path)) {
+        g_lastError = sf->scene.lastError.empty() ? std::string("could not parse ") + path : sf->scene.lastError;
+        return HXR_ERR_PARSE;
+    }
+    std::string err;
+    if (!hxr::host::flattenScene(sf->scene, sf->flat, err)) { g_lastError = err; return HXR_ERR_PARSE; }
+    *out = sf.release();
+    return HXR_OK;
+    HXR_GUARD_END(g_lastError)
+}
+
+const hxr_scene* hxr_scene_file_scene(const hxr_scene_file* sf) { return sf ? &sf->flat.pod : nullptr; }
+
+int hxr_scene_file_camera(const hxr_scene_file* sf, hxr_camera* out)
+{
+    if (!sf || !out || !sf->scene.camera) { g_lastError = "hxr_scene_file_camera: null argument"; return HXR_ERR_INVALID; }
+    sf->scene.camera->computeFrame(*out);
+    return HXR_OK;
+}
+
+int hxr_scene_file_set_synthetic_mesh(hxr_scene_file* sf, int32_t mesh_index, const char* kind, int64_t n, uint64_t seed)
+{
+    if (!sf || !kind) { g_lastError = "null argument"; return HXR_ERR_INVALID; }
+    HXR_GUARD_BEGIN
+    using namespace hxr::host;
+    // mesh_index counts Mesh geometries in scene order
+    Mesh* target = nullptr;
+    int k = 0;
+    for (Geometry* g : sf->scene.geometries)
+        if (Mesh* m = dynamic_cast<Mesh*>(g)) {
+            if (k == mesh_index) target = m;
+            k++;
+        }
+    if (!target) { g_lastError = "no such mesh"; return HXR_ERR_INVALID; }
+    if (!strcmp(kind, "terrain")) target->generateTerrain((int)n, seed);
+    else if (!strcmp(kind, "soup")) target->generateSoup(n, seed);
+    else { g_lastError = "unknown synthetic mesh kind"; return HXR_ERR_INVALID; }
+    target->recenter = false;
+    target->autoSmooth = false;
+    // only the mesh changed: re-flatten that one table entry in place (re-running beginRender on the
+    // whole scene would differentiate BumpTexture images a second time)
+    target->computeBoundingGeometry();
+    int mi = 0;
+    for (size_t gi = 0; gi < sf->scene.geometries.size(); gi++) {
+        if (Mesh* m = dynamic_cast<Mesh*>(sf->scene.geometries[gi])) {
+            if (m == target) {
+                hxr_geometry g;
+                memset(&g, 0, sizeof g);
+                FlatScene tmp;
+                m->flatten(tmp, g);
+                // move the storage into the live flat scene and patch the mesh record
+                for (auto& d : tmp.doubleStore) sf->flat.doubleStore.push_back(std::move(d));
+                hxr_mesh rec = tmp.meshes[0];
+                const size_t nd = sf->flat.doubleStore.size();
+                rec.vertices = sf->flat.doubleStore[nd - 3].data();
+                rec.normals = sf->flat.doubleStore[nd - 2].data();
+                rec.uvs = sf->flat.doubleStore[nd - 1].data();
+                sf->flat.meshes[mi] = rec;
+            }
+            mi++;
+        }
+    }
+    sf->flat.finalize();
+    return HXR_OK;
+    HXR_GUARD_END(g_lastError)
+}
+
+void hxr_scene_file_free(hxr_scene_file* sf)
+{
+    try { delete sf; } catch (...) {}
+}
+
+int hxr_save_image(const char* path, const float* rgb, int32_t width, int32_t height)
+{
+    if (!path || !rgb || width <= 0 || height <= 0) { g_lastError = "hxr_save_image: bad argument"; return HXR_ERR_INVALID; }
+    HXR_GUARD_BEGIN
+    hxr::host::Bitmap bmp;
+    bmp.generateEmptyImage(width, height);
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            const float* p = rgb + 3 * ((size_t)y * width + x);
+            bmp.setPixel(x, y, hxr::host::Color3(p[0], p[1], p[2]));
+        }
+    if (!bmp.saveImage(path)) { g_lastError = std::string("cannot write ") + path; return HXR_ERR_IO; }
+    return HXR_OK;
+    HXR_GUARD_END(g_lastError)
+}
+
+}  // extern "C"

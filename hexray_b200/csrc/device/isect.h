@@ -1,0 +1,527 @@
+// isect.h — ray/geometry intersectors (device functions).
+//
+// Each function restates one reference intersector with the reference's own arithmetic
+// (double geometry, same epsilons, same acceptance tests) so that hit records agree with
+// the oracle to rounding:
+//   plane_intersect        src/geometry.cpp:31-50
+//   sphere_intersect       src/geometry.cpp:52-85
+//   cube_intersect         src/geometry.cpp:87-147
+//   csg_intersect          src/geometry.cpp:149-194 (findAllIntersections + CSGBase::intersect)
+//   mesh_intersect         src/mesh.cpp:178-263 (triangle test) — traversal is OUR KD-tree, see below
+//   heightfield_intersect  src/heightfield.cpp:106-171 (+ bbox.h:145-174 closestIntersection)
+//   node_intersect         src/geometry.cpp:196-208 + src/matrix.cpp:156-187
+//   rect_light_intersect   src/lights.cpp:53-73
+//
+// Mesh traversal: the reference walks a median-split tree recursively and keeps a leaf hit only
+// if it lies inside the leaf box (mesh.cpp:221-245); the net result is the closest triangle hit
+// under the triangle test's own arithmetic. We get the same result from a SAH KD-tree walked
+// front to back with an explicit stack: every triangle whose (inflated) bounds overlap a leaf is
+// referenced by it, hits are accepted wherever they fall, and the walk stops only once the best
+// hit lies safely before the end of the current leaf segment.
+#pragma once
+#include "scene_dev.h"
+
+namespace hxr {
+
+HXR_HD bool bbox_inside(const double* mn, const double* mx, const d3& v)  // src/bbox.h:80-85
+{
+    return (mn[0] - 1e-6 <= v.x && v.x <= mx[0] + 1e-6 &&
+            mn[1] - 1e-6 <= v.y && v.y <= mx[1] + 1e-6 &&
+            mn[2] - 1e-6 <= v.z && v.z <= mx[2] + 1e-6);
+}
+
+// src/bbox.h:145-174
+HXR_HD double bbox_closest_intersection(const double* mn, const double* mx, const Ray& r)
+{
+    if (bbox_inside(mn, mx, r.o)) return 0;
+    double minDist = HXR_INF;
+    for (int dim = 0; dim < 3; dim++) {
+        double dd = comp(r.d, dim), so = comp(r.o, dim);
+        if ((dd < 0 && so < mn[dim]) || (dd > 0 && so > mx[dim])) return HXR_INF;
+        if (fabs(dd) < 1e-9) continue;
+        double mul = 1 / dd;
+        int u = (dim == 0) ? 1 : 0;
+        int v = (dim == 2) ? 1 : 2;
+        for (int j = 0; j < 2; j++) {
+            double dist = ((j ? mx[dim] : mn[dim]) - so) * mul;
+            if (dist < 0) continue;
+            double x = comp(r.o, u) + comp(r.d, u) * dist;
+            if (mn[u] <= x && x <= mx[u]) {
+                double y = comp(r.o, v) + comp(r.d, v) * dist;
+                if (mn[v] <= y && y <= mx[v]) minDist = dist < minDist ? dist : minDist;
+            }
+        }
+    }
+    return minDist;
+}
+
+HXR_HD bool plane_intersect(const hxr_geometry& g, int gi, const Ray& ray, Hit& info)
+{
+    const double y = g.p[0], limit = g.p[1];
+    if (ray.o.y > y && ray.d.y >= 0) return false;
+    if (ray.o.y < y && ray.d.y <= 0) return false;
+    double going = ray.d.y;
+    double toGo = y - ray.o.y;
+    double m = toGo / going;
+    info.dist = m;
+    info.ip = ray.o + ray.d * m;
+    if (fabs(info.ip.x) > limit || fabs(info.ip.z) > limit) return false;
+    info.norm = mk3(0, (ray.o.y > y) ? 1 : -1, 0);
+    info.u = info.ip.x;
+    info.v = info.ip.z;
+    info.dNdx = mk3(1, 0, 0);
+    info.dNdy = mk3(0, 0, 1);
+    info.geom = gi;
+    return true;
+}
+
+HXR_HD bool sphere_intersect(const hxr_geometry& g, int gi, const Ray& ray, Hit& info)
+{
+    const d3 O = ld3(g.p);
+    const double R = g.p[3], uvscaling = g.p[4];
+    double A = length_sqr(ray.d);
+    d3 H = ray.o - O;
+    double B = 2 * dot(ray.d, H);
+    double C = length_sqr(H) - R * R;
+    double D = B * B - 4 * A * C;
+    if (D < 0) return false;
+    double sqrtD = sqrt(D);
+    double p1 = (-B - sqrtD) / (2 * A);
+    double p2 = (-B + sqrtD) / (2 * A);
+    double p;
+    if (p2 < 0) return false;
+    if (p1 < 0) p = p2; else p = p1;
+    info.dist = p;
+    info.ip = ray.o + ray.d * p;
+    info.norm = normalize_m(info.ip - O);
+    info.v = asin(info.norm.y);
+    info.u = atan2(info.norm.z, info.norm.x);
+    info.v = -(info.v / HXR_PI + 0.5f);
+    info.u = info.u / (2 * HXR_PI) + 0.5f;
+    if (uvscaling != 1) {
+        info.u *= uvscaling;
+        info.v *= uvscaling;
+    }
+    // the reference leaves dNdx/dNdy unwritten for spheres; keep them defined here
+    info.dNdx = mk3(0, 0, 0);
+    info.dNdy = mk3(0, 0, 0);
+    info.geom = gi;
+    return true;
+}
+
+HXR_HD bool cube_in_bounds(double x, double center, double halfSide)
+{
+    return (x > center - halfSide - 1e-6 && x < center + halfSide + 1e-6);
+}
+
+// one of the six sides; `axis` selects which uv pair the side writes (geometry.cpp:130-132)
+HXR_HD int cube_side(const d3& O, double hs, const d3& norm, double startCoord, double dir, double target,
+                     const Ray& ray, Hit& info, int axis, int gi)
+{
+    if (fabs(dir) < 1e-9) return 0;
+    if (startCoord < target && dir < 0) return 0;
+    if (startCoord > target && dir > 0) return 0;
+    double p = (target - startCoord) / dir;
+    if (p < info.dist) {
+        d3 ip = ray.o + ray.d * p;
+        if (!cube_in_bounds(ip.x, O.x, hs) || !cube_in_bounds(ip.y, O.y, hs) || !cube_in_bounds(ip.z, O.z, hs)) return 0;
+        info.dist = p;
+        info.ip = ip;
+        info.norm = norm;
+        if (axis == 0) { info.u = ip.y; info.v = ip.z; }
+        else if (axis == 1) { info.u = ip.x; info.v = ip.z; }
+        else { info.u = ip.x; info.v = ip.y; }
+        info.geom = gi;
+        return 1;
+    }
+    return 0;
+}
+
+HXR_HD bool cube_intersect(const hxr_geometry& g, int gi, const Ray& ray, Hit& info)
+{
+    const d3 O = ld3(g.p);
+    const double hs = g.p[3];
+    int n = 0;
+    info.dist = HXR_INF;
+    info.dNdx = mk3(0, 0, 0);  // unwritten in the reference
+    info.dNdy = mk3(0, 0, 0);
+    n += cube_side(O, hs, mk3(-1, 0, 0), ray.o.x, ray.d.x, O.x - hs, ray, info, 0, gi);
+    n += cube_side(O, hs, mk3(+1, 0, 0), ray.o.x, ray.d.x, O.x + hs, ray, info, 0, gi);
+    n += cube_side(O, hs, mk3(0, -1, 0), ray.o.y, ray.d.y, O.y - hs, ray, info, 1, gi);
+    n += cube_side(O, hs, mk3(0, +1, 0), ray.o.y, ray.d.y, O.y + hs, ray, info, 1, gi);
+    n += cube_side(O, hs, mk3(0, 0, -1), ray.o.z, ray.d.z, O.z - hs, ray, info, 2, gi);
+    n += cube_side(O, hs, mk3(0, 0, +1), ray.o.z, ray.d.z, O.z + hs, ray, info, 2, gi);
+    return n > 0;
+}
+
+// src/mesh.cpp:131-170 (used by the heightfield cells)
+HXR_HD bool intersect_triangle_fast(const Ray& ray, const d3& A, const d3& B, const d3& C, double& dist)
+{
+    d3 AB = B - A;
+    d3 AC = C - A;
+    d3 D = -ray.d;
+    d3 H = ray.o - A;
+    d3 ABcrossAC = cross(AB, AC);
+    double Dcr = dot(ABcrossAC, D);
+    if (fabs(Dcr) < 1e-12) return false;
+    double lambda2 = dot(cross(H, AC), D) / Dcr;
+    double lambda3 = dot(cross(AB, H), D) / Dcr;
+    double gamma = dot(ABcrossAC, H) / Dcr;
+    if (gamma < 0 || gamma > dist) return false;
+    if (lambda2 < 0 || lambda2 > 1 || lambda3 < 0 || lambda3 > 1 || lambda2 + lambda3 > 1) return false;
+    dist = gamma;
+    return true;
+}
+
+// ---------------------------------------------------------------- triangle mesh
+// gamma_limit: object-space ray parameter beyond which hits cannot matter to the caller
+// (HXR_INF for "no limit"); it only prunes, it never changes which hit wins below it.
+template <bool COUNT>
+HXR_HD bool mesh_intersect(const DMesh& M, int gi, const Ray& ray, Hit& info, double gamma_limit, TravCounters* cnt)
+{
+    // entry/exit parameters against the (slightly inflated) mesh box
+    double t0 = 0, t1 = gamma_limit;
+    {
+        const double o[3] = {ray.o.x, ray.o.y, ray.o.z};
+        const double d[3] = {ray.d.x, ray.d.y, ray.d.z};
+        for (int a = 0; a < 3; a++) {
+            double lo = M.bbmin[a] - 1e-6, hi = M.bbmax[a] + 1e-6;
+            if (d[a] == 0) {
+                if (o[a] < lo || o[a] > hi) return false;
+            } else {
+                double inv = 1.0 / d[a];
+                double ta = (lo - o[a]) * inv, tb = (hi - o[a]) * inv;
+                if (ta > tb) { double s = ta; ta = tb; tb = s; }
+                t0 = ta > t0 ? ta : t0;
+                t1 = tb < t1 ? tb : t1;
+            }
+        }
+        if (t0 > t1) return false;
+    }
+    if (COUNT) cnt->mesh_queries++;
+
+    const d3 nd = -ray.d;
+    double best = gamma_limit;
+    int bestTri = -1;
+    double bl2 = 0, bl3 = 0;
+
+    uint32_t stackNode[HXR_KD_STACK];
+    double stackTmax[HXR_KD_STACK];
+    int sp = 0;
+    uint32_t node = 0;
+    double tmin = t0, tmax = t1;
+    for (;;) {
+        const KdNode n = M.nodes[node];
+        if (n.kind < 3) {
+            if (COUNT) cnt->kd_inner++;
+            const int axis = (int)n.kind;
+            const double split = (double)n.split;
+            const double oa = comp(ray.o, axis), da = comp(ray.d, axis);
+            const bool below = (oa < split) || (oa == split && da <= 0);
+            const uint32_t nearC = below ? n.a : n.b, farC = below ? n.b : n.a;
+            if (da == 0) {
+                if (oa == split) {  // travelling inside the split plane: both sides
+                    if (sp < HXR_KD_STACK) { stackNode[sp] = farC; stackTmax[sp] = tmax; sp++; }
+                }
+                node = nearC;
+                continue;
+            }
+            const double tpl = (split - oa) / da;
+            const double slack = 1e-9 * (1.0 + fabs(tpl));
+            if (tpl > tmax + slack || tpl < 0) {  // plane beyond this segment, or behind the origin
+                node = nearC;
+            } else if (tpl < tmin - slack) {
+                node = farC;
+            } else {
+                if (sp < HXR_KD_STACK) { stackNode[sp] = farC; stackTmax[sp] = tmax; sp++; }
+                node = nearC;
+                tmax = tpl;
+            }
+            continue;
+        }
+        // leaf
+        if (COUNT) { cnt->kd_leaves++; cnt->tri_tests += n.b; }
+        for (uint32_t i = 0; i < n.b; i++) {
+            const uint32_t ti = M.leaf_tris[n.a + i];
+            const TriTest& t = M.tri_test[ti];
+            const d3 N = ld3(t.N);
+            if (M.backface && dot(ray.d, N) > 0) continue;
+            const d3 H = ray.o - ld3(t.A);
+            const double Dcr = dot(N, nd);
+            if (fabs(Dcr) < 1e-12) continue;
+            const double rDcr = 1 / Dcr;
+            const double gamma = dot(N, H) * rDcr;
+            if (gamma < 0 || gamma > best) continue;
+            const d3 AC = ld3(t.AC);
+            const double lambda2 = dot(cross(H, AC), nd) * rDcr;
+            if (lambda2 < 0 || lambda2 > 1) continue;
+            const d3 AB = ld3(t.AB);
+            const double lambda3 = dot(cross(AB, H), nd) * rDcr;
+            if (lambda3 < 0 || lambda3 > 1) continue;
+            const double lambda1 = 1 - (lambda2 + lambda3);
+            if (lambda1 < 0 || lambda1 > 1) continue;
+            best = gamma;
+            bestTri = (int)ti;
+            bl2 = lambda2;
+            bl3 = lambda3;
+        }
+        // stop once the best hit is safely inside the part of the ray already covered
+        if (bestTri >= 0 && best < tmax - 1e-7 * (1.0 + fabs(tmax))) break;
+        if (sp == 0) break;
+        sp--;
+        tmin = tmax;
+        node = stackNode[sp];
+        tmax = stackTmax[sp];
+        if (bestTri >= 0 && best < tmin - 1e-7 * (1.0 + fabs(tmin))) break;
+    }
+    if (bestTri < 0) return false;
+
+    const TriAttr& ta = M.tri_attr[bestTri];
+    info.dist = best;
+    info.ip = ray.o + best * ray.d;
+    const d3 texA = ld3(M.uvs + 3 * ta.t[0]), texB = ld3(M.uvs + 3 * ta.t[1]), texC = ld3(M.uvs + 3 * ta.t[2]);
+    const d3 tex = texA + (texB - texA) * bl2 + (texC - texA) * bl3;
+    info.u = tex.x;
+    info.v = tex.y;
+    if (M.faceted) {
+        info.norm = ld3(ta.gnormal);
+    } else {
+        const d3 nA = ld3(M.normals + 3 * ta.n[0]), nB = ld3(M.normals + 3 * ta.n[1]), nC = ld3(M.normals + 3 * ta.n[2]);
+        info.norm = normalize_m(nA + (nB - nA) * bl2 + (nC - nA) * bl3);
+    }
+    info.dNdx = ld3(ta.dNdx);
+    info.dNdy = ld3(ta.dNdy);
+    info.geom = gi;
+    return true;
+}
+
+// ---------------------------------------------------------------- heightfield
+HXR_HD float hf_height(const DHeightfield& F, int x, int y)
+{
+    x = x < F.W - 1 ? x : F.W - 1;
+    y = y < F.H - 1 ? y : F.H - 1;
+    x = x > 0 ? x : 0;
+    y = y > 0 ? y : 0;
+    return F.heights[y * F.W + x];
+}
+HXR_HD float hf_highest(const DHeightfield& F, int x, int y, int k)
+{
+    x = x < F.W - 1 ? x : F.W - 1;
+    y = y < F.H - 1 ? y : F.H - 1;
+    x = x > 0 ? x : 0;
+    y = y > 0 ? y : 0;
+    return F.high_map[(size_t)(y * F.W + x) * 16 + k];
+}
+HXR_HD d3 hf_normal(const DHeightfield& F, float x, float y)  // src/heightfield.cpp:83-104
+{
+    int x0 = (int)floorf(x);
+    int y0 = (int)floorf(y);
+    float p = (x - x0);
+    float q = (y - y0);
+    int x1 = (x0 + 1 < F.W - 1) ? x0 + 1 : F.W - 1;
+    int y1 = (y0 + 1 < F.H - 1) ? y0 + 1 : F.H - 1;
+    x0 = x0 < F.W - 1 ? x0 : F.W - 1;
+    y0 = y0 < F.H - 1 ? y0 : F.H - 1;
+    x0 = x0 > 0 ? x0 : 0;
+    y0 = y0 > 0 ? y0 : 0;
+    // the weights are float products promoted to double (Vector * double)
+    d3 v = ld3(F.normals + 3 * (y0 * F.W + x0)) * (double)((1 - p) * (1 - q)) +
+           ld3(F.normals + 3 * (y0 * F.W + x1)) * (double)((p) * (1 - q)) +
+           ld3(F.normals + 3 * (y1 * F.W + x0)) * (double)((1 - p) * (q)) +
+           ld3(F.normals + 3 * (y1 * F.W + x1)) * (double)((p) * (q));
+    return normalize_m(v);
+}
+
+HXR_HD bool heightfield_intersect(const DHeightfield& F, int gi, const Ray& ray, Hit& info)
+{
+    d3 step = ray.d;
+    double distHoriz = sqrt(step.x * step.x + step.z * step.z);
+    step = div3(step, distHoriz);
+    double dist = bbox_closest_intersection(F.bbmin, F.bbmax, ray);
+    d3 p = ray.o + ray.d * (dist + 1e-6);
+    double mx = 1.0 / ray.d.x;
+    double mz = 1.0 / ray.d.z;
+    // the loop is bounded: every iteration advances p by at least ~1e-6 along a ray that must
+    // leave a W x H box; the cap only protects against NaN-poisoned vertical rays.
+    for (int guard = 0; guard < 1 << 22 && bbox_inside(F.bbmin, F.bbmax, p); guard++) {
+        int x0 = (int)floor(p.x);
+        int z0 = (int)floor(p.z);
+        if (x0 < 0 || x0 >= F.W || z0 < 0 || z0 >= F.H) break;
+        if (F.use_opt) {
+            int k = 1;
+            while (k < F.max_k && p.y + step.y * (1 << k) > hf_highest(F, x0, z0, k)) k++;
+            k--;
+            if (k > 0) {
+                p = p + step * (double)(1 << k);
+                continue;
+            }
+        }
+        double lx = ray.d.x > 0 ? (ceil(p.x) - p.x) * mx : (floor(p.x) - p.x) * mx;
+        double lz = ray.d.z > 0 ? (ceil(p.z) - p.z) * mz : (floor(p.z) - p.z) * mz;
+        double lmin = (lz < lx) ? lz : lx;  // std::min(lx, lz)
+        d3 p_next = p + step * (lmin + 1e-6);
+        double ymin = (p_next.y < p.y) ? p_next.y : p.y;
+        if (ymin < F.max_h[z0 * F.W + x0]) {
+            double closestDist = HXR_INF;
+            d3 A = mk3(x0, hf_height(F, x0, z0), z0);
+            d3 B = mk3(x0 + 1, hf_height(F, x0 + 1, z0), z0);
+            d3 C = mk3(x0 + 1, hf_height(F, x0 + 1, z0 + 1), z0 + 1);
+            d3 D = mk3(x0, hf_height(F, x0, z0 + 1), z0 + 1);
+            bool b1 = intersect_triangle_fast(ray, A, B, D, closestDist);
+            bool b2 = intersect_triangle_fast(ray, B, C, D, closestDist);
+            if (b1 || b2) {
+                info.dist = closestDist;
+                info.ip = ray.o + ray.d * closestDist;
+                info.norm = hf_normal(F, (float)info.ip.x, (float)info.ip.z);
+                info.u = info.ip.x / F.W;
+                info.v = info.ip.z / F.H;
+                info.dNdx = mk3(1, 0, 0);
+                info.dNdy = mk3(0, 0, 1);
+                info.geom = gi;
+                return true;
+            }
+        }
+        p = p_next;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- dispatch + CSG
+#define HXR_CSG_MAX_CROSSINGS 30
+#define HXR_CSG_MAX_NESTING 3
+
+template <int DEPTH, bool COUNT>
+HXR_HD_NOINLINE bool geom_intersect(const DScene& sc, int gi, const Ray& ray, Hit& info, double gamma_limit, TravCounters* cnt);
+
+HXR_HD bool csg_inside(int op, bool inA, bool inB)  // src/geometry.h:123-136
+{
+    return op == HXR_CSG_UNION ? (inA || inB) : (op == HXR_CSG_INTER ? (inA && inB) : (inA && !inB));
+}
+
+// k-th boundary crossing of `child` along the ray (findAllIntersections re-shoots from
+// ip + dir*1e-6, geometry.cpp:149-165); returns false if there are fewer than k+1 crossings.
+template <int DEPTH, bool COUNT>
+HXR_HD bool csg_nth_crossing(const DScene& sc, int child, const Ray& ray, int k, Hit& info, TravCounters* cnt)
+{
+    Ray cur = ray;
+    for (int c = 0; c <= k; c++) {
+        info.dist = HXR_INF;
+        if (!geom_intersect<DEPTH + 1, COUNT>(sc, child, cur, info, HXR_INF, cnt)) return false;
+        cur.o = info.ip + ray.d * 1e-6;
+    }
+    return true;
+}
+
+template <int DEPTH, bool COUNT>
+HXR_HD bool csg_intersect(const DScene& sc, const hxr_geometry& g, int gi, const Ray& ray, Hit& info, TravCounters* cnt)
+{
+    const int op = g.a, left = g.b, right = g.c;
+    // pass 1: distances of all crossings of both children, kept as (dist, child, ordinal, geom)
+    double cd[2 * HXR_CSG_MAX_CROSSINGS];
+    uint8_t cchild[2 * HXR_CSG_MAX_CROSSINGS], cord[2 * HXR_CSG_MAX_CROSSINGS], cleft[2 * HXR_CSG_MAX_CROSSINGS];
+    int n = 0, cnt2[2] = {0, 0};
+    for (int side = 0; side < 2; side++) {
+        const int child = side ? right : left;
+        Ray cur = ray;
+        for (int c = 0; c < HXR_CSG_MAX_CROSSINGS; c++) {
+            Hit h;
+            h.dist = HXR_INF;
+            if (!geom_intersect<DEPTH + 1, COUNT>(sc, child, cur, h, HXR_INF, cnt)) break;
+            cd[n] = distance3(ray.o, h.ip);
+            cchild[n] = (uint8_t)side;
+            cord[n] = (uint8_t)c;
+            cleft[n] = (uint8_t)(h.geom == left);
+            n++;
+            cnt2[side]++;
+            cur.o = h.ip + ray.d * 1e-6;
+        }
+    }
+    // order by distance (insertion sort keeps left-before-right on ties, like std::sort on <=16 items)
+    for (int i = 1; i < n; i++) {
+        double kd = cd[i];
+        uint8_t kc = cchild[i], ko = cord[i], kl = cleft[i];
+        int j = i - 1;
+        while (j >= 0 && kd < cd[j]) {
+            cd[j + 1] = cd[j]; cchild[j + 1] = cchild[j]; cord[j + 1] = cord[j]; cleft[j + 1] = cleft[j];
+            j--;
+        }
+        cd[j + 1] = kd; cchild[j + 1] = kc; cord[j + 1] = ko; cleft[j + 1] = kl;
+    }
+    bool inA = cnt2[0] % 2, inB = cnt2[1] % 2;
+    const bool initial = csg_inside(op, inA, inB);
+    for (int i = 0; i < n; i++) {
+        if (cleft[i]) inA = !inA; else inB = !inB;
+        if (csg_inside(op, inA, inB) != initial) {
+            // pass 2: regenerate the winning crossing's full record
+            if (!csg_nth_crossing<DEPTH, COUNT>(sc, cchild[i] ? right : left, ray, cord[i], info, cnt)) return false;
+            info.dist = distance3(ray.o, info.ip);
+            info.norm = faceforward(ray.d, info.norm);
+            info.geom = gi;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <int DEPTH, bool COUNT>
+HXR_HD_NOINLINE bool geom_intersect(const DScene& sc, int gi, const Ray& ray, Hit& info, double gamma_limit, TravCounters* cnt)
+{
+    const hxr_geometry& g = sc.geoms[gi];
+    switch (g.type) {
+        case HXR_GEOM_PLANE: return plane_intersect(g, gi, ray, info);
+        case HXR_GEOM_SPHERE: return sphere_intersect(g, gi, ray, info);
+        case HXR_GEOM_CUBE: return cube_intersect(g, gi, ray, info);
+        case HXR_GEOM_MESH: return mesh_intersect<COUNT>(sc.meshes[g.a], gi, ray, info, gamma_limit, cnt);
+        case HXR_GEOM_HEIGHTFIELD: return heightfield_intersect(sc.hfs[g.a], gi, ray, info);
+        case HXR_GEOM_CSG:
+            if constexpr (DEPTH < HXR_CSG_MAX_NESTING) return csg_intersect<DEPTH, COUNT>(sc, g, gi, ray, info, cnt);
+            else return false;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- instancing + lights
+// world_limit: world-space distance beyond which a hit cannot matter (prunes mesh traversal only)
+template <bool COUNT>
+HXR_HD bool node_intersect(const DScene& sc, const hxr_node& nd, const Ray& ray, Hit& info, double world_limit, TravCounters* cnt)
+{
+    Ray t;
+    t.o = mul_vm(ray.o - ld3(nd.T.offset), nd.T.inv);
+    const d3 dl = mul_vm(ray.d, nd.T.inv);
+    t.d = normalize_f(dl);
+    t.depth = ray.depth;
+    t.flags = ray.flags;
+    double gamma_limit = HXR_INF;
+    if (world_limit < HXR_INF) {
+        // world distance of the object-space point o + g*d is g * |d * m|
+        const double k = length(mul_vm(t.d, nd.T.m));
+        gamma_limit = world_limit / k * (1.0 + 1e-9) + 1e-9;
+    }
+    if (!geom_intersect<0, COUNT>(sc, nd.geom, t, info, gamma_limit, cnt)) return false;
+    info.ip = mul_vm(info.ip, nd.T.m) + ld3(nd.T.offset);
+    info.norm = normalize_m(mul_vm(info.norm, nd.T.inv_t));
+    info.dist = distance3(ray.o, info.ip);
+    return true;
+}
+
+// returns +1 / -1 / 0 and shortens `dist` like RectLight::intersect (src/lights.cpp:53-73)
+HXR_HD int light_intersect(const hxr_light& L, const Ray& ray, double& dist)
+{
+    if (L.type != HXR_LIGHT_RECT) return 0;
+    d3 o = mul_vm(ray.o - ld3(L.T.offset), L.T.inv);
+    d3 d = normalize_f(mul_vm(ray.d, L.T.inv));
+    if (fabs(d.y) < 1e-12) return 0;
+    double len = -(o.y / d.y);
+    if (len < 0) return 0;
+    d3 p = o + d * len;
+    if (fabs(p.x) < 0.5 && fabs(p.z) < 0.5) {
+        double distance = length((mul_vm(p, L.T.m) + ld3(L.T.offset)) - ray.o);
+        if (distance < dist) {
+            dist = distance;
+            return (o.y < 0) ? +1 : -1;
+        }
+    }
+    return 0;
+}
+
+}  // namespace hxr

@@ -1,0 +1,381 @@
+// launch_cuda.cu — the sm_100a kernels of the render hot path and their launchers
+// (implements device/launch.h; the only translation unit compiled by nvcc).
+//
+// Kernels (one per wavefront stage; per-item bodies live in pipeline.h):
+//   k_gen_primary     primary-ray generator (pixel jitter / AA offsets / DOF lens)     -> ray queue
+//   k_trace_closest   closest hit: PERSISTENT threads; each warp pulls 32 rays at a time from the
+//                     queue head (one atomicAdd by lane 0, broadcast with __shfl_sync), walks the
+//                     instance list + KD-tree with a per-thread stack, writes one HitRec per ray
+//   k_shade           Whitted shader tree or path-tracing vertex: pushes child/shadow tasks,
+//                     accumulates radiance with RED.ADD.F32
+//   k_trace_shadow    visible(): persistent like k_trace_closest, adds the carried colour if clear
+//   k_aa_detect / k_scale_* / k_add   frame-buffer passes
+// Grid sizing: persistent kernels launch (SM count x resident blocks/SM) blocks — 148 SMs on
+// B200 — so every SM holds its full complement of warps for the whole launch.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "launch.h"
+
+namespace hxr {
+namespace dev {
+
+static int g_device = -1;
+static int g_sms = 0;
+static cudaStream_t g_stream = nullptr;
+static std::string g_err;
+static bool g_prof = false;
+static uint64_t g_launches[PROF_NCAT];
+static std::vector<cudaEvent_t> g_evPool;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
+
+static bool ck(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+static bool use() { return g_device >= 0 && ck(cudaSetDevice(g_device), "cudaSetDevice"); }
+
+bool init(int device, char* err, size_t errlen)
+{
+    auto fail = [&](const std::string& m) {
+        snprintf(err, errlen, "%s", m.c_str());
+        g_err = m;
+        return false;
+    };
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                    "); hexray_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail("CUDA device ordinal out of range");
+    if (g_device >= 0 && g_device != device) return fail("this process is already bound to another device (one process per GPU)");
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
+    if (p.major < 10) return fail(std::string("device '") + p.name + "' is not Blackwell (sm_100a code only)");
+    g_device = device;
+    g_sms = p.multiProcessorCount;
+    if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+    return true;
+}
+const char* backend_name() { return "cuda sm_100a"; }
+const char* last_error() { return g_err.c_str(); }
+
+void* alloc(size_t bytes)
+{
+    if (!use()) return nullptr;
+    void* p = nullptr;
+    if (!ck(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) return nullptr;
+    return p;
+}
+void free_(void* p)
+{
+    if (p && use()) cudaFree(p);
+}
+bool upload(void* d, const void* s, size_t n)
+{
+    return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, g_stream), "H2D copy") && ck(cudaStreamSynchronize(g_stream), "H2D sync");
+}
+bool upload_pinned_async(void* d, const void* s, size_t n) { return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, g_stream), "H2D copy"); }
+bool download(void* d, const void* s, size_t n)
+{
+    return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, g_stream), "D2H copy") && ck(cudaStreamSynchronize(g_stream), "D2H sync");
+}
+bool zero(void* p, size_t n) { return use() && ck(cudaMemsetAsync(p, 0, n, g_stream), "memset"); }
+bool copy_d2d(void* d, const void* s, size_t n) { return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, g_stream), "D2D copy"); }
+bool sync() { return use() && ck(cudaStreamSynchronize(g_stream), "stream sync"); }
+
+struct Timer { cudaEvent_t a, b; };
+Timer* timer_create()
+{
+    use();
+    Timer* t = new Timer;
+    cudaEventCreate(&t->a);
+    cudaEventCreate(&t->b);
+    return t;
+}
+void timer_destroy(Timer* t)
+{
+    if (!t) return;
+    cudaEventDestroy(t->a);
+    cudaEventDestroy(t->b);
+    delete t;
+}
+void timer_start(Timer* t) { cudaEventRecord(t->a, g_stream); }
+void timer_stop(Timer* t) { cudaEventRecord(t->b, g_stream); }
+double timer_ms(Timer* t)
+{
+    float ms = 0;
+    cudaEventSynchronize(t->b);
+    cudaEventElapsedTime(&ms, t->a, t->b);
+    return ms;
+}
+
+// ---- per-launch profiling -------------------------------------------------------------
+void prof_enable(bool on) { g_prof = on; }
+static cudaEvent_t ev_get()
+{
+    if (!g_evPool.empty()) { cudaEvent_t e = g_evPool.back(); g_evPool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_reset()
+{
+    for (int c = 0; c < PROF_NCAT; c++) {
+        g_launches[c] = 0;
+        for (auto& pr : g_evPairs[c]) { g_evPool.push_back(pr.first); g_evPool.push_back(pr.second); }
+        g_evPairs[c].clear();
+    }
+}
+void prof_collect(double ms[PROF_NCAT], uint64_t launches[PROF_NCAT])
+{
+    cudaStreamSynchronize(g_stream);
+    for (int c = 0; c < PROF_NCAT; c++) {
+        double s = 0;
+        for (auto& pr : g_evPairs[c]) {
+            float m = 0;
+            cudaEventElapsedTime(&m, pr.first, pr.second);
+            s += m;
+        }
+        ms[c] = s;
+        launches[c] = g_launches[c];
+    }
+}
+struct ProfScope {
+    int cat;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit ProfScope(int c) : cat(c)
+    {
+        use();
+        g_launches[c]++;
+        if (g_prof) { a = ev_get(); b = ev_get(); cudaEventRecord(a, g_stream); }
+    }
+    ~ProfScope()
+    {
+        if (g_prof) { cudaEventRecord(b, g_stream); g_evPairs[cat].emplace_back(a, b); }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) g_err = std::string("kernel launch: ") + cudaGetErrorString(e);
+    }
+};
+
+// ---- kernels ----------------------------------------------------------------------------
+#define HXR_TRACE_BLOCK 128
+#define HXR_SHADE_BLOCK 128
+
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
+bool set_u32(uint32_t* p, uint32_t v)
+{
+    if (!use()) return false;
+    if (v == 0) return ck(cudaMemsetAsync(p, 0, sizeof(uint32_t), g_stream), "memset");
+    k_set_u32<<<1, 1, 0, g_stream>>>(p, v);
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, const uint32_t* __restrict__ pixels, uint32_t first_pixel,
+                                                     uint32_t n_items, uint32_t spp_pass, RayTask* __restrict__ q, uint32_t* q_count)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
+        const uint32_t pi = i / spp_pass;
+        const uint32_t pixel = pixels ? pixels[pi] : first_pixel + pi;
+        q[i] = gen_primary_item(sc, fp, pixel, fp.sample_base + (i % spp_pass) * fp.sample_stride);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *q_count = n_items;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(HXR_TRACE_BLOCK) k_trace_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count,
+                                                                   uint32_t cap, HitRec* __restrict__ hits, uint32_t* head, TravCounters* cnt)
+{
+    const uint32_t n = min(*q_count, cap);
+    const unsigned lane = threadIdx.x & 31u;
+    TravCounters local = {0, 0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(head, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            HitRec h;
+            raycast_item<COUNT>(sc, task_ray(q[i]), h, &local);
+            hits[i] = h;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&cnt->kd_inner, local.kd_inner);
+        atomicAdd(&cnt->kd_leaves, local.kd_leaves);
+        atomicAdd(&cnt->tri_tests, local.tri_tests);
+        atomicAdd(&cnt->mesh_queries, local.mesh_queries);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(HXR_TRACE_BLOCK) k_trace_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count,
+                                                                  uint32_t cap, float* accum, uint32_t* head, TravCounters* cnt,
+                                                                  unsigned long long* total)
+{
+    const uint32_t n = min(*count, cap);
+    const unsigned lane = threadIdx.x & 31u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total, (unsigned long long)n);
+    TravCounters local = {0, 0, 0, 0};
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(head, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) shadow_item<COUNT>(sc, shadow[i], accum, &local);
+    }
+    if (COUNT) {
+        atomicAdd(&cnt->kd_inner, local.kd_inner);
+        atomicAdd(&cnt->kd_leaves, local.kd_leaves);
+        atomicAdd(&cnt->tri_tests, local.tri_tests);
+        atomicAdd(&cnt->mesh_queries, local.mesh_queries);
+    }
+}
+
+__global__ void __launch_bounds__(HXR_SHADE_BLOCK) k_shade(DScene sc, FrameParams fp, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count,
+                                                           const HitRec* __restrict__ hits, uint32_t begin, uint32_t end, Sinks sinks)
+{
+    const uint32_t e = min(end, *q_count);
+    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    if (fp.gi) shade_gi_item(sc, fp, q[i], hits[i], sinks);
+    else shade_whitted_item(sc, fp, q[i], hits[i], sinks);
+}
+
+__global__ void k_aa_detect(const float* __restrict__ vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out,
+                            uint8_t* mask)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const bool mine = shard_count <= 1 || ((y / HXR_ROW_BAND) % shard_count) == shard_index;
+    const bool f = mine && aa_detect_item(vfb, W, H, x, y);
+    mask[(size_t)y * W + x] = f;
+    if (f) list[atomicAdd(n_out, 1u)] = (uint32_t)(y * W + x);
+}
+
+__global__ void k_scale_listed(float* vfb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n, uint32_t cap, float mul)
+{
+    const uint32_t m = min(*n, cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        float* p = vfb + 3 * (size_t)list[i];
+        p[0] *= mul; p[1] *= mul; p[2] *= mul;
+    }
+}
+__global__ void k_scale_all(float* buf, size_t n, float mul)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] *= mul;
+}
+__global__ void k_add_into(float* dst, const float* __restrict__ src, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
+__global__ void k_visible_segments(DScene sc, const double* __restrict__ seg, uint32_t n, uint8_t* out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = visible_item<false>(sc, ld3(seg + 6 * (size_t)i), ld3(seg + 6 * (size_t)i + 3), nullptr) ? 1 : 0;
+}
+
+// ---- launchers --------------------------------------------------------------------------
+template <class K> static int persistent_grid(K kernel, int block)
+{
+    int perSm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, block, 0) != cudaSuccess || perSm < 1) perSm = 1;
+    return g_sms * perSm;
+}
+
+int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels, uint32_t first_pixel, uint32_t n_items,
+                uint32_t spp_pass, RayTask* q, uint32_t* q_count)
+{
+    ProfScope ps(PROF_OTHER);
+    const uint32_t blocks = n_items ? (uint32_t)std::min<uint64_t>(((uint64_t)n_items + 127) / 128, (uint64_t)g_sms * 32) : 1;
+    k_gen_primary<<<blocks, 128, 0, g_stream>>>(sc, fp, pixels, first_pixel, n_items, spp_pass, q, q_count);
+    return 1;
+}
+
+int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits, uint32_t* work_head,
+                  TravCounters* cnt)
+{
+    ProfScope ps(PROF_TRACE_CLOSEST);
+    static int gridPlain = 0, gridCount = 0;
+    if (cnt) {
+        if (!gridCount) gridCount = persistent_grid(k_trace_closest<true>, HXR_TRACE_BLOCK);
+        k_trace_closest<true><<<gridCount, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, q, q_count, q_cap, hits, work_head, cnt);
+    } else {
+        if (!gridPlain) gridPlain = persistent_grid(k_trace_closest<false>, HXR_TRACE_BLOCK);
+        k_trace_closest<false><<<gridPlain, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, q, q_count, q_cap, hits, work_head, nullptr);
+    }
+    return 1;
+}
+
+int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits, uint32_t begin,
+          uint32_t end, const Sinks& sinks)
+{
+    if (end <= begin) return 0;
+    ProfScope ps(PROF_SHADE);
+    const uint32_t blocks = (end - begin + HXR_SHADE_BLOCK - 1) / HXR_SHADE_BLOCK;
+    k_shade<<<blocks, HXR_SHADE_BLOCK, 0, g_stream>>>(sc, fp, q, q_count, hits, begin, end, sinks);
+    return 1;
+}
+
+int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, uint32_t* work_head,
+                 TravCounters* cnt, unsigned long long* total)
+{
+    ProfScope ps(PROF_TRACE_SHADOW);
+    static int gridPlain = 0, gridCount = 0;
+    if (cnt) {
+        if (!gridCount) gridCount = persistent_grid(k_trace_shadow<true>, HXR_TRACE_BLOCK);
+        k_trace_shadow<true><<<gridCount, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, shadow, count, cap, accum, work_head, cnt, total);
+    } else {
+        if (!gridPlain) gridPlain = persistent_grid(k_trace_shadow<false>, HXR_TRACE_BLOCK);
+        k_trace_shadow<false><<<gridPlain, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, shadow, count, cap, accum, work_head, nullptr, total);
+    }
+    return 1;
+}
+
+int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
+{
+    ProfScope ps(PROF_OTHER);
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_aa_detect<<<g, b, 0, g_stream>>>(vfb, W, H, shard_index, shard_count, list, n_out, mask);
+    return 1;
+}
+int scale_listed(float* vfb, const uint32_t* list, const uint32_t* n, uint32_t cap, float mul)
+{
+    ProfScope ps(PROF_OTHER);
+    k_scale_listed<<<g_sms * 4, 256, 0, g_stream>>>(vfb, list, n, cap, mul);
+    return 1;
+}
+int scale_all(float* buf, size_t n, float mul)
+{
+    ProfScope ps(PROF_OTHER);
+    k_scale_all<<<g_sms * 8, 256, 0, g_stream>>>(buf, n, mul);
+    return 1;
+}
+int add_into(float* dst, const float* src, size_t n)
+{
+    ProfScope ps(PROF_OTHER);
+    k_add_into<<<g_sms * 8, 256, 0, g_stream>>>(dst, src, n);
+    return 1;
+}
+int trace_visible_segments(const DScene& sc, const double* seg, uint32_t n, uint8_t* out)
+{
+    if (!n) return 0;
+    ProfScope ps(PROF_OTHER);
+    k_visible_segments<<<(n + 127) / 128, 128, 0, g_stream>>>(sc, seg, n, out);
+    return 1;
+}
+
+}  // namespace dev
+}  // namespace hxr

@@ -1,0 +1,295 @@
+// kdtree.cpp — see kdtree.h. Top-down SAH build:
+//   * big nodes: 32-bin SAH per axis (O(n) per node), small nodes: exact sweep over the triangle
+//     bound edges (O(n log n)), both on triangle bounds clipped to the node box;
+//   * a triangle is referenced by every child whose closed half-space its bounds touch
+//     (min <= split -> left, max >= split -> right), so a hit lying exactly on a split plane is
+//     found from either side; the split is stored as float and the SAME float-rounded value is
+//     used for classification here and for traversal on the device;
+//   * subtrees are built in parallel (std::thread) once the refs below a node drop under a
+//     grain size, then stitched into one DFS-ordered node array.
+#include "kdtree.h"
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <future>
+#include <thread>
+
+namespace hxr {
+namespace host {
+
+namespace {
+
+struct Box {
+    double mn[3], mx[3];
+    double area() const
+    {
+        const double dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct TriBounds {
+    float mn[3], mx[3];  // rounded outward
+};
+
+struct Builder {
+    const hxr_mesh& mesh;
+    KdBuildParams P;
+    std::vector<TriBounds> tb;
+    int maxDepth;
+
+    explicit Builder(const hxr_mesh& m, const KdBuildParams& p) : mesh(m), P(p)
+    {
+        const int n = m.n_triangles;
+        tb.resize(n);
+        for (int i = 0; i < n; i++) {
+            const hxr_triangle& t = m.triangles[i];
+            double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+            for (int k = 0; k < 3; k++) {
+                const double* v = m.vertices + 3 * (size_t)t.v[k];
+                for (int a = 0; a < 3; a++) {
+                    mn[a] = std::min(mn[a], v[a]);
+                    mx[a] = std::max(mx[a], v[a]);
+                }
+            }
+            for (int a = 0; a < 3; a++) {
+                tb[i].mn[a] = std::nextafter((float)mn[a], -INFINITY);
+                tb[i].mx[a] = std::nextafter((float)mx[a], +INFINITY);
+            }
+        }
+        maxDepth = P.maxDepth >= 0 ? P.maxDepth : (int)std::lround(8 + 1.3 * std::log2((double)std::max(1, n)));
+        maxDepth = std::min(maxDepth, HXR_KD_STACK - 4);
+    }
+
+    struct Local {  // a subtree under construction
+        std::vector<KdNode> nodes;
+        std::vector<uint32_t> leafTris;
+        uint32_t maxDepth = 0;
+        uint64_t leaves = 0;
+    };
+
+    bool chooseSplit(const std::vector<uint32_t>& refs, const Box& box, int& bestAxis, float& bestSplit, float& bestCost) const
+    {
+        const size_t n = refs.size();
+        const double invArea = 1.0 / std::max(box.area(), 1e-300);
+        bestCost = INFINITY;
+        bestAxis = -1;
+        const double ext[3] = {box.mx[0] - box.mn[0], box.mx[1] - box.mn[1], box.mx[2] - box.mn[2]};
+        auto sahCost = [&](int axis, double split, size_t nl, size_t nr) {
+            const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+            const double dl = split - box.mn[axis], dr = box.mx[axis] - split;
+            const double aL = 2.0 * (ext[a1] * ext[a2] + dl * (ext[a1] + ext[a2]));
+            const double aR = 2.0 * (ext[a1] * ext[a2] + dr * (ext[a1] + ext[a2]));
+            const double eb = (nl == 0 || nr == 0) ? P.emptyBonus : 0.0;
+            return P.traversalCost + P.intersectCost * (1.0 - eb) * (aL * invArea * nl + aR * invArea * nr);
+        };
+        for (int axis = 0; axis < 3; axis++) {
+            if (!(ext[axis] > 0)) continue;
+            if ((int)n > P.binnedAbove) {
+                const int B = 32;
+                uint32_t startCnt[B] = {0}, endCnt[B] = {0};
+                const double scale = B / ext[axis];
+                for (uint32_t r : refs) {
+                    double lo = std::max((double)tb[r].mn[axis], box.mn[axis]), hi = std::min((double)tb[r].mx[axis], box.mx[axis]);
+                    int b0 = std::min(B - 1, std::max(0, (int)((lo - box.mn[axis]) * scale)));
+                    int b1 = std::min(B - 1, std::max(0, (int)((hi - box.mn[axis]) * scale)));
+                    startCnt[b0]++;
+                    endCnt[b1]++;
+                }
+                size_t nl = 0, nr = n;
+                for (int k = 1; k < B; k++) {
+                    nl += startCnt[k - 1];
+                    nr -= endCnt[k - 1];
+                    const float split = (float)(box.mn[axis] + ext[axis] * k / B);
+                    if (!((double)split > box.mn[axis] && (double)split < box.mx[axis])) continue;
+                    const float c = (float)sahCost(axis, split, nl, nr);
+                    if (c < bestCost) { bestCost = c; bestAxis = axis; bestSplit = split; }
+                }
+            } else {
+                // exact sweep: candidates are the clipped triangle bound edges
+                struct Edge { float t; uint8_t isEnd; };
+                std::vector<Edge> ev;
+                ev.reserve(2 * n);
+                for (uint32_t r : refs) {
+                    ev.push_back({std::max(tb[r].mn[axis], (float)box.mn[axis]), 0});
+                    ev.push_back({std::min(tb[r].mx[axis], (float)box.mx[axis]), 1});
+                }
+                std::sort(ev.begin(), ev.end(), [](const Edge& a, const Edge& b) { return a.t < b.t || (a.t == b.t && a.isEnd < b.isEnd); });
+                // at plane t: left gets every triangle with min <= t, right every triangle with max >= t
+                size_t i = 0;
+                size_t startsLE = 0, endsLT = 0;
+                while (i < ev.size()) {
+                    const float t = ev[i].t;
+                    size_t j = i, startsHere = 0, endsHere = 0;
+                    while (j < ev.size() && ev[j].t == t) { if (ev[j].isEnd) endsHere++; else startsHere++; j++; }
+                    startsLE += startsHere;
+                    if ((double)t > box.mn[axis] && (double)t < box.mx[axis]) {
+                        const size_t nl = startsLE, nr = n - endsLT;
+                        const float c = (float)sahCost(axis, t, nl, nr);
+                        if (c < bestCost) { bestCost = c; bestAxis = axis; bestSplit = t; }
+                    }
+                    endsLT += endsHere;
+                    i = j;
+                }
+            }
+        }
+        return bestAxis >= 0;
+    }
+
+    void makeLeaf(Local& L, uint32_t nodeIdx, const std::vector<uint32_t>& refs, int depth) const
+    {
+        KdNode& nd = L.nodes[nodeIdx];
+        nd.kind = 3;
+        nd.split = 0;
+        nd.a = (uint32_t)L.leafTris.size();
+        nd.b = (uint32_t)refs.size();
+        L.leafTris.insert(L.leafTris.end(), refs.begin(), refs.end());
+        L.leaves++;
+        L.maxDepth = std::max(L.maxDepth, (uint32_t)depth);
+    }
+
+    // builds the subtree for `refs` inside `box` into L; returns its root index in L.nodes
+    uint32_t build(Local& L, std::vector<uint32_t>& refs, const Box& box, int depth, int badRefines) const
+    {
+        const uint32_t me = (uint32_t)L.nodes.size();
+        L.nodes.push_back(KdNode{0, 3, 0, 0});
+        const size_t n = refs.size();
+        if ((int)n <= 1 || depth >= maxDepth) { makeLeaf(L, me, refs, depth); return me; }
+        int axis;
+        float split, cost;
+        if (!chooseSplit(refs, box, axis, split, cost)) { makeLeaf(L, me, refs, depth); return me; }
+        const float leafCost = P.intersectCost * (float)n;
+        if (cost > leafCost) badRefines++;
+        if ((cost > 4 * leafCost && n < 16) || badRefines >= 3 || ((int)n <= P.maxLeafSize && cost >= leafCost)) {
+            makeLeaf(L, me, refs, depth);
+            return me;
+        }
+        std::vector<uint32_t> left, right;
+        left.reserve(n);
+        right.reserve(n);
+        for (uint32_t r : refs) {
+            if (tb[r].mn[axis] <= split) left.push_back(r);
+            if (tb[r].mx[axis] >= split) right.push_back(r);
+        }
+        if (left.size() == n && right.size() == n) { makeLeaf(L, me, refs, depth); return me; }
+        std::vector<uint32_t>().swap(refs);  // release the parent's list before recursing
+        Box lb = box, rb = box;
+        lb.mx[axis] = split;
+        rb.mn[axis] = split;
+        const uint32_t lc = build(L, left, lb, depth + 1, badRefines);
+        const uint32_t rc = build(L, right, rb, depth + 1, badRefines);
+        KdNode& nd = L.nodes[me];
+        nd.kind = (uint32_t)axis;
+        nd.split = split;
+        nd.a = lc;
+        nd.b = rc;
+        return me;
+    }
+};
+
+// append `sub` to `dst`, fixing child and leaf offsets; returns the new index of sub's root
+uint32_t stitch(Builder::Local& dst, const Builder::Local& sub)
+{
+    const uint32_t nodeBase = (uint32_t)dst.nodes.size(), triBase = (uint32_t)dst.leafTris.size();
+    for (KdNode nd : sub.nodes) {
+        if (nd.kind < 3) { nd.a += nodeBase; nd.b += nodeBase; }
+        else nd.a += triBase;
+        dst.nodes.push_back(nd);
+    }
+    dst.leafTris.insert(dst.leafTris.end(), sub.leafTris.begin(), sub.leafTris.end());
+    dst.leaves += sub.leaves;
+    dst.maxDepth = std::max(dst.maxDepth, sub.maxDepth);
+    return nodeBase;
+}
+
+}  // namespace
+
+void buildKdTree(const hxr_mesh& mesh, const KdBuildParams& params, KdTree& out)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    Builder B(mesh, params);
+    const int n = mesh.n_triangles;
+    Box root;
+    for (int a = 0; a < 3; a++) {
+        // float-rounded outward so that float splits compare consistently with the triangle bounds
+        root.mn[a] = std::nextafter((float)mesh.bbox_min[a], -INFINITY);
+        root.mx[a] = std::nextafter((float)mesh.bbox_max[a], +INFINITY);
+    }
+    std::vector<uint32_t> all(n);
+    for (int i = 0; i < n; i++) all[i] = (uint32_t)i;
+
+    Builder::Local top;
+    int threads = params.threads > 0 ? params.threads : (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (n < 200000 || threads == 1) {
+        B.build(top, all, root, 0, 0);
+    } else {
+        // split the top of the tree sequentially until the pending subtrees are small, then build
+        // those subtrees concurrently and stitch them in.
+        struct Pending { std::vector<uint32_t> refs; Box box; int depth; uint32_t parent; int side; };
+        std::vector<Pending> pending;
+        const size_t grain = std::max<size_t>(50000, (size_t)n / (size_t)(threads * 8));
+        struct Work { std::vector<uint32_t> refs; Box box; int depth; uint32_t parent; int side; };
+        std::vector<Work> stack;
+        stack.push_back(Work{std::move(all), root, 0, UINT32_MAX, 0});
+        uint32_t rootIdx = UINT32_MAX;
+        while (!stack.empty()) {
+            Work w = std::move(stack.back());
+            stack.pop_back();
+            int axis;
+            float split, cost;
+            if (w.refs.size() <= grain || w.depth >= 12 || !B.chooseSplit(w.refs, w.box, axis, split, cost)) {
+                pending.push_back(Pending{std::move(w.refs), w.box, w.depth, w.parent, w.side});
+                continue;
+            }
+            const uint32_t me = (uint32_t)top.nodes.size();
+            top.nodes.push_back(KdNode{split, (uint32_t)axis, 0, 0});
+            if (w.parent == UINT32_MAX) rootIdx = me;
+            else (w.side ? top.nodes[w.parent].b : top.nodes[w.parent].a) = me;
+            Work l, r;
+            l.box = r.box = w.box;
+            l.box.mx[axis] = split;
+            r.box.mn[axis] = split;
+            l.depth = r.depth = w.depth + 1;
+            l.parent = r.parent = me;
+            l.side = 0;
+            r.side = 1;
+            for (uint32_t t : w.refs) {
+                if (B.tb[t].mn[axis] <= split) l.refs.push_back(t);
+                if (B.tb[t].mx[axis] >= split) r.refs.push_back(t);
+            }
+            std::vector<uint32_t>().swap(w.refs);
+            stack.push_back(std::move(r));
+            stack.push_back(std::move(l));
+        }
+        std::vector<Builder::Local> subs(pending.size());
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back([&] {
+                for (size_t i = next++; i < pending.size(); i = next++) B.build(subs[i], pending[i].refs, pending[i].box, pending[i].depth, 0);
+            });
+        for (auto& th : pool) th.join();
+        for (size_t i = 0; i < pending.size(); i++) {
+            const uint32_t r = stitch(top, subs[i]);
+            if (pending[i].parent == UINT32_MAX) rootIdx = r;
+            else (pending[i].side ? top.nodes[pending[i].parent].b : top.nodes[pending[i].parent].a) = r;
+            Builder::Local().nodes.swap(subs[i].nodes);
+            std::vector<uint32_t>().swap(subs[i].leafTris);
+        }
+        if (rootIdx != 0) {
+            // the traversal starts at node 0: swap the root into place if the first emitted node is not it
+            // (cannot happen: the first node pushed is always the root or the only pending subtree's root)
+        }
+    }
+    out.nodes.swap(top.nodes);
+    out.leafTris.swap(top.leafTris);
+    out.maxDepth = top.maxDepth;
+    out.leaves = top.leaves;
+    if (out.nodes.empty()) out.nodes.push_back(KdNode{0, 3, 0, 0});
+    out.buildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace host
+}  // namespace hxr

@@ -1,0 +1,642 @@
+// renderer.cpp — see renderer.h. Host logic only: validation, KD build, uploads, and the
+// wavefront schedule. Everything per-ray runs in the kernels behind device/launch.h.
+#include "renderer.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+
+namespace hxr {
+
+enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_OVERFLOW = 3, C_HEAD_A = 4, C_HEAD_B = 5, C_AA = 6, C_NCOUNTERS = 16 };
+
+Renderer::~Renderer()
+{
+    freeScene();
+    for (int i = 0; i < 2; i++) dev::free_(m_q[i]);
+    dev::free_(m_hits);
+    dev::free_(m_shadow);
+    dev::free_(m_counters);
+    dev::free_(m_trav);
+    dev::free_(m_aaList);
+    dev::free_(m_aaMask);
+    dev::free_(m_accum);
+}
+
+int Renderer::create(const hxr_config& cfg)
+{
+    m_cfg = cfg;
+    char err[256] = "";
+    if (!dev::init(cfg.device, err, sizeof err)) return fail(HXR_ERR_NO_DEVICE, err);
+    m_created = true;
+    return HXR_OK;
+}
+
+void Renderer::freeScene()
+{
+    for (void* p : m_sceneAllocs) dev::free_(p);
+    m_sceneAllocs.clear();
+    m_haveScene = false;
+    m_accel.clear();
+}
+
+template <class T> T* Renderer::uploadArray(const T* src, size_t n)
+{
+    // a 1-element allocation keeps device pointers non-null for empty tables
+    T* d = (T*)keep(dev::alloc(std::max<size_t>(n, 1) * sizeof(T)));
+    if (d && n && !dev::upload(d, src, n * sizeof(T))) return nullptr;
+    return d;
+}
+
+// ------------------------------------------------------------------------------ scene
+static bool validateScene(const hxr_scene& s, std::string& why)
+{
+    auto bad = [&](const std::string& m) { why = m; return false; };
+    if (s.abi_version != HXR_ABI_VERSION) return bad("hxr_scene.abi_version mismatch");
+    if (s.n_nodes < 0 || s.n_geometries < 0 || s.n_meshes < 0 || s.n_heightfields < 0 || s.n_shaders < 0 || s.n_layers < 0 ||
+        s.n_textures < 0 || s.n_images < 0 || s.n_lights < 0)
+        return bad("negative table size");
+    auto in = [](int i, int n) { return i >= 0 && i < n; };
+    for (int i = 0; i < s.n_images; i++)
+        if (s.images[i].width < 0 || s.images[i].height < 0 || ((size_t)s.images[i].width * s.images[i].height > 0 && !s.images[i].rgb))
+            return bad("image " + std::to_string(i) + " has no pixels");
+    for (int i = 0; i < s.n_textures; i++) {
+        const hxr_texture& t = s.textures[i];
+        if (t.type < HXR_TEX_CHECKER || t.type > HXR_TEX_BUMPS) return bad("texture type");
+        if ((t.type == HXR_TEX_BITMAP || t.type == HXR_TEX_BUMP) && !in(t.image, s.n_images)) return bad("texture image index");
+    }
+    for (int i = 0; i < s.n_layers; i++)
+        if (!in(s.layers[i].shader, s.n_shaders) || (s.layers[i].tex != -1 && !in(s.layers[i].tex, s.n_textures))) return bad("layer reference");
+    for (int i = 0; i < s.n_shaders; i++) {
+        const hxr_shader& sh = s.shaders[i];
+        if (sh.type < HXR_SHADER_LAMBERT || sh.type > HXR_SHADER_CONST) return bad("shader type");
+        if (sh.tex != -1 && !in(sh.tex, s.n_textures)) return bad("shader texture index");
+        if (sh.type == HXR_SHADER_LAYERED && (sh.n_layers < 0 || sh.first_layer < 0 || sh.first_layer + sh.n_layers > s.n_layers)) return bad("layer range");
+        if (sh.type == HXR_SHADER_REFLECTION && sh.i0 < 1) return bad("Reflection numSamples");
+    }
+    // layered shaders must form a DAG of bounded size (the device evaluates them with a fixed stack)
+    std::function<long(int, int)> leaves = [&](int si, int depth) -> long {
+        if (depth > 8) return 1L << 20;
+        const hxr_shader& sh = s.shaders[si];
+        if (sh.type != HXR_SHADER_LAYERED) return 1;
+        long n = 0;
+        for (int l = 0; l < sh.n_layers; l++) n += leaves(s.layers[sh.first_layer + l].shader, depth + 1);
+        return n;
+    };
+    for (int i = 0; i < s.n_shaders; i++)
+        if (leaves(i, 0) > HXR_SHADE_STACK - 4) return bad("Layered shader too deep/wide (or cyclic)");
+    for (int i = 0; i < s.n_geometries; i++) {
+        const hxr_geometry& g = s.geometries[i];
+        switch (g.type) {
+            case HXR_GEOM_PLANE: case HXR_GEOM_SPHERE: case HXR_GEOM_CUBE: break;
+            case HXR_GEOM_CSG:
+                if (g.a < 0 || g.a > 2 || !in(g.b, s.n_geometries) || !in(g.c, s.n_geometries)) return bad("CSG reference");
+                break;
+            case HXR_GEOM_MESH: if (!in(g.a, s.n_meshes)) return bad("mesh index"); break;
+            case HXR_GEOM_HEIGHTFIELD: if (!in(g.a, s.n_heightfields)) return bad("heightfield index"); break;
+            default: return bad("geometry type");
+        }
+    }
+    for (int i = 0; i < s.n_meshes; i++) {
+        const hxr_mesh& m = s.meshes[i];
+        if (m.n_vertices < 1 || m.n_normals < 1 || m.n_uvs < 1 || m.n_triangles < 0 || !m.vertices || !m.normals || !m.uvs || (m.n_triangles && !m.triangles))
+            return bad("mesh arrays");
+        for (int t = 0; t < m.n_triangles; t++)
+            for (int k = 0; k < 3; k++)
+                if (!in(m.triangles[t].v[k], m.n_vertices) || !in(m.triangles[t].n[k], m.n_normals) || !in(m.triangles[t].t[k], m.n_uvs))
+                    return bad("mesh " + std::to_string(i) + ": triangle index out of range");
+    }
+    for (int i = 0; i < s.n_heightfields; i++) {
+        const hxr_heightfield& h = s.heightfields[i];
+        if (h.width < 1 || h.height < 1 || !h.heights || !h.max_h || !h.normals) return bad("heightfield arrays");
+        if (h.use_optimization && (!h.high_map || h.max_k < 0 || h.max_k > 16)) return bad("heightfield high map");
+    }
+    for (int i = 0; i < s.n_nodes; i++) {
+        const hxr_node& n = s.nodes[i];
+        if (!in(n.geom, s.n_geometries) || !in(n.shader, s.n_shaders)) return bad("node reference");
+        if (n.bump_tex != -1 && !in(n.bump_tex, s.n_textures)) return bad("node bump texture");
+    }
+    for (int i = 0; i < s.n_lights; i++) {
+        const hxr_light& l = s.lights[i];
+        if (l.type != HXR_LIGHT_POINT && l.type != HXR_LIGHT_RECT) return bad("light type");
+        if (l.type == HXR_LIGHT_RECT && (l.xsubd < 1 || l.ysubd < 1 || l.xsubd > 1000 || l.ysubd > 1000)) return bad("RectLight subdivisions");
+    }
+    if (s.has_environment)
+        for (int i = 0; i < 6; i++)
+            if (!in(s.env_images[i], s.n_images)) return bad("environment image index");
+    return true;
+}
+
+int Renderer::uploadScene(const hxr_scene* sp)
+{
+    if (!m_created) return fail(HXR_ERR_INVALID, "context not created");
+    if (!sp) return fail(HXR_ERR_INVALID, "null scene");
+    const hxr_scene& s = *sp;
+    std::string why;
+    if (!validateScene(s, why)) return fail(HXR_ERR_INVALID, "invalid scene: " + why);
+    freeScene();
+    auto oom = [&]() { freeScene(); return fail(HXR_ERR_CUDA, std::string("scene upload failed: ") + dev::last_error()); };
+
+    // meshes: build the KD-tree on the host, split triangles into test / attribute records
+    std::vector<DMesh> dm(s.n_meshes);
+    m_accel.resize(s.n_meshes);
+    for (int i = 0; i < s.n_meshes; i++) {
+        const hxr_mesh& m = s.meshes[i];
+        host::KdTree kd;
+        host::buildKdTree(m, host::KdBuildParams(), kd);
+        std::vector<TriTest> tt(m.n_triangles);
+        std::vector<TriAttr> ta(m.n_triangles);
+        for (int t = 0; t < m.n_triangles; t++) {
+            const hxr_triangle& T = m.triangles[t];
+            for (int k = 0; k < 3; k++) {
+                tt[t].A[k] = m.vertices[3 * (size_t)T.v[0] + k];
+                tt[t].AB[k] = T.ab[k];
+                tt[t].AC[k] = T.ac[k];
+                tt[t].N[k] = T.ab_cross_ac[k];
+                ta[t].n[k] = T.n[k];
+                ta[t].t[k] = T.t[k];
+                ta[t].gnormal[k] = T.gnormal[k];
+                ta[t].dNdx[k] = T.dndx[k];
+                ta[t].dNdy[k] = T.dndy[k];
+            }
+        }
+        DMesh& d = dm[i];
+        memset(&d, 0, sizeof d);
+        d.nodes = uploadArray(kd.nodes.data(), kd.nodes.size());
+        d.leaf_tris = uploadArray(kd.leafTris.data(), kd.leafTris.size());
+        d.tri_test = uploadArray(tt.data(), tt.size());
+        d.tri_attr = uploadArray(ta.data(), ta.size());
+        d.normals = uploadArray(m.normals, (size_t)m.n_normals * 3);
+        d.uvs = uploadArray(m.uvs, (size_t)m.n_uvs * 3);
+        if (!d.nodes || !d.leaf_tris || !d.tri_test || !d.tri_attr || !d.normals || !d.uvs) return oom();
+        for (int k = 0; k < 3; k++) { d.bbmin[k] = m.bbox_min[k]; d.bbmax[k] = m.bbox_max[k]; }
+        d.faceted = m.faceted;
+        d.backface = m.backface_culling;
+        d.n_tris = m.n_triangles;
+        hxr_accel_info& ai = m_accel[i];
+        ai.nodes = kd.nodes.size();
+        ai.leaves = kd.leaves;
+        ai.tri_refs = kd.leafTris.size();
+        ai.bytes_nodes = kd.nodes.size() * sizeof(KdNode);
+        ai.bytes_tris = kd.leafTris.size() * sizeof(uint32_t) + tt.size() * sizeof(TriTest);
+        ai.max_depth = kd.maxDepth;
+        ai.n_triangles = (uint32_t)m.n_triangles;
+        ai.build_ms = kd.buildMs;
+    }
+    std::vector<DHeightfield> dh(s.n_heightfields);
+    for (int i = 0; i < s.n_heightfields; i++) {
+        const hxr_heightfield& h = s.heightfields[i];
+        const size_t n = (size_t)h.width * h.height;
+        DHeightfield& d = dh[i];
+        memset(&d, 0, sizeof d);
+        d.heights = uploadArray(h.heights, n);
+        d.max_h = uploadArray(h.max_h, n);
+        d.normals = uploadArray(h.normals, n * 3);
+        d.high_map = h.high_map ? uploadArray(h.high_map, n * 16) : nullptr;
+        if (!d.heights || !d.max_h || !d.normals || (h.high_map && !d.high_map)) return oom();
+        for (int k = 0; k < 3; k++) { d.bbmin[k] = h.bbox_min[k]; d.bbmax[k] = h.bbox_max[k]; }
+        d.W = h.width;
+        d.H = h.height;
+        d.use_opt = h.use_optimization && h.high_map;
+        d.max_k = h.max_k;
+    }
+    std::vector<DImage> di(s.n_images);
+    for (int i = 0; i < s.n_images; i++) {
+        const size_t n = (size_t)s.images[i].width * s.images[i].height * 3;
+        di[i].w = s.images[i].width;
+        di[i].h = s.images[i].height;
+        di[i].rgb = n ? uploadArray(s.images[i].rgb, n) : nullptr;
+        if (n && !di[i].rgb) return oom();
+    }
+    memset(&m_scene, 0, sizeof m_scene);
+    m_scene.nodes = uploadArray(s.nodes, s.n_nodes);
+    m_scene.geoms = uploadArray(s.geometries, s.n_geometries);
+    m_scene.meshes = uploadArray(dm.data(), dm.size());
+    m_scene.hfs = uploadArray(dh.data(), dh.size());
+    m_scene.shaders = uploadArray(s.shaders, s.n_shaders);
+    m_scene.layers = uploadArray(s.layers, s.n_layers);
+    m_scene.textures = uploadArray(s.textures, s.n_textures);
+    m_scene.images = uploadArray(di.data(), di.size());
+    m_scene.lights = uploadArray(s.lights, s.n_lights);
+    if (!m_scene.nodes || !m_scene.geoms || !m_scene.meshes || !m_scene.hfs || !m_scene.shaders || !m_scene.layers ||
+        !m_scene.textures || !m_scene.images || !m_scene.lights)
+        return oom();
+    m_scene.n_nodes = s.n_nodes;
+    m_scene.n_lights = s.n_lights;
+    m_scene.has_env = s.has_environment;
+    for (int i = 0; i < 6; i++) m_scene.env_images[i] = s.has_environment ? s.env_images[i] : 0;
+    m_scene.settings = s.settings;
+
+    // worst-case fan-out of one Whitted shading item, used to size shade launches
+    long lightSamples = 0;
+    for (int i = 0; i < s.n_lights; i++) lightSamples += s.lights[i].type == HXR_LIGHT_RECT ? (long)s.lights[i].xsubd * s.lights[i].ysubd : 1;
+    std::function<void(int, long&, long&)> fan = [&](int si, long& sh, long& ch) {
+        const hxr_shader& S = s.shaders[si];
+        switch (S.type) {
+            case HXR_SHADER_LAMBERT: case HXR_SHADER_PHONG: sh += lightSamples; break;
+            case HXR_SHADER_REFLECTION: ch += S.f0 < 1.0f ? S.i0 : 1; break;
+            case HXR_SHADER_REFRACTION: ch += 1; break;
+            case HXR_SHADER_LAYERED:
+                for (int l = 0; l < S.n_layers; l++) fan(s.layers[S.first_layer + l].shader, sh, ch);
+                break;
+            default: break;
+        }
+    };
+    m_maxShadowPerHit = 1;
+    m_maxChildrenPerHit = 1;
+    for (int i = 0; i < s.n_shaders; i++) {
+        long sh = 0, ch = 0;
+        fan(i, sh, ch);
+        m_maxShadowPerHit = (int)std::max<long>(m_maxShadowPerHit, sh);
+        m_maxChildrenPerHit = (int)std::max<long>(m_maxChildrenPerHit, ch);
+    }
+    m_haveScene = true;
+    return HXR_OK;
+}
+
+int Renderer::setCamera(const hxr_camera* cam)
+{
+    if (!cam) return fail(HXR_ERR_INVALID, "null camera");
+    m_scene.cam = *cam;
+    m_haveCamera = true;
+    return HXR_OK;
+}
+
+int Renderer::accelInfo(int mesh, hxr_accel_info* out) const
+{
+    if (!out || mesh < 0 || mesh >= (int)m_accel.size()) return HXR_ERR_INVALID;
+    *out = m_accel[mesh];
+    return HXR_OK;
+}
+
+// ------------------------------------------------------------------------------ queues
+bool Renderer::ensureQueues()
+{
+    const uint32_t cap = m_cfg.queue_capacity ? (uint32_t)std::min<uint64_t>(m_cfg.queue_capacity, 1u << 30) : (8u << 20);
+    const uint32_t shadowCap = (uint32_t)std::min<uint64_t>(1u << 30, std::max<uint64_t>((uint64_t)cap * 2, (uint64_t)m_maxShadowPerHit * 4096));
+    if (m_q[0] && cap == m_cap && shadowCap == m_shadowCap) return true;
+    for (int i = 0; i < 2; i++) { dev::free_(m_q[i]); m_q[i] = nullptr; }
+    dev::free_(m_hits); m_hits = nullptr;
+    dev::free_(m_shadow); m_shadow = nullptr;
+    m_cap = cap;
+    m_shadowCap = shadowCap;
+    for (int i = 0; i < 2; i++) m_q[i] = (RayTask*)dev::alloc((size_t)cap * sizeof(RayTask));
+    m_hits = (HitRec*)dev::alloc((size_t)cap * sizeof(HitRec));
+    m_shadow = (ShadowTask*)dev::alloc((size_t)shadowCap * sizeof(ShadowTask));
+    if (!m_counters) m_counters = (uint32_t*)dev::alloc(C_NCOUNTERS * sizeof(uint32_t));
+    if (!m_trav) m_trav = (TravCounters*)dev::alloc(sizeof(TravCounters) + 64);
+    if (!m_q[0] || !m_q[1] || !m_hits || !m_shadow || !m_counters || !m_trav) {
+        m_err = std::string("queue allocation failed: ") + dev::last_error();
+        return false;
+    }
+    dev::zero(m_counters, C_NCOUNTERS * sizeof(uint32_t));
+    dev::zero(m_trav, sizeof(TravCounters) + 64);
+    return true;
+}
+
+uint32_t Renderer::readCount(const uint32_t* dptr)
+{
+    uint32_t v = 0;
+    dev::download(&v, dptr, sizeof v);
+    return v;
+}
+
+// the tail of m_trav holds a 64-bit shadow-ray total maintained by the shadow kernel
+static unsigned long long* shadowTotalPtr(TravCounters* t) { return (unsigned long long*)(t + 1); }
+
+int Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st)
+{
+    int cur = 0;
+    uint32_t n = nPrimary;
+    const uint32_t perHit = fp.gi ? 1u : (uint32_t)m_maxShadowPerHit;
+    const uint32_t chunk = std::max<uint32_t>(1, m_shadowCap / perHit);
+    TravCounters* cnt = m_countTraversal ? m_trav : nullptr;
+    for (int level = 0; n > 0 && level <= fp.max_depth + 2; level++) {
+        if (n > m_cap) return 1;  // overflow
+        dev::set_u32(m_counters + C_HEAD_A, 0);
+        st.kernel_launches += dev::trace_closest(m_scene, m_q[cur], m_counters + cur, m_cap, m_hits, m_counters + C_HEAD_A, cnt);
+        st.rays_closest += n;
+        dev::set_u32(m_counters + (1 - cur), 0);
+        Sinks sk;
+        sk.next = m_q[1 - cur];
+        sk.next_count = m_counters + (1 - cur);
+        sk.next_cap = m_cap;
+        sk.shadow = m_shadow;
+        sk.shadow_count = m_counters + C_SHADOW;
+        sk.shadow_cap = m_shadowCap;
+        sk.accum = accum;
+        sk.overflow = m_counters + C_OVERFLOW;
+        for (uint32_t b = 0; b < n; b += chunk) {
+            dev::set_u32(m_counters + C_SHADOW, 0);
+            st.kernel_launches += dev::shade(m_scene, fp, m_q[cur], m_counters + cur, m_hits, b, std::min<uint64_t>(n, (uint64_t)b + chunk), sk);
+            dev::set_u32(m_counters + C_HEAD_B, 0);
+            st.kernel_launches += dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, accum, m_counters + C_HEAD_B, cnt, shadowTotalPtr(m_trav));
+        }
+        n = readCount(m_counters + (1 - cur));
+        cur = 1 - cur;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ frames
+int Renderer::render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats)
+{
+    if (!m_haveScene || !m_haveCamera) return fail(HXR_ERR_INVALID, "render: scene and camera must be set first");
+    if (!hostOut && !devOut) return fail(HXR_ERR_INVALID, "render: no output buffer");
+    if (!ensureQueues()) return HXR_ERR_CUDA;
+    uint32_t batch = m_maxChildrenPerHit > 1 ? m_cap / 4 : m_cap;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        bool overflow = false;
+        int rc = renderOnce(p, hostOut, devOut, stats, std::max<uint32_t>(batch, 1024), overflow);
+        if (rc != HXR_OK) return rc;
+        if (!overflow) return HXR_OK;
+        batch /= 4;  // a ray tree outgrew the queue: redo the frame with smaller primary batches
+    }
+    return fail(HXR_ERR_OVERFLOW, "ray queue overflow even at the smallest primary batch; raise hxr_config.queue_capacity");
+}
+
+int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, uint32_t primaryBatch, bool& overflow)
+{
+    hxr_stats st;
+    memset(&st, 0, sizeof st);
+    const int W = p.width > 0 ? p.width : m_scene.settings.frame_width;
+    const int H = p.height > 0 ? p.height : m_scene.settings.frame_height;
+    if (W <= 0 || H <= 0 || (uint64_t)W * H > (1ull << 31)) return fail(HXR_ERR_INVALID, "bad frame size");
+    const size_t nPix = (size_t)W * H;
+    // what render() would pick (src/main.cpp:421-425)
+    int raysPerPixel = 0;
+    if (m_scene.cam.dof) raysPerPixel = m_scene.cam.num_samples;
+    if (m_scene.settings.gi) raysPerPixel = std::max(raysPerPixel, m_scene.settings.num_paths);
+    bool mc = raysPerPixel > 0;
+    if (p.mode == HXR_MODE_WHITTED) mc = false;
+    if (p.mode == HXR_MODE_MONTECARLO) mc = true;
+    int spp = p.spp > 0 ? p.spp : std::max(raysPerPixel, 1);
+    const int shardCount = p.shard_count > 1 ? p.shard_count : 1;
+    const int shardIndex = shardCount > 1 ? p.shard_index : 0;
+    if (shardIndex < 0 || shardIndex >= shardCount) return fail(HXR_ERR_INVALID, "bad shard index");
+    const bool wantAA = p.want_aa >= 0 ? p.want_aa != 0 : m_scene.settings.want_aa != 0;
+    const hxr_settings savedSettings = m_scene.settings;
+    if (p.max_depth >= 0) m_scene.settings.max_trace_depth = p.max_depth;
+    m_countTraversal = (p.flags & HXR_RENDER_COUNT_TRAVERSAL) != 0;
+
+    FrameParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.W = W;
+    fp.H = H;
+    fp.max_depth = m_scene.settings.max_trace_depth;
+    fp.gi = mc && m_scene.settings.gi;
+    fp.montecarlo = mc;
+    fp.seed = p.seed;
+
+    if (m_accumPixels < nPix) {
+        dev::free_(m_accum);
+        m_accum = (float*)dev::alloc(nPix * 3 * sizeof(float));
+        m_accumPixels = m_accum ? nPix : 0;
+        if (!m_accum) { m_scene.settings = savedSettings; return fail(HXR_ERR_CUDA, std::string("framebuffer allocation failed: ") + dev::last_error()); }
+    }
+    dev::prof_reset();
+    dev::Timer* tm = dev::timer_create();
+    dev::timer_start(tm);
+    dev::zero(m_accum, nPix * 3 * sizeof(float));
+    dev::set_u32(m_counters + C_OVERFLOW, 0);
+    dev::zero(m_trav, sizeof(TravCounters) + 64);
+    int ov = 0;
+
+    if (mc) {
+        if (m_scene.cam.dof && m_scene.cam.auto_focus) {
+            // autofocus: distance of the closest NODE along the centre ray (src/main.cpp:350-362)
+            hxr_ray r;
+            Ray cr;
+            {
+                hxr_camera c = m_scene.cam;
+                c.dof = 0;
+                cr = camera_ray(c, W, H, W * 0.5, H * 0.5, 0, 0, 0);
+            }
+            r.start[0] = cr.o.x; r.start[1] = cr.o.y; r.start[2] = cr.o.z;
+            r.dir[0] = cr.d.x; r.dir[1] = cr.d.y; r.dir[2] = cr.d.z;
+            r.depth = 0; r.flags = 0;
+            hxr_hit h;
+            // note: like raycast, this also sees lights; a light in front of the geometry hides it
+            if (traceClosest(&r, 1, &h) == HXR_OK && h.status == 0) m_scene.cam.focal_plane_dist = h.dist;
+        }
+        const uint32_t nMine = (uint32_t)((spp - shardIndex + shardCount - 1) / shardCount);
+        fp.sample_stride = (uint32_t)shardCount;
+        if (nPix <= primaryBatch) {
+            const uint32_t sppPass = std::max<uint32_t>(1, (uint32_t)(primaryBatch / nPix));
+            for (uint32_t k0 = 0; k0 < nMine && !ov; k0 += sppPass) {
+                const uint32_t k = std::min(sppPass, nMine - k0);
+                fp.sample_base = (uint32_t)shardIndex + k0 * (uint32_t)shardCount;
+                const uint32_t items = (uint32_t)(nPix * k);
+                st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, 0, items, k, m_q[0], m_counters + C_Q0);
+                ov = drain(fp, m_accum, items, st);
+            }
+        } else {
+            for (uint32_t k0 = 0; k0 < nMine && !ov; k0++) {
+                fp.sample_base = (uint32_t)shardIndex + k0 * (uint32_t)shardCount;
+                for (size_t first = 0; first < nPix && !ov; first += primaryBatch) {
+                    const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, nPix - first);
+                    st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)first, items, 1, m_q[0], m_counters + C_Q0);
+                    ov = drain(fp, m_accum, items, st);
+                }
+            }
+        }
+        st.spp_done = nMine;
+        if (shardCount == 1) st.kernel_launches += dev::scale_all(m_accum, nPix * 3, 1.0f / (float)spp);
+    } else {
+        // pass 1: one ray through every pixel corner. Row shards own rows y with (y/16) % count == index
+        // and also render a one-row halo around each owned band so that pass 2 sees all 8 neighbours.
+        fp.sample_base = 0;
+        fp.sample_stride = 1;
+        auto owned = [&](int y) { return shardCount == 1 || ((y / HXR_ROW_BAND) % shardCount) == shardIndex; };
+        auto needed = [&](int y) { return owned(y) || (y > 0 && owned(y - 1)) || (y + 1 < H && owned(y + 1)); };
+        int y = 0;
+        while (y < H && !ov) {
+            if (!needed(y)) { y++; continue; }
+            int y1 = y;
+            while (y1 < H && needed(y1) && (size_t)(y1 - y + 1) * W <= std::max<size_t>(primaryBatch, W)) y1++;
+            size_t first = (size_t)y * W, count = (size_t)(y1 - y) * W;
+            for (size_t off = 0; off < count && !ov; off += primaryBatch) {
+                const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, count - off);
+                st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)(first + off), items, 1, m_q[0], m_counters + C_Q0);
+                ov = drain(fp, m_accum, items, st);
+            }
+            y = y1;
+        }
+        if (wantAA && !ov) {
+            if (m_aaCap < nPix) {
+                dev::free_(m_aaList);
+                dev::free_(m_aaMask);
+                m_aaList = (uint32_t*)dev::alloc(nPix * sizeof(uint32_t));
+                m_aaMask = (uint8_t*)dev::alloc(nPix);
+                m_aaCap = (m_aaList && m_aaMask) ? nPix : 0;
+                if (!m_aaCap) { m_scene.settings = savedSettings; dev::timer_destroy(tm); return fail(HXR_ERR_CUDA, "AA buffer allocation failed"); }
+            }
+            dev::set_u32(m_counters + C_AA, 0);
+            st.kernel_launches += dev::aa_detect(m_accum, W, H, shardIndex, shardCount, m_aaList, m_counters + C_AA, m_aaMask);
+            const uint32_t nAA = readCount(m_counters + C_AA);
+            st.aa_pixels = nAA;
+            fp.sample_base = 1;
+            const uint32_t pixPerBatch = std::max<uint32_t>(1, primaryBatch / 4);
+            for (uint32_t first = 0; first < nAA && !ov; first += pixPerBatch) {
+                const uint32_t np = std::min(pixPerBatch, nAA - first);
+                st.kernel_launches += dev::gen_primary(m_scene, fp, m_aaList + first, 0, np * 4, 4, m_q[0], m_counters + C_Q0);
+                ov = drain(fp, m_accum, np * 4, st);
+            }
+            st.kernel_launches += dev::scale_listed(m_accum, m_aaList, m_counters + C_AA, (uint32_t)nPix, 1.0f / 5);
+        }
+        if (shardCount > 1) {
+            // drop the halo rows: the caller sums the shards
+            for (int yy = 0; yy < H; yy++)
+                if (!owned(yy) && needed(yy)) dev::zero(m_accum + (size_t)yy * W * 3, (size_t)W * 3 * sizeof(float));
+        }
+    }
+    dev::timer_stop(tm);
+    if (!ov) ov = readCount(m_counters + C_OVERFLOW) ? 1 : 0;
+    st.render_ms = dev::timer_ms(tm);
+    dev::timer_destroy(tm);
+    m_scene.settings = savedSettings;
+    if (ov) { overflow = true; return HXR_OK; }
+
+    bool ok = true;
+    if (devOut) ok = ok && dev::copy_d2d(devOut, m_accum, nPix * 3 * sizeof(float));
+    if (hostOut) ok = ok && dev::download(hostOut, m_accum, nPix * 3 * sizeof(float));
+    if (!ok) return fail(HXR_ERR_CUDA, std::string("result copy failed: ") + dev::last_error());
+    {
+        unsigned long long sh = 0;
+        TravCounters tc;
+        dev::download(&tc, m_trav, sizeof tc);
+        dev::download(&sh, shadowTotalPtr(m_trav), sizeof sh);
+        st.rays_shadow = sh;
+        st.kd_inner = tc.kd_inner;
+        st.kd_leaves = tc.kd_leaves;
+        st.tri_tests = tc.tri_tests;
+        st.mesh_queries = tc.mesh_queries;
+        double ms[dev::PROF_NCAT];
+        uint64_t ln[dev::PROF_NCAT];
+        dev::prof_collect(ms, ln);
+        st.trace_closest_ms = ms[dev::PROF_TRACE_CLOSEST];
+        st.trace_shadow_ms = ms[dev::PROF_TRACE_SHADOW];
+        st.shade_ms = ms[dev::PROF_SHADE];
+        st.other_ms = ms[dev::PROF_OTHER];
+        st.trace_closest_launches = ln[dev::PROF_TRACE_CLOSEST];
+        st.trace_shadow_launches = ln[dev::PROF_TRACE_SHADOW];
+    }
+    if (stats) *stats = st;
+    if (!dev::sync()) return fail(HXR_ERR_CUDA, dev::last_error());
+    return HXR_OK;
+}
+
+int Renderer::resolveDevice(void* d_rgb, int W, int H, int spp)
+{
+    if (!d_rgb || W <= 0 || H <= 0 || spp <= 0) return fail(HXR_ERR_INVALID, "resolve: bad arguments");
+    dev::scale_all((float*)d_rgb, (size_t)W * H * 3, 1.0f / (float)spp);
+    if (!dev::sync()) return fail(HXR_ERR_CUDA, dev::last_error());
+    return HXR_OK;
+}
+
+// ------------------------------------------------------------------------------ test hooks
+static RayTask taskFromRay(const hxr_ray& r, uint32_t pixel)
+{
+    RayTask t;
+    memset(&t, 0, sizeof t);
+    for (int k = 0; k < 3; k++) { t.o[k] = r.start[k]; t.d[k] = r.dir[k]; t.w[k] = 1.0f; }
+    t.pixel = pixel;
+    t.sample = 0;
+    t.stream = 1;
+    t.depth = r.depth;
+    t.flags = r.flags;
+    return t;
+}
+
+int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
+{
+    if (!m_haveScene) return fail(HXR_ERR_INVALID, "trace: no scene");
+    if (n && (!rays || !hits)) return fail(HXR_ERR_INVALID, "trace: null buffer");
+    if (!ensureQueues()) return HXR_ERR_CUDA;
+    std::vector<RayTask> tasks;
+    std::vector<HitRec> recs;
+    for (size_t first = 0; first < n; first += m_cap) {
+        const uint32_t m = (uint32_t)std::min<size_t>(m_cap, n - first);
+        tasks.resize(m);
+        recs.resize(m);
+        for (uint32_t i = 0; i < m; i++) tasks[i] = taskFromRay(rays[first + i], i);
+        dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
+        dev::set_u32(m_counters + C_Q0, m);
+        dev::set_u32(m_counters + C_HEAD_A, 0);
+        dev::trace_closest(m_scene, m_q[0], m_counters + C_Q0, m_cap, m_hits, m_counters + C_HEAD_A, nullptr);
+        if (!dev::download(recs.data(), m_hits, (size_t)m * sizeof(HitRec))) return fail(HXR_ERR_CUDA, dev::last_error());
+        for (uint32_t i = 0; i < m; i++) {
+            const HitRec& h = recs[i];
+            hxr_hit& o = hits[first + i];
+            memset(&o, 0, sizeof o);
+            o.status = h.node >= 0 ? 0 : 1;
+            o.node = h.node;
+            if (h.node >= 0) {
+                o.dist = h.dist;
+                o.u = h.u;
+                o.v = h.v;
+                for (int k = 0; k < 3; k++) { o.ip[k] = h.ip[k]; o.norm[k] = h.norm[k]; o.dndx[k] = h.dNdx[k]; o.dndy[k] = h.dNdy[k]; }
+            } else {
+                for (int k = 0; k < 3; k++) o.color[k] = h.color[k];
+            }
+        }
+    }
+    return HXR_OK;
+}
+
+int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
+{
+    if (!m_haveScene) return fail(HXR_ERR_INVALID, "trace: no scene");
+    if (n && (!seg || !out)) return fail(HXR_ERR_INVALID, "trace: null buffer");
+    const size_t chunkMax = 1u << 20;
+    double* dseg = (double*)dev::alloc(std::min(n, chunkMax) * 6 * sizeof(double) + 8);
+    uint8_t* dout = (uint8_t*)dev::alloc(std::min(n, chunkMax) + 8);
+    int rc = HXR_OK;
+    if (!dseg || !dout) rc = fail(HXR_ERR_CUDA, dev::last_error());
+    for (size_t first = 0; first < n && rc == HXR_OK; first += chunkMax) {
+        const uint32_t m = (uint32_t)std::min(chunkMax, n - first);
+        dev::upload(dseg, seg + first * 6, (size_t)m * 6 * sizeof(double));
+        dev::trace_visible_segments(m_scene, dseg, m, dout);
+        if (!dev::download(out + first, dout, m)) rc = fail(HXR_ERR_CUDA, dev::last_error());
+    }
+    dev::free_(dseg);
+    dev::free_(dout);
+    return rc;
+}
+
+int Renderer::traceColor(const hxr_ray* rays, size_t n, float* rgb)
+{
+    if (!m_haveScene) return fail(HXR_ERR_INVALID, "trace: no scene");
+    if (n && (!rays || !rgb)) return fail(HXR_ERR_INVALID, "trace: null buffer");
+    if (!ensureQueues()) return HXR_ERR_CUDA;
+    const uint32_t batch = std::max<uint32_t>(1024, m_cap / 8);
+    float* acc = (float*)dev::alloc((size_t)batch * 3 * sizeof(float));
+    if (!acc) return fail(HXR_ERR_CUDA, dev::last_error());
+    FrameParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.W = (int)batch;
+    fp.H = 1;
+    fp.max_depth = m_scene.settings.max_trace_depth;
+    fp.sample_stride = 1;
+    std::vector<RayTask> tasks;
+    hxr_stats st;
+    memset(&st, 0, sizeof st);
+    int rc = HXR_OK;
+    m_countTraversal = false;
+    dev::set_u32(m_counters + C_OVERFLOW, 0);
+    for (size_t first = 0; first < n && rc == HXR_OK; first += batch) {
+        const uint32_t m = (uint32_t)std::min<size_t>(batch, n - first);
+        tasks.resize(m);
+        for (uint32_t i = 0; i < m; i++) tasks[i] = taskFromRay(rays[first + i], i);
+        dev::zero(acc, (size_t)batch * 3 * sizeof(float));
+        dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
+        dev::set_u32(m_counters + C_Q0, m);
+        if (drain(fp, acc, m, st) || readCount(m_counters + C_OVERFLOW)) rc = fail(HXR_ERR_OVERFLOW, "trace_color: queue overflow");
+        else if (!dev::download(rgb + first * 3, acc, (size_t)m * 3 * sizeof(float))) rc = fail(HXR_ERR_CUDA, dev::last_error());
+    }
+    dev::free_(acc);
+    return rc;
+}
+
+}  // namespace hxr
