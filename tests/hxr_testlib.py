@@ -1,0 +1,149 @@
+"""Shared checks, parameterised by the library under test (product on GPU / emulation on CPU)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+
+import hexray_b200 as hx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE = os.path.join(ROOT, "oracle", "_ref", "hexray_ref")
+
+WHITTED_SCENES = ["simple", "meshes", "kdtree_test", "heightfield", "bumpmap", "Lecture8", "beer"]
+MC_SCENES = ["cornell_box", "smallpt", "hw12/sphtri", "zaphod", "hw10/bokeh"]
+PRIMARY_SCENES = ["kdtree_test", "meshes", "heightfield", "smallpt", "simple", "hw10/bokeh", "boxed"]
+
+# Parity tolerances (BASELINE.json north_star):
+#   deterministic scenes: |clamp(ours) - clamp(reference)| <= 1/255 per channel on >= 99.9 % of pixels
+#   stochastic scenes   : RMSE(ours@N, converged reference) <= 1.25 * RMSE(ours@N seed A, ours@N seed B)/sqrt(2) + 0.004
+#                         and per-channel mean |delta| <= 0.004 (clamped images)
+PIXEL_TOL = 1.0 / 255.0
+PIXEL_FRACTION = 0.999
+
+
+def tag(name):
+    return name.replace("/", "_")
+
+
+def golden(kind, scene):
+    return np.load(os.path.join(GOLDEN, "%s_%s.npz" % (kind, tag(scene))))
+
+
+def scene_path(scene):
+    return os.path.join(hx.data_root(), scene + ".hexray")
+
+
+def have_oracle():
+    return os.path.exists(ORACLE) and os.access(ORACLE, os.X_OK)
+
+
+def oracle_render(scene, W, H, spp=0, extra=()):
+    out = "/tmp/hxr_oracle_%d.f32" % os.getpid()
+    args = [ORACLE, "render", scene_path(scene), "--width", str(W), "--height", str(H), "--out", out] + list(extra)
+    if spp:
+        args += ["--spp", str(spp)]
+    p = subprocess.run(args, cwd=os.path.dirname(hx.data_root()), capture_output=True, text=True, check=True)
+    info = json.loads(p.stdout.strip().splitlines()[-1])
+    return np.fromfile(out, dtype=np.float32).reshape(H, W, 3), info
+
+
+class Session:
+    """Caches loaded scenes per library so a test module pays the parse/upload once per scene."""
+
+    def __init__(self, api, queue_capacity=0):
+        self.api = api
+        self.qc = queue_capacity
+        self.cache = {}
+
+    def renderer(self, scene):
+        if scene not in self.cache:
+            sf = hx.SceneFile(scene_path(scene), api_=self.api)
+            r = hx.Renderer(api_=self.api, queue_capacity=self.qc)
+            r.load(sf)
+            self.cache[scene] = (sf, r)
+        return self.cache[scene][1]
+
+    def close(self):
+        for sf, r in self.cache.values():
+            r.close()
+            sf.close()
+        self.cache.clear()
+
+
+def clamp01(x):
+    return np.clip(np.asarray(x, dtype=np.float32), 0.0, 1.0)
+
+
+def pixel_match_fraction(a, b):
+    d = np.abs(clamp01(a) - clamp01(b)).max(axis=2)
+    return float((d <= PIXEL_TOL + 1e-6).mean()), float(d.max())
+
+
+def check_whitted(sess, scene):
+    g = golden("whitted", scene)
+    ref = g["img"].astype(np.float32)
+    H, W = ref.shape[:2]
+    img, st = sess.renderer(scene).render(width=W, height=H)
+    # the fixture is stored as float16: allow its rounding (2^-11 relative) on top of 1/255
+    d = np.abs(clamp01(img) - clamp01(ref)).max(axis=2)
+    frac = float((d <= PIXEL_TOL + 6e-4).mean())
+    assert frac >= PIXEL_FRACTION, "%s: only %.4f%% of pixels within 1/255 (max diff %.4f)" % (scene, frac * 100, d.max())
+    assert st["rays_closest"] > 0
+    return frac, st
+
+
+def rmse(a, b):
+    return float(np.sqrt(((clamp01(a) - clamp01(b)) ** 2).mean()))
+
+
+def check_mc(sess, scene, spp):
+    g = golden("mc", scene)
+    ref = g["img"].astype(np.float32)
+    H, W = ref.shape[:2]
+    r = sess.renderer(scene)
+    a, st = r.render(width=W, height=H, spp=spp, seed=11)
+    b, _ = r.render(width=W, height=H, spp=spp, seed=22)
+    own = rmse(a, b) / np.sqrt(2.0)  # noise of ONE render against the truth
+    err = rmse(a, ref)
+    mean_delta = np.abs(clamp01(a).mean(axis=(0, 1)) - clamp01(ref).mean(axis=(0, 1)))
+    assert err <= 1.25 * own + 0.004, "%s: rmse vs converged reference %.4f, own noise %.4f" % (scene, err, own)
+    assert mean_delta.max() <= 0.004, "%s: mean delta %s" % (scene, mean_delta)
+    return err, own, st
+
+
+def check_primary(sess, scene):
+    g = golden("primary", scene)
+    rays, ref = g["rays"], g["hits"]
+    hits = sess.renderer(scene).trace_closest(rays)
+    status_ref = ref[:, 0].astype(np.int32)
+    node_ref = ref[:, 1].astype(np.int32)
+    agree = (hits["status"] == status_ref) & (hits["node"] == node_ref)
+    assert agree.mean() >= 0.9995, "%s: hit/miss or node differs on %d of %d rays" % (scene, (~agree).sum(), len(rays))
+    m = agree & (status_ref == 0)
+    rel = np.abs(hits["dist"][m] - ref[m, 2]) / np.maximum(1.0, np.abs(ref[m, 2]))
+    # the blurred heightfield is summed in float by a -ffast-math reference build: its heights (and so the
+    # hit distances) carry ~1e-6 relative noise; everything else agrees to ~1e-12
+    tol = 1e-5 if scene == "heightfield" else 1e-8
+    ok = rel < tol
+    assert ok.mean() >= 0.999, "%s: dist differs (max rel %.3g)" % (scene, rel.max())
+    sel = np.where(m)[0][ok]
+    scale = np.maximum(1.0, np.abs(ref[sel, 3:6]).max())
+    assert np.abs(hits["ip"][sel] - ref[sel, 3:6]).max() < tol * 100 * scale
+    assert np.abs(hits["norm"][sel] - ref[sel, 6:9]).max() < tol * 1000
+    uvs = np.maximum(1.0, np.abs(ref[sel, 9:11]).max())
+    assert np.abs(hits["u"][sel] - ref[sel, 9]).max() < tol * 100 * uvs and np.abs(hits["v"][sel] - ref[sel, 10]).max() < tol * 100 * uvs
+    e = status_ref == 1
+    both = e & agree
+    if both.any():
+        assert np.abs(hits["color"][both] - ref[both, 17:20]).max() < 1e-4
+    return float(agree.mean())
+
+
+def check_visible(sess, scene):
+    g = golden("visible", scene)
+    vis = sess.renderer(scene).trace_visible(g["seg"])
+    agree = (vis == (g["vis"] != 0)).mean()
+    assert agree >= 0.999, "%s: visible() differs on %.2f%% of segments" % (scene, (1 - agree) * 100)
+    return float(agree)

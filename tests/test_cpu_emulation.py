@@ -1,0 +1,32 @@
+"""CPU tier: the host front-end, the frame driver and the per-ray functions (compiled for the host,
+tests/emu) against the committed reference fixtures. The product itself is exercised by test_gpu_*.py."""
+import pytest
+
+import hxr_testlib as T
+
+
+@pytest.fixture(scope="module")
+def sess(emu_api):
+    s = T.Session(emu_api, queue_capacity=1 << 20)
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("scene", ["kdtree_test", "heightfield", "smallpt", "boxed", "hw10/bokeh"])
+def test_primary_hits(sess, scene):
+    T.check_primary(sess, scene)
+
+
+@pytest.mark.parametrize("scene", ["kdtree_test", "smallpt", "boxed"])
+def test_visible(sess, scene):
+    T.check_visible(sess, scene)
+
+
+@pytest.mark.parametrize("scene", ["simple", "meshes", "kdtree_test", "heightfield", "bumpmap"])
+def test_whitted_parity(sess, scene):
+    T.check_whitted(sess, scene)
+
+
+@pytest.mark.parametrize("scene,spp", [("hw12/sphtri", 48), ("zaphod", 32)])
+def test_montecarlo_parity(sess, scene, spp):
+    T.check_mc(sess, scene, spp)
