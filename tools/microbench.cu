@@ -2,6 +2,7 @@
 // FP32 FFMA and FP64 DFMA issue rates, L2 read bandwidth (working set << L2) and HBM read
 // bandwidth (working set >> L2). Prints one JSON object. Build: see tools/build_tools.sh.
 #include <cuda_runtime.h>
+#include <cstdint>
 #include <cstdio>
 #include <vector>
 
