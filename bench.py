@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the render hot path (contract: see the task statement / DESIGN.md §6).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU renderer (oracle/_ref), rank 0 only
+
+Workload (BASELINE.json configs[4]): the synthetic 10 M-triangle terrain inside a
+five-wall Lambert box under one 4x4 RectLight, path traced (gi on, depth 8) at 1920x1080, a fixed
+number of samples per pixel per GPU per step; sample passes are sharded across ranks and the
+per-rank sums are reduced with NCCL (weak scaling: total spp = spp_per_gpu x N).
+
+A step = one frame: ray generation -> closest hit -> shading -> shadow rays -> ... -> accumulate
+(-> reduce -> resolve). metric = Mrays/s, rays = closest-hit queries past the depth guard +
+visible() queries, the same definition the reference counters use.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TERRAIN_SCENE = """GlobalSettings {{
+	frameWidth {W}
+	frameHeight {H}
+	ambientLight (0, 0, 0)
+	maxTraceDepth 8
+	gi 1
+	numPaths {spp}
+}}
+Camera camera {{
+	pos (0, 150, -600)
+	aspectRatio 1.77778
+	pitch -15
+	fov 70
+}}
+RectLight {{
+	scale (300, 1, 300)
+	translate (0, 400, 0)
+	xSubd 4
+	ySubd 4
+	power 1100000
+}}
+Mesh terrain {{
+	file "{mesh}"
+}}
+Plane wall {{
+	limit 520
+}}
+Lambert grey {{
+	color (0.75, 0.75, 0.75)
+}}
+Lambert ground {{
+	color (0.55, 0.6, 0.4)
+}}
+Node terrain {{
+	geometry terrain
+	shader ground
+}}
+Node floor {{
+	geometry wall
+	shader grey
+	translate (0, -40, 0)
+}}
+Node left {{
+	geometry wall
+	shader grey
+	rotate (0, 0, 90)
+	translate (-520, 0, 0)
+}}
+Node right {{
+	geometry wall
+	shader grey
+	rotate (0, 0, -90)
+	translate (520, 0, 0)
+}}
+Node back {{
+	geometry wall
+	shader grey
+	rotate (0, 90, 0)
+	translate (0, 0, 520)
+}}
+Node front {{
+	geometry wall
+	shader grey
+	rotate (0, -90, 0)
+	translate (0, 0, -700)
+}}
+"""
+
+# algorithmic bytes per ray of the traversal roofline: 64 B ray+hit record,
+# 32 B per inner node visited, 48 B per triangle tested, 16 B per leaf entered
+B_RECORD, B_INNER, B_TRI, B_LEAF = 64, 32, 48, 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="terrain", choices=["terrain", "cornell_box", "kdtree_test", "smallpt"])
+    ap.add_argument("--grid-side", type=int, default=2237, help="terrain vertices per side (2237 -> 9 999 392 triangles)")
+    ap.add_argument("--spp", type=int, default=32, help="samples per pixel per GPU per step")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--ref-width", type=int, default=192, help="reference arm: bounded sample resolution")
+    ap.add_argument("--ref-height", type=int, default=108)
+    ap.add_argument("--ref-spp", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--queue-capacity", type=int, default=16 << 20)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    if a.workload == "terrain":
+        ntri = 2 * (a.grid_side - 1) ** 2
+        return "synthetic terrain %d triangles (grid %d^2, seed 0x5EED) in a 5-wall Lambert box, 1 RectLight 4x4, GI depth 8" % (ntri, a.grid_side)
+    return "data/%s.hexray" % a.workload
+
+
+def scene_text(a, mesh_file, W, H, spp):
+    return TERRAIN_SCENE.format(W=W, H=H, spp=spp, mesh=mesh_file)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference_sample(a, workdir, threads=0, repeat=1):
+    """Time the reference's own CPU renderer (oracle/_ref/hexray_ref: the unmodified reference sources behind a
+    headless shim) on a bounded sample of the workload. Returns (Mrays/s best, info dict)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "hexray_ref_count")
+    if not os.path.exists(ref):
+        return None, {"unavailable": "oracle/_ref/hexray_ref_count not built (run `make -C oracle` where /root/reference exists)"}
+    import hexray_b200 as hx
+    if a.workload == "terrain":
+        obj = os.path.join(workdir, "terrain_%d.obj" % a.grid_side)
+        scene = os.path.join(workdir, "terrain_ref_%d.hexray" % a.grid_side)
+        if not os.path.exists(obj):
+            # the procedural mesh is produced by the host front-end (pure host code) and handed to the reference as an OBJ
+            gen = os.path.join(workdir, "terrain_gen_%d.hexray" % a.grid_side)
+            with open(gen, "w") as f:
+                f.write(scene_text(a, "synthetic:terrain:%d:0x5EED" % a.grid_side, a.ref_width, a.ref_height, a.ref_spp))
+            sf = hx.SceneFile(gen)
+            sf.write_obj(0, obj + ".tmp")
+            sf.close()
+            os.replace(obj + ".tmp", obj)
+        with open(scene, "w") as f:
+            f.write(scene_text(a, os.path.basename(obj), a.ref_width, a.ref_height, a.ref_spp))
+        cwd = workdir
+    else:
+        scene = os.path.join(hx.data_root(), a.workload + ".hexray")
+        cwd = os.path.dirname(hx.data_root())
+    cmd = [ref, "render", scene, "--width", str(a.ref_width), "--height", str(a.ref_height), "--spp", str(a.ref_spp), "--repeat", str(repeat)]
+    if threads:
+        cmd += ["--threads", str(threads)]
+    t0 = time.time()
+    p = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True)
+    if p.returncode != 0:
+        return None, {"unavailable": "reference run failed: " + p.stderr[-300:]}
+    info = json.loads(p.stdout.strip().splitlines()[-1])
+    info["wall_s"] = time.time() - t0
+    rays = info["rays_closest"] + info["rays_shadow"]
+    info["rays"] = rays
+    return rays / info["best_ms"] / 1e3, info
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workdir = os.path.join(tempfile.gettempdir(), "hexray_b200_bench")
+    os.makedirs(workdir, exist_ok=True)
+    total = a.steps + a.warmup
+    mr, info = run_reference_sample(a, workdir, repeat=total)
+    line = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "width": a.width, "height": a.height, "spp_per_gpu": a.spp}}
+    if mr is None:
+        line["unavailable"] = info["unavailable"]
+        print(json.dumps(line))
+        return
+    times = info["render_ms"][a.warmup:]
+    ms = sum(times) / len(times)
+    value = info["rays"] / ms / 1e3
+    sample = "%dx%d x %d spp of the same scene (%d rays per step), %d host threads; KD build %.1f s and OBJ parse %.1f s outside the timed region" % (
+        a.ref_width, a.ref_height, a.ref_spp, info["rays"], info["threads"], info["begin_render_ms"] / 1e3, info["parse_ms"] / 1e3)
+    line.update({"value": value, "ms_per_step": ms,
+                 "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": info["threads"], "kind": "reference", "sample": sample},
+                 "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hexray_b200 as hx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    W, H = a.width, a.height
+    spp_total = a.spp * world
+
+    workdir = os.path.join(tempfile.gettempdir(), "hexray_b200_bench")
+    os.makedirs(workdir, exist_ok=True)
+    if a.workload == "terrain":
+        path = os.path.join(workdir, "terrain_%d_rank%d.hexray" % (a.grid_side, rank))
+        with open(path, "w") as f:
+            f.write(scene_text(a, "synthetic:terrain:%d:0x5EED" % a.grid_side, W, H, spp_total))
+    else:
+        path = os.path.join(hx.data_root(), a.workload + ".hexray")
+    t0 = time.time()
+    sf = hx.SceneFile(path)
+    r = hx.Renderer(device=local, queue_capacity=a.queue_capacity)
+    r.load(sf)
+    setup_s = time.time() - t0
+    accel = r.accel_info(0) if sf.pod.contents.n_meshes > 0 else {}
+    cam = sf.camera()
+    mode = hx.MODE_MONTECARLO
+    geometry_bytes = sum(r.accel_info(i)["bytes_nodes"] + r.accel_info(i)["bytes_tris"] for i in range(sf.pod.contents.n_meshes))
+    flush = None
+    if geometry_bytes < (256 << 20):
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > L2: written between timed iterations
+
+    acc = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    host = torch.empty(H * W * 3, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(i, to_host):
+        """one frame: this rank's sample passes -> (NCCL reduce) -> resolve [-> host]"""
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+        if to_host:
+            r.set_camera(cam)  # the per-frame input of the C ABI (hxr_set_camera), host -> device
+        if world == 1 and to_host:
+            _, st = r.render(width=W, height=H, mode=mode, spp=spp_total, seed=i, out=host.numpy().reshape(H, W, 3))
+            return st
+        st = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=spp_total, seed=i, shard=(rank, world))
+        if world > 1:
+            dist.reduce(acc, dst=0)
+            torch.cuda.synchronize(dev)  # NCCL runs on torch's stream, the resolve kernel on the library's
+            if rank == 0:
+                r.resolve_device(acc.data_ptr(), W, H, spp_total)
+        if to_host and rank == 0:
+            host.copy_(acc, non_blocking=False)
+        torch.cuda.synchronize(dev)
+        return st
+
+    def run(n, to_host, first_seed):
+        rays = np.zeros(2, dtype=np.float64)
+        prof = {"trace_closest_ms": 0.0, "trace_shadow_ms": 0.0, "shade_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0,
+                "trace_closest_launches": 0, "trace_shadow_launches": 0, "kernel_launches": 0}
+        for i in range(n):
+            st = step(first_seed + i, to_host)
+            rays += (st["rays_closest"], st["rays_shadow"])
+            for k in prof:
+                prof[k] += st[k]
+        return rays, prof
+
+    # ---- device-resident throughput ("value")
+    r.set_profiling(True)
+    run(a.warmup, False, 1000)
+    barrier()
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        rays, prof = run(a.steps, False, 0)
+        barrier()
+        dt = time.perf_counter() - t0
+    # ---- end to end through the C ABI with host buffers ("e2e")
+    run(min(a.warmup, 1), True, 2000)
+    barrier()
+    t0 = time.perf_counter()
+    rays_e, _ = run(a.steps, True, 0)
+    barrier()
+    dt_e = time.perf_counter() - t0
+    r.set_profiling(False)
+
+    def allsum(x):
+        t = torch.tensor(x, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rays = allsum(rays)
+    rays_e = allsum(rays_e)
+    dt = allmax(dt)
+    dt_e = allmax(dt_e)
+
+    # ---- traversal counters (a separate, un-timed counting pass of the same workload at 1 spp per rank)
+    cst = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=world, seed=0, shard=(rank, world), flags=hx.RENDER_COUNT_TRAVERSAL)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        total_rays = float(rays.sum())
+        value = total_rays / dt / 1e6
+        n_rays_cnt = cst["rays_closest"] + cst["rays_shadow"]
+        per_ray = {"inner": cst["kd_inner"] / max(1, n_rays_cnt), "tri": cst["tri_tests"] / max(1, n_rays_cnt),
+                   "leaf": cst["kd_leaves"] / max(1, n_rays_cnt), "mesh_queries": cst["mesh_queries"] / max(1, n_rays_cnt)}
+        b_ray = B_RECORD + B_INNER * per_ray["inner"] + B_TRI * per_ray["tri"] + B_LEAF * per_ray["leaf"]
+        trav_ms = prof["trace_closest_ms"] + prof["trace_shadow_ms"]
+        trav_launches = prof["trace_closest_launches"] + prof["trace_shadow_launches"]
+        my_rays = total_rays / world  # rank 0's share (shards are equal)
+        achieved = my_rays * b_ray / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        hbm_bound = geometry_bytes > (126 << 20)
+        peak = peaks["hbm_gbs"] if hbm_bound else 23149.0
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "width": W, "height": H, "spp_per_gpu": a.spp, "spp_total": spp_total,
+                       "integrator": "path tracing (gi), maxTraceDepth 8", "sharding": "sample passes s %% N == rank, NCCL reduce of the sum buffer",
+                       "l2": "geometry %.2f GB >> 126 MB L2" % (geometry_bytes / 1e9) if flush is None else "512 MB buffer written between timed iterations",
+                       "rays_per_step": total_rays / a.steps, "setup_s": setup_s, "kd": accel},
+            "ms_per_frame": dt / a.steps * 1e3,
+            "e2e": {"value": float(rays_e.sum()) / dt_e / 1e6, "unit": "Mrays/s", "ms_per_step": dt_e / a.steps * 1e3,
+                    "h2d_bytes_per_step": 256, "d2h_bytes_per_step": W * H * 12},
+            "gpu_launches": int(prof["kernel_launches"]),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm" if hbm_bound else "l2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "k_trace_closest + k_trace_shadow (KD traversal)", "peak_source": peak_src if hbm_bound else "tools/microbench L2 read (profiles/microbench_r1.json)",
+                         "bytes_per_ray": b_ray, "per_ray": per_ray, "launches": int(trav_launches),
+                         "avg_launch_ms": trav_ms / max(1, trav_launches), "traversal_share_of_step": trav_ms / max(1e-9, prof["render_ms"])},
+            "kernel_ms_per_step": {k: prof[k] / a.steps for k in ("trace_closest_ms", "trace_shadow_ms", "shade_ms", "other_ms", "render_ms")},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            b = argparse.Namespace(**vars(a))
+            note = ""
+            if a.workload == "terrain" and a.grid_side > 709:
+                b.grid_side = 709  # the reference needs ~2 min to parse + build the 10 M mesh: that is what --impl reference times
+                note = " (1 002 528-triangle variant of the terrain; the full mesh is timed by --impl reference)"
+            mr, info = run_reference_sample(b, workdir)
+            if mr is None:
+                line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": info["unavailable"]}
+            else:
+                line["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": info["threads"], "kind": "reference",
+                                        "sample": "%dx%d x %d spp, %d rays, %.1f s wall incl. load%s" % (b.ref_width, b.ref_height, b.ref_spp, info["rays"], info["wall_s"], note)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    r.close()
+    sf.close()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours(a)
+
+
+if __name__ == "__main__":
+    main()

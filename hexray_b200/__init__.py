@@ -72,6 +72,9 @@ class SceneFile:
     def set_synthetic_mesh(self, mesh_index, kind, n, seed):
         self.api.check(self.api.lib.hxr_scene_file_set_synthetic_mesh(self.handle, mesh_index, kind.encode(), int(n), int(seed)))
 
+    def write_obj(self, mesh_index, path):
+        self.api.check(self.api.lib.hxr_scene_file_write_obj(self.handle, mesh_index, path.encode()))
+
     def close(self):
         if self.handle:
             self.api.lib.hxr_scene_file_free(self.handle)
@@ -168,6 +171,9 @@ class Renderer:
         out = np.zeros((len(rays), 3), dtype=np.float32)
         self._check(self.api.lib.hxr_trace_color(self.ctx, rays.ctypes.data, len(rays), out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+    def set_profiling(self, on):
+        self._check(self.api.lib.hxr_set_profiling(self.ctx, 1 if on else 0))
 
     def accel_info(self, mesh):
         info = capi.AccelInfo()

@@ -137,8 +137,8 @@ assert RAY_DTYPE.itemsize == 56 and HIT_DTYPE.itemsize == 144
 # every symbol include/hxr.h declares (tests check that the built library exports them all)
 SYMBOLS = ["hxr_create", "hxr_destroy", "hxr_last_error", "hxr_upload_scene", "hxr_set_camera", "hxr_render",
            "hxr_render_device", "hxr_resolve_device", "hxr_trace_closest", "hxr_trace_visible", "hxr_trace_color",
-           "hxr_get_accel_info", "hxr_scene_load", "hxr_scene_file_scene", "hxr_scene_file_camera",
-           "hxr_scene_file_set_synthetic_mesh", "hxr_scene_file_free", "hxr_save_image"]
+           "hxr_get_accel_info", "hxr_set_profiling", "hxr_scene_load", "hxr_scene_file_scene", "hxr_scene_file_camera",
+           "hxr_scene_file_set_synthetic_mesh", "hxr_scene_file_write_obj", "hxr_scene_file_free", "hxr_save_image"]
 
 
 class Api:
@@ -164,12 +164,14 @@ class Api:
         L.hxr_trace_closest.argtypes = [vp, vp, C.c_size_t, vp]
         L.hxr_trace_visible.argtypes = [vp, C.POINTER(c_f64), C.c_size_t, C.POINTER(C.c_uint8)]
         L.hxr_trace_color.argtypes = [vp, vp, C.c_size_t, C.POINTER(c_f32)]
+        L.hxr_set_profiling.argtypes = [vp, c_i32]
         L.hxr_get_accel_info.argtypes = [vp, c_i32, C.POINTER(AccelInfo)]
         L.hxr_scene_load.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.hxr_scene_file_scene.argtypes = [vp]
         L.hxr_scene_file_scene.restype = C.POINTER(Scene)
         L.hxr_scene_file_camera.argtypes = [vp, C.POINTER(Camera)]
         L.hxr_scene_file_set_synthetic_mesh.argtypes = [vp, c_i32, C.c_char_p, C.c_int64, c_u64]
+        L.hxr_scene_file_write_obj.argtypes = [vp, c_i32, C.c_char_p]
         L.hxr_scene_file_free.argtypes = [vp]
         L.hxr_scene_file_free.restype = None
         L.hxr_save_image.argtypes = [C.c_char_p, C.POINTER(c_f32), c_i32, c_i32]

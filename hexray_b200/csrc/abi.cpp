@@ -84,6 +84,7 @@ int hxr_render_device(hxr_ctx* ctx, const hxr_render_params* p, void* d_rgb, hxr
     HXR_CTX_CALL(ctx->r.render(*p, nullptr, d_rgb, stats))
 }
 int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t w, int32_t h, int32_t spp) { HXR_CTX_CALL(ctx->r.resolveDevice(d_rgb, w, h, spp)) }
+int hxr_set_profiling(hxr_ctx* ctx, int32_t on) { HXR_CTX_CALL((hxr::dev::prof_enable(on != 0), HXR_OK)) }
 int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits) { HXR_CTX_CALL(ctx->r.traceClosest(rays, n, hits)) }
 int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->r.traceVisible(seg, n, vis)) }
 int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { HXR_CTX_CALL(ctx->r.traceColor(rays, n, rgb)) }
@@ -161,6 +162,24 @@ int hxr_scene_file_set_synthetic_mesh(hxr_scene_file* sf, int32_t mesh_index, co
     }
     sf->flat.finalize();
     return HXR_OK;
+    HXR_GUARD_END(g_lastError)
+}
+
+int hxr_scene_file_write_obj(const hxr_scene_file* sf, int32_t mesh_index, const char* path)
+{
+    if (!sf || !path) { g_lastError = "null argument"; return HXR_ERR_INVALID; }
+    HXR_GUARD_BEGIN
+    int k = 0;
+    for (hxr::host::Geometry* g : sf->scene.geometries)
+        if (auto* m = dynamic_cast<hxr::host::Mesh*>(g)) {
+            if (k == mesh_index) {
+                if (!m->saveOBJ(path)) { g_lastError = std::string("cannot write ") + path; return HXR_ERR_IO; }
+                return HXR_OK;
+            }
+            k++;
+        }
+    g_lastError = "no such mesh";
+    return HXR_ERR_INVALID;
     HXR_GUARD_END(g_lastError)
 }
 

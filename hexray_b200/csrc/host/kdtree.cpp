@@ -1,10 +1,13 @@
 // kdtree.cpp — see kdtree.h. Top-down SAH build:
 //   * big nodes: 32-bin SAH per axis (O(n) per node), small nodes: exact sweep over the triangle
 //     bound edges (O(n log n)), both on triangle bounds clipped to the node box;
-//   * a triangle is referenced by every child whose closed half-space its bounds touch
-//     (min <= split -> left, max >= split -> right), so a hit lying exactly on a split plane is
-//     found from either side; the split is stored as float and the SAME float-rounded value is
-//     used for classification here and for traversal on the device;
+//   * a triangle goes LEFT if its bounds reach below the split (min < split) or it lies entirely
+//     in the split plane, RIGHT if they reach above it (max > split). A triangle that only
+//     touches the plane from one side is NOT duplicated (on grid-aligned meshes that rule alone
+//     decides between ~1.5x and ~20x reference duplication); a hit exactly on the plane is still
+//     found because the traversal visits both children whenever the plane parameter lies within
+//     the node's [tmin, tmax] (with slack). The split is stored as float and the SAME
+//     float-rounded value is used for classification here and for traversal on the device;
 //   * subtrees are built in parallel (std::thread) once the refs below a node drop under a
 //     grain size, then stitched into one DFS-ordered node array.
 #include "kdtree.h"
@@ -30,7 +33,7 @@ struct Box {
 };
 
 struct TriBounds {
-    float mn[3], mx[3];  // rounded outward
+    double mn[3], mx[3];  // exact vertex extents
 };
 
 struct Builder {
@@ -54,13 +57,20 @@ struct Builder {
                 }
             }
             for (int a = 0; a < 3; a++) {
-                tb[i].mn[a] = std::nextafter((float)mn[a], -INFINITY);
-                tb[i].mx[a] = std::nextafter((float)mx[a], +INFINITY);
+                tb[i].mn[a] = mn[a];
+                tb[i].mx[a] = mx[a];
             }
         }
         maxDepth = P.maxDepth >= 0 ? P.maxDepth : (int)std::lround(8 + 1.3 * std::log2((double)std::max(1, n)));
         maxDepth = std::min(maxDepth, HXR_KD_STACK - 4);
     }
+
+    static bool goesLeft(const TriBounds& b, int axis, float split)
+    {
+        const double s = (double)split;
+        return b.mn[axis] < s || (b.mn[axis] == s && b.mx[axis] == s);
+    }
+    static bool goesRight(const TriBounds& b, int axis, float split) { return b.mx[axis] > (double)split; }
 
     struct Local {  // a subtree under construction
         std::vector<KdNode> nodes;
@@ -107,30 +117,32 @@ struct Builder {
                     if (c < bestCost) { bestCost = c; bestAxis = axis; bestSplit = split; }
                 }
             } else {
-                // exact sweep: candidates are the clipped triangle bound edges
-                struct Edge { float t; uint8_t isEnd; };
-                std::vector<Edge> ev;
-                ev.reserve(2 * n);
-                for (uint32_t r : refs) {
-                    ev.push_back({std::max(tb[r].mn[axis], (float)box.mn[axis]), 0});
-                    ev.push_back({std::min(tb[r].mx[axis], (float)box.mx[axis]), 1});
+                // exact sweep: candidates are the (float-rounded) triangle bound edges inside the node
+                std::vector<double> mins(n), maxs(n), planar;
+                std::vector<float> cand;
+                cand.reserve(2 * n);
+                for (size_t i = 0; i < n; i++) {
+                    const TriBounds& b = tb[refs[i]];
+                    mins[i] = b.mn[axis];
+                    maxs[i] = b.mx[axis];
+                    if (b.mn[axis] == b.mx[axis]) planar.push_back(b.mn[axis]);
+                    cand.push_back((float)b.mn[axis]);
+                    cand.push_back((float)b.mx[axis]);
                 }
-                std::sort(ev.begin(), ev.end(), [](const Edge& a, const Edge& b) { return a.t < b.t || (a.t == b.t && a.isEnd < b.isEnd); });
-                // at plane t: left gets every triangle with min <= t, right every triangle with max >= t
-                size_t i = 0;
-                size_t startsLE = 0, endsLT = 0;
-                while (i < ev.size()) {
-                    const float t = ev[i].t;
-                    size_t j = i, startsHere = 0, endsHere = 0;
-                    while (j < ev.size() && ev[j].t == t) { if (ev[j].isEnd) endsHere++; else startsHere++; j++; }
-                    startsLE += startsHere;
-                    if ((double)t > box.mn[axis] && (double)t < box.mx[axis]) {
-                        const size_t nl = startsLE, nr = n - endsLT;
-                        const float c = (float)sahCost(axis, t, nl, nr);
-                        if (c < bestCost) { bestCost = c; bestAxis = axis; bestSplit = t; }
-                    }
-                    endsLT += endsHere;
-                    i = j;
+                std::sort(mins.begin(), mins.end());
+                std::sort(maxs.begin(), maxs.end());
+                std::sort(planar.begin(), planar.end());
+                std::sort(cand.begin(), cand.end());
+                cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+                for (float t : cand) {
+                    const double td = (double)t;
+                    if (!(td > box.mn[axis] && td < box.mx[axis])) continue;
+                    const size_t below = (size_t)(std::lower_bound(mins.begin(), mins.end(), td) - mins.begin());
+                    const auto pr = std::equal_range(planar.begin(), planar.end(), td);
+                    const size_t nl = below + (size_t)(pr.second - pr.first);
+                    const size_t nr = n - (size_t)(std::upper_bound(maxs.begin(), maxs.end(), td) - maxs.begin());
+                    const float c = (float)sahCost(axis, td, nl, nr);
+                    if (c < bestCost) { bestCost = c; bestAxis = axis; bestSplit = t; }
                 }
             }
         }
@@ -169,8 +181,8 @@ struct Builder {
         left.reserve(n);
         right.reserve(n);
         for (uint32_t r : refs) {
-            if (tb[r].mn[axis] <= split) left.push_back(r);
-            if (tb[r].mx[axis] >= split) right.push_back(r);
+            if (goesLeft(tb[r], axis, split)) left.push_back(r);
+            if (goesRight(tb[r], axis, split)) right.push_back(r);
         }
         if (left.size() == n && right.size() == n) { makeLeaf(L, me, refs, depth); return me; }
         std::vector<uint32_t>().swap(refs);  // release the parent's list before recursing
@@ -256,8 +268,8 @@ void buildKdTree(const hxr_mesh& mesh, const KdBuildParams& params, KdTree& out)
             l.side = 0;
             r.side = 1;
             for (uint32_t t : w.refs) {
-                if (B.tb[t].mn[axis] <= split) l.refs.push_back(t);
-                if (B.tb[t].mx[axis] >= split) r.refs.push_back(t);
+                if (Builder::goesLeft(B.tb[t], axis, split)) l.refs.push_back(t);
+                if (Builder::goesRight(B.tb[t], axis, split)) r.refs.push_back(t);
             }
             std::vector<uint32_t>().swap(w.refs);
             stack.push_back(std::move(r));

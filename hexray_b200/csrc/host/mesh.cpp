@@ -243,6 +243,31 @@ void Mesh::generateTerrain(int n, uint64_t seed)
     faceted = false;
 }
 
+bool Mesh::saveOBJ(const char* filename) const
+{
+    FILE* f = fopen(filename, "wt");
+    if (!f) return false;
+    std::vector<char> buf(1 << 20);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    for (size_t i = 1; i < vertices.size(); i++) fprintf(f, "v %.17g %.17g %.17g\n", vertices[i].x, vertices[i].y, vertices[i].z);
+    for (size_t i = 1; i < uvs.size(); i++) fprintf(f, "vt %.17g %.17g\n", uvs[i].x, uvs[i].y);
+    for (size_t i = 1; i < normals.size(); i++) fprintf(f, "vn %.17g %.17g %.17g\n", normals[i].x, normals[i].y, normals[i].z);
+    const bool hasN = normals.size() > 1, hasT = uvs.size() > 1;
+    for (const auto& t : triangles) {
+        fputs("f", f);
+        for (int k = 0; k < 3; k++) {
+            if (hasN && hasT) fprintf(f, " %d/%d/%d", t.v[k], t.t[k], t.n[k]);
+            else if (hasT) fprintf(f, " %d/%d", t.v[k], t.t[k]);
+            else if (hasN) fprintf(f, " %d//%d", t.v[k], t.n[k]);
+            else fprintf(f, " %d", t.v[k]);
+        }
+        fputs("\n", f);
+    }
+    bool ok = !ferror(f);
+    fclose(f);
+    return ok;
+}
+
 // soup: nTriangles random triangles, centroids uniform in [-500,500]^3, edge ~ N(2, 0.5): worst-case incoherence
 void Mesh::generateSoup(int64_t nTris, uint64_t seed)
 {

@@ -182,6 +182,7 @@ public:
     // procedural meshes for the large-scene configuration
     void generateTerrain(int gridSide, uint64_t seed);
     void generateSoup(int64_t nTriangles, uint64_t seed);
+    bool saveOBJ(const char* filename) const;  // v/vt/vn/f text, so the reference can load a procedural mesh
     void fillProperties(ParsedBlock& pb) override;
     void beginRender() override;
     void flatten(FlatScene& fs, hxr_geometry& g) const override;

@@ -300,6 +300,10 @@ int hxr_render_device(hxr_ctx* ctx, const hxr_render_params* p, void* d_rgb, hxr
 /* scale a reduced device sum buffer by 1/spp in place (Monte-Carlo resolve, src/main.cpp:376). */
 int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t width, int32_t height, int32_t spp);
 
+/* when on, every kernel launch of this context is bracketed by CUDA events and hxr_stats carries the
+ * per-kernel-class device times (trace_closest_ms, trace_shadow_ms, shade_ms, other_ms) */
+int hxr_set_profiling(hxr_ctx* ctx, int32_t on);
+
 /* test hooks: explicit rays in, raycast()/visible() results out (host buffers) */
 int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits);
 int hxr_trace_visible(hxr_ctx* ctx, const double* segments /* n*6: A,B */, size_t n, uint8_t* visible);
@@ -327,6 +331,9 @@ int hxr_scene_file_camera(const hxr_scene_file* sf, hxr_camera* out);
 /* procedural meshes for the large-scene configuration: replaces mesh `mesh_index`
  * (or appends when -1) with a generated one. kind: "terrain" (n = grid vertices per side) or "soup" (n = triangles) */
 int hxr_scene_file_set_synthetic_mesh(hxr_scene_file* sf, int32_t mesh_index, const char* kind, int64_t n, uint64_t seed);
+/* write mesh `mesh_index` (counting Mesh geometries in scene order) as a Wavefront OBJ, so that the
+ * reference renderer can load a procedural mesh for side-by-side timing */
+int hxr_scene_file_write_obj(const hxr_scene_file* sf, int32_t mesh_index, const char* path);
 void hxr_scene_file_free(hxr_scene_file* sf);
 
 /* Bitmap::saveImage equivalent: ".bmp" (8-bit through the reference's sRGB LUT, src/color.h:36-47 +

@@ -22,9 +22,11 @@
 //              visible: in 6 doubles (A, B), out 1 double
 //
 // When built with -DHXR_COUNTING the included main.cpp is a sed-piped stream of the
-// reference file with two counter macros inserted (see oracle/Makefile); that variant
-// is used only to COUNT rays (closest-hit queries past the depth guard + visible()
-// queries), never for timing or parity.
+// reference file with two counter macros inserted (see oracle/Makefile): closest-hit queries
+// past the depth guard + visible() queries. Each counter is one increment of
+// a thread-private, cache-line-padded slot (< 1 % of the cheapest ray), so bench.py times this
+// variant to get rays and milliseconds from the same run; parity tests use the unmodified
+// hexray_ref.
 #include <atomic>
 #include <chrono>
 #include <cstdio>
