@@ -205,6 +205,20 @@ def save_image(path, rgb, api_=None):
         raise HxrError(st, a.last_error(None))
 
 
+def load_image(path, api_=None):
+    """Bitmap::loadImage: returns float32 [H, W, 3]."""
+    a = api_ or api()
+    w, h = C.c_int32(), C.c_int32()
+    st = a.lib.hxr_load_image(path.encode(), C.byref(w), C.byref(h), None, 0)
+    if st != capi.HXR_OK:
+        raise HxrError(st, a.last_error(None))
+    out = np.empty((h.value, w.value, 3), dtype=np.float32)
+    st = a.lib.hxr_load_image(path.encode(), C.byref(w), C.byref(h), out.ctypes.data_as(C.POINTER(C.c_float)), out.size)
+    if st != capi.HXR_OK:
+        raise HxrError(st, a.last_error(None))
+    return out
+
+
 def render_file(path, device=0, **kw):
     """parse + upload + render one frame; returns (image, stats)."""
     sf = SceneFile(path)

@@ -204,4 +204,22 @@ int hxr_save_image(const char* path, const float* rgb, int32_t width, int32_t he
     HXR_GUARD_END(g_lastError)
 }
 
+int hxr_load_image(const char* path, int32_t* width, int32_t* height, float* rgb_out, size_t capacity_floats)
+{
+    if (!path || !width || !height) { g_lastError = "hxr_load_image: bad argument"; return HXR_ERR_INVALID; }
+    HXR_GUARD_BEGIN
+    hxr::host::Bitmap bmp;
+    if (!bmp.loadImage(path) || !bmp.isOK()) { g_lastError = std::string("cannot load ") + path; return HXR_ERR_IO; }
+    *width = bmp.getWidth();
+    *height = bmp.getHeight();
+    const size_t n = (size_t)bmp.getWidth() * bmp.getHeight();
+    if (rgb_out) {
+        if (capacity_floats < n * 3) { g_lastError = "hxr_load_image: buffer too small"; return HXR_ERR_INVALID; }
+        const auto& px = bmp.data();
+        for (size_t i = 0; i < n; i++) { rgb_out[i * 3] = px[i].r; rgb_out[i * 3 + 1] = px[i].g; rgb_out[i * 3 + 2] = px[i].b; }
+    }
+    return HXR_OK;
+    HXR_GUARD_END(g_lastError)
+}
+
 }  // extern "C"

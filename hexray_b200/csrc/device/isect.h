@@ -174,124 +174,230 @@ HXR_HD bool intersect_triangle_fast(const Ray& ray, const d3& A, const d3& B, co
 }
 
 // ---------------------------------------------------------------- triangle mesh
-// gamma_limit: object-space ray parameter beyond which hits cannot matter to the caller
-// (HXR_INF for "no limit"); it only prunes, it never changes which hit wins below it.
-template <bool COUNT>
-HXR_HD bool mesh_intersect(const DMesh& M, int gi, const Ray& ray, Hit& info, double gamma_limit, TravCounters* cnt)
+// The mesh query is split into pieces so that the same arithmetic serves (i) the simple per-ray
+// function used for CSG children, small meshes and the host emulation, and (ii) the persistent
+// state-machine traversal kernel (launch_cuda.cu), which interleaves these steps across lanes:
+//   mesh_slab          ray parameters [t0, t1] against the (slightly inflated) mesh box
+//   tri_test           the reference's triangle test (src/mesh.cpp:178-196), verbatim arithmetic
+//   kd_descend         one inner-node step of the front-to-back KD walk
+//   kd_after_leaf      termination test + pop after a leaf has been exhausted
+//   mesh_fill_hit      IntersectionInfo of the winning triangle (src/mesh.cpp:197-218)
+
+struct MeshBest {  // winner so far inside one mesh, in object space
+    double gamma, l2, l3;
+    int tri;
+};
+
+HXR_HD bool mesh_slab(const DMesh& M, const Ray& ray, double gamma_limit, double& t0, double& t1)
 {
-    // entry/exit parameters against the (slightly inflated) mesh box
-    double t0 = 0, t1 = gamma_limit;
-    {
-        const double o[3] = {ray.o.x, ray.o.y, ray.o.z};
-        const double d[3] = {ray.d.x, ray.d.y, ray.d.z};
-        for (int a = 0; a < 3; a++) {
-            double lo = M.bbmin[a] - 1e-6, hi = M.bbmax[a] + 1e-6;
-            if (d[a] == 0) {
-                if (o[a] < lo || o[a] > hi) return false;
-            } else {
-                double inv = 1.0 / d[a];
-                double ta = (lo - o[a]) * inv, tb = (hi - o[a]) * inv;
-                if (ta > tb) { double s = ta; ta = tb; tb = s; }
-                t0 = ta > t0 ? ta : t0;
-                t1 = tb < t1 ? tb : t1;
-            }
+    t0 = 0;
+    t1 = gamma_limit;
+    const double o[3] = {ray.o.x, ray.o.y, ray.o.z};
+    const double d[3] = {ray.d.x, ray.d.y, ray.d.z};
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int a = 0; a < 3; a++) {
+        const double lo = M.bbmin[a] - 1e-6, hi = M.bbmax[a] + 1e-6;
+        if (d[a] == 0) {
+            if (o[a] < lo || o[a] > hi) return false;
+        } else {
+            const double inv = 1.0 / d[a];
+            double ta = (lo - o[a]) * inv, tb = (hi - o[a]) * inv;
+            if (ta > tb) { const double s = ta; ta = tb; tb = s; }
+            t0 = ta > t0 ? ta : t0;
+            t1 = tb < t1 ? tb : t1;
         }
-        if (t0 > t1) return false;
     }
-    if (COUNT) cnt->mesh_queries++;
+    return t0 <= t1;
+}
 
+// loads one 96-byte triangle record with 128-bit loads
+struct TriRec {
+    d3 A, AB, AC, N;
+};
+HXR_HD TriRec load_tri(const TriTest* p)
+{
+    TriRec r;
+#if defined(__CUDA_ARCH__)
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
+    r.A = mk3(a.x, a.y, b.x);
+    r.AB = mk3(b.y, c.x, c.y);
+    r.AC = mk3(d.x, d.y, e.x);
+    r.N = mk3(e.y, f.x, f.y);
+#else
+    r.A = ld3(p->A); r.AB = ld3(p->AB); r.AC = ld3(p->AC); r.N = ld3(p->N);
+#endif
+    return r;
+}
+
+// returns true (and updates best) if triangle `ti` is hit at a parameter in [0, best.gamma]
+HXR_HD bool tri_test(const TriTest* tris, bool backface, const Ray& ray, uint32_t ti, MeshBest& best)
+{
+    const TriRec t = load_tri(tris + ti);
+    if (backface && dot(ray.d, t.N) > 0) return false;
     const d3 nd = -ray.d;
-    double best = gamma_limit;
-    int bestTri = -1;
-    double bl2 = 0, bl3 = 0;
+    const d3 H = ray.o - t.A;
+    const double Dcr = dot(t.N, nd);
+    if (fabs(Dcr) < 1e-12) return false;
+    const double rDcr = 1 / Dcr;
+    const double gamma = dot(t.N, H) * rDcr;
+    if (gamma < 0 || gamma > best.gamma) return false;
+    const double lambda2 = dot(cross(H, t.AC), nd) * rDcr;
+    if (lambda2 < 0 || lambda2 > 1) return false;
+    const double lambda3 = dot(cross(t.AB, H), nd) * rDcr;
+    if (lambda3 < 0 || lambda3 > 1) return false;
+    const double lambda1 = 1 - (lambda2 + lambda3);
+    if (lambda1 < 0 || lambda1 > 1) return false;
+    best.gamma = gamma;
+    best.tri = (int)ti;
+    best.l2 = lambda2;
+    best.l3 = lambda3;
+    return true;
+}
 
+HXR_HD KdNode load_node(const KdNode* p)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    KdNode n;
+    n.split = __uint_as_float(v.x);
+    n.kind = v.y;
+    n.a = v.z;
+    n.b = v.w;
+    return n;
+#else
+    return *p;
+#endif
+}
+
+// KD walk state of one ray inside one mesh
+struct KdWalk {
+    double tmin, tmax;
+    uint32_t node;
+    int sp;
+};
+
+// one inner-node step; pushes the far child when both sides are crossed
+HXR_HD void kd_descend(const KdNode& n, const Ray& ray, KdWalk& w, uint32_t* stackNode, double* stackTmax)
+{
+    const int axis = (int)n.kind;
+    const double split = (double)n.split;
+    const double oa = comp(ray.o, axis), da = comp(ray.d, axis);
+    const bool below = (oa < split) || (oa == split && da <= 0);
+    const uint32_t nearC = below ? n.a : n.b, farC = below ? n.b : n.a;
+    if (da == 0) {
+        if (oa == split && w.sp < HXR_KD_STACK) {  // travelling inside the split plane: both sides
+            stackNode[w.sp] = farC;
+            stackTmax[w.sp] = w.tmax;
+            w.sp++;
+        }
+        w.node = nearC;
+        return;
+    }
+    const double tpl = (split - oa) / da;
+    const double slack = 1e-9 * (1.0 + fabs(tpl));
+    if (tpl > w.tmax + slack || tpl < 0) {  // plane beyond this segment, or behind the origin
+        w.node = nearC;
+    } else if (tpl < w.tmin - slack) {
+        w.node = farC;
+    } else {
+        if (w.sp < HXR_KD_STACK) {
+            stackNode[w.sp] = farC;
+            stackTmax[w.sp] = w.tmax;
+            w.sp++;
+        }
+        w.node = nearC;
+        w.tmax = tpl;
+    }
+}
+
+// after a leaf: returns false when the walk is finished (best hit safely inside the covered part of
+// the ray, or nothing left on the stack), true after popping the next segment
+HXR_HD bool kd_after_leaf(KdWalk& w, const MeshBest& best, const uint32_t* stackNode, const double* stackTmax)
+{
+    if (best.tri >= 0 && best.gamma < w.tmax - 1e-7 * (1.0 + fabs(w.tmax))) return false;
+    if (w.sp == 0) return false;
+    w.sp--;
+    w.tmin = w.tmax;
+    w.node = stackNode[w.sp];
+    w.tmax = stackTmax[w.sp];
+    if (best.tri >= 0 && best.gamma < w.tmin - 1e-7 * (1.0 + fabs(w.tmin))) return false;
+    return true;
+}
+
+template <bool COUNT>
+HXR_HD bool mesh_closest(const DMesh& M, const Ray& ray, double gamma_limit, MeshBest& best, TravCounters* cnt)
+{
+    KdWalk w;
+    if (!mesh_slab(M, ray, gamma_limit, w.tmin, w.tmax)) return false;
+    if (COUNT) cnt->mesh_queries++;
+    best.gamma = gamma_limit;
+    best.tri = -1;
+    best.l2 = best.l3 = 0;
     uint32_t stackNode[HXR_KD_STACK];
     double stackTmax[HXR_KD_STACK];
-    int sp = 0;
-    uint32_t node = 0;
-    double tmin = t0, tmax = t1;
+    w.sp = 0;
+    w.node = 0;
     for (;;) {
-        const KdNode n = M.nodes[node];
+        const KdNode n = load_node(M.nodes + w.node);
         if (n.kind < 3) {
             if (COUNT) cnt->kd_inner++;
-            const int axis = (int)n.kind;
-            const double split = (double)n.split;
-            const double oa = comp(ray.o, axis), da = comp(ray.d, axis);
-            const bool below = (oa < split) || (oa == split && da <= 0);
-            const uint32_t nearC = below ? n.a : n.b, farC = below ? n.b : n.a;
-            if (da == 0) {
-                if (oa == split) {  // travelling inside the split plane: both sides
-                    if (sp < HXR_KD_STACK) { stackNode[sp] = farC; stackTmax[sp] = tmax; sp++; }
-                }
-                node = nearC;
-                continue;
-            }
-            const double tpl = (split - oa) / da;
-            const double slack = 1e-9 * (1.0 + fabs(tpl));
-            if (tpl > tmax + slack || tpl < 0) {  // plane beyond this segment, or behind the origin
-                node = nearC;
-            } else if (tpl < tmin - slack) {
-                node = farC;
-            } else {
-                if (sp < HXR_KD_STACK) { stackNode[sp] = farC; stackTmax[sp] = tmax; sp++; }
-                node = nearC;
-                tmax = tpl;
-            }
+            kd_descend(n, ray, w, stackNode, stackTmax);
             continue;
         }
-        // leaf
         if (COUNT) { cnt->kd_leaves++; cnt->tri_tests += n.b; }
-        for (uint32_t i = 0; i < n.b; i++) {
-            const uint32_t ti = M.leaf_tris[n.a + i];
-            const TriTest& t = M.tri_test[ti];
-            const d3 N = ld3(t.N);
-            if (M.backface && dot(ray.d, N) > 0) continue;
-            const d3 H = ray.o - ld3(t.A);
-            const double Dcr = dot(N, nd);
-            if (fabs(Dcr) < 1e-12) continue;
-            const double rDcr = 1 / Dcr;
-            const double gamma = dot(N, H) * rDcr;
-            if (gamma < 0 || gamma > best) continue;
-            const d3 AC = ld3(t.AC);
-            const double lambda2 = dot(cross(H, AC), nd) * rDcr;
-            if (lambda2 < 0 || lambda2 > 1) continue;
-            const d3 AB = ld3(t.AB);
-            const double lambda3 = dot(cross(AB, H), nd) * rDcr;
-            if (lambda3 < 0 || lambda3 > 1) continue;
-            const double lambda1 = 1 - (lambda2 + lambda3);
-            if (lambda1 < 0 || lambda1 > 1) continue;
-            best = gamma;
-            bestTri = (int)ti;
-            bl2 = lambda2;
-            bl3 = lambda3;
-        }
-        // stop once the best hit is safely inside the part of the ray already covered
-        if (bestTri >= 0 && best < tmax - 1e-7 * (1.0 + fabs(tmax))) break;
-        if (sp == 0) break;
-        sp--;
-        tmin = tmax;
-        node = stackNode[sp];
-        tmax = stackTmax[sp];
-        if (bestTri >= 0 && best < tmin - 1e-7 * (1.0 + fabs(tmin))) break;
+        for (uint32_t i = 0; i < n.b; i++) tri_test(M.tri_test, M.backface != 0, ray, M.leaf_tris[n.a + i], best);
+        if (!kd_after_leaf(w, best, stackNode, stackTmax)) break;
     }
-    if (bestTri < 0) return false;
+    return best.tri >= 0;
+}
 
-    const TriAttr& ta = M.tri_attr[bestTri];
-    info.dist = best;
-    info.ip = ray.o + best * ray.d;
+// all triangles in index order: exactly the reference's brute-force path (src/mesh.cpp:255-262);
+// used for meshes so small that a tree walk costs more than it saves
+HXR_HD bool mesh_bruteforce(const DMesh& M, const Ray& ray, double gamma_limit, MeshBest& best)
+{
+    double t0, t1;
+    if (!mesh_slab(M, ray, gamma_limit, t0, t1)) return false;
+    best.gamma = gamma_limit;
+    best.tri = -1;
+    best.l2 = best.l3 = 0;
+    for (int i = 0; i < M.n_tris; i++) tri_test(M.tri_test, M.backface != 0, ray, (uint32_t)i, best);
+    return best.tri >= 0;
+}
+
+HXR_HD void mesh_fill_hit(const DMesh& M, int gi, const Ray& ray, const MeshBest& best, Hit& info)
+{
+    const TriAttr& ta = M.tri_attr[best.tri];
+    info.dist = best.gamma;
+    info.ip = ray.o + best.gamma * ray.d;
     const d3 texA = ld3(M.uvs + 3 * ta.t[0]), texB = ld3(M.uvs + 3 * ta.t[1]), texC = ld3(M.uvs + 3 * ta.t[2]);
-    const d3 tex = texA + (texB - texA) * bl2 + (texC - texA) * bl3;
+    const d3 tex = texA + (texB - texA) * best.l2 + (texC - texA) * best.l3;
     info.u = tex.x;
     info.v = tex.y;
     if (M.faceted) {
         info.norm = ld3(ta.gnormal);
     } else {
         const d3 nA = ld3(M.normals + 3 * ta.n[0]), nB = ld3(M.normals + 3 * ta.n[1]), nC = ld3(M.normals + 3 * ta.n[2]);
-        info.norm = normalize_m(nA + (nB - nA) * bl2 + (nC - nA) * bl3);
+        info.norm = normalize_m(nA + (nB - nA) * best.l2 + (nC - nA) * best.l3);
     }
     info.dNdx = ld3(ta.dNdx);
     info.dNdy = ld3(ta.dNdy);
     info.geom = gi;
+}
+
+#define HXR_SMALL_MESH 24 /* meshes with at most this many triangles are tested by brute force */
+
+// gamma_limit: object-space ray parameter beyond which hits cannot matter to the caller
+// (HXR_INF for "no limit"); it only prunes, it never changes which hit wins below it.
+template <bool COUNT>
+HXR_HD bool mesh_intersect(const DMesh& M, int gi, const Ray& ray, Hit& info, double gamma_limit, TravCounters* cnt)
+{
+    MeshBest best;
+    const bool hit = M.n_tris <= HXR_SMALL_MESH ? mesh_bruteforce(M, ray, gamma_limit, best) : mesh_closest<COUNT>(M, ray, gamma_limit, best, cnt);
+    if (!hit) return false;
+    mesh_fill_hit(M, gi, ray, best, info);
     return true;
 }
 

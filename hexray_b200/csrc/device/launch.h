@@ -48,18 +48,19 @@ void prof_collect(double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);  // block
 int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels, uint32_t first_pixel,
                 uint32_t n_items, uint32_t spp_pass, RayTask* q, uint32_t* q_count);
 
-// closest hit for q[0 .. *q_count) (count read on the device) -> hits[i]
+// closest hit for q[0 .. *q_count) (count read on the device) -> hits[i]. Three stages:
+// setup (inline nodes + queue big-mesh walks) -> walk (persistent KD traversal) -> finalize.
 int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits,
-                  uint32_t* work_head, TravCounters* cnt);
+                  const TraceScratch& ts, TravCounters* cnt);
 
 // shade q[begin .. min(end, *q_count)); gi selects pathtrace vs Whitted
 int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits,
           uint32_t begin, uint32_t end, const Sinks& sinks);
 
-// visible() for shadow[0 .. *count) adding the carried colour when unoccluded; resets nothing
-// *total += *count (64-bit running total of shadow rays, kept on the device)
+// visible() for shadow[0 .. *count): ts.occluded[i] = 1 if blocked; when accum != nullptr the carried colour of
+// every unblocked task is added to its pixel. *total += *count (64-bit running total kept on the device).
 int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum,
-                 uint32_t* work_head, TravCounters* cnt, unsigned long long* total);
+                 const TraceScratch& ts, TravCounters* cnt, unsigned long long* total);
 
 // needsAA flags -> compacted pixel list (order unspecified) ; *n_out = number of flagged pixels
 // rows restricted to y with ((y / HXR_ROW_BAND) % shard_count) == shard_index
@@ -71,9 +72,6 @@ int scale_listed(float* vfb, const uint32_t* list, const uint32_t* n, uint32_t c
 int scale_all(float* buf, size_t n, float mul);
 // dst[i] += src[i]
 int add_into(float* dst, const float* src, size_t n);
-
-// test hooks
-int trace_visible_segments(const DScene& sc, const double* seg, uint32_t n, uint8_t* out);
 
 }  // namespace dev
 }  // namespace hxr

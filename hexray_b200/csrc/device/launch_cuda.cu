@@ -3,16 +3,22 @@
 //
 // Kernels (one per wavefront stage; per-item bodies live in pipeline.h):
 //   k_gen_primary     primary-ray generator (pixel jitter / AA offsets / DOF lens)     -> ray queue
-//   k_trace_closest   closest hit: PERSISTENT threads; each warp pulls 32 rays at a time from the
-//                     queue head (one atomicAdd by lane 0, broadcast with __shfl_sync), walks the
-//                     instance list + KD-tree with a per-thread stack, writes one HitRec per ray
+//   k_setup_closest   per ray: every inline node (analytic primitives, CSG, heightfield, tiny meshes) in scene
+//                     order; each big mesh whose box the ray enters becomes a (ray, node) walk task
+//   k_walk            the KD-tree walk: PERSISTENT warps running a per-lane state machine. A lane that
+//                     finishes its task takes a new one (idle lanes found with __ballot_sync, one
+//                     atomicAdd on the queue head by the first idle lane, broadcast with __shfl_sync), so
+//                     lanes stay busy although rays need very different numbers of steps. One step =
+//                     one inner node (a single 128-bit node load) or one triangle test (six 128-bit loads).
+//   k_finalize_closest winner across inline nodes and walks, IntersectionInfo, lights, environment, bump
 //   k_shade           Whitted shader tree or path-tracing vertex: pushes child/shadow tasks,
 //                     accumulates radiance with RED.ADD.F32
-//   k_trace_shadow    visible(): persistent like k_trace_closest, adds the carried colour if clear
+//   k_setup_shadow / k_walk<shadow> / k_accum_shadow   visible() in the same three stages (any-hit walk)
 //   k_aa_detect / k_scale_* / k_add   frame-buffer passes
 // Grid sizing: persistent kernels launch (SM count x resident blocks/SM) blocks — 148 SMs on
 // B200 — so every SM holds its full complement of warps for the whole launch.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -188,49 +194,185 @@ __global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, 
     if (blockIdx.x == 0 && threadIdx.x == 0) *q_count = n_items;
 }
 
+#define HXR_WALK_BLOCK 128
+#ifndef HXR_WALK_MIN_BLOCKS
+#define HXR_WALK_MIN_BLOCKS 5
+#endif
+#ifndef HXR_REFILL_MIN
+#define HXR_REFILL_MIN 8  /* refill as soon as this many lanes of a warp are idle */
+#endif
+#ifndef HXR_WALK_STEPS
+#define HXR_WALK_STEPS 4  /* state-machine steps between two refill checks */
+#endif
+
 template <bool COUNT>
-__global__ void __launch_bounds__(HXR_TRACE_BLOCK) k_trace_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count,
-                                                                   uint32_t cap, HitRec* __restrict__ hits, uint32_t* head, TravCounters* cnt)
+__global__ void __launch_bounds__(128) k_setup_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
+                                                       TraceScratch ts, TravCounters* cnt)
 {
     const uint32_t n = min(*q_count, cap);
-    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
     TravCounters local = {0, 0, 0, 0};
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(head, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            HitRec h;
-            raycast_item<COUNT>(sc, task_ray(q[i]), h, &local);
-            hits[i] = h;
-        }
-    }
-    if (COUNT) {
-        atomicAdd(&cnt->kd_inner, local.kd_inner);
-        atomicAdd(&cnt->kd_leaves, local.kd_leaves);
-        atomicAdd(&cnt->tri_tests, local.tri_tests);
-        atomicAdd(&cnt->mesh_queries, local.mesh_queries);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_closest_item<COUNT>(sc, task_ray(q[i]), i, ts, &local);
+    if (COUNT && local.mesh_queries) atomicAdd(&cnt->mesh_queries, local.mesh_queries);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_finalize_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
+                                                          TraceScratch ts, HitRec* __restrict__ hits, TravCounters* cnt)
+{
+    const uint32_t n = min(*q_count, cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TravCounters local = {0, 0, 0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        HitRec h;
+        finalize_closest_item<COUNT>(sc, task_ray(q[i]), i, ts, h, &local);
+        hits[i] = h;
     }
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(HXR_TRACE_BLOCK) k_trace_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count,
-                                                                  uint32_t cap, float* accum, uint32_t* head, TravCounters* cnt,
-                                                                  unsigned long long* total)
+__global__ void __launch_bounds__(128) k_setup_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap,
+                                                      TraceScratch ts, TravCounters* cnt, unsigned long long* total)
 {
     const uint32_t n = min(*count, cap);
-    const unsigned lane = threadIdx.x & 31u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(total, (unsigned long long)n);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(total, (unsigned long long)n);
     TravCounters local = {0, 0, 0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_shadow_item<COUNT>(sc, shadow[i], i, ts, &local);
+}
+
+__global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap, TraceScratch ts,
+                                                      float* accum)
+{
+    const uint32_t n = min(*count, cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) accumulate_shadow_item(shadow[i], i, ts, accum);
+}
+
+// The KD walk. SHADOW = any-hit against |AB| (visible()), otherwise closest hit.
+template <bool SHADOW, bool COUNT>
+__global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayTask* __restrict__ rays,
+                                                                              const ShadowTask* __restrict__ shadows, TraceScratch ts,
+                                                                              TravCounters* cnt)
+{
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t n = min(*ts.task_count, ts.task_cap);
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t stackNode[HXR_KD_STACK];
+    double stackTmax[HXR_KD_STACK];
+    bool active = false, drained = false;
+    Ray t;                          // object-space ray of the current task
+    const KdNode* nodes = nullptr;  // the current mesh
+    const uint32_t* leafTris = nullptr;
+    const TriTest* tris = nullptr;
+    bool backface = false;
+    KdWalk w;
+    MeshBest best;
+    uint32_t leafPos = 0, leafLeft = 0, taskRay = 0, taskNode = 0;
+    TravCounters local = {0, 0, 0, 0};
+    w.tmin = w.tmax = 0; w.node = 0; w.sp = 0;
+    best.gamma = 0; best.l2 = best.l3 = 0; best.tri = -1;
+
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(head, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) shadow_item<COUNT>(sc, shadow[i], accum, &local);
+        // ---- refill: idle lanes take new tasks
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (!drained && (idle == FULL || __popc(idle) >= HXR_REFILL_MIN)) {
+            const int c = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(ts.head, (uint32_t)c);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + (uint32_t)c >= n) drained = true;
+            if (!active) {
+                const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
+                if (k < n) {
+                    const MeshTask task = ts.tasks[k];
+                    taskRay = task.ray;
+                    taskNode = task.node;
+                    const hxr_node& nd = sc.nodes[taskNode];
+                    const DMesh& M = sc.meshes[sc.geoms[nd.geom].a];
+                    double limit;
+                    bool skip = false;
+                    if (SHADOW) {
+                        double D;
+                        const Ray wr = shadow_ray(shadows[taskRay], D);
+                        t = object_ray(nd, wr);
+                        limit = gamma_limit_for(nd, t, D);
+                        skip = ts.occluded[taskRay] != 0;
+                    } else {
+                        t = object_ray(nd, task_ray(rays[taskRay]));
+                        limit = gamma_limit_for(nd, t, ts.pre[taskRay].dist);
+                    }
+                    if (!skip && mesh_slab(M, t, limit, w.tmin, w.tmax)) {
+                        nodes = M.nodes;
+                        leafTris = M.leaf_tris;
+                        tris = M.tri_test;
+                        backface = M.backface != 0;
+                        best.gamma = limit;
+                        best.tri = -1;
+                        best.l2 = best.l3 = 0;
+                        w.sp = 0;
+                        w.node = 0;
+                        leafLeft = 0;
+                        active = true;
+                        if (COUNT) local.mesh_queries++;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0) {
+            if (drained) break;
+            continue;
+        }
+        // ---- a few steps of the walk for every active lane
+#pragma unroll 1
+        for (int it = 0; it < HXR_WALK_STEPS; it++) {
+            if (!active) continue;
+            bool finished = false;
+            if (leafLeft) {
+                const uint32_t ti = __ldg(leafTris + leafPos);
+                leafPos++;
+                leafLeft--;
+                if (COUNT) local.tri_tests++;
+                const bool hit = tri_test(tris, backface, t, ti, best);
+                if (SHADOW && hit) {
+                    // the exact test of visible(): world distance of the hit against |AB|
+                    double D;
+                    const Ray wr = shadow_ray(shadows[taskRay], D);
+                    const hxr_node& nd = sc.nodes[taskNode];
+                    const d3 ipw = mul_vm(t.o + best.gamma * t.d, nd.T.m) + ld3(nd.T.offset);
+                    if (distance3(wr.o, ipw) < D) {
+                        ts.occluded[taskRay] = 1;
+                        active = false;
+                        continue;
+                    }
+                }
+                if (leafLeft == 0) finished = !kd_after_leaf(w, best, stackNode, stackTmax);
+            } else {
+                const KdNode nd = load_node(nodes + w.node);
+                if (nd.kind < 3) {
+                    if (COUNT) local.kd_inner++;
+                    kd_descend(nd, t, w, stackNode, stackTmax);
+                } else {
+                    if (COUNT) local.kd_leaves++;
+                    leafPos = nd.a;
+                    leafLeft = nd.b;
+                    if (leafLeft == 0) finished = !kd_after_leaf(w, best, stackNode, stackTmax);
+                }
+            }
+            if (finished) {
+                active = false;
+                if (!SHADOW && best.tri >= 0) {
+                    const hxr_node& nd = sc.nodes[taskNode];
+                    const d3 wo = ld3(rays[taskRay].o);
+                    const d3 ipw = mul_vm(t.o + best.gamma * t.d, nd.T.m) + ld3(nd.T.offset);
+                    MeshRes r;
+                    r.dist = distance3(wo, ipw);
+                    r.gamma = best.gamma; r.l2 = best.l2; r.l3 = best.l3; r.tri = best.tri; r.node = (int32_t)taskNode;
+                    ts.res[(size_t)sc.node_slot[taskNode] * ts.res_stride + taskRay] = r;
+                }
+            }
+        }
     }
     if (COUNT) {
         atomicAdd(&cnt->kd_inner, local.kd_inner);
@@ -280,13 +422,6 @@ __global__ void k_add_into(float* dst, const float* __restrict__ src, size_t n)
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
 }
-__global__ void k_visible_segments(DScene sc, const double* __restrict__ seg, uint32_t n, uint8_t* out)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    out[i] = visible_item<false>(sc, ld3(seg + 6 * (size_t)i), ld3(seg + 6 * (size_t)i + 3), nullptr) ? 1 : 0;
-}
-
 // ---- launchers --------------------------------------------------------------------------
 template <class K> static int persistent_grid(K kernel, int block)
 {
@@ -304,19 +439,37 @@ int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels,
     return 1;
 }
 
-int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits, uint32_t* work_head,
+// per-item stage kernels are grid-stride loops over a count that only the device knows
+static uint32_t stage_grid(uint32_t cap) { return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)cap + 127) / 128, (uint64_t)g_sms * 16)); }
+
+template <class K> static int walk_grid(K kernel)
+{
+    int perSm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, HXR_WALK_BLOCK, 0) != cudaSuccess || perSm < 1) perSm = 1;
+    return g_sms * perSm;
+}
+
+int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits, const TraceScratch& ts,
                   TravCounters* cnt)
 {
     ProfScope ps(PROF_TRACE_CLOSEST);
+    g_launches[PROF_TRACE_CLOSEST] += 2;
     static int gridPlain = 0, gridCount = 0;
+    cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
+    cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
+    const uint32_t nb = stage_grid(q_cap);
     if (cnt) {
-        if (!gridCount) gridCount = persistent_grid(k_trace_closest<true>, HXR_TRACE_BLOCK);
-        k_trace_closest<true><<<gridCount, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, q, q_count, q_cap, hits, work_head, cnt);
+        if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
+        k_setup_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, cnt);
+        if (sc.n_big) k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, cnt);
+        k_finalize_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
     } else {
-        if (!gridPlain) gridPlain = persistent_grid(k_trace_closest<false>, HXR_TRACE_BLOCK);
-        k_trace_closest<false><<<gridPlain, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, q, q_count, q_cap, hits, work_head, nullptr);
+        if (!gridPlain) gridPlain = walk_grid(k_walk<false, false>);
+        k_setup_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
+        if (sc.n_big) k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, nullptr);
+        k_finalize_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
     }
-    return 1;
+    return sc.n_big ? 3 : 2;
 }
 
 int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits, uint32_t begin,
@@ -329,19 +482,27 @@ int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint3
     return 1;
 }
 
-int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, uint32_t* work_head,
+int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, const TraceScratch& ts,
                  TravCounters* cnt, unsigned long long* total)
 {
     ProfScope ps(PROF_TRACE_SHADOW);
+    g_launches[PROF_TRACE_SHADOW] += 2;
     static int gridPlain = 0, gridCount = 0;
+    cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
+    cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
+    const uint32_t nb = stage_grid(cap);
+    int launches = 1;
     if (cnt) {
-        if (!gridCount) gridCount = persistent_grid(k_trace_shadow<true>, HXR_TRACE_BLOCK);
-        k_trace_shadow<true><<<gridCount, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, shadow, count, cap, accum, work_head, cnt, total);
+        if (!gridCount) gridCount = walk_grid(k_walk<true, true>);
+        k_setup_shadow<true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
+        if (sc.n_big) { k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, cnt); launches++; }
     } else {
-        if (!gridPlain) gridPlain = persistent_grid(k_trace_shadow<false>, HXR_TRACE_BLOCK);
-        k_trace_shadow<false><<<gridPlain, HXR_TRACE_BLOCK, 0, g_stream>>>(sc, shadow, count, cap, accum, work_head, nullptr, total);
+        if (!gridPlain) gridPlain = walk_grid(k_walk<true, false>);
+        k_setup_shadow<false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
+        if (sc.n_big) { k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, nullptr); launches++; }
     }
-    return 1;
+    if (accum) { k_accum_shadow<<<nb, 256, 0, g_stream>>>(shadow, count, cap, ts, accum); launches++; }
+    return launches;
 }
 
 int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
@@ -369,13 +530,5 @@ int add_into(float* dst, const float* src, size_t n)
     k_add_into<<<g_sms * 8, 256, 0, g_stream>>>(dst, src, n);
     return 1;
 }
-int trace_visible_segments(const DScene& sc, const double* seg, uint32_t n, uint8_t* out)
-{
-    if (!n) return 0;
-    ProfScope ps(PROF_OTHER);
-    k_visible_segments<<<(n + 127) / 128, 128, 0, g_stream>>>(sc, seg, n, out);
-    return 1;
-}
-
 }  // namespace dev
 }  // namespace hxr

@@ -16,13 +16,13 @@ namespace hxr {
 
 // KD-tree node. inner: kind = axis (0..2), a = left child, b = right child.
 //               leaf : kind = 3,           a = first entry in leaf_tris, b = triangle count.
-struct KdNode {
+struct alignas(16) KdNode {
     float split;
     uint32_t kind;
     uint32_t a, b;
 };
 
-struct TriTest {
+struct alignas(16) TriTest {
     double A[3], AB[3], AC[3], N[3];
 };
 
@@ -67,6 +67,10 @@ struct DScene {
     const hxr_texture* textures;
     const DImage* images;
     const hxr_light* lights;
+    // per node: slot of its traversal results if its geometry is a "big" mesh (walked by the persistent
+    // traversal kernel), -1 otherwise (analytic primitives, CSG, heightfields, meshes <= HXR_SMALL_MESH)
+    const int32_t* node_slot;
+    int32_t n_big;
     int32_t n_nodes, n_lights;
     int32_t has_env;
     int32_t env_images[6];

@@ -9,7 +9,7 @@
 
 namespace hxr {
 
-enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_OVERFLOW = 3, C_HEAD_A = 4, C_HEAD_B = 5, C_AA = 6, C_NCOUNTERS = 16 };
+enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_OVERFLOW = 3, C_HEAD_A = 4, C_HEAD_B = 5, C_AA = 6, C_TASKS = 7, C_NCOUNTERS = 16 };
 
 Renderer::~Renderer()
 {
@@ -19,6 +19,10 @@ Renderer::~Renderer()
     dev::free_(m_shadow);
     dev::free_(m_counters);
     dev::free_(m_trav);
+    dev::free_(m_pre);
+    dev::free_(m_tasks);
+    dev::free_(m_res);
+    dev::free_(m_occluded);
     dev::free_(m_aaList);
     dev::free_(m_aaMask);
     dev::free_(m_accum);
@@ -222,6 +226,18 @@ int Renderer::uploadScene(const hxr_scene* sp)
     if (!m_scene.nodes || !m_scene.geoms || !m_scene.meshes || !m_scene.hfs || !m_scene.shaders || !m_scene.layers ||
         !m_scene.textures || !m_scene.images || !m_scene.lights)
         return oom();
+    {
+        // nodes whose geometry is a mesh too big for the inline brute-force test get a result slot
+        std::vector<int32_t> slot(std::max(1, s.n_nodes), -1);
+        m_nBig = 0;
+        for (int i = 0; i < s.n_nodes; i++) {
+            const hxr_geometry& g = s.geometries[s.nodes[i].geom];
+            if (g.type == HXR_GEOM_MESH && s.meshes[g.a].n_triangles > HXR_SMALL_MESH) slot[i] = m_nBig++;
+        }
+        m_scene.node_slot = uploadArray(slot.data(), slot.size());
+        if (!m_scene.node_slot) return oom();
+        m_scene.n_big = m_nBig;
+    }
     m_scene.n_nodes = s.n_nodes;
     m_scene.n_lights = s.n_lights;
     m_scene.has_env = s.has_environment;
@@ -275,24 +291,48 @@ bool Renderer::ensureQueues()
 {
     const uint32_t cap = m_cfg.queue_capacity ? (uint32_t)std::min<uint64_t>(m_cfg.queue_capacity, 1u << 30) : (8u << 20);
     const uint32_t shadowCap = (uint32_t)std::min<uint64_t>(1u << 30, std::max<uint64_t>((uint64_t)cap * 2, (uint64_t)m_maxShadowPerHit * 4096));
-    if (m_q[0] && cap == m_cap && shadowCap == m_shadowCap) return true;
+    const uint32_t taskCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)std::max(cap, shadowCap) * (uint64_t)std::max(1, m_nBig));
+    if (m_q[0] && cap == m_cap && shadowCap == m_shadowCap && taskCap == m_taskCap) return true;
     for (int i = 0; i < 2; i++) { dev::free_(m_q[i]); m_q[i] = nullptr; }
     dev::free_(m_hits); m_hits = nullptr;
     dev::free_(m_shadow); m_shadow = nullptr;
+    dev::free_(m_pre); m_pre = nullptr;
+    dev::free_(m_tasks); m_tasks = nullptr;
+    dev::free_(m_res); m_res = nullptr;
+    dev::free_(m_occluded); m_occluded = nullptr;
     m_cap = cap;
     m_shadowCap = shadowCap;
+    m_taskCap = taskCap;
+    m_pre = (RayPre*)dev::alloc((size_t)cap * sizeof(RayPre));
+    m_tasks = (MeshTask*)dev::alloc((size_t)taskCap * sizeof(MeshTask));
+    m_res = (MeshRes*)dev::alloc((size_t)cap * std::max(1, m_nBig) * sizeof(MeshRes));
+    m_occluded = (uint8_t*)dev::alloc((size_t)shadowCap);
     for (int i = 0; i < 2; i++) m_q[i] = (RayTask*)dev::alloc((size_t)cap * sizeof(RayTask));
     m_hits = (HitRec*)dev::alloc((size_t)cap * sizeof(HitRec));
     m_shadow = (ShadowTask*)dev::alloc((size_t)shadowCap * sizeof(ShadowTask));
     if (!m_counters) m_counters = (uint32_t*)dev::alloc(C_NCOUNTERS * sizeof(uint32_t));
     if (!m_trav) m_trav = (TravCounters*)dev::alloc(sizeof(TravCounters) + 64);
-    if (!m_q[0] || !m_q[1] || !m_hits || !m_shadow || !m_counters || !m_trav) {
+    if (!m_q[0] || !m_q[1] || !m_hits || !m_shadow || !m_counters || !m_trav || !m_pre || !m_tasks || !m_res || !m_occluded) {
         m_err = std::string("queue allocation failed: ") + dev::last_error();
         return false;
     }
     dev::zero(m_counters, C_NCOUNTERS * sizeof(uint32_t));
     dev::zero(m_trav, sizeof(TravCounters) + 64);
     return true;
+}
+
+TraceScratch Renderer::scratch(uint32_t headCounter) const
+{
+    TraceScratch ts;
+    ts.pre = m_pre;
+    ts.tasks = m_tasks;
+    ts.task_count = m_counters + C_TASKS;
+    ts.task_cap = m_taskCap;
+    ts.res = m_res;
+    ts.res_stride = m_cap;
+    ts.occluded = m_occluded;
+    ts.head = m_counters + headCounter;
+    return ts;
 }
 
 uint32_t Renderer::readCount(const uint32_t* dptr)
@@ -314,8 +354,7 @@ int Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_
     TravCounters* cnt = m_countTraversal ? m_trav : nullptr;
     for (int level = 0; n > 0 && level <= fp.max_depth + 2; level++) {
         if (n > m_cap) return 1;  // overflow
-        dev::set_u32(m_counters + C_HEAD_A, 0);
-        st.kernel_launches += dev::trace_closest(m_scene, m_q[cur], m_counters + cur, m_cap, m_hits, m_counters + C_HEAD_A, cnt);
+        st.kernel_launches += dev::trace_closest(m_scene, m_q[cur], m_counters + cur, m_cap, m_hits, scratch(C_HEAD_A), cnt);
         st.rays_closest += n;
         dev::set_u32(m_counters + (1 - cur), 0);
         Sinks sk;
@@ -330,8 +369,7 @@ int Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_
         for (uint32_t b = 0; b < n; b += chunk) {
             dev::set_u32(m_counters + C_SHADOW, 0);
             st.kernel_launches += dev::shade(m_scene, fp, m_q[cur], m_counters + cur, m_hits, b, std::min<uint64_t>(n, (uint64_t)b + chunk), sk);
-            dev::set_u32(m_counters + C_HEAD_B, 0);
-            st.kernel_launches += dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, accum, m_counters + C_HEAD_B, cnt, shadowTotalPtr(m_trav));
+            st.kernel_launches += dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, accum, scratch(C_HEAD_B), cnt, shadowTotalPtr(m_trav));
         }
         n = readCount(m_counters + (1 - cur));
         cur = 1 - cur;
@@ -563,8 +601,7 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
         for (uint32_t i = 0; i < m; i++) tasks[i] = taskFromRay(rays[first + i], i);
         dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
         dev::set_u32(m_counters + C_Q0, m);
-        dev::set_u32(m_counters + C_HEAD_A, 0);
-        dev::trace_closest(m_scene, m_q[0], m_counters + C_Q0, m_cap, m_hits, m_counters + C_HEAD_A, nullptr);
+        dev::trace_closest(m_scene, m_q[0], m_counters + C_Q0, m_cap, m_hits, scratch(C_HEAD_A), nullptr);
         if (!dev::download(recs.data(), m_hits, (size_t)m * sizeof(HitRec))) return fail(HXR_ERR_CUDA, dev::last_error());
         for (uint32_t i = 0; i < m; i++) {
             const HitRec& h = recs[i];
@@ -589,20 +626,24 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
 {
     if (!m_haveScene) return fail(HXR_ERR_INVALID, "trace: no scene");
     if (n && (!seg || !out)) return fail(HXR_ERR_INVALID, "trace: null buffer");
-    const size_t chunkMax = 1u << 20;
-    double* dseg = (double*)dev::alloc(std::min(n, chunkMax) * 6 * sizeof(double) + 8);
-    uint8_t* dout = (uint8_t*)dev::alloc(std::min(n, chunkMax) + 8);
-    int rc = HXR_OK;
-    if (!dseg || !dout) rc = fail(HXR_ERR_CUDA, dev::last_error());
-    for (size_t first = 0; first < n && rc == HXR_OK; first += chunkMax) {
-        const uint32_t m = (uint32_t)std::min(chunkMax, n - first);
-        dev::upload(dseg, seg + first * 6, (size_t)m * 6 * sizeof(double));
-        dev::trace_visible_segments(m_scene, dseg, m, dout);
-        if (!dev::download(out + first, dout, m)) rc = fail(HXR_ERR_CUDA, dev::last_error());
+    if (!ensureQueues()) return HXR_ERR_CUDA;
+    std::vector<ShadowTask> tasks;
+    std::vector<uint8_t> occ;
+    for (size_t first = 0; first < n; first += m_shadowCap) {
+        const uint32_t m = (uint32_t)std::min<size_t>(m_shadowCap, n - first);
+        tasks.resize(m);
+        occ.resize(m);
+        for (uint32_t i = 0; i < m; i++) {
+            memset(&tasks[i], 0, sizeof(ShadowTask));
+            for (int k = 0; k < 3; k++) { tasks[i].a[k] = seg[(first + i) * 6 + k]; tasks[i].b[k] = seg[(first + i) * 6 + 3 + k]; }
+        }
+        dev::upload(m_shadow, tasks.data(), (size_t)m * sizeof(ShadowTask));
+        dev::set_u32(m_counters + C_SHADOW, m);
+        dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, nullptr, scratch(C_HEAD_B), nullptr, nullptr);
+        if (!dev::download(occ.data(), m_occluded, m)) return fail(HXR_ERR_CUDA, dev::last_error());
+        for (uint32_t i = 0; i < m; i++) out[first + i] = occ[i] ? 0 : 1;
     }
-    dev::free_(dseg);
-    dev::free_(dout);
-    return rc;
+    return HXR_OK;
 }
 
 int Renderer::traceColor(const hxr_ray* rays, size_t n, float* rgb)

@@ -50,6 +50,14 @@ private:
     ShadowTask* m_shadow = nullptr;
     uint32_t* m_counters = nullptr;  // [0],[1] queue counts, [2] shadow count, [3] overflow, [4] work head A, [5] work head B, [6] aa count
     TravCounters* m_trav = nullptr;
+    // traversal scratch (device/pipeline.h: TraceScratch)
+    RayPre* m_pre = nullptr;
+    MeshTask* m_tasks = nullptr;
+    MeshRes* m_res = nullptr;
+    uint8_t* m_occluded = nullptr;
+    uint32_t m_taskCap = 0;
+    int m_nBig = 0;
+    TraceScratch scratch(uint32_t headCounter) const;
     uint32_t* m_aaList = nullptr;
     uint8_t* m_aaMask = nullptr;
     float* m_accum = nullptr;

@@ -340,6 +340,10 @@ void hxr_scene_file_free(hxr_scene_file* sf);
  * src/sdl.cpp:404-419) or ".exr" (HALF RGBA, alpha 1). rgb: w*h*3 floats top-down. */
 int hxr_save_image(const char* path, const float* rgb, int32_t width, int32_t height);
 
+/* Bitmap::loadImage equivalent (".bmp" 8/24/32 bpp, ".exr" scan-line NONE/RLE/ZIPS/ZIP/PIZ): fills *width / *height;
+ * when rgb_out is non-NULL and capacity_floats >= width*height*3 also the pixels (float RGB, top-down). */
+int hxr_load_image(const char* path, int32_t* width, int32_t* height, float* rgb_out, size_t capacity_floats);
+
 #ifdef __cplusplus
 }
 #endif

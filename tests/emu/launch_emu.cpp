@@ -84,16 +84,26 @@ int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels,
     return 1;
 }
 
-int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t, HitRec* hits, uint32_t*, TravCounters* cnt)
+int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t, HitRec* hits, const TraceScratch& ts, TravCounters* cnt)
 {
     const uint32_t n = *q_count;
+    *ts.task_count = 0;
+    auto stage = [&](uint32_t m, auto f) {
+        if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
+    };
     if (cnt) {
-        for (uint32_t i = 0; i < n; i++) raycast_item<true>(sc, task_ray(q[i]), hits[i], cnt);
+        stage(n, [&](uint32_t i) { setup_closest_item<true>(sc, task_ray(q[i]), i, ts, cnt); });
+        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
+        stage(nt, [&](uint32_t k) { walk_closest_item<true>(sc, task_ray(q[ts.tasks[k].ray]), ts.tasks[k], ts, cnt); });
+        stage(n, [&](uint32_t i) { finalize_closest_item<true>(sc, task_ray(q[i]), i, ts, hits[i], cnt); });
     } else {
-        parallel_for(n, [&](uint32_t i) { raycast_item<false>(sc, task_ray(q[i]), hits[i], nullptr); });
+        stage(n, [&](uint32_t i) { setup_closest_item<false>(sc, task_ray(q[i]), i, ts, nullptr); });
+        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
+        stage(nt, [&](uint32_t k) { walk_closest_item<false>(sc, task_ray(q[ts.tasks[k].ray]), ts.tasks[k], ts, nullptr); });
+        stage(n, [&](uint32_t i) { finalize_closest_item<false>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
     }
-    g_launches[PROF_TRACE_CLOSEST]++;
-    return 1;
+    g_launches[PROF_TRACE_CLOSEST] += 3;
+    return 3;
 }
 
 int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits, uint32_t begin,
@@ -110,18 +120,27 @@ int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint3
     return 1;
 }
 
-int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, uint32_t*,
+int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, const TraceScratch& ts,
                  TravCounters* cnt, unsigned long long* total)
 {
     const uint32_t n = std::min(*count, cap);
+    *ts.task_count = 0;
+    auto stage = [&](uint32_t m, auto f) {
+        if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
+    };
     if (cnt) {
-        for (uint32_t i = 0; i < n; i++) shadow_item<true>(sc, shadow[i], accum, cnt);
+        stage(n, [&](uint32_t i) { setup_shadow_item<true>(sc, shadow[i], i, ts, cnt); });
+        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
+        stage(nt, [&](uint32_t k) { walk_shadow_item<true>(sc, shadow[ts.tasks[k].ray], ts.tasks[k], ts, cnt); });
     } else {
-        parallel_for(n, [&](uint32_t i) { shadow_item<false>(sc, shadow[i], accum, nullptr); });
+        stage(n, [&](uint32_t i) { setup_shadow_item<false>(sc, shadow[i], i, ts, nullptr); });
+        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
+        stage(nt, [&](uint32_t k) { walk_shadow_item<false>(sc, shadow[ts.tasks[k].ray], ts.tasks[k], ts, nullptr); });
     }
-    *total += n;
-    g_launches[PROF_TRACE_SHADOW]++;
-    return 1;
+    if (accum) stage(n, [&](uint32_t i) { accumulate_shadow_item(shadow[i], i, ts, accum); });
+    if (total) *total += n;
+    g_launches[PROF_TRACE_SHADOW] += 3;
+    return 3;
 }
 
 int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
@@ -160,14 +179,5 @@ int add_into(float* dst, const float* src, size_t n)
     g_launches[PROF_OTHER]++;
     return 1;
 }
-int trace_visible_segments(const DScene& sc, const double* seg, uint32_t n, uint8_t* out)
-{
-    parallel_for(n, [&](uint32_t i) {
-        out[i] = visible_item<false>(sc, ld3(seg + 6 * (size_t)i), ld3(seg + 6 * (size_t)i + 3), nullptr) ? 1 : 0;
-    });
-    g_launches[PROF_OTHER]++;
-    return 1;
-}
-
 }  // namespace dev
 }  // namespace hxr
