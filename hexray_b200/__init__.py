@@ -18,7 +18,8 @@ import os
 import numpy as np
 
 from . import capi
-from .capi import HxrError, MODE_AUTO, MODE_MONTECARLO, MODE_WHITTED, RENDER_COUNT_TRAVERSAL  # noqa: F401
+from .capi import (HxrError, MODE_AUTO, MODE_MONTECARLO, MODE_WHITTED, RENDER_COUNT_TRAVERSAL,  # noqa: F401
+                   CFG_BRUTE_FORCE_MESHES)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhexray_b200.so")
 _api = None
@@ -90,10 +91,10 @@ class SceneFile:
 class Renderer:
     """One GPU context (one process per GPU)."""
 
-    def __init__(self, device=0, queue_capacity=0, api_=None):
+    def __init__(self, device=0, queue_capacity=0, api_=None, flags=0):
         self.api = api_ or api()
         self.ctx = C.c_void_p()
-        cfg = capi.Config(device, 0, queue_capacity)
+        cfg = capi.Config(device, flags, queue_capacity)
         st = self.api.lib.hxr_create(C.byref(cfg), C.byref(self.ctx))
         if st != capi.HXR_OK:
             raise HxrError(st, self.api.last_error(None))

@@ -17,6 +17,7 @@ STATUS_NAMES = {0: "HXR_OK", -1: "HXR_ERR_INVALID", -2: "HXR_ERR_NO_DEVICE", -3:
                 -4: "HXR_ERR_PARSE", -5: "HXR_ERR_IO", -6: "HXR_ERR_OVERFLOW"}
 MODE_AUTO, MODE_WHITTED, MODE_MONTECARLO = 0, 1, 2
 RENDER_COUNT_TRAVERSAL = 1
+CFG_BRUTE_FORCE_MESHES = 1
 
 
 class HxrError(RuntimeError):
@@ -101,7 +102,7 @@ class Camera(C.Structure):
 
 
 class Config(C.Structure):
-    _fields_ = [("device", c_i32), ("reserved", c_i32), ("queue_capacity", c_u64)]
+    _fields_ = [("device", c_i32), ("flags", c_i32), ("queue_capacity", c_u64)]
 
 
 class RenderParams(C.Structure):

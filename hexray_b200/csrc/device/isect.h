@@ -175,13 +175,16 @@ HXR_HD bool intersect_triangle_fast(const Ray& ray, const d3& A, const d3& B, co
 
 // ---------------------------------------------------------------- triangle mesh
 // The mesh query is split into pieces so that the same arithmetic serves (i) the simple per-ray
-// function used for CSG children, small meshes and the host emulation, and (ii) the persistent
-// state-machine traversal kernel (launch_cuda.cu), which interleaves these steps across lanes:
+// function used for CSG children and the host emulation, and (ii) the persistent traversal kernel
+// (launch_cuda.cu), which walks the same tree with conservative FP32 plane arithmetic:
 //   mesh_slab          ray parameters [t0, t1] against the (slightly inflated) mesh box
 //   tri_test           the reference's triangle test (src/mesh.cpp:178-196), verbatim arithmetic
-//   kd_descend         one inner-node step of the front-to-back KD walk
-//   kd_after_leaf      termination test + pop after a leaf has been exhausted
+//   mesh_closest       front-to-back KD walk, one binary node at a time, double plane arithmetic
 //   mesh_fill_hit      IntersectionInfo of the winning triangle (src/mesh.cpp:197-218)
+//
+// Which hit wins: the smallest gamma; among exactly equal gammas the HIGHEST triangle index. That is what the
+// reference's loops produce (ascending index order, `gamma > info.dist` rejects, so an equal hit overwrites:
+// src/mesh.cpp:189, 255-262) and it makes the result independent of the order in which leaves are visited.
 
 struct MeshBest {  // winner so far inside one mesh, in object space
     double gamma, l2, l3;
@@ -244,6 +247,7 @@ HXR_HD bool tri_test(const TriTest* tris, bool backface, const Ray& ray, uint32_
     const double rDcr = 1 / Dcr;
     const double gamma = dot(t.N, H) * rDcr;
     if (gamma < 0 || gamma > best.gamma) return false;
+    if (gamma == best.gamma && (int)ti < best.tri) return false;
     const double lambda2 = dot(cross(H, t.AC), nd) * rDcr;
     if (lambda2 < 0 || lambda2 > 1) return false;
     const double lambda3 = dot(cross(t.AB, H), nd) * rDcr;
@@ -257,99 +261,255 @@ HXR_HD bool tri_test(const TriTest* tris, bool backface, const Ray& ray, uint32_
     return true;
 }
 
-HXR_HD KdNode load_node(const KdNode* p)
+HXR_HD KdBlock load_block(const KdBlock* p)
 {
 #if defined(__CUDA_ARCH__)
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-    KdNode n;
-    n.split = __uint_as_float(v.x);
-    n.kind = v.y;
-    n.a = v.z;
-    n.b = v.w;
-    return n;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p)), v = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    KdBlock b;
+    b.split[0] = __uint_as_float(u.x); b.split[1] = __uint_as_float(u.y); b.split[2] = __uint_as_float(u.z);
+    b.meta = u.w;
+    b.ref[0] = v.x; b.ref[1] = v.y; b.ref[2] = v.z; b.ref[3] = v.w;
+    return b;
 #else
     return *p;
 #endif
 }
 
-// KD walk state of one ray inside one mesh
-struct KdWalk {
-    double tmin, tmax;
-    uint32_t node;
-    int sp;
-};
-
-// one inner-node step; pushes the far child when both sides are crossed
-HXR_HD void kd_descend(const KdNode& n, const Ray& ray, KdWalk& w, uint32_t* stackNode, double* stackTmax)
-{
-    const int axis = (int)n.kind;
-    const double split = (double)n.split;
-    const double oa = comp(ray.o, axis), da = comp(ray.d, axis);
-    const bool below = (oa < split) || (oa == split && da <= 0);
-    const uint32_t nearC = below ? n.a : n.b, farC = below ? n.b : n.a;
-    if (da == 0) {
-        if (oa == split && w.sp < HXR_KD_STACK) {  // travelling inside the split plane: both sides
-            stackNode[w.sp] = farC;
-            stackTmax[w.sp] = w.tmax;
-            w.sp++;
-        }
-        w.node = nearC;
-        return;
-    }
-    const double tpl = (split - oa) / da;
-    const double slack = 1e-9 * (1.0 + fabs(tpl));
-    if (tpl > w.tmax + slack || tpl < 0) {  // plane beyond this segment, or behind the origin
-        w.node = nearC;
-    } else if (tpl < w.tmin - slack) {
-        w.node = farC;
-    } else {
-        if (w.sp < HXR_KD_STACK) {
-            stackNode[w.sp] = farC;
-            stackTmax[w.sp] = w.tmax;
-            w.sp++;
-        }
-        w.node = nearC;
-        w.tmax = tpl;
-    }
-}
-
-// after a leaf: returns false when the walk is finished (best hit safely inside the covered part of
-// the ray, or nothing left on the stack), true after popping the next segment
-HXR_HD bool kd_after_leaf(KdWalk& w, const MeshBest& best, const uint32_t* stackNode, const double* stackTmax)
-{
-    if (best.tri >= 0 && best.gamma < w.tmax - 1e-7 * (1.0 + fabs(w.tmax))) return false;
-    if (w.sp == 0) return false;
-    w.sp--;
-    w.tmin = w.tmax;
-    w.node = stackNode[w.sp];
-    w.tmax = stackTmax[w.sp];
-    if (best.tri >= 0 && best.gamma < w.tmin - 1e-7 * (1.0 + fabs(w.tmin))) return false;
-    return true;
-}
-
+// Front-to-back walk, one binary node per step. Cursor: HXR_KD_LEAF | first entry, or (block << 2) | sub.
 template <bool COUNT>
 HXR_HD bool mesh_closest(const DMesh& M, const Ray& ray, double gamma_limit, MeshBest& best, TravCounters* cnt)
 {
-    KdWalk w;
-    if (!mesh_slab(M, ray, gamma_limit, w.tmin, w.tmax)) return false;
+    double tmin, tmax;
+    if (!mesh_slab(M, ray, gamma_limit, tmin, tmax)) return false;
     if (COUNT) cnt->mesh_queries++;
     best.gamma = gamma_limit;
     best.tri = -1;
     best.l2 = best.l3 = 0;
-    uint32_t stackNode[HXR_KD_STACK];
-    double stackTmax[HXR_KD_STACK];
-    w.sp = 0;
-    w.node = 0;
+    uint32_t stRef[HXR_KD_STACK];
+    double stMin[HXR_KD_STACK], stMax[HXR_KD_STACK];
+    int sp = 0;
+    uint32_t cur = 0;
     for (;;) {
-        const KdNode n = load_node(M.nodes + w.node);
-        if (n.kind < 3) {
-            if (COUNT) cnt->kd_inner++;
-            kd_descend(n, ray, w, stackNode, stackTmax);
+        if (cur & HXR_KD_LEAF) {
+            if (cur != HXR_KD_EMPTY) {
+                if (COUNT) cnt->kd_leaves++;
+                for (uint32_t p = cur & ~HXR_KD_LEAF;; p++) {
+                    const uint32_t e = M.leaf_tris[p];
+                    if (COUNT) cnt->tri_tests++;
+                    tri_test(M.tri_test, M.backface != 0, ray, e & ~HXR_TRI_LAST, best);
+                    if (e & HXR_TRI_LAST) break;
+                }
+            }
+            // next pending segment that can still hold a hit at or before the best one
+            bool found = false;
+            while (sp > 0) {
+                sp--;
+                if (stMin[sp] - 1e-7 * (1.0 + fabs(stMin[sp])) > best.gamma) continue;
+                cur = stRef[sp]; tmin = stMin[sp]; tmax = stMax[sp];
+                found = true;
+                break;
+            }
+            if (!found) break;
             continue;
         }
-        if (COUNT) { cnt->kd_leaves++; cnt->tri_tests += n.b; }
-        for (uint32_t i = 0; i < n.b; i++) tri_test(M.tri_test, M.backface != 0, ray, M.leaf_tris[n.a + i], best);
-        if (!kd_after_leaf(w, best, stackNode, stackTmax)) break;
+        const uint32_t blk = cur >> 2, sub = cur & 3u;
+        const KdBlock B = load_block(M.blocks + blk);
+        if (COUNT && sub == 0) cnt->kd_inner++;
+        const int axis = (int)((B.meta >> (2 * sub)) & 3u);
+        const double split = (double)B.split[sub];
+        uint32_t cl, cr;
+        if (sub == 0) {
+            cl = ((B.meta >> 2) & 3u) == 3u ? B.ref[0] : ((blk << 2) | 1u);
+            cr = ((B.meta >> 4) & 3u) == 3u ? B.ref[2] : ((blk << 2) | 2u);
+        } else {
+            cl = B.ref[2 * (sub - 1)];
+            cr = B.ref[2 * (sub - 1) + 1];
+            if (!(cl & HXR_KD_LEAF)) cl <<= 2;
+            if (!(cr & HXR_KD_LEAF)) cr <<= 2;
+        }
+        // "first" is the side the ray is on BEFORE it crosses the plane (left = coordinates <= split), whatever
+        // side of the plane the origin lies on: an origin outside the node's box says nothing about the segment
+        const double oa = comp(ray.o, axis), da = comp(ray.d, axis);
+        if (da == 0) {
+            if (oa == split && sp < HXR_KD_STACK) {  // travelling inside the split plane: both sides
+                stRef[sp] = cr; stMin[sp] = tmin; stMax[sp] = tmax; sp++;
+                cur = cl;
+            } else {
+                cur = oa < split ? cl : cr;
+            }
+            continue;
+        }
+        const uint32_t firstC = da > 0 ? cl : cr, secondC = da > 0 ? cr : cl;
+        const double tpl = (split - oa) / da;
+        const double slack = 1e-9 * (1.0 + fabs(tpl));
+        if (tpl > tmax + slack) {  // the plane is crossed after this segment
+            cur = firstC;
+        } else if (tpl < tmin - slack) {  // ... or before it (also: behind the origin)
+            cur = secondC;
+        } else {
+            if (sp < HXR_KD_STACK) { stRef[sp] = secondC; stMin[sp] = tpl; stMax[sp] = tmax; sp++; }
+            cur = firstC;
+            tmax = tpl;
+        }
+    }
+    return best.tri >= 0;
+}
+
+// ---- the conservative FP32 walk (what the traversal kernel runs; the host form below is used by the CPU tests)
+// The tree is walked with FP32 plane arithmetic made CONSERVATIVE: every plane parameter carries an error bound
+// and the two children get overlapping parameter ranges, so a leaf is visited whenever the exact ray could touch
+// it, while every triangle is still tested with the reference's double arithmetic (tri_test). The walk only
+// decides WHICH triangles are tested; the winner is the same as for mesh_closest and for brute force.
+HXR_HD float f32_below(double x)  // largest float <= x (round toward -inf)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2float_rd(x);
+#else
+    float f = (float)x;
+    return (double)f > x ? nextafterf(f, -INFINITY) : f;
+#endif
+}
+HXR_HD float f32_above(double x)  // smallest float >= x (round toward +inf)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2float_ru(x);
+#else
+    float f = (float)x;
+    return (double)f < x ? nextafterf(f, INFINITY) : f;
+#endif
+}
+
+struct WalkRay {  // the object-space ray as the walk sees it
+    float ox, oy, oz;  // origin, rounded to nearest
+    float ix, iy, iz;  // 1 / direction (0 on parallel axes)
+    uint32_t par;      // bit a: |d[a]| < 1e-18, treated as parallel to the planes of axis a
+};
+HXR_HD WalkRay walk_ray(const Ray& t)
+{
+    WalkRay w;
+    w.ox = (float)t.o.x; w.oy = (float)t.o.y; w.oz = (float)t.o.z;
+    const float dx = (float)t.d.x, dy = (float)t.d.y, dz = (float)t.d.z;
+    w.par = (fabsf(dx) < 1e-18f ? 1u : 0u) | (fabsf(dy) < 1e-18f ? 2u : 0u) | (fabsf(dz) < 1e-18f ? 4u : 0u);
+    w.ix = (w.par & 1u) ? 0.0f : 1.0f / dx;
+    w.iy = (w.par & 2u) ? 0.0f : 1.0f / dy;
+    w.iz = (w.par & 4u) ? 0.0f : 1.0f / dz;
+    return w;
+}
+
+struct PlaneX {  // conservative range [tlo, thi] of the parameter at which the ray crosses a split plane
+    float tlo, thi;
+    bool leftFirst;  // the ray is on the left (coordinate <= split) before the crossing
+};
+HXR_HD PlaneX plane_cross(float s, uint32_t axis, const WalkRay& w, float tmaxSeg)
+{
+    const float o = axis == 0 ? w.ox : (axis == 1 ? w.oy : w.oz);
+    const float inv = axis == 0 ? w.ix : (axis == 1 ? w.iy : w.iz);
+    PlaneX r;
+    // tpl = (s - o) / d in float: relative error <= 2^-22 (o and d rounded from double, one subtraction, one
+    // reciprocal, one product) plus |o| 2^-24 |inv| from the rounding of o; both bounds doubled.
+    const float tpl = (s - o) * inv;
+    const float e = fmaf(fabsf(tpl), 4.76837158e-7f, fabsf(inv * o) * 1.1920929e-7f);
+    r.tlo = tpl - e;
+    r.thi = tpl + e;
+    r.leftFirst = inv > 0;
+    if ((w.par >> axis) & 1u) {
+        // parallel to the plane for every parameter that matters: pick sides by position
+        const float tol = fmaf(fabsf(o), 2.38418579e-7f, 1e-18f * tmaxSeg) + 1e-30f;
+        r.leftFirst = true;
+        r.thi = (o <= s + tol) ? INFINITY : -INFINITY;
+        r.tlo = (o >= s - tol) ? -INFINITY : INFINITY;
+    }
+    return r;
+}
+
+struct WalkEnt {  // a subtree (block index or leaf reference) and the parameter range in which the ray can be inside it
+    uint32_t ref;
+    float lo, hi;
+};
+HXR_HD bool ent_valid(const WalkEnt& e) { return e.lo <= e.hi && e.ref != HXR_KD_EMPTY; }
+
+// One block = a node and both its children: up to four grandchildren e0..e3, FRONT TO BACK (test ent_valid on each).
+HXR_HD void block_step(const KdBlock& B, const WalkRay& w, float tmin, float tmax, float tbest, WalkEnt& e0, WalkEnt& e1, WalkEnt& e2, WalkEnt& e3)
+{
+    const uint32_t a0 = B.meta & 3u, aL = (B.meta >> 2) & 3u, aR = (B.meta >> 4) & 3u;
+    const float tE = fminf(tmax, tbest);
+    const PlaneX p0 = plane_cross(B.split[0], a0, w, tmax);
+    const float nHi = fminf(tE, p0.thi), fLo = fmaxf(tmin, p0.tlo);
+    const float lLo = p0.leftFirst ? tmin : fLo, lHi = p0.leftFirst ? nHi : tE;
+    const float rLo = p0.leftFirst ? fLo : tmin, rHi = p0.leftFirst ? tE : nHi;
+    WalkEnt l0, l1, r0, r1;
+    {
+        const PlaneX pl = plane_cross(B.split[1], aL, w, tmax);
+        const bool leaf = aL == 3u;
+        const bool lf = pl.leftFirst || leaf;
+        l0.ref = lf ? B.ref[0] : B.ref[1];
+        l1.ref = leaf ? HXR_KD_EMPTY : (lf ? B.ref[1] : B.ref[0]);
+        l0.lo = lLo; l0.hi = leaf ? lHi : fminf(lHi, pl.thi);
+        l1.lo = fmaxf(lLo, pl.tlo); l1.hi = lHi;
+    }
+    {
+        const PlaneX pr = plane_cross(B.split[2], aR, w, tmax);
+        const bool leaf = aR == 3u;
+        const bool lf = pr.leftFirst || leaf;
+        r0.ref = lf ? B.ref[2] : B.ref[3];
+        r1.ref = leaf ? HXR_KD_EMPTY : (lf ? B.ref[3] : B.ref[2]);
+        r0.lo = rLo; r0.hi = leaf ? rHi : fminf(rHi, pr.thi);
+        r1.lo = fmaxf(rLo, pr.tlo); r1.hi = rHi;
+    }
+    e0 = p0.leftFirst ? l0 : r0; e1 = p0.leftFirst ? l1 : r1; e2 = p0.leftFirst ? r0 : l0; e3 = p0.leftFirst ? r1 : l1;
+}
+
+// host form of the kernel's walk: same steps, one ray at a time
+template <bool COUNT>
+HXR_HD bool mesh_closest_f32(const DMesh& M, const Ray& ray, double gamma_limit, MeshBest& best, TravCounters* cnt)
+{
+    double t0, t1;
+    if (!mesh_slab(M, ray, gamma_limit, t0, t1)) return false;
+    if (COUNT) cnt->mesh_queries++;
+    best.gamma = gamma_limit;
+    best.tri = -1;
+    best.l2 = best.l3 = 0;
+    const WalkRay w = walk_ray(ray);
+    float tmin = f32_below(t0), tmax = f32_above(t1), tbest = f32_above(gamma_limit);
+    WalkEnt st[HXR_KD_STACK];
+    int sp = 0;
+    uint32_t cur = 0;
+    for (;;) {
+        if (cur & HXR_KD_LEAF) {
+            for (uint32_t p = cur & ~HXR_KD_LEAF;; p++) {
+                const uint32_t e = M.leaf_tris[p];
+                if (COUNT) cnt->tri_tests++;
+                if (tri_test(M.tri_test, M.backface != 0, ray, e & ~HXR_TRI_LAST, best)) tbest = f32_above(best.gamma);
+                if (e & HXR_TRI_LAST) break;
+            }
+            if (COUNT) cnt->kd_leaves++;
+            bool found = false;
+            while (sp > 0) {
+                sp--;
+                if (st[sp].lo <= tbest) { cur = st[sp].ref; tmin = st[sp].lo; tmax = st[sp].hi; found = true; break; }
+            }
+            if (!found) break;
+            continue;
+        }
+        if (COUNT) cnt->kd_inner++;
+        WalkEnt e[4];
+        block_step(load_block(M.blocks + cur), w, tmin, tmax, tbest, e[0], e[1], e[2], e[3]);
+        bool have = false;
+        WalkEnt c;
+        c.ref = 0; c.lo = c.hi = 0;
+        for (int k = 3; k >= 0; k--) {
+            if (!ent_valid(e[k])) continue;
+            if (have && sp < HXR_KD_STACK) st[sp++] = c;
+            c = e[k];
+            have = true;
+        }
+        if (have) { cur = c.ref; tmin = c.lo; tmax = c.hi; continue; }
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            if (st[sp].lo <= tbest) { cur = st[sp].ref; tmin = st[sp].lo; tmax = st[sp].hi; found = true; break; }
+        }
+        if (!found) break;
     }
     return best.tri >= 0;
 }
@@ -395,7 +555,7 @@ template <bool COUNT>
 HXR_HD bool mesh_intersect(const DMesh& M, int gi, const Ray& ray, Hit& info, double gamma_limit, TravCounters* cnt)
 {
     MeshBest best;
-    const bool hit = M.n_tris <= HXR_SMALL_MESH ? mesh_bruteforce(M, ray, gamma_limit, best) : mesh_closest<COUNT>(M, ray, gamma_limit, best, cnt);
+    const bool hit = M.brute ? mesh_bruteforce(M, ray, gamma_limit, best) : mesh_closest<COUNT>(M, ray, gamma_limit, best, cnt);
     if (!hit) return false;
     mesh_fill_hit(M, gi, ray, best, info);
     return true;

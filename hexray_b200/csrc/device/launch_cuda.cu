@@ -249,29 +249,66 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) accumulate_shadow_item(shadow[i], i, ts, accum);
 }
 
-// The KD walk. SHADOW = any-hit against |AB| (visible()), otherwise closest hit.
+// ---- the KD walk -------------------------------------------------------------------------------------
+// One lane = one (ray, mesh) task. The loop is "while-while" (Aila & Laine): all lanes of a warp first step
+// through tree BLOCKS until each holds a leaf, then all test triangles; a lane that runs out of work is
+// refilled from the task queue (__ballot_sync finds idle lanes, one atomicAdd per warp, __shfl_sync broadcast).
+//
+// Precision: the tree is walked with FP32 plane arithmetic made CONSERVATIVE — every plane parameter carries
+// an error bound and the two children get overlapping parameter ranges, so a leaf is visited whenever the
+// exact ray could touch it — while every triangle is tested with the reference's own double arithmetic
+// (tri_test). The walk therefore only decides WHICH triangles are tested; the winner (smallest gamma, highest
+// index on ties) is the same as for the double walk in isect.h (mesh_closest) and for brute force.
+//
+// State: ~30 registers per lane; the double ray (48 B) and the first HXR_SSTACK stack entries (12 B each) live in
+// shared memory, deeper entries overflow to local memory (rare: the stack is shallow for almost all rays).
+#define HXR_SSTACK 12
+#define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
+
+struct WalkShared {
+    double ray[6][HXR_WALK_BLOCK];
+    uint32_t stRef[HXR_SSTACK][HXR_WALK_BLOCK];
+    float stMin[HXR_SSTACK][HXR_WALK_BLOCK];
+    float stMax[HXR_SSTACK][HXR_WALK_BLOCK];
+};
+
 template <bool SHADOW, bool COUNT>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayTask* __restrict__ rays,
                                                                               const ShadowTask* __restrict__ shadows, TraceScratch ts,
                                                                               TravCounters* cnt)
 {
+    __shared__ WalkShared sh;
     const unsigned FULL = 0xffffffffu;
     const uint32_t n = min(*ts.task_count, ts.task_cap);
-    const unsigned lane = threadIdx.x & 31u;
-    uint32_t stackNode[HXR_KD_STACK];
-    double stackTmax[HXR_KD_STACK];
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    uint32_t ovRef[HXR_KD_STACK - HXR_SSTACK];
+    float ovMin[HXR_KD_STACK - HXR_SSTACK], ovMax[HXR_KD_STACK - HXR_SSTACK];
     bool active = false, drained = false;
-    Ray t;                          // object-space ray of the current task
-    const KdNode* nodes = nullptr;  // the current mesh
+    WalkRay wr;
+    wr.ox = wr.oy = wr.oz = wr.ix = wr.iy = wr.iz = 0;
+    wr.par = 0;
+    const KdBlock* blocks = nullptr;  // the current mesh
     const uint32_t* leafTris = nullptr;
     const TriTest* tris = nullptr;
     bool backface = false;
-    KdWalk w;
+    uint32_t cur = HXR_POP;
+    float tmin = 0, tmax = 0, tbest = 0;
+    int sp = 0;
     MeshBest best;
-    uint32_t leafPos = 0, leafLeft = 0, taskRay = 0, taskNode = 0;
+    uint32_t taskRay = 0, taskNode = 0;
     TravCounters local = {0, 0, 0, 0};
-    w.tmin = w.tmax = 0; w.node = 0; w.sp = 0;
     best.gamma = 0; best.l2 = best.l3 = 0; best.tri = -1;
+
+    auto push = [&](const WalkEnt& e) {
+        if (sp < HXR_SSTACK) {
+            sh.stRef[sp][tid] = e.ref; sh.stMin[sp][tid] = e.lo; sh.stMax[sp][tid] = e.hi;
+        } else if (sp < HXR_KD_STACK) {
+            ovRef[sp - HXR_SSTACK] = e.ref; ovMin[sp - HXR_SSTACK] = e.lo; ovMax[sp - HXR_SSTACK] = e.hi;
+        } else {
+            return;  // unreachable: the build caps the depth at HXR_KD_MAX_DEPTH (<= 1.5 pushes per level)
+        }
+        sp++;
+    };
 
     for (;;) {
         // ---- refill: idle lanes take new tasks
@@ -291,6 +328,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                     taskNode = task.node;
                     const hxr_node& nd = sc.nodes[taskNode];
                     const DMesh& M = sc.meshes[sc.geoms[nd.geom].a];
+                    Ray t;
                     double limit;
                     bool skip = false;
                     if (SHADOW) {
@@ -303,17 +341,23 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         t = object_ray(nd, task_ray(rays[taskRay]));
                         limit = gamma_limit_for(nd, t, ts.pre[taskRay].dist);
                     }
-                    if (!skip && mesh_slab(M, t, limit, w.tmin, w.tmax)) {
-                        nodes = M.nodes;
+                    double t0, t1;
+                    if (!skip && mesh_slab(M, t, limit, t0, t1)) {
+                        blocks = M.blocks;
                         leafTris = M.leaf_tris;
                         tris = M.tri_test;
                         backface = M.backface != 0;
+                        sh.ray[0][tid] = t.o.x; sh.ray[1][tid] = t.o.y; sh.ray[2][tid] = t.o.z;
+                        sh.ray[3][tid] = t.d.x; sh.ray[4][tid] = t.d.y; sh.ray[5][tid] = t.d.z;
+                        wr = walk_ray(t);
+                        tmin = f32_below(t0);
+                        tmax = f32_above(t1);
+                        tbest = f32_above(limit);
                         best.gamma = limit;
                         best.tri = -1;
                         best.l2 = best.l3 = 0;
-                        w.sp = 0;
-                        w.node = 0;
-                        leafLeft = 0;
+                        sp = 0;
+                        cur = 0;
                         active = true;
                         if (COUNT) local.mesh_queries++;
                     }
@@ -324,18 +368,60 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             if (drained) break;
             continue;
         }
-        // ---- a few steps of the walk for every active lane
-#pragma unroll 1
-        for (int it = 0; it < HXR_WALK_STEPS; it++) {
-            if (!active) continue;
-            bool finished = false;
-            if (leafLeft) {
-                const uint32_t ti = __ldg(leafTris + leafPos);
-                leafPos++;
-                leafLeft--;
-                if (COUNT) local.tri_tests++;
-                const bool hit = tri_test(tris, backface, t, ti, best);
-                if (SHADOW && hit) {
+        // ---- phase 1: step through blocks until every active lane holds a leaf (or has finished)
+        while (__any_sync(FULL, active && !(cur >> 31))) {
+            if (!active || (cur >> 31)) continue;
+            if (cur == HXR_POP) {
+                if (sp == 0) {
+                    // nothing left: this task is done
+                    active = false;
+                    if (!SHADOW && best.tri >= 0) {
+                        const hxr_node& nd = sc.nodes[taskNode];
+                        const d3 wo = ld3(rays[taskRay].o);
+                        const d3 to = mk3(sh.ray[0][tid], sh.ray[1][tid], sh.ray[2][tid]), td = mk3(sh.ray[3][tid], sh.ray[4][tid], sh.ray[5][tid]);
+                        const d3 ipw = mul_vm(to + best.gamma * td, nd.T.m) + ld3(nd.T.offset);
+                        MeshRes r;
+                        r.dist = distance3(wo, ipw);
+                        r.gamma = best.gamma; r.l2 = best.l2; r.l3 = best.l3; r.tri = best.tri; r.node = (int32_t)taskNode;
+                        ts.res[(size_t)sc.node_slot[taskNode] * ts.res_stride + taskRay] = r;
+                    }
+                    continue;
+                }
+                sp--;
+                WalkEnt e;
+                if (sp < HXR_SSTACK) { e.ref = sh.stRef[sp][tid]; e.lo = sh.stMin[sp][tid]; e.hi = sh.stMax[sp][tid]; }
+                else { e.ref = ovRef[sp - HXR_SSTACK]; e.lo = ovMin[sp - HXR_SSTACK]; e.hi = ovMax[sp - HXR_SSTACK]; }
+                if (e.lo <= tbest) { cur = e.ref; tmin = e.lo; tmax = e.hi; }  // else: cannot hold a closer hit, keep popping
+                continue;
+            }
+            // one block = a node and both its children: up to four grandchildren, front to back
+            if (COUNT) local.kd_inner++;
+            const KdBlock B = load_block(blocks + cur);
+            WalkEnt e0, e1, e2, e3;
+            block_step(B, wr, tmin, tmax, tbest, e0, e1, e2, e3);
+            // nearest valid entry becomes the cursor, the others are pushed far-to-near
+            WalkEnt c;
+            c.ref = HXR_POP; c.lo = 0; c.hi = 0;
+            bool have = false;
+            if (ent_valid(e3)) { c = e3; have = true; }
+            if (ent_valid(e2)) { if (have) push(c); c = e2; have = true; }
+            if (ent_valid(e1)) { if (have) push(c); c = e1; have = true; }
+            if (ent_valid(e0)) { if (have) push(c); c = e0; have = true; }
+            cur = c.ref; tmin = c.lo; tmax = c.hi;
+        }
+        // ---- phase 2: every lane that holds a leaf tests its triangles, one per iteration
+        while (__any_sync(FULL, active && (cur >> 31))) {
+            if (!active || !(cur >> 31)) continue;
+            const uint32_t e = __ldg(leafTris + (cur & ~HXR_KD_LEAF));
+            if (COUNT) { local.tri_tests++; if (e & HXR_TRI_LAST) local.kd_leaves++; }
+            Ray t;
+            t.o = mk3(sh.ray[0][tid], sh.ray[1][tid], sh.ray[2][tid]);
+            t.d = mk3(sh.ray[3][tid], sh.ray[4][tid], sh.ray[5][tid]);
+            const bool hit = tri_test(tris, backface, t, e & ~HXR_TRI_LAST, best);
+            cur = (e & HXR_TRI_LAST) ? HXR_POP : cur + 1u;
+            if (hit) {
+                tbest = f32_above(best.gamma);
+                if (SHADOW) {
                     // the exact test of visible(): world distance of the hit against |AB|
                     double D;
                     const Ray wr = shadow_ray(shadows[taskRay], D);
@@ -344,32 +430,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                     if (distance3(wr.o, ipw) < D) {
                         ts.occluded[taskRay] = 1;
                         active = false;
-                        continue;
                     }
-                }
-                if (leafLeft == 0) finished = !kd_after_leaf(w, best, stackNode, stackTmax);
-            } else {
-                const KdNode nd = load_node(nodes + w.node);
-                if (nd.kind < 3) {
-                    if (COUNT) local.kd_inner++;
-                    kd_descend(nd, t, w, stackNode, stackTmax);
-                } else {
-                    if (COUNT) local.kd_leaves++;
-                    leafPos = nd.a;
-                    leafLeft = nd.b;
-                    if (leafLeft == 0) finished = !kd_after_leaf(w, best, stackNode, stackTmax);
-                }
-            }
-            if (finished) {
-                active = false;
-                if (!SHADOW && best.tri >= 0) {
-                    const hxr_node& nd = sc.nodes[taskNode];
-                    const d3 wo = ld3(rays[taskRay].o);
-                    const d3 ipw = mul_vm(t.o + best.gamma * t.d, nd.T.m) + ld3(nd.T.offset);
-                    MeshRes r;
-                    r.dist = distance3(wo, ipw);
-                    r.gamma = best.gamma; r.l2 = best.l2; r.l3 = best.l3; r.tri = best.tri; r.node = (int32_t)taskNode;
-                    ts.res[(size_t)sc.node_slot[taskNode] * ts.res_stride + taskRay] = r;
                 }
             }
         }

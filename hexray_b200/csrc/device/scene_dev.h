@@ -2,7 +2,9 @@
 //
 // Layout notes (B200): the per-scene tables (nodes, geometries, shaders, lights) are a few
 // hundred bytes and stay L1/L2 resident; the per-mesh arrays are the HBM traffic:
-//   KdNode   16 B  one 128-bit load per traversal step
+//   KdBlock  32 B  one L2 sector = TWO levels of the KD-tree (a node and both its children): one fetch
+//                  (two 128-bit loads) decides up to four grandchildren; leaves are not nodes at all but
+//                  tagged references into leaf_tris
 //   TriTest  96 B  the four vectors the reference's triangle test reads (A, AB, AC, AB^AC),
 //                  in double so the test is the reference's arithmetic (src/mesh.cpp:178-196)
 //   TriAttr  96 B  read once per ray for the winning triangle (normals/uv indices, dNdx/dNdy)
@@ -10,17 +12,34 @@
 #include "hd.h"
 #include "../../../include/hxr.h"
 
-#define HXR_KD_STACK 64 /* device traversal stack entries; the host build caps the tree depth below it */
+#define HXR_KD_MAX_DEPTH 60 /* the host build caps the tree depth here */
+#define HXR_KD_STACK 96     /* traversal stack entries: a block step (two levels) pushes at most three */
 
 namespace hxr {
 
-// KD-tree node. inner: kind = axis (0..2), a = left child, b = right child.
-//               leaf : kind = 3,           a = first entry in leaf_tris, b = triangle count.
+// Host-side binary KD node (build intermediate, never uploaded).
+//   inner: kind = axis (0..2), a = left child, b = right child.
+//   leaf : kind = 3,           a = first entry in leaf_tris, b = triangle count.
 struct alignas(16) KdNode {
     float split;
     uint32_t kind;
     uint32_t a, b;
 };
+
+// Device KD-tree: 32-byte blocks holding a node (sub 0) and its two children (sub 1 = left, sub 2 = right).
+//   meta bits 0-1 / 2-3 / 4-5 = split axis of sub 0 / 1 / 2; axis 3 marks a child that is a LEAF.
+//   ref[0], ref[1] = children of sub 1 (or ref[0] = its leaf reference), ref[2], ref[3] likewise for sub 2.
+//   A reference is either a block index (bit 31 clear) or HXR_KD_LEAF | first entry in leaf_tris; HXR_KD_EMPTY is
+//   a leaf without triangles. The last entry of every leaf's list carries HXR_TRI_LAST.
+//   "left" holds coordinates <= split, "right" >= split.
+struct alignas(32) KdBlock {
+    float split[3];
+    uint32_t meta;
+    uint32_t ref[4];
+};
+#define HXR_KD_LEAF 0x80000000u
+#define HXR_KD_EMPTY 0xFFFFFFFFu
+#define HXR_TRI_LAST 0x80000000u
 
 struct alignas(16) TriTest {
     double A[3], AB[3], AC[3], N[3];
@@ -32,7 +51,7 @@ struct TriAttr {
 };
 
 struct DMesh {
-    const KdNode* nodes;
+    const KdBlock* blocks;
     const uint32_t* leaf_tris;
     const TriTest* tri_test;
     const TriAttr* tri_attr;
@@ -40,7 +59,8 @@ struct DMesh {
     const double* uvs;
     double bbmin[3], bbmax[3];
     int32_t faceted, backface;
-    int32_t n_tris, pad;
+    int32_t n_tris;
+    int32_t brute;  // test all triangles in index order (tiny meshes, or HXR_CFG_BRUTE_FORCE_MESHES) instead of walking the tree
 };
 
 struct DHeightfield {

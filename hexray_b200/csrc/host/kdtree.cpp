@@ -62,7 +62,7 @@ struct Builder {
             }
         }
         maxDepth = P.maxDepth >= 0 ? P.maxDepth : (int)std::lround(8 + 1.3 * std::log2((double)std::max(1, n)));
-        maxDepth = std::min(maxDepth, HXR_KD_STACK - 4);
+        maxDepth = std::min(maxDepth, HXR_KD_MAX_DEPTH);
     }
 
     static bool goesLeft(const TriBounds& b, int axis, float split)
@@ -215,6 +215,60 @@ uint32_t stitch(Builder::Local& dst, const Builder::Local& sub)
     return nodeBase;
 }
 
+// ---- binary tree -> 32-byte blocks (two levels per block), DFS pre-order
+uint32_t leafRef(KdTree& t, const KdNode& n)
+{
+    if (n.b == 0) return HXR_KD_EMPTY;
+    t.leafTris[(size_t)n.a + n.b - 1] |= HXR_TRI_LAST;
+    return HXR_KD_LEAF | n.a;
+}
+
+uint32_t makeBlock(KdTree& t, uint32_t nodeIdx)
+{
+    const uint32_t me = (uint32_t)t.blocks.size();
+    t.blocks.push_back(KdBlock{});
+    const KdNode n = t.nodes[nodeIdx];
+    KdBlock b{};
+    b.split[0] = n.split;
+    b.meta = n.kind;
+    for (int c = 0; c < 2; c++) {
+        const KdNode child = t.nodes[c ? n.b : n.a];
+        if (child.kind == 3) {
+            b.meta |= 3u << (2 + 2 * c);
+            b.split[1 + c] = 0;
+            b.ref[2 * c] = leafRef(t, child);
+            b.ref[2 * c + 1] = HXR_KD_EMPTY;
+        } else {
+            b.meta |= child.kind << (2 + 2 * c);
+            b.split[1 + c] = child.split;
+            for (int k = 0; k < 2; k++) {
+                const uint32_t gi = k ? child.b : child.a;
+                const KdNode g = t.nodes[gi];
+                b.ref[2 * c + k] = g.kind == 3 ? leafRef(t, g) : makeBlock(t, gi);
+            }
+        }
+    }
+    t.blocks[me] = b;
+    return me;
+}
+
+void makeBlocks(KdTree& t, const hxr_mesh& mesh)
+{
+    t.blocks.clear();
+    if (t.nodes[0].kind == 3) {
+        // the whole mesh is one leaf: a block whose plane lies beyond the mesh puts everything on its left
+        KdBlock b{};
+        b.split[0] = std::nextafter((float)mesh.bbox_max[0], INFINITY) + 1.0f + 1e-3f * std::fabs((float)mesh.bbox_max[0]);
+        b.meta = 0u | (3u << 2) | (3u << 4);
+        b.ref[0] = leafRef(t, t.nodes[0]);
+        b.ref[1] = b.ref[2] = b.ref[3] = HXR_KD_EMPTY;
+        t.blocks.push_back(b);
+        return;
+    }
+    t.blocks.reserve(t.nodes.size() / 3 + 16);
+    makeBlock(t, 0);
+}
+
 }  // namespace
 
 void buildKdTree(const hxr_mesh& mesh, const KdBuildParams& params, KdTree& out)
@@ -300,6 +354,7 @@ void buildKdTree(const hxr_mesh& mesh, const KdBuildParams& params, KdTree& out)
     out.maxDepth = top.maxDepth;
     out.leaves = top.leaves;
     if (out.nodes.empty()) out.nodes.push_back(KdNode{0, 3, 0, 0});
+    makeBlocks(out, mesh);
     out.buildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 

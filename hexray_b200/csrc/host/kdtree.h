@@ -11,8 +11,9 @@ namespace hxr {
 namespace host {
 
 struct KdTree {
-    std::vector<KdNode> nodes;        // node 0 = root; children stored explicitly (DFS pre-order)
-    std::vector<uint32_t> leafTris;   // triangle indices, leaf after leaf, ascending inside a leaf
+    std::vector<KdNode> nodes;        // binary tree (build intermediate): node 0 = root, DFS pre-order
+    std::vector<KdBlock> blocks;      // what the device walks: two tree levels per 32-byte block, block 0 = root
+    std::vector<uint32_t> leafTris;   // triangle indices, leaf after leaf, ascending inside a leaf; last entry | HXR_TRI_LAST
     uint32_t maxDepth = 0;
     uint64_t leaves = 0;
     double buildMs = 0;
@@ -23,7 +24,7 @@ struct KdBuildParams {
     float intersectCost = 2.0f;
     float emptyBonus = 0.2f;
     int maxLeafSize = 4;
-    int maxDepth = -1;      // -1: 8 + 1.3 log2(N), capped so the device stack (HXR_KD_STACK) cannot overflow
+    int maxDepth = -1;      // -1: 8 + 1.3 log2(N), capped at HXR_KD_MAX_DEPTH so the device stack cannot overflow
     int binnedAbove = 192;  // nodes with more triangles than this use 32-bin SAH, smaller ones an exact sweep
     int threads = 0;        // 0: hardware concurrency
 };

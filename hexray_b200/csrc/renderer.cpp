@@ -167,22 +167,23 @@ int Renderer::uploadScene(const hxr_scene* sp)
         }
         DMesh& d = dm[i];
         memset(&d, 0, sizeof d);
-        d.nodes = uploadArray(kd.nodes.data(), kd.nodes.size());
+        d.blocks = uploadArray(kd.blocks.data(), kd.blocks.size());
         d.leaf_tris = uploadArray(kd.leafTris.data(), kd.leafTris.size());
         d.tri_test = uploadArray(tt.data(), tt.size());
         d.tri_attr = uploadArray(ta.data(), ta.size());
         d.normals = uploadArray(m.normals, (size_t)m.n_normals * 3);
         d.uvs = uploadArray(m.uvs, (size_t)m.n_uvs * 3);
-        if (!d.nodes || !d.leaf_tris || !d.tri_test || !d.tri_attr || !d.normals || !d.uvs) return oom();
+        if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_attr || !d.normals || !d.uvs) return oom();
         for (int k = 0; k < 3; k++) { d.bbmin[k] = m.bbox_min[k]; d.bbmax[k] = m.bbox_max[k]; }
         d.faceted = m.faceted;
         d.backface = m.backface_culling;
         d.n_tris = m.n_triangles;
+        d.brute = (m.n_triangles <= HXR_SMALL_MESH || (m_cfg.flags & HXR_CFG_BRUTE_FORCE_MESHES)) ? 1 : 0;
         hxr_accel_info& ai = m_accel[i];
-        ai.nodes = kd.nodes.size();
+        ai.nodes = kd.blocks.size();
         ai.leaves = kd.leaves;
         ai.tri_refs = kd.leafTris.size();
-        ai.bytes_nodes = kd.nodes.size() * sizeof(KdNode);
+        ai.bytes_nodes = kd.blocks.size() * sizeof(KdBlock);
         ai.bytes_tris = kd.leafTris.size() * sizeof(uint32_t) + tt.size() * sizeof(TriTest);
         ai.max_depth = kd.maxDepth;
         ai.n_triangles = (uint32_t)m.n_triangles;
@@ -232,7 +233,7 @@ int Renderer::uploadScene(const hxr_scene* sp)
         m_nBig = 0;
         for (int i = 0; i < s.n_nodes; i++) {
             const hxr_geometry& g = s.geometries[s.nodes[i].geom];
-            if (g.type == HXR_GEOM_MESH && s.meshes[g.a].n_triangles > HXR_SMALL_MESH) slot[i] = m_nBig++;
+            if (g.type == HXR_GEOM_MESH && !dm[g.a].brute) slot[i] = m_nBig++;
         }
         m_scene.node_slot = uploadArray(slot.data(), slot.size());
         if (!m_scene.node_slot) return oom();

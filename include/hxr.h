@@ -218,9 +218,13 @@ typedef struct hxr_camera { /* results of Camera::beginFrame (src/camera.cpp:30-
 
 /* ---------------------------------------------------------------- rendering */
 
+/* test hook: test every triangle of every mesh in index order instead of walking the KD-tree — the reference's
+ * `useKDTree false` path (src/mesh.cpp:255-262); results are identical, only (much) slower */
+#define HXR_CFG_BRUTE_FORCE_MESHES 1
+
 typedef struct hxr_config {
     int32_t device;           /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t flags;            /* HXR_CFG_* */
     uint64_t queue_capacity;  /* ray-queue capacity in rays; 0 = default */
 } hxr_config;
 

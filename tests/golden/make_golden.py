@@ -96,5 +96,81 @@ def main():
         print("primary", name, rec.shape, "hits", int(ok.sum()))
 
 
+def terrain(side=320):
+    """C5-style synthetic terrain (the bench workload at a size the reference renders in a minute): explicit rays
+    from the bench camera (its x = 0 lies exactly ON a top-level split plane of the grid), from inside the box,
+    secondary rays leaving the surface, shadow segments, and a converged GI frame."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import hexray_b200 as hx
+    import argparse
+    work = "/tmp/hxr_golden_terrain"
+    os.makedirs(work, exist_ok=True)
+    W, H, spp = 96, 54, 1024
+    a = argparse.Namespace(grid_side=side)
+    gen = os.path.join(work, "gen.hexray")
+    with open(gen, "w") as f:
+        f.write(bench.scene_text(a, "synthetic:terrain:%d:0x5EED" % side, W, H, spp))
+    sf = hx.SceneFile(gen)  # host front-end only (no GPU needed)
+    sf.write_obj(0, os.path.join(work, "terrain.obj"))
+    sf.close()
+    ref_scene = os.path.join(work, "ref.hexray")
+    with open(ref_scene, "w") as f:
+        f.write(bench.scene_text(a, "terrain.obj", W, H, spp))
+
+    def oracle(args):
+        p = subprocess.run([REF] + args, cwd=work, capture_output=True, text=True)
+        if p.returncode != 0:
+            sys.exit("oracle failed: %s\n%s" % (args, p.stderr))
+        return json.loads(p.stdout.strip().splitlines()[-1])
+
+    rng = np.random.default_rng(77)
+    n = 3000
+    cam_o = np.tile(np.array([[0.0, 150.0, -600.0]]), (n, 1))
+    cam_d = np.stack([rng.uniform(-0.7, 0.7, n), rng.uniform(-0.6, 0.1, n), np.ones(n)], 1)
+    in_o = np.stack([rng.uniform(-500, 500, n), rng.uniform(-30, 300, n), rng.uniform(-500, 500, n)], 1)
+    in_d = rng.normal(size=(n, 3))
+    O, D = np.concatenate([cam_o, in_o]), np.concatenate([cam_d, in_d])
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+    tmp = os.path.join(work, "io.bin")
+
+    def raycast(O, D):
+        r8 = np.zeros((len(O), 8))
+        r8[:, 0:3], r8[:, 3:6] = O, D
+        r8.tofile(tmp + ".in")
+        oracle(["rays", ref_scene, "--in", tmp + ".in", "--out", tmp])
+        return np.fromfile(tmp, dtype=np.float64).reshape(-1, 24)
+
+    h1 = raycast(O, D)
+    ok = (h1[:, 0] == 0) & (h1[:, 1] == 0)  # hits on the terrain node
+    ip, nn = h1[ok][:, 3:6], h1[ok][:, 6:9]
+    d2 = rng.normal(size=ip.shape)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    d2[(d2 * nn).sum(1) < 0] *= -1
+    o2 = ip + nn * 1e-6
+    h2 = raycast(o2, d2)
+    rays = np.concatenate([np.concatenate([O, D], 1), np.concatenate([o2, d2], 1)])
+    hits = np.concatenate([h1, h2])
+    light = np.array([[0.0, 400.0 - 1e-6, 0.0]]) + rng.uniform(-150, 150, (len(o2), 3)) * np.array([1.0, 0.0, 1.0])
+    # shadow segments: light -> surface, and between random pairs of hit points (many cross or graze the terrain)
+    pts = hits[hits[:, 0] == 0][:, 3:6]
+    m = 4000
+    pa = pts[rng.integers(0, len(pts), m)] + rng.normal(0, 0.5, (m, 3))
+    pb = pts[rng.integers(0, len(pts), m)] + rng.normal(0, 0.5, (m, 3))
+    seg = np.concatenate([np.concatenate([light, o2], axis=1), np.concatenate([pa, pb], axis=1)])
+    seg.tofile(tmp + ".in")
+    oracle(["rays", ref_scene, "--in", tmp + ".in", "--out", tmp, "--mode", "visible"])
+    vis = np.fromfile(tmp, dtype=np.float64)
+    info = oracle(["render", ref_scene, "--out", tmp])
+    img = np.fromfile(tmp, dtype=np.float32).reshape(H, W, 3)
+    np.savez_compressed(os.path.join(HERE, "terrain_%d.npz" % side), rays=rays, hits=hits[:, :20], seg=seg, vis=vis.astype(np.uint8),
+                        img=img.astype(np.float16), spp=spp, side=side, W=W, H=H, info=json.dumps(info),
+                        cmd="hexray_ref rays|render <bench.py terrain scene, OBJ written by hxr_scene_file_write_obj>")
+    print("terrain", side, "rays", len(rays), "terrain hits", int(ok.sum()), "visible", float(vis.mean()), "img mean", float(img.mean()), info["best_ms"])
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "terrain":
+        terrain()
+    else:
+        main()

@@ -147,3 +147,46 @@ def check_visible(sess, scene):
     agree = (vis == (g["vis"] != 0)).mean()
     assert agree >= 0.999, "%s: visible() differs on %.2f%% of segments" % (scene, (1 - agree) * 100)
     return float(agree)
+
+
+# ---------------------------------------------------------------------------- synthetic terrain (the bench workload)
+def terrain_scene_file(api, side, W=96, H=54, spp=16, tmpdir="/tmp"):
+    """The bench.py terrain scene with a `side` x `side` vertex grid (procedural mesh, host generator)."""
+    import argparse
+    import bench
+    path = os.path.join(tmpdir, "hxr_terrain_%d_%d.hexray" % (side, os.getpid()))
+    with open(path, "w") as f:
+        f.write(bench.scene_text(argparse.Namespace(grid_side=side), "synthetic:terrain:%d:0x5EED" % side, W, H, spp))
+    return hx.SceneFile(path, api_=api)
+
+
+def check_terrain(api, queue_capacity=1 << 20, spp=64):
+    """Explicit rays / shadow segments / a GI frame on the 203k-triangle terrain against the compiled reference."""
+    g = np.load(os.path.join(GOLDEN, "terrain_320.npz"))
+    side, W, H = int(g["side"]), int(g["W"]), int(g["H"])
+    sf = terrain_scene_file(api, side, W, H)
+    r = hx.Renderer(api_=api, queue_capacity=queue_capacity).load(sf)
+    try:
+        rays, ref = g["rays"], g["hits"]
+        hits = r.trace_closest(np.concatenate([rays, np.zeros((len(rays), 2))], axis=1))
+        agree = (hits["status"] == ref[:, 0].astype(np.int32)) & (hits["node"] == ref[:, 1].astype(np.int32))
+        assert agree.all(), "terrain: hit/miss or node differs on %d of %d rays" % ((~agree).sum(), len(rays))
+        m = ref[:, 0] == 0
+        rel = np.abs(hits["dist"][m] - ref[m, 2]) / np.maximum(1.0, np.abs(ref[m, 2]))
+        assert rel.max() < 1e-9, "terrain: dist differs (max rel %.3g)" % rel.max()
+        assert np.abs(hits["norm"][m] - ref[m, 6:9]).max() < 1e-7
+        vis = r.trace_visible(g["seg"])
+        assert (vis == (g["vis"] != 0)).mean() >= 0.9995
+        # GI frame against the converged reference frame
+        refimg = g["img"].astype(np.float32)
+        a, st = r.render(width=W, height=H, spp=spp, seed=3)
+        b, _ = r.render(width=W, height=H, spp=spp, seed=4)
+        own = rmse(a, b) / np.sqrt(2.0)
+        err = rmse(a, refimg)
+        mean_delta = np.abs(clamp01(a).mean(axis=(0, 1)) - clamp01(refimg).mean(axis=(0, 1)))
+        assert err <= 1.25 * own + 0.006, "terrain GI: rmse vs converged reference %.4f, own noise %.4f" % (err, own)
+        assert mean_delta.max() <= 0.006, "terrain GI: mean delta %s" % mean_delta
+        return err, own, st
+    finally:
+        r.close()
+        sf.close()

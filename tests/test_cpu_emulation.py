@@ -30,3 +30,8 @@ def test_whitted_parity(sess, scene):
 @pytest.mark.parametrize("scene,spp", [("hw12/sphtri", 48), ("zaphod", 32)])
 def test_montecarlo_parity(sess, scene, spp):
     T.check_mc(sess, scene, spp)
+
+
+def test_terrain_walk(emu_api):
+    # the conservative FP32 block walk (host form) on the bench's terrain; its camera sits ON a split plane
+    T.check_terrain(emu_api, spp=8)

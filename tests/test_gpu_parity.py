@@ -131,3 +131,34 @@ def test_edge_cases(gpu_api, tmp_path):
     assert len(r.trace_closest(np.zeros((0, 8)))) == 0
     r.close()
     sf.close()
+
+
+def test_terrain_against_reference(gpu_api):
+    # 203k-triangle version of the bench workload: explicit rays, visible() and a GI frame vs the compiled reference
+    T.check_terrain(gpu_api, spp=256)
+
+
+@pytest.mark.parametrize("side", [320, 2237])
+def test_walk_equals_brute_force(gpu_api, side):
+    """Size-independent property, up to the bench's full 10 M triangles: the KD walk returns exactly the hit that
+    testing EVERY triangle in index order returns (the reference's useKDTree=false path, src/mesh.cpp:255-262)."""
+    rng = np.random.default_rng(side)
+    n = 2048 if side <= 320 else 192
+    o = np.concatenate([np.tile([[0.0, 150.0, -600.0]], (n // 2, 1)),
+                        np.stack([rng.uniform(-500, 500, n // 2), rng.uniform(-30, 200, n // 2), rng.uniform(-500, 500, n // 2)], 1)])
+    d = np.concatenate([np.stack([rng.uniform(-0.7, 0.7, n // 2), rng.uniform(-0.6, 0.05, n // 2), np.ones(n // 2)], 1), rng.normal(size=(n // 2, 3))])
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.zeros((n, 2))], axis=1)
+    sf = T.terrain_scene_file(gpu_api, side)
+    out = []
+    for flags in (0, hx.CFG_BRUTE_FORCE_MESHES):
+        r = hx.Renderer(api_=gpu_api, queue_capacity=1 << 20, flags=flags).load(sf)
+        out.append(r.trace_closest(rays).copy())
+        r.close()
+    sf.close()
+    walk, brute = out
+    assert (walk["node"] == brute["node"]).all() and (walk["status"] == brute["status"]).all()
+    assert (walk["node"] == 0).sum() > n // 4  # the terrain is actually being hit
+    m = walk["status"] == 0
+    assert np.array_equal(walk["dist"][m], brute["dist"][m]) and np.array_equal(walk["ip"][m], brute["ip"][m])
+    assert np.array_equal(walk["norm"][m], brute["norm"][m])
