@@ -235,8 +235,10 @@ HXR_HD TriRec load_tri(const TriTest* p)
     return r;
 }
 
-// returns true (and updates best) if triangle `ti` is hit at a parameter in [0, best.gamma]
-HXR_HD bool tri_test(const TriTest* tris, bool backface, const Ray& ray, uint32_t ti, MeshBest& best)
+// The reference's triangle test (src/mesh.cpp:178-196) against the best hit so far (bestGamma, bestTri): true if
+// triangle `ti` is hit at a parameter in [0, bestGamma] (at exactly bestGamma only if ti > bestTri).
+HXR_HD bool tri_core(const TriTest* tris, bool backface, const Ray& ray, uint32_t ti, double bestGamma, int bestTri, double& gamma,
+                     double& lambda2, double& lambda3)
 {
     const TriRec t = load_tri(tris + ti);
     if (backface && dot(ray.d, t.N) > 0) return false;
@@ -245,20 +247,41 @@ HXR_HD bool tri_test(const TriTest* tris, bool backface, const Ray& ray, uint32_
     const double Dcr = dot(t.N, nd);
     if (fabs(Dcr) < 1e-12) return false;
     const double rDcr = 1 / Dcr;
-    const double gamma = dot(t.N, H) * rDcr;
-    if (gamma < 0 || gamma > best.gamma) return false;
-    if (gamma == best.gamma && (int)ti < best.tri) return false;
-    const double lambda2 = dot(cross(H, t.AC), nd) * rDcr;
+    gamma = dot(t.N, H) * rDcr;
+    if (gamma < 0 || gamma > bestGamma) return false;
+    if (gamma == bestGamma && (int)ti < bestTri) return false;
+    lambda2 = dot(cross(H, t.AC), nd) * rDcr;
     if (lambda2 < 0 || lambda2 > 1) return false;
-    const double lambda3 = dot(cross(t.AB, H), nd) * rDcr;
+    lambda3 = dot(cross(t.AB, H), nd) * rDcr;
     if (lambda3 < 0 || lambda3 > 1) return false;
     const double lambda1 = 1 - (lambda2 + lambda3);
     if (lambda1 < 0 || lambda1 > 1) return false;
+    return true;
+}
+
+// returns true (and updates best) if triangle `ti` beats the best hit so far
+HXR_HD bool tri_test(const TriTest* tris, bool backface, const Ray& ray, uint32_t ti, MeshBest& best)
+{
+    double gamma, l2, l3;
+    if (!tri_core(tris, backface, ray, ti, best.gamma, best.tri, gamma, l2, l3)) return false;
     best.gamma = gamma;
     best.tri = (int)ti;
-    best.l2 = lambda2;
-    best.l3 = lambda3;
+    best.l2 = l2;
+    best.l3 = l3;
     return true;
+}
+
+// gamma and barycentrics of a triangle already known to be hit (the expressions of tri_test, no range checks)
+HXR_HD void tri_eval(const TriTest* tris, const Ray& ray, uint32_t ti, MeshBest& best)
+{
+    const TriRec t = load_tri(tris + ti);
+    const d3 nd = -ray.d;
+    const d3 H = ray.o - t.A;
+    const double rDcr = 1 / dot(t.N, nd);
+    best.gamma = dot(t.N, H) * rDcr;
+    best.l2 = dot(cross(H, t.AC), nd) * rDcr;
+    best.l3 = dot(cross(t.AB, H), nd) * rDcr;
+    best.tri = (int)ti;
 }
 
 HXR_HD KdBlock load_block(const KdBlock* p)
@@ -293,12 +316,9 @@ HXR_HD bool mesh_closest(const DMesh& M, const Ray& ray, double gamma_limit, Mes
         if (cur & HXR_KD_LEAF) {
             if (cur != HXR_KD_EMPTY) {
                 if (COUNT) cnt->kd_leaves++;
-                for (uint32_t p = cur & ~HXR_KD_LEAF;; p++) {
-                    const uint32_t e = M.leaf_tris[p];
-                    if (COUNT) cnt->tri_tests++;
-                    tri_test(M.tri_test, M.backface != 0, ray, e & ~HXR_TRI_LAST, best);
-                    if (e & HXR_TRI_LAST) break;
-                }
+                const uint32_t* list = M.leaf_tris + (cur & ~HXR_KD_LEAF);
+                if (COUNT) cnt->tri_tests += list[0];
+                for (uint32_t k = 1; k <= list[0]; k++) tri_test(M.tri_test, M.backface != 0, ray, list[k], best);
             }
             // next pending segment that can still hold a hit at or before the best one
             bool found = false;
@@ -476,12 +496,10 @@ HXR_HD bool mesh_closest_f32(const DMesh& M, const Ray& ray, double gamma_limit,
     uint32_t cur = 0;
     for (;;) {
         if (cur & HXR_KD_LEAF) {
-            for (uint32_t p = cur & ~HXR_KD_LEAF;; p++) {
-                const uint32_t e = M.leaf_tris[p];
-                if (COUNT) cnt->tri_tests++;
-                if (tri_test(M.tri_test, M.backface != 0, ray, e & ~HXR_TRI_LAST, best)) tbest = f32_above(best.gamma);
-                if (e & HXR_TRI_LAST) break;
-            }
+            const uint32_t* list = M.leaf_tris + (cur & ~HXR_KD_LEAF);
+            if (COUNT) cnt->tri_tests += list[0];
+            for (uint32_t k = 1; k <= list[0]; k++)
+                if (tri_test(M.tri_test, M.backface != 0, ray, list[k], best)) tbest = f32_above(best.gamma);
             if (COUNT) cnt->kd_leaves++;
             bool found = false;
             while (sp > 0) {

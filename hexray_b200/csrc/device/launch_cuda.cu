@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "launch.h"
@@ -32,6 +33,8 @@ static int g_sms = 0;
 static cudaStream_t g_stream = nullptr;
 static std::string g_err;
 static bool g_prof = false;
+// walk-loop tunables (uniform kernel arguments; HXR_WALK_STEPS / HXR_REFILL_MIN in the environment override the defaults)
+static int g_walkSteps = 3, g_refillMin = 8;
 static uint64_t g_launches[PROF_NCAT];
 static std::vector<cudaEvent_t> g_evPool;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
@@ -64,6 +67,8 @@ bool init(int device, char* err, size_t errlen)
     if (p.major < 10) return fail(std::string("device '") + p.name + "' is not Blackwell (sm_100a code only)");
     g_device = device;
     g_sms = p.multiProcessorCount;
+    if (const char* e = getenv("HXR_WALK_STEPS")) g_walkSteps = std::max(1, atoi(e));
+    if (const char* e = getenv("HXR_REFILL_MIN")) g_refillMin = std::min(32, std::max(1, atoi(e)));
     if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
     return true;
 }
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, 
 #define HXR_REFILL_MIN 8  /* refill as soon as this many lanes of a warp are idle */
 #endif
 #ifndef HXR_WALK_STEPS
-#define HXR_WALK_STEPS 4  /* state-machine steps between two refill checks */
+#define HXR_WALK_STEPS 3  /* block steps per round of the walk loop */
 #endif
 
 template <bool COUNT>
@@ -250,18 +255,21 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
 }
 
 // ---- the KD walk -------------------------------------------------------------------------------------
-// One lane = one (ray, mesh) task. The loop is "while-while" (Aila & Laine): all lanes of a warp first step
-// through tree BLOCKS until each holds a leaf, then all test triangles; a lane that runs out of work is
-// refilled from the task queue (__ballot_sync finds idle lanes, one atomicAdd per warp, __shfl_sync broadcast).
+// One lane = one (ray, mesh) task; lanes that run out of work are refilled from the task queue (__ballot_sync finds
+// idle lanes, one atomicAdd per warp, __shfl_sync broadcast). Each round of the loop has two phases:
+//   1. HXR_WALK_STEPS block steps: every lane whose cursor is a tree block pops / steps (block_step: one 32-byte
+//      fetch = two tree levels, up to four grandchildren front to back, the far ones pushed on the stack);
+//   2. the leaves reached so far are tested WARP-COOPERATIVELY: the (ray, triangle) pairs of all lanes' leaves are
+//      dealt out evenly over the 32 lanes (prefix sum of the leaf sizes + binary search by shuffle), so a lane
+//      with a long leaf does not hold up the others; hits are merged back into the owning lane.
+// Bounding phase 1 keeps lanes from idling while one ray of the warp descends a long path (the measured SIMD
+// efficiency of an unbounded while-while loop on incoherent GI rays was 20 %).
 //
-// Precision: the tree is walked with FP32 plane arithmetic made CONSERVATIVE — every plane parameter carries
-// an error bound and the two children get overlapping parameter ranges, so a leaf is visited whenever the
-// exact ray could touch it — while every triangle is tested with the reference's own double arithmetic
-// (tri_test). The walk therefore only decides WHICH triangles are tested; the winner (smallest gamma, highest
-// index on ties) is the same as for the double walk in isect.h (mesh_closest) and for brute force.
+// Precision: the tree is walked with conservative FP32 plane arithmetic (isect.h: plane_cross / block_step) and
+// every triangle is tested with the reference's double arithmetic (tri_core); see isect.h.
 //
-// State: ~30 registers per lane; the double ray (48 B) and the first HXR_SSTACK stack entries (12 B each) live in
-// shared memory, deeper entries overflow to local memory (rare: the stack is shallow for almost all rays).
+// State: the double ray (48 B) and the first HXR_SSTACK stack entries (12 B each) of every lane live in shared
+// memory, deeper entries overflow to local memory (rare: the stack is shallow for almost all rays).
 #define HXR_SSTACK 12
 #define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
 
@@ -275,12 +283,12 @@ struct WalkShared {
 template <bool SHADOW, bool COUNT>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayTask* __restrict__ rays,
                                                                               const ShadowTask* __restrict__ shadows, TraceScratch ts,
-                                                                              TravCounters* cnt)
+                                                                              TravCounters* cnt, int walkSteps, int refillMin)
 {
     __shared__ WalkShared sh;
     const unsigned FULL = 0xffffffffu;
     const uint32_t n = min(*ts.task_count, ts.task_cap);
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warpBase = tid & ~31u;
     uint32_t ovRef[HXR_KD_STACK - HXR_SSTACK];
     float ovMin[HXR_KD_STACK - HXR_SSTACK], ovMax[HXR_KD_STACK - HXR_SSTACK];
     bool active = false, drained = false;
@@ -291,13 +299,14 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     const uint32_t* leafTris = nullptr;
     const TriTest* tris = nullptr;
     bool backface = false;
-    uint32_t cur = HXR_POP;
+    int meshIdx = -1;
+    uint32_t cur = HXR_POP, leafCnt = 0;
     float tmin = 0, tmax = 0, tbest = 0;
     int sp = 0;
-    MeshBest best;
+    double bestG = 0;
+    int bestTri = -1;
     uint32_t taskRay = 0, taskNode = 0;
     TravCounters local = {0, 0, 0, 0};
-    best.gamma = 0; best.l2 = best.l3 = 0; best.tri = -1;
 
     auto push = [&](const WalkEnt& e) {
         if (sp < HXR_SSTACK) {
@@ -309,11 +318,17 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         }
         sp++;
     };
+    auto my_ray = [&]() {
+        Ray t;
+        t.o = mk3(sh.ray[0][tid], sh.ray[1][tid], sh.ray[2][tid]);
+        t.d = mk3(sh.ray[3][tid], sh.ray[4][tid], sh.ray[5][tid]);
+        return t;
+    };
 
     for (;;) {
         // ---- refill: idle lanes take new tasks
         const unsigned idle = __ballot_sync(FULL, !active);
-        if (!drained && (idle == FULL || __popc(idle) >= HXR_REFILL_MIN)) {
+        if (!drained && (idle == FULL || __popc(idle) >= refillMin)) {
             const int c = __popc(idle);
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
@@ -327,14 +342,15 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                     taskRay = task.ray;
                     taskNode = task.node;
                     const hxr_node& nd = sc.nodes[taskNode];
-                    const DMesh& M = sc.meshes[sc.geoms[nd.geom].a];
+                    const int mi = sc.geoms[nd.geom].a;
+                    const DMesh& M = sc.meshes[mi];
                     Ray t;
                     double limit;
                     bool skip = false;
                     if (SHADOW) {
                         double D;
-                        const Ray wr = shadow_ray(shadows[taskRay], D);
-                        t = object_ray(nd, wr);
+                        const Ray wray = shadow_ray(shadows[taskRay], D);
+                        t = object_ray(nd, wray);
                         limit = gamma_limit_for(nd, t, D);
                         skip = ts.occluded[taskRay] != 0;
                     } else {
@@ -343,6 +359,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                     }
                     double t0, t1;
                     if (!skip && mesh_slab(M, t, limit, t0, t1)) {
+                        meshIdx = mi;
                         blocks = M.blocks;
                         leafTris = M.leaf_tris;
                         tris = M.tri_test;
@@ -353,9 +370,8 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         tmin = f32_below(t0);
                         tmax = f32_above(t1);
                         tbest = f32_above(limit);
-                        best.gamma = limit;
-                        best.tri = -1;
-                        best.l2 = best.l3 = 0;
+                        bestG = limit;
+                        bestTri = -1;
                         sp = 0;
                         cur = 0;
                         active = true;
@@ -368,66 +384,121 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             if (drained) break;
             continue;
         }
-        // ---- phase 1: step through blocks until every active lane holds a leaf (or has finished)
-        while (__any_sync(FULL, active && !(cur >> 31))) {
-            if (!active || (cur >> 31)) continue;
-            if (cur == HXR_POP) {
+        // ---- phase 1: a few block steps for every lane whose cursor is not a leaf
+#pragma unroll 1
+        for (int it = 0; it < walkSteps; it++) {
+            const bool stepping = active && !(cur >> 31);
+            if (stepping && cur == HXR_POP) {
                 if (sp == 0) {
                     // nothing left: this task is done
                     active = false;
-                    if (!SHADOW && best.tri >= 0) {
+                    if (!SHADOW && bestTri >= 0) {
                         const hxr_node& nd = sc.nodes[taskNode];
-                        const d3 wo = ld3(rays[taskRay].o);
-                        const d3 to = mk3(sh.ray[0][tid], sh.ray[1][tid], sh.ray[2][tid]), td = mk3(sh.ray[3][tid], sh.ray[4][tid], sh.ray[5][tid]);
-                        const d3 ipw = mul_vm(to + best.gamma * td, nd.T.m) + ld3(nd.T.offset);
+                        const Ray t = my_ray();
+                        const d3 ipw = mul_vm(t.o + bestG * t.d, nd.T.m) + ld3(nd.T.offset);
                         MeshRes r;
-                        r.dist = distance3(wo, ipw);
-                        r.gamma = best.gamma; r.l2 = best.l2; r.l3 = best.l3; r.tri = best.tri; r.node = (int32_t)taskNode;
+                        r.dist = distance3(ld3(rays[taskRay].o), ipw);
+                        r.tri = bestTri;
+                        r.node = (int32_t)taskNode;
                         ts.res[(size_t)sc.node_slot[taskNode] * ts.res_stride + taskRay] = r;
                     }
-                    continue;
+                } else {
+                    sp--;
+                    WalkEnt e;
+                    if (sp < HXR_SSTACK) { e.ref = sh.stRef[sp][tid]; e.lo = sh.stMin[sp][tid]; e.hi = sh.stMax[sp][tid]; }
+                    else { e.ref = ovRef[sp - HXR_SSTACK]; e.lo = ovMin[sp - HXR_SSTACK]; e.hi = ovMax[sp - HXR_SSTACK]; }
+                    if (e.lo <= tbest) { cur = e.ref; tmin = e.lo; tmax = e.hi; }  // else it cannot hold a closer hit: keep popping
                 }
-                sp--;
-                WalkEnt e;
-                if (sp < HXR_SSTACK) { e.ref = sh.stRef[sp][tid]; e.lo = sh.stMin[sp][tid]; e.hi = sh.stMax[sp][tid]; }
-                else { e.ref = ovRef[sp - HXR_SSTACK]; e.lo = ovMin[sp - HXR_SSTACK]; e.hi = ovMax[sp - HXR_SSTACK]; }
-                if (e.lo <= tbest) { cur = e.ref; tmin = e.lo; tmax = e.hi; }  // else: cannot hold a closer hit, keep popping
-                continue;
             }
-            // one block = a node and both its children: up to four grandchildren, front to back
-            if (COUNT) local.kd_inner++;
-            const KdBlock B = load_block(blocks + cur);
-            WalkEnt e0, e1, e2, e3;
-            block_step(B, wr, tmin, tmax, tbest, e0, e1, e2, e3);
-            // nearest valid entry becomes the cursor, the others are pushed far-to-near
-            WalkEnt c;
-            c.ref = HXR_POP; c.lo = 0; c.hi = 0;
-            bool have = false;
-            if (ent_valid(e3)) { c = e3; have = true; }
-            if (ent_valid(e2)) { if (have) push(c); c = e2; have = true; }
-            if (ent_valid(e1)) { if (have) push(c); c = e1; have = true; }
-            if (ent_valid(e0)) { if (have) push(c); c = e0; have = true; }
-            cur = c.ref; tmin = c.lo; tmax = c.hi;
+            __syncwarp();  // lanes that popped and lanes that did not take the block step together
+            if (stepping && active && cur < HXR_POP) {
+                // one block = a node and both its children: up to four grandchildren, front to back
+                if (COUNT) local.kd_inner++;
+                const KdBlock B = load_block(blocks + cur);
+                WalkEnt e0, e1, e2, e3;
+                block_step(B, wr, tmin, tmax, tbest, e0, e1, e2, e3);
+                // nearest valid entry becomes the cursor, the others are pushed far-to-near
+                WalkEnt c;
+                c.ref = HXR_POP; c.lo = 0; c.hi = 0;
+                bool have = false;
+                if (ent_valid(e3)) { c = e3; have = true; }
+                if (ent_valid(e2)) { if (have) push(c); c = e2; have = true; }
+                if (ent_valid(e1)) { if (have) push(c); c = e1; have = true; }
+                if (ent_valid(e0)) { if (have) push(c); c = e0; have = true; }
+                cur = c.ref; tmin = c.lo; tmax = c.hi;
+            }
+            if (stepping && active && (cur >> 31)) leafCnt = __ldg(leafTris + (cur & ~HXR_KD_LEAF));  // in flight while the others keep stepping
+            __syncwarp();
         }
-        // ---- phase 2: every lane that holds a leaf tests its triangles, one per iteration
-        while (__any_sync(FULL, active && (cur >> 31))) {
-            if (!active || !(cur >> 31)) continue;
-            const uint32_t e = __ldg(leafTris + (cur & ~HXR_KD_LEAF));
-            if (COUNT) { local.tri_tests++; if (e & HXR_TRI_LAST) local.kd_leaves++; }
-            Ray t;
-            t.o = mk3(sh.ray[0][tid], sh.ray[1][tid], sh.ray[2][tid]);
-            t.d = mk3(sh.ray[3][tid], sh.ray[4][tid], sh.ray[5][tid]);
-            const bool hit = tri_test(tris, backface, t, e & ~HXR_TRI_LAST, best);
-            cur = (e & HXR_TRI_LAST) ? HXR_POP : cur + 1u;
-            if (hit) {
-                tbest = f32_above(best.gamma);
+        // ---- phase 2: all (ray, triangle) pairs of the leaves held by this warp, dealt out over its 32 lanes
+        const bool hasLeaf = active && (cur >> 31);
+        if (__ballot_sync(FULL, hasLeaf) == 0) continue;
+        const uint32_t cntMine = hasLeaf ? leafCnt : 0u;
+        uint32_t incl = cntMine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const uint32_t excl = incl - cntMine;
+        const uint32_t myFirst = (cur & ~HXR_KD_LEAF) + 1u;
+        bool ownerHit = false;
+        for (uint32_t base = 0; base < total; base += 32u) {
+            const uint32_t pair = base + lane;
+            int o = 0;  // owner of this pair: the first lane whose inclusive prefix exceeds it
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t v = __shfl_sync(FULL, incl, o + step - 1);
+                if (v <= pair) o += step;
+            }
+            const uint32_t oExcl = __shfl_sync(FULL, excl, o);
+            const uint32_t oFirst = __shfl_sync(FULL, myFirst, o);
+            const int oMesh = __shfl_sync(FULL, meshIdx, o);
+            double g = __shfl_sync(FULL, bestG, o);  // snapshot of the owner's best (prunes; the merge below decides)
+            const int bt = __shfl_sync(FULL, bestTri, o);
+            bool hit = false;
+            uint32_t ti = 0;
+            if (pair < total) {
+                const uint32_t* lt = leafTris;
+                const TriTest* tt = tris;
+                bool bf = backface;
+                if (oMesh != meshIdx) {
+                    const DMesh& M = sc.meshes[oMesh];
+                    lt = M.leaf_tris; tt = M.tri_test; bf = M.backface != 0;
+                }
+                ti = __ldg(lt + oFirst + (pair - oExcl));
+                const unsigned ot = warpBase | (unsigned)o;
+                Ray t;
+                t.o = mk3(sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot]);
+                t.d = mk3(sh.ray[3][ot], sh.ray[4][ot], sh.ray[5][ot]);
+                double gamma, l2, l3;
+                hit = tri_core(tt, bf, t, ti, g, bt, gamma, l2, l3);
+                g = gamma;
+            }
+            unsigned hm = __ballot_sync(FULL, hit);
+            while (hm) {
+                const int w = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int ow = __shfl_sync(FULL, o, w);
+                const double gw = __shfl_sync(FULL, g, w);
+                const int tw = (int)__shfl_sync(FULL, ti, w);
+                if ((int)lane == ow && (gw < bestG || (gw == bestG && tw > bestTri))) { bestG = gw; bestTri = tw; ownerHit = true; }
+            }
+        }
+        if (hasLeaf) {
+            if (COUNT) { local.kd_leaves++; local.tri_tests += leafCnt; }
+            cur = HXR_POP;
+            if (ownerHit) {
+                tbest = f32_above(bestG);
                 if (SHADOW) {
                     // the exact test of visible(): world distance of the hit against |AB|
                     double D;
-                    const Ray wr = shadow_ray(shadows[taskRay], D);
+                    const Ray wray = shadow_ray(shadows[taskRay], D);
                     const hxr_node& nd = sc.nodes[taskNode];
-                    const d3 ipw = mul_vm(t.o + best.gamma * t.d, nd.T.m) + ld3(nd.T.offset);
-                    if (distance3(wr.o, ipw) < D) {
+                    const Ray t = my_ray();
+                    const d3 ipw = mul_vm(t.o + bestG * t.d, nd.T.m) + ld3(nd.T.offset);
+                    if (distance3(wray.o, ipw) < D) {
                         ts.occluded[taskRay] = 1;
                         active = false;
                     }
@@ -522,12 +593,12 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
     if (cnt) {
         if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
         k_setup_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, cnt);
-        if (sc.n_big) k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, cnt);
+        if (sc.n_big) k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, cnt, g_walkSteps, g_refillMin);
         k_finalize_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
     } else {
         if (!gridPlain) gridPlain = walk_grid(k_walk<false, false>);
         k_setup_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
-        if (sc.n_big) k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, nullptr);
+        if (sc.n_big) k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, nullptr, g_walkSteps, g_refillMin);
         k_finalize_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
     }
     return sc.n_big ? 3 : 2;
@@ -556,11 +627,11 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
     if (cnt) {
         if (!gridCount) gridCount = walk_grid(k_walk<true, true>);
         k_setup_shadow<true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
-        if (sc.n_big) { k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, cnt); launches++; }
+        if (sc.n_big) { k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, cnt, g_walkSteps, g_refillMin); launches++; }
     } else {
         if (!gridPlain) gridPlain = walk_grid(k_walk<true, false>);
         k_setup_shadow<false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
-        if (sc.n_big) { k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, nullptr); launches++; }
+        if (sc.n_big) { k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, nullptr, g_walkSteps, g_refillMin); launches++; }
     }
     if (accum) { k_accum_shadow<<<nb, 256, 0, g_stream>>>(shadow, count, cap, ts, accum); launches++; }
     return launches;

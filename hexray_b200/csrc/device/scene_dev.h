@@ -29,8 +29,8 @@ struct alignas(16) KdNode {
 // Device KD-tree: 32-byte blocks holding a node (sub 0) and its two children (sub 1 = left, sub 2 = right).
 //   meta bits 0-1 / 2-3 / 4-5 = split axis of sub 0 / 1 / 2; axis 3 marks a child that is a LEAF.
 //   ref[0], ref[1] = children of sub 1 (or ref[0] = its leaf reference), ref[2], ref[3] likewise for sub 2.
-//   A reference is either a block index (bit 31 clear) or HXR_KD_LEAF | first entry in leaf_tris; HXR_KD_EMPTY is
-//   a leaf without triangles. The last entry of every leaf's list carries HXR_TRI_LAST.
+//   A reference is either a block index (bit 31 clear) or HXR_KD_LEAF | position of the leaf's list in leaf_tris
+//   ([count, triangle indices...]); HXR_KD_EMPTY is a leaf without triangles.
 //   "left" holds coordinates <= split, "right" >= split.
 struct alignas(32) KdBlock {
     float split[3];
@@ -39,7 +39,6 @@ struct alignas(32) KdBlock {
 };
 #define HXR_KD_LEAF 0x80000000u
 #define HXR_KD_EMPTY 0xFFFFFFFFu
-#define HXR_TRI_LAST 0x80000000u
 
 struct alignas(16) TriTest {
     double A[3], AB[3], AC[3], N[3];

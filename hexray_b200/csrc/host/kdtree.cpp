@@ -216,14 +216,22 @@ uint32_t stitch(Builder::Local& dst, const Builder::Local& sub)
 }
 
 // ---- binary tree -> 32-byte blocks (two levels per block), DFS pre-order
-uint32_t leafRef(KdTree& t, const KdNode& n)
+// device leaf lists: [count, index 0, index 1, ...] per leaf, in block (DFS) order
+struct LeafLists {
+    const std::vector<uint32_t>& raw;  // the build's lists (KdNode::a = first, b = count)
+    std::vector<uint32_t> out;
+};
+
+uint32_t leafRef(LeafLists& ll, const KdNode& n)
 {
     if (n.b == 0) return HXR_KD_EMPTY;
-    t.leafTris[(size_t)n.a + n.b - 1] |= HXR_TRI_LAST;
-    return HXR_KD_LEAF | n.a;
+    const size_t off = ll.out.size();
+    ll.out.push_back(n.b);
+    ll.out.insert(ll.out.end(), ll.raw.begin() + n.a, ll.raw.begin() + n.a + n.b);
+    return HXR_KD_LEAF | (uint32_t)off;
 }
 
-uint32_t makeBlock(KdTree& t, uint32_t nodeIdx)
+uint32_t makeBlock(KdTree& t, LeafLists& ll, uint32_t nodeIdx)
 {
     const uint32_t me = (uint32_t)t.blocks.size();
     t.blocks.push_back(KdBlock{});
@@ -236,7 +244,7 @@ uint32_t makeBlock(KdTree& t, uint32_t nodeIdx)
         if (child.kind == 3) {
             b.meta |= 3u << (2 + 2 * c);
             b.split[1 + c] = 0;
-            b.ref[2 * c] = leafRef(t, child);
+            b.ref[2 * c] = leafRef(ll, child);
             b.ref[2 * c + 1] = HXR_KD_EMPTY;
         } else {
             b.meta |= child.kind << (2 + 2 * c);
@@ -244,7 +252,7 @@ uint32_t makeBlock(KdTree& t, uint32_t nodeIdx)
             for (int k = 0; k < 2; k++) {
                 const uint32_t gi = k ? child.b : child.a;
                 const KdNode g = t.nodes[gi];
-                b.ref[2 * c + k] = g.kind == 3 ? leafRef(t, g) : makeBlock(t, gi);
+                b.ref[2 * c + k] = g.kind == 3 ? leafRef(ll, g) : makeBlock(t, ll, gi);
             }
         }
     }
@@ -255,18 +263,22 @@ uint32_t makeBlock(KdTree& t, uint32_t nodeIdx)
 void makeBlocks(KdTree& t, const hxr_mesh& mesh)
 {
     t.blocks.clear();
+    LeafLists ll{t.leafTris, {}};
+    ll.out.reserve(t.leafTris.size() + t.leaves + 4);
     if (t.nodes[0].kind == 3) {
         // the whole mesh is one leaf: a block whose plane lies beyond the mesh puts everything on its left
         KdBlock b{};
         b.split[0] = std::nextafter((float)mesh.bbox_max[0], INFINITY) + 1.0f + 1e-3f * std::fabs((float)mesh.bbox_max[0]);
         b.meta = 0u | (3u << 2) | (3u << 4);
-        b.ref[0] = leafRef(t, t.nodes[0]);
+        b.ref[0] = leafRef(ll, t.nodes[0]);
         b.ref[1] = b.ref[2] = b.ref[3] = HXR_KD_EMPTY;
         t.blocks.push_back(b);
-        return;
+    } else {
+        t.blocks.reserve(t.nodes.size() / 3 + 16);
+        makeBlock(t, ll, 0);
     }
-    t.blocks.reserve(t.nodes.size() / 3 + 16);
-    makeBlock(t, 0);
+    ll.out.resize(ll.out.size() + 32, 0);  // readers may fetch (and then ignore) a few entries past a list
+    t.leafTris.swap(ll.out);
 }
 
 }  // namespace

@@ -13,7 +13,7 @@ namespace host {
 struct KdTree {
     std::vector<KdNode> nodes;        // binary tree (build intermediate): node 0 = root, DFS pre-order
     std::vector<KdBlock> blocks;      // what the device walks: two tree levels per 32-byte block, block 0 = root
-    std::vector<uint32_t> leafTris;   // triangle indices, leaf after leaf, ascending inside a leaf; last entry | HXR_TRI_LAST
+    std::vector<uint32_t> leafTris;   // per leaf: [count, triangle indices ascending]; a leaf reference points at its count
     uint32_t maxDepth = 0;
     uint64_t leaves = 0;
     double buildMs = 0;
