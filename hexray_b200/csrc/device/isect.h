@@ -404,17 +404,17 @@ struct WalkRay {  // the object-space ray as the walk sees it
     float ix, iy, iz;  // 1 / direction (0 on parallel axes)
     uint32_t par;      // bit a: |d[a]| < 1e-18, treated as parallel to the planes of axis a
 };
-HXR_HD WalkRay walk_ray(const Ray& t)
+HXR_HD WalkRay walk_ray_f(float ox, float oy, float oz, float dx, float dy, float dz)
 {
     WalkRay w;
-    w.ox = (float)t.o.x; w.oy = (float)t.o.y; w.oz = (float)t.o.z;
-    const float dx = (float)t.d.x, dy = (float)t.d.y, dz = (float)t.d.z;
+    w.ox = ox; w.oy = oy; w.oz = oz;
     w.par = (fabsf(dx) < 1e-18f ? 1u : 0u) | (fabsf(dy) < 1e-18f ? 2u : 0u) | (fabsf(dz) < 1e-18f ? 4u : 0u);
     w.ix = (w.par & 1u) ? 0.0f : 1.0f / dx;
     w.iy = (w.par & 2u) ? 0.0f : 1.0f / dy;
     w.iz = (w.par & 4u) ? 0.0f : 1.0f / dz;
     return w;
 }
+HXR_HD WalkRay walk_ray(const Ray& t) { return walk_ray_f((float)t.o.x, (float)t.o.y, (float)t.o.z, (float)t.d.x, (float)t.d.y, (float)t.d.z); }
 
 struct PlaneX {  // conservative range [tlo, thi] of the parameter at which the ray crosses a split plane
     float tlo, thi;
@@ -479,57 +479,57 @@ HXR_HD void block_step(const KdBlock& B, const WalkRay& w, float tmin, float tma
     e0 = p0.leftFirst ? l0 : r0; e1 = p0.leftFirst ? l1 : r1; e2 = p0.leftFirst ? r0 : l0; e3 = p0.leftFirst ? r1 : l1;
 }
 
-// host form of the kernel's walk: same steps, one ray at a time
-template <bool COUNT>
-HXR_HD bool mesh_closest_f32(const DMesh& M, const Ray& ray, double gamma_limit, MeshBest& best, TravCounters* cnt)
+// ---- the FP32 triangle filter
+// The walk does not run the exact triangle test; it runs the SAME formulas in float on a float copy of the triangle
+// (TriF32) together with a running bound on the rounding error of every quantity, and sorts each (ray, triangle)
+// pair into: MISS (the exact test certainly rejects it, or its hit lies certainly beyond the best known one),
+// CERTAIN (the exact test certainly accepts it, at a parameter <= ghi) or MAYBE. CERTAIN and MAYBE pairs go to the
+// exact test (pipeline.h: confirm_*); CERTAIN ones also shorten the walk (tbest). Error model, eps = 2^-24:
+//   every component of H = o - A carries |dH| <= err (rounding of o, of A and of the subtraction; task.err),
+//   so |d((H x AC).nd)| <= 2 err |AC|_1 + 16 eps |H|_1 |AC|_1, likewise for (AB x H).nd and N.H, and
+//   |d(N.nd)| <= 8 eps |N|_1 (|nd| = 1; the constants are the operation counts, doubled).
+#define HXR_TF_MISS 0
+#define HXR_TF_MAYBE 1
+#define HXR_TF_CERTAIN 2
+
+HXR_HD int tri_filter(const TriF32* p, bool backface, float ox, float oy, float oz, float dx, float dy, float dz, float err, float tbest,
+                      float& ghi)
 {
-    double t0, t1;
-    if (!mesh_slab(M, ray, gamma_limit, t0, t1)) return false;
-    if (COUNT) cnt->mesh_queries++;
-    best.gamma = gamma_limit;
-    best.tri = -1;
-    best.l2 = best.l3 = 0;
-    const WalkRay w = walk_ray(ray);
-    float tmin = f32_below(t0), tmax = f32_above(t1), tbest = f32_above(gamma_limit);
-    WalkEnt st[HXR_KD_STACK];
-    int sp = 0;
-    uint32_t cur = 0;
-    for (;;) {
-        if (cur & HXR_KD_LEAF) {
-            const uint32_t* list = M.leaf_tris + (cur & ~HXR_KD_LEAF);
-            if (COUNT) cnt->tri_tests += list[0];
-            for (uint32_t k = 1; k <= list[0]; k++)
-                if (tri_test(M.tri_test, M.backface != 0, ray, list[k], best)) tbest = f32_above(best.gamma);
-            if (COUNT) cnt->kd_leaves++;
-            bool found = false;
-            while (sp > 0) {
-                sp--;
-                if (st[sp].lo <= tbest) { cur = st[sp].ref; tmin = st[sp].lo; tmax = st[sp].hi; found = true; break; }
-            }
-            if (!found) break;
-            continue;
-        }
-        if (COUNT) cnt->kd_inner++;
-        WalkEnt e[4];
-        block_step(load_block(M.blocks + cur), w, tmin, tmax, tbest, e[0], e[1], e[2], e[3]);
-        bool have = false;
-        WalkEnt c;
-        c.ref = 0; c.lo = c.hi = 0;
-        for (int k = 3; k >= 0; k--) {
-            if (!ent_valid(e[k])) continue;
-            if (have && sp < HXR_KD_STACK) st[sp++] = c;
-            c = e[k];
-            have = true;
-        }
-        if (have) { cur = c.ref; tmin = c.lo; tmax = c.hi; continue; }
-        bool found = false;
-        while (sp > 0) {
-            sp--;
-            if (st[sp].lo <= tbest) { cur = st[sp].ref; tmin = st[sp].lo; tmax = st[sp].hi; found = true; break; }
-        }
-        if (!found) break;
+#if defined(__CUDA_ARCH__)
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(p)), q1 = __ldg(reinterpret_cast<const float4*>(p) + 1),
+                 q2 = __ldg(reinterpret_cast<const float4*>(p) + 2);
+    const float ax = q0.x, ay = q0.y, az = q0.z, abx = q0.w, aby = q1.x, abz = q1.y, acx = q1.z, acy = q1.w, acz = q2.x, nx = q2.y, ny = q2.z,
+                nz = q2.w;
+#else
+    const float ax = p->A[0], ay = p->A[1], az = p->A[2], abx = p->AB[0], aby = p->AB[1], abz = p->AB[2], acx = p->AC[0], acy = p->AC[1],
+                acz = p->AC[2], nx = p->N[0], ny = p->N[1], nz = p->N[2];
+#endif
+    const float eps = 5.9604645e-8f;
+    const float hx = ox - ax, hy = oy - ay, hz = oz - az;
+    const float ex = -dx, ey = -dy, ez = -dz;
+    const float Dcr = nx * ex + ny * ey + nz * ez;
+    const float Ng = nx * hx + ny * hy + nz * hz;
+    const float c2 = (hy * acz - hz * acy) * ex + (hz * acx - hx * acz) * ey + (hx * acy - hy * acx) * ez;
+    const float c3 = (aby * hz - abz * hy) * ex + (abz * hx - abx * hz) * ey + (abx * hy - aby * hx) * ez;
+    const float H1 = fabsf(hx) + fabsf(hy) + fabsf(hz);
+    const float AC1 = fabsf(acx) + fabsf(acy) + fabsf(acz), AB1 = fabsf(abx) + fabsf(aby) + fabsf(abz), N1 = fabsf(nx) + fabsf(ny) + fabsf(nz);
+    const float eh = 2.0f * err + 16.0f * eps * H1;
+    const float E2 = AC1 * eh, E3 = AB1 * eh, EG = N1 * eh, ED = 8.0f * eps * N1;
+    if (backface && Dcr < -ED) return HXR_TF_MISS;  // dot(d, N) = -Dcr is certainly positive: culled
+    const float aD = fabsf(Dcr);
+    if (!(aD > ED)) return HXR_TF_MAYBE;  // grazing (or a degenerate triangle): not even the sign is known
+    const bool neg = Dcr < 0;
+    const float a2 = neg ? -c2 : c2, a3 = neg ? -c3 : c3, aG = neg ? -Ng : Ng;
+    const float a1 = aD - a2 - a3;
+    const float E1 = ED + E2 + E3 + 4.0f * eps * (aD + fabsf(a2) + fabsf(a3));
+    if (a2 < -E2 || a3 < -E3 || a1 < -E1 || aG < -EG) return HXR_TF_MISS;
+    if (aG - EG > tbest * (aD + ED)) return HXR_TF_MISS;  // certainly beyond the best known hit
+    const float den = aD - ED;
+    if (a2 >= E2 && a3 >= E3 && a1 >= E1 && aG >= EG && den > 1e-11f) {
+        ghi = (aG + EG) / den * (1.0f + 4.0f * eps);
+        return HXR_TF_CERTAIN;
     }
-    return best.tri >= 0;
+    return HXR_TF_MAYBE;
 }
 
 // all triangles in index order: exactly the reference's brute-force path (src/mesh.cpp:255-262);

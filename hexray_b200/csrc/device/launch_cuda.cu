@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, 
 
 #define HXR_WALK_BLOCK 128
 #ifndef HXR_WALK_MIN_BLOCKS
-#define HXR_WALK_MIN_BLOCKS 5
+#define HXR_WALK_MIN_BLOCKS 8
 #endif
 #ifndef HXR_REFILL_MIN
 #define HXR_REFILL_MIN 8  /* refill as soon as this many lanes of a warp are idle */
@@ -255,35 +255,38 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
 }
 
 // ---- the KD walk -------------------------------------------------------------------------------------
-// One lane = one (ray, mesh) task; lanes that run out of work are refilled from the task queue (__ballot_sync finds
-// idle lanes, one atomicAdd per warp, __shfl_sync broadcast). Each round of the loop has two phases:
-//   1. HXR_WALK_STEPS block steps: every lane whose cursor is a tree block pops / steps (block_step: one 32-byte
+// One lane = one walk task (a ray inside one big mesh); lanes that run out of work are refilled from the task queue
+// (__ballot_sync finds idle lanes, one atomicAdd per warp, __shfl_sync broadcast). Each round of the loop has two phases:
+//   1. `walkSteps` block steps: every lane whose cursor is a tree block pops / steps (block_step: one 32-byte
 //      fetch = two tree levels, up to four grandchildren front to back, the far ones pushed on the stack);
-//   2. the leaves reached so far are tested WARP-COOPERATIVELY: the (ray, triangle) pairs of all lanes' leaves are
+//   2. the leaves reached so far are filtered WARP-COOPERATIVELY: the (ray, triangle) pairs of all lanes' leaves are
 //      dealt out evenly over the 32 lanes (prefix sum of the leaf sizes + binary search by shuffle), so a lane
-//      with a long leaf does not hold up the others; hits are merged back into the owning lane.
+//      with a long leaf does not hold up the others.
 // Bounding phase 1 keeps lanes from idling while one ray of the warp descends a long path (the measured SIMD
 // efficiency of an unbounded while-while loop on incoherent GI rays was 20 %).
 //
-// Precision: the tree is walked with conservative FP32 plane arithmetic (isect.h: plane_cross / block_step) and
-// every triangle is tested with the reference's double arithmetic (tri_core); see isect.h.
+// The kernel is FP32 only: conservative plane arithmetic (isect.h: block_step) and the conservative triangle
+// filter (tri_filter). Pairs the filter cannot rule out are appended to a list for the exact double test
+// (k_confirm_*); certain hits shorten the walk. No double arithmetic keeps the kernel at <= 64 registers
+// (8 blocks = 1024 lanes per SM) and halves the triangle bytes (48 B instead of 96 B).
 //
-// State: the double ray (48 B) and the first HXR_SSTACK stack entries (12 B each) of every lane live in shared
-// memory, deeper entries overflow to local memory (rare: the stack is shallow for almost all rays).
-#define HXR_SSTACK 12
+// State per lane in shared memory: the float ray (24 B), the best-hit bound (4 B, lowered with atomicMin by whichever
+// lane filters a certain hit) and the first HXR_SSTACK stack entries (12 B each); deeper entries overflow to local
+// memory (rare: the stack is shallow for almost all rays).
+#define HXR_SSTACK 10
 #define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
 
 struct WalkShared {
-    double ray[6][HXR_WALK_BLOCK];
+    float ray[6][HXR_WALK_BLOCK];
+    uint32_t tb[HXR_WALK_BLOCK];  // bits of the (non-negative) float bound; 0 = shadow ray certainly blocked
     uint32_t stRef[HXR_SSTACK][HXR_WALK_BLOCK];
     float stMin[HXR_SSTACK][HXR_WALK_BLOCK];
     float stMax[HXR_SSTACK][HXR_WALK_BLOCK];
 };
 
 template <bool SHADOW, bool COUNT>
-__global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayTask* __restrict__ rays,
-                                                                              const ShadowTask* __restrict__ shadows, TraceScratch ts,
-                                                                              TravCounters* cnt, int walkSteps, int refillMin)
+__global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, TraceScratch ts, TravCounters* cnt, int walkSteps,
+                                                                              int refillMin)
 {
     __shared__ WalkShared sh;
     const unsigned FULL = 0xffffffffu;
@@ -297,15 +300,13 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     wr.par = 0;
     const KdBlock* blocks = nullptr;  // the current mesh
     const uint32_t* leafTris = nullptr;
-    const TriTest* tris = nullptr;
+    const TriF32* tris = nullptr;
     bool backface = false;
     int meshIdx = -1;
     uint32_t cur = HXR_POP, leafCnt = 0;
-    float tmin = 0, tmax = 0, tbest = 0;
+    float tmin = 0, tmax = 0, tbest = 0, err = 0, occ = 0;
     int sp = 0;
-    double bestG = 0;
-    int bestTri = -1;
-    uint32_t taskRay = 0, taskNode = 0;
+    uint32_t taskIdx = 0, taskRay = 0;
     TravCounters local = {0, 0, 0, 0};
 
     auto push = [&](const WalkEnt& e) {
@@ -317,12 +318,6 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             return;  // unreachable: the build caps the depth at HXR_KD_MAX_DEPTH (<= 1.5 pushes per level)
         }
         sp++;
-    };
-    auto my_ray = [&]() {
-        Ray t;
-        t.o = mk3(sh.ray[0][tid], sh.ray[1][tid], sh.ray[2][tid]);
-        t.d = mk3(sh.ray[3][tid], sh.ray[4][tid], sh.ray[5][tid]);
-        return t;
     };
 
     for (;;) {
@@ -338,40 +333,28 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             if (!active) {
                 const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
                 if (k < n) {
-                    const MeshTask task = ts.tasks[k];
-                    taskRay = task.ray;
-                    taskNode = task.node;
-                    const hxr_node& nd = sc.nodes[taskNode];
-                    const int mi = sc.geoms[nd.geom].a;
-                    const DMesh& M = sc.meshes[mi];
-                    Ray t;
-                    double limit;
-                    bool skip = false;
-                    if (SHADOW) {
-                        double D;
-                        const Ray wray = shadow_ray(shadows[taskRay], D);
-                        t = object_ray(nd, wray);
-                        limit = gamma_limit_for(nd, t, D);
-                        skip = ts.occluded[taskRay] != 0;
-                    } else {
-                        t = object_ray(nd, task_ray(rays[taskRay]));
-                        limit = gamma_limit_for(nd, t, ts.pre[taskRay].dist);
-                    }
-                    double t0, t1;
-                    if (!skip && mesh_slab(M, t, limit, t0, t1)) {
-                        meshIdx = mi;
+                    const uint4* tp = reinterpret_cast<const uint4*>(ts.tasks + k);
+                    const uint4 w0 = __ldg(tp), w1 = __ldg(tp + 1), w2 = __ldg(tp + 2), w3 = __ldg(tp + 3);
+                    taskRay = w0.x;
+                    if (!(SHADOW && ts.occluded[taskRay])) {
+                        taskIdx = k;
+                        const float ox = __uint_as_float(w0.z), oy = __uint_as_float(w0.w), oz = __uint_as_float(w1.x);
+                        const float dx = __uint_as_float(w1.y), dy = __uint_as_float(w1.z), dz = __uint_as_float(w1.w);
+                        wr = walk_ray_f(ox, oy, oz, dx, dy, dz);
+                        sh.ray[0][tid] = ox; sh.ray[1][tid] = oy; sh.ray[2][tid] = oz;
+                        sh.ray[3][tid] = dx; sh.ray[4][tid] = dy; sh.ray[5][tid] = dz;
+                        tmin = __uint_as_float(w2.x);
+                        tmax = __uint_as_float(w2.y);
+                        tbest = __uint_as_float(w2.z);
+                        occ = __uint_as_float(w2.w);
+                        err = __uint_as_float(w3.x);
+                        meshIdx = (int)w3.y;
+                        sh.tb[tid] = __float_as_uint(tbest);
+                        const DMesh& M = sc.meshes[meshIdx];
                         blocks = M.blocks;
                         leafTris = M.leaf_tris;
-                        tris = M.tri_test;
+                        tris = M.tri_f32;
                         backface = M.backface != 0;
-                        sh.ray[0][tid] = t.o.x; sh.ray[1][tid] = t.o.y; sh.ray[2][tid] = t.o.z;
-                        sh.ray[3][tid] = t.d.x; sh.ray[4][tid] = t.d.y; sh.ray[5][tid] = t.d.z;
-                        wr = walk_ray(t);
-                        tmin = f32_below(t0);
-                        tmax = f32_above(t1);
-                        tbest = f32_above(limit);
-                        bestG = limit;
-                        bestTri = -1;
                         sp = 0;
                         cur = 0;
                         active = true;
@@ -390,18 +373,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             const bool stepping = active && !(cur >> 31);
             if (stepping && cur == HXR_POP) {
                 if (sp == 0) {
-                    // nothing left: this task is done
-                    active = false;
-                    if (!SHADOW && bestTri >= 0) {
-                        const hxr_node& nd = sc.nodes[taskNode];
-                        const Ray t = my_ray();
-                        const d3 ipw = mul_vm(t.o + bestG * t.d, nd.T.m) + ld3(nd.T.offset);
-                        MeshRes r;
-                        r.dist = distance3(ld3(rays[taskRay].o), ipw);
-                        r.tri = bestTri;
-                        r.node = (int32_t)taskNode;
-                        ts.res[(size_t)sc.node_slot[taskNode] * ts.res_stride + taskRay] = r;
-                    }
+                    active = false;  // nothing left: this task is done (its hits are in the pair list)
                 } else {
                     sp--;
                     WalkEnt e;
@@ -443,7 +415,6 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         const uint32_t total = __shfl_sync(FULL, incl, 31);
         const uint32_t excl = incl - cntMine;
         const uint32_t myFirst = (cur & ~HXR_KD_LEAF) + 1u;
-        bool ownerHit = false;
         for (uint32_t base = 0; base < total; base += 32u) {
             const uint32_t pair = base + lane;
             int o = 0;  // owner of this pair: the first lane whose inclusive prefix exceeds it
@@ -455,54 +426,55 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             const uint32_t oExcl = __shfl_sync(FULL, excl, o);
             const uint32_t oFirst = __shfl_sync(FULL, myFirst, o);
             const int oMesh = __shfl_sync(FULL, meshIdx, o);
-            double g = __shfl_sync(FULL, bestG, o);  // snapshot of the owner's best (prunes; the merge below decides)
-            const int bt = __shfl_sync(FULL, bestTri, o);
-            bool hit = false;
+            const float oErr = __shfl_sync(FULL, err, o);
+            const uint32_t oTask = __shfl_sync(FULL, taskIdx, o);
+            const float oOcc = SHADOW ? __shfl_sync(FULL, occ, o) : 0.0f;
+            bool emit = false;
             uint32_t ti = 0;
             if (pair < total) {
                 const uint32_t* lt = leafTris;
-                const TriTest* tt = tris;
+                const TriF32* tt = tris;
                 bool bf = backface;
                 if (oMesh != meshIdx) {
                     const DMesh& M = sc.meshes[oMesh];
-                    lt = M.leaf_tris; tt = M.tri_test; bf = M.backface != 0;
+                    lt = M.leaf_tris; tt = M.tri_f32; bf = M.backface != 0;
                 }
                 ti = __ldg(lt + oFirst + (pair - oExcl));
                 const unsigned ot = warpBase | (unsigned)o;
-                Ray t;
-                t.o = mk3(sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot]);
-                t.d = mk3(sh.ray[3][ot], sh.ray[4][ot], sh.ray[5][ot]);
-                double gamma, l2, l3;
-                hit = tri_core(tt, bf, t, ti, g, bt, gamma, l2, l3);
-                g = gamma;
+                const float oBest = __uint_as_float(sh.tb[ot]);  // the freshest bound (other lanes may have lowered it this round)
+                float ghi;
+                const int cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[3][ot], sh.ray[4][ot], sh.ray[5][ot],
+                                           oErr, oBest, ghi);
+                if (cls == HXR_TF_CERTAIN) {
+                    if (SHADOW && ghi < oOcc) atomicMin(&sh.tb[ot], 0u);  // certainly blocked: no exact test needed
+                    else { atomicMin(&sh.tb[ot], __float_as_uint(ghi)); emit = true; }
+                } else if (cls == HXR_TF_MAYBE) {
+                    emit = true;
+                }
             }
-            unsigned hm = __ballot_sync(FULL, hit);
-            while (hm) {
-                const int w = __ffs(hm) - 1;
-                hm &= hm - 1;
-                const int ow = __shfl_sync(FULL, o, w);
-                const double gw = __shfl_sync(FULL, g, w);
-                const int tw = (int)__shfl_sync(FULL, ti, w);
-                if ((int)lane == ow && (gw < bestG || (gw == bestG && tw > bestTri))) { bestG = gw; bestTri = tw; ownerHit = true; }
+            // append the surviving pairs to the confirmation list, one atomic per warp
+            const unsigned em = __ballot_sync(FULL, emit);
+            if (em) {
+                const int leader = __ffs(em) - 1;
+                uint32_t pb = 0;
+                if ((int)lane == leader) pb = atomicAdd(ts.pair_count, (uint32_t)__popc(em));
+                pb = __shfl_sync(FULL, pb, leader);
+                if (emit) {
+                    const uint32_t k = pb + __popc(em & ((1u << lane) - 1u));
+                    if (k < ts.pair_cap) { PairRec pr; pr.task = oTask; pr.tri = ti; ts.pairs[k] = pr; }
+                    else atomicExch(ts.overflow, 1u);
+                }
             }
         }
+        __syncwarp();
         if (hasLeaf) {
             if (COUNT) { local.kd_leaves++; local.tri_tests += leafCnt; }
             cur = HXR_POP;
-            if (ownerHit) {
-                tbest = f32_above(bestG);
-                if (SHADOW) {
-                    // the exact test of visible(): world distance of the hit against |AB|
-                    double D;
-                    const Ray wray = shadow_ray(shadows[taskRay], D);
-                    const hxr_node& nd = sc.nodes[taskNode];
-                    const Ray t = my_ray();
-                    const d3 ipw = mul_vm(t.o + bestG * t.d, nd.T.m) + ld3(nd.T.offset);
-                    if (distance3(wray.o, ipw) < D) {
-                        ts.occluded[taskRay] = 1;
-                        active = false;
-                    }
-                }
+            const uint32_t tb = sh.tb[tid];
+            tbest = __uint_as_float(tb);
+            if (SHADOW && tb == 0u) {
+                ts.occluded[taskRay] = 1;
+                active = false;
             }
         }
     }
@@ -512,6 +484,26 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         atomicAdd(&cnt->tri_tests, local.tri_tests);
         atomicAdd(&cnt->mesh_queries, local.mesh_queries);
     }
+}
+
+// the exact test of the pairs the walk left undecided (one thread per pair; the count lives on the device)
+__global__ void __launch_bounds__(128) k_confirm_closest_a(DScene sc, const RayTask* __restrict__ q, TraceScratch ts)
+{
+    const uint32_t n = min(*ts.pair_count, ts.pair_cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) confirm_closest_a_item(sc, q, i, ts);
+}
+__global__ void __launch_bounds__(256) k_confirm_closest_b(DScene sc, TraceScratch ts)
+{
+    const uint32_t n = min(*ts.pair_count, ts.pair_cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) confirm_closest_b_item(sc, i, ts);
+}
+__global__ void __launch_bounds__(128) k_confirm_shadow(DScene sc, const ShadowTask* __restrict__ shadows, TraceScratch ts)
+{
+    const uint32_t n = min(*ts.pair_count, ts.pair_cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) confirm_shadow_item(sc, shadows, i, ts);
 }
 
 __global__ void __launch_bounds__(HXR_SHADE_BLOCK) k_shade(DScene sc, FrameParams fp, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count,
@@ -585,23 +577,30 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
                   TravCounters* cnt)
 {
     ProfScope ps(PROF_TRACE_CLOSEST);
-    g_launches[PROF_TRACE_CLOSEST] += 2;
     static int gridPlain = 0, gridCount = 0;
     cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
+    cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
     const uint32_t nb = stage_grid(q_cap);
-    if (cnt) {
-        if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
-        k_setup_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, cnt);
-        if (sc.n_big) k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, cnt, g_walkSteps, g_refillMin);
-        k_finalize_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
-    } else {
-        if (!gridPlain) gridPlain = walk_grid(k_walk<false, false>);
-        k_setup_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
-        if (sc.n_big) k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, q, nullptr, ts, nullptr, g_walkSteps, g_refillMin);
-        k_finalize_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
+    int launches = 2;
+    if (cnt) k_setup_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, cnt);
+    else k_setup_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
+    if (sc.n_big) {
+        if (cnt) {
+            if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
+            k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin);
+        } else {
+            if (!gridPlain) gridPlain = walk_grid(k_walk<false, false>);
+            k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin);
+        }
+        k_confirm_closest_a<<<nb, 128, 0, g_stream>>>(sc, q, ts);
+        k_confirm_closest_b<<<nb, 256, 0, g_stream>>>(sc, ts);
+        launches += 3;
     }
-    return sc.n_big ? 3 : 2;
+    if (cnt) k_finalize_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
+    else k_finalize_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
+    g_launches[PROF_TRACE_CLOSEST] += launches - 1;
+    return launches;
 }
 
 int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits, uint32_t begin,
@@ -618,22 +617,27 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
                  TravCounters* cnt, unsigned long long* total)
 {
     ProfScope ps(PROF_TRACE_SHADOW);
-    g_launches[PROF_TRACE_SHADOW] += 2;
     static int gridPlain = 0, gridCount = 0;
     cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
+    cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
     const uint32_t nb = stage_grid(cap);
     int launches = 1;
-    if (cnt) {
-        if (!gridCount) gridCount = walk_grid(k_walk<true, true>);
-        k_setup_shadow<true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
-        if (sc.n_big) { k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, cnt, g_walkSteps, g_refillMin); launches++; }
-    } else {
-        if (!gridPlain) gridPlain = walk_grid(k_walk<true, false>);
-        k_setup_shadow<false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
-        if (sc.n_big) { k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, nullptr, shadow, ts, nullptr, g_walkSteps, g_refillMin); launches++; }
+    if (cnt) k_setup_shadow<true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
+    else k_setup_shadow<false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
+    if (sc.n_big) {
+        if (cnt) {
+            if (!gridCount) gridCount = walk_grid(k_walk<true, true>);
+            k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin);
+        } else {
+            if (!gridPlain) gridPlain = walk_grid(k_walk<true, false>);
+            k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin);
+        }
+        k_confirm_shadow<<<nb, 128, 0, g_stream>>>(sc, shadow, ts);
+        launches += 2;
     }
     if (accum) { k_accum_shadow<<<nb, 256, 0, g_stream>>>(shadow, count, cap, ts, accum); launches++; }
+    g_launches[PROF_TRACE_SHADOW] += launches - 1;
     return launches;
 }
 

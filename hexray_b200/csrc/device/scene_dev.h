@@ -5,6 +5,7 @@
 //   KdBlock  32 B  one L2 sector = TWO levels of the KD-tree (a node and both its children): one fetch
 //                  (two 128-bit loads) decides up to four grandchildren; leaves are not nodes at all but
 //                  tagged references into leaf_tris
+//   TriF32   48 B  float copy of TriTest: what the walk's conservative triangle filter reads (3 x 128-bit loads)
 //   TriTest  96 B  the four vectors the reference's triangle test reads (A, AB, AC, AB^AC),
 //                  in double so the test is the reference's arithmetic (src/mesh.cpp:178-196)
 //   TriAttr  96 B  read once per ray for the winning triangle (normals/uv indices, dNdx/dNdy)
@@ -44,6 +45,10 @@ struct alignas(16) TriTest {
     double A[3], AB[3], AC[3], N[3];
 };
 
+struct alignas(16) TriF32 {  // 48 B: the same four vectors rounded to float, for the walk's triangle filter (isect.h: tri_filter)
+    float A[3], AB[3], AC[3], N[3];
+};
+
 struct TriAttr {
     int32_t n[3], t[3];
     double gnormal[3], dNdx[3], dNdy[3];
@@ -53,12 +58,15 @@ struct DMesh {
     const KdBlock* blocks;
     const uint32_t* leaf_tris;
     const TriTest* tri_test;
+    const TriF32* tri_f32;
     const TriAttr* tri_attr;
     const double* normals;
     const double* uvs;
     double bbmin[3], bbmax[3];
     int32_t faceted, backface;
     int32_t n_tris;
+    float abs_max;  // largest |coordinate| of the mesh box (error bound of the float filter)
+    int32_t pad;
     int32_t brute;  // test all triangles in index order (tiny meshes, or HXR_CFG_BRUTE_FORCE_MESHES) instead of walking the tree
 };
 

@@ -9,7 +9,7 @@
 
 namespace hxr {
 
-enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_OVERFLOW = 3, C_HEAD_A = 4, C_HEAD_B = 5, C_AA = 6, C_TASKS = 7, C_NCOUNTERS = 16 };
+enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_OVERFLOW = 3, C_HEAD_A = 4, C_HEAD_B = 5, C_AA = 6, C_TASKS = 7, C_PAIRS = 8, C_NCOUNTERS = 16 };
 
 Renderer::~Renderer()
 {
@@ -21,6 +21,8 @@ Renderer::~Renderer()
     dev::free_(m_trav);
     dev::free_(m_pre);
     dev::free_(m_tasks);
+    dev::free_(m_pairs);
+    dev::free_(m_pairGamma);
     dev::free_(m_res);
     dev::free_(m_occluded);
     dev::free_(m_aaList);
@@ -151,6 +153,7 @@ int Renderer::uploadScene(const hxr_scene* sp)
         host::buildKdTree(m, host::KdBuildParams(), kd);
         std::vector<TriTest> tt(m.n_triangles);
         std::vector<TriAttr> ta(m.n_triangles);
+        std::vector<TriF32> tf(m.n_triangles);
         for (int t = 0; t < m.n_triangles; t++) {
             const hxr_triangle& T = m.triangles[t];
             for (int k = 0; k < 3; k++) {
@@ -158,6 +161,10 @@ int Renderer::uploadScene(const hxr_scene* sp)
                 tt[t].AB[k] = T.ab[k];
                 tt[t].AC[k] = T.ac[k];
                 tt[t].N[k] = T.ab_cross_ac[k];
+                tf[t].A[k] = (float)tt[t].A[k];
+                tf[t].AB[k] = (float)tt[t].AB[k];
+                tf[t].AC[k] = (float)tt[t].AC[k];
+                tf[t].N[k] = (float)tt[t].N[k];
                 ta[t].n[k] = T.n[k];
                 ta[t].t[k] = T.t[k];
                 ta[t].gnormal[k] = T.gnormal[k];
@@ -170,11 +177,18 @@ int Renderer::uploadScene(const hxr_scene* sp)
         d.blocks = uploadArray(kd.blocks.data(), kd.blocks.size());
         d.leaf_tris = uploadArray(kd.leafTris.data(), kd.leafTris.size());
         d.tri_test = uploadArray(tt.data(), tt.size());
+        d.tri_f32 = uploadArray(tf.data(), tf.size());
         d.tri_attr = uploadArray(ta.data(), ta.size());
         d.normals = uploadArray(m.normals, (size_t)m.n_normals * 3);
         d.uvs = uploadArray(m.uvs, (size_t)m.n_uvs * 3);
-        if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_attr || !d.normals || !d.uvs) return oom();
-        for (int k = 0; k < 3; k++) { d.bbmin[k] = m.bbox_min[k]; d.bbmax[k] = m.bbox_max[k]; }
+        if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_f32 || !d.tri_attr || !d.normals || !d.uvs) return oom();
+        double amax = 0;
+        for (int k = 0; k < 3; k++) {
+            d.bbmin[k] = m.bbox_min[k];
+            d.bbmax[k] = m.bbox_max[k];
+            amax = std::max(amax, std::max(std::fabs(m.bbox_min[k]), std::fabs(m.bbox_max[k])));
+        }
+        d.abs_max = std::nextafter((float)amax, INFINITY);
         d.faceted = m.faceted;
         d.backface = m.backface_culling;
         d.n_tris = m.n_triangles;
@@ -184,7 +198,7 @@ int Renderer::uploadScene(const hxr_scene* sp)
         ai.leaves = kd.leaves;
         ai.tri_refs = kd.leafTris.size();
         ai.bytes_nodes = kd.blocks.size() * sizeof(KdBlock);
-        ai.bytes_tris = kd.leafTris.size() * sizeof(uint32_t) + tt.size() * sizeof(TriTest);
+        ai.bytes_tris = kd.leafTris.size() * sizeof(uint32_t) + tf.size() * sizeof(TriF32) + tt.size() * sizeof(TriTest);
         ai.max_depth = kd.maxDepth;
         ai.n_triangles = (uint32_t)m.n_triangles;
         ai.build_ms = kd.buildMs;
@@ -299,13 +313,19 @@ bool Renderer::ensureQueues()
     dev::free_(m_shadow); m_shadow = nullptr;
     dev::free_(m_pre); m_pre = nullptr;
     dev::free_(m_tasks); m_tasks = nullptr;
+    dev::free_(m_pairs); m_pairs = nullptr;
+    dev::free_(m_pairGamma); m_pairGamma = nullptr;
     dev::free_(m_res); m_res = nullptr;
     dev::free_(m_occluded); m_occluded = nullptr;
     m_cap = cap;
     m_shadowCap = shadowCap;
     m_taskCap = taskCap;
     m_pre = (RayPre*)dev::alloc((size_t)cap * sizeof(RayPre));
-    m_tasks = (MeshTask*)dev::alloc((size_t)taskCap * sizeof(MeshTask));
+    m_tasks = (WalkTask*)dev::alloc((size_t)taskCap * sizeof(WalkTask));
+    // (task, triangle) pairs the FP32 filter leaves for the exact test: about one per task (the hit itself) plus near misses
+    m_pairCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)taskCap * 2 + 4096);
+    m_pairs = (PairRec*)dev::alloc((size_t)m_pairCap * sizeof(PairRec));
+    m_pairGamma = (double*)dev::alloc((size_t)m_pairCap * sizeof(double));
     m_res = (MeshRes*)dev::alloc((size_t)cap * std::max(1, m_nBig) * sizeof(MeshRes));
     m_occluded = (uint8_t*)dev::alloc((size_t)shadowCap);
     for (int i = 0; i < 2; i++) m_q[i] = (RayTask*)dev::alloc((size_t)cap * sizeof(RayTask));
@@ -313,7 +333,7 @@ bool Renderer::ensureQueues()
     m_shadow = (ShadowTask*)dev::alloc((size_t)shadowCap * sizeof(ShadowTask));
     if (!m_counters) m_counters = (uint32_t*)dev::alloc(C_NCOUNTERS * sizeof(uint32_t));
     if (!m_trav) m_trav = (TravCounters*)dev::alloc(sizeof(TravCounters) + 64);
-    if (!m_q[0] || !m_q[1] || !m_hits || !m_shadow || !m_counters || !m_trav || !m_pre || !m_tasks || !m_res || !m_occluded) {
+    if (!m_q[0] || !m_q[1] || !m_hits || !m_shadow || !m_counters || !m_trav || !m_pre || !m_tasks || !m_res || !m_occluded || !m_pairs || !m_pairGamma) {
         m_err = std::string("queue allocation failed: ") + dev::last_error();
         return false;
     }
@@ -333,6 +353,11 @@ TraceScratch Renderer::scratch(uint32_t headCounter) const
     ts.res_stride = m_cap;
     ts.occluded = m_occluded;
     ts.head = m_counters + headCounter;
+    ts.pairs = m_pairs;
+    ts.pair_gamma = m_pairGamma;
+    ts.pair_count = m_counters + C_PAIRS;
+    ts.pair_cap = m_pairCap;
+    ts.overflow = m_counters + C_OVERFLOW;
     return ts;
 }
 
@@ -602,8 +627,10 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
         for (uint32_t i = 0; i < m; i++) tasks[i] = taskFromRay(rays[first + i], i);
         dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
         dev::set_u32(m_counters + C_Q0, m);
+        dev::set_u32(m_counters + C_OVERFLOW, 0);
         dev::trace_closest(m_scene, m_q[0], m_counters + C_Q0, m_cap, m_hits, scratch(C_HEAD_A), nullptr);
         if (!dev::download(recs.data(), m_hits, (size_t)m * sizeof(HitRec))) return fail(HXR_ERR_CUDA, dev::last_error());
+        if (readCount(m_counters + C_OVERFLOW)) return fail(HXR_ERR_OVERFLOW, "trace_closest: traversal scratch overflow; raise hxr_config.queue_capacity");
         for (uint32_t i = 0; i < m; i++) {
             const HitRec& h = recs[i];
             hxr_hit& o = hits[first + i];
@@ -640,8 +667,10 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
         }
         dev::upload(m_shadow, tasks.data(), (size_t)m * sizeof(ShadowTask));
         dev::set_u32(m_counters + C_SHADOW, m);
+        dev::set_u32(m_counters + C_OVERFLOW, 0);
         dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, nullptr, scratch(C_HEAD_B), nullptr, nullptr);
         if (!dev::download(occ.data(), m_occluded, m)) return fail(HXR_ERR_CUDA, dev::last_error());
+        if (readCount(m_counters + C_OVERFLOW)) return fail(HXR_ERR_OVERFLOW, "trace_visible: traversal scratch overflow; raise hxr_config.queue_capacity");
         for (uint32_t i = 0; i < m; i++) out[first + i] = occ[i] ? 0 : 1;
     }
     return HXR_OK;

@@ -52,7 +52,10 @@ private:
     TravCounters* m_trav = nullptr;
     // traversal scratch (device/pipeline.h: TraceScratch)
     RayPre* m_pre = nullptr;
-    MeshTask* m_tasks = nullptr;
+    WalkTask* m_tasks = nullptr;
+    PairRec* m_pairs = nullptr;
+    double* m_pairGamma = nullptr;
+    uint32_t m_pairCap = 0;
     MeshRes* m_res = nullptr;
     uint8_t* m_occluded = nullptr;
     uint32_t m_taskCap = 0;

@@ -88,22 +88,22 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
 {
     const uint32_t n = *q_count;
     *ts.task_count = 0;
+    *ts.pair_count = 0;
     auto stage = [&](uint32_t m, auto f) {
         if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
     };
-    if (cnt) {
-        stage(n, [&](uint32_t i) { setup_closest_item<true>(sc, task_ray(q[i]), i, ts, cnt); });
-        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
-        stage(nt, [&](uint32_t k) { walk_closest_item<true>(sc, task_ray(q[ts.tasks[k].ray]), ts.tasks[k], ts, cnt); });
-        stage(n, [&](uint32_t i) { finalize_closest_item<true>(sc, task_ray(q[i]), i, ts, hits[i], cnt); });
-    } else {
-        stage(n, [&](uint32_t i) { setup_closest_item<false>(sc, task_ray(q[i]), i, ts, nullptr); });
-        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
-        stage(nt, [&](uint32_t k) { walk_closest_item<false>(sc, task_ray(q[ts.tasks[k].ray]), ts.tasks[k], ts, nullptr); });
-        stage(n, [&](uint32_t i) { finalize_closest_item<false>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
-    }
-    g_launches[PROF_TRACE_CLOSEST] += 3;
-    return 3;
+    if (cnt) stage(n, [&](uint32_t i) { setup_closest_item<true>(sc, task_ray(q[i]), i, ts, cnt); });
+    else stage(n, [&](uint32_t i) { setup_closest_item<false>(sc, task_ray(q[i]), i, ts, nullptr); });
+    const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
+    if (cnt) stage(nt, [&](uint32_t k) { walk_item<false, true>(sc, k, ts, cnt); });
+    else stage(nt, [&](uint32_t k) { walk_item<false, false>(sc, k, ts, nullptr); });
+    const uint32_t np = std::min(*ts.pair_count, ts.pair_cap);
+    stage(np, [&](uint32_t i) { confirm_closest_a_item(sc, q, i, ts); });
+    stage(np, [&](uint32_t i) { confirm_closest_b_item(sc, i, ts); });
+    if (cnt) stage(n, [&](uint32_t i) { finalize_closest_item<true>(sc, task_ray(q[i]), i, ts, hits[i], cnt); });
+    else stage(n, [&](uint32_t i) { finalize_closest_item<false>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
+    g_launches[PROF_TRACE_CLOSEST] += 5;
+    return 5;
 }
 
 int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits, uint32_t begin,
@@ -125,22 +125,21 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
 {
     const uint32_t n = std::min(*count, cap);
     *ts.task_count = 0;
+    *ts.pair_count = 0;
     auto stage = [&](uint32_t m, auto f) {
         if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
     };
-    if (cnt) {
-        stage(n, [&](uint32_t i) { setup_shadow_item<true>(sc, shadow[i], i, ts, cnt); });
-        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
-        stage(nt, [&](uint32_t k) { walk_shadow_item<true>(sc, shadow[ts.tasks[k].ray], ts.tasks[k], ts, cnt); });
-    } else {
-        stage(n, [&](uint32_t i) { setup_shadow_item<false>(sc, shadow[i], i, ts, nullptr); });
-        const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
-        stage(nt, [&](uint32_t k) { walk_shadow_item<false>(sc, shadow[ts.tasks[k].ray], ts.tasks[k], ts, nullptr); });
-    }
+    if (cnt) stage(n, [&](uint32_t i) { setup_shadow_item<true>(sc, shadow[i], i, ts, cnt); });
+    else stage(n, [&](uint32_t i) { setup_shadow_item<false>(sc, shadow[i], i, ts, nullptr); });
+    const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
+    if (cnt) stage(nt, [&](uint32_t k) { walk_item<true, true>(sc, k, ts, cnt); });
+    else stage(nt, [&](uint32_t k) { walk_item<true, false>(sc, k, ts, nullptr); });
+    const uint32_t np = std::min(*ts.pair_count, ts.pair_cap);
+    stage(np, [&](uint32_t i) { confirm_shadow_item(sc, shadow, i, ts); });
     if (accum) stage(n, [&](uint32_t i) { accumulate_shadow_item(shadow[i], i, ts, accum); });
     if (total) *total += n;
-    g_launches[PROF_TRACE_SHADOW] += 3;
-    return 3;
+    g_launches[PROF_TRACE_SHADOW] += 4;
+    return 4;
 }
 
 int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
