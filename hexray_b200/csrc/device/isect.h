@@ -403,6 +403,8 @@ struct WalkRay {  // the object-space ray as the walk sees it
     float ox, oy, oz;  // origin, rounded to nearest
     float ix, iy, iz;  // 1 / direction (0 on parallel axes)
     uint32_t par;      // bit a: |d[a]| < 1e-18, treated as parallel to the planes of axis a
+    HXR_HD float o(uint32_t axis) const { return axis == 0 ? ox : (axis == 1 ? oy : oz); }
+    HXR_HD float inv(uint32_t axis) const { return axis == 0 ? ix : (axis == 1 ? iy : iz); }
 };
 HXR_HD WalkRay walk_ray_f(float ox, float oy, float oz, float dx, float dy, float dz)
 {
@@ -420,10 +422,13 @@ struct PlaneX {  // conservative range [tlo, thi] of the parameter at which the 
     float tlo, thi;
     bool leftFirst;  // the ray is on the left (coordinate <= split) before the crossing
 };
-HXR_HD PlaneX plane_cross(float s, uint32_t axis, const WalkRay& w, float tmaxSeg)
+// RAY provides o(axis), inv(axis) and par (WalkRay above; the kernel reads them from shared memory by axis).
+// PAR = false skips the parallel-axis case (the caller has checked par == 0).
+template <bool PAR, class RAY>
+HXR_HD PlaneX plane_cross(float s, uint32_t axis, const RAY& w, float tmaxSeg)
 {
-    const float o = axis == 0 ? w.ox : (axis == 1 ? w.oy : w.oz);
-    const float inv = axis == 0 ? w.ix : (axis == 1 ? w.iy : w.iz);
+    const float o = w.o(axis);
+    const float inv = w.inv(axis);
     PlaneX r;
     // tpl = (s - o) / d in float: relative error <= 2^-22 (o and d rounded from double, one subtraction, one
     // reciprocal, one product) plus |o| 2^-24 |inv| from the rounding of o; both bounds doubled.
@@ -432,7 +437,7 @@ HXR_HD PlaneX plane_cross(float s, uint32_t axis, const WalkRay& w, float tmaxSe
     r.tlo = tpl - e;
     r.thi = tpl + e;
     r.leftFirst = inv > 0;
-    if ((w.par >> axis) & 1u) {
+    if (PAR && ((w.par >> axis) & 1u)) {
         // parallel to the plane for every parameter that matters: pick sides by position
         const float tol = fmaf(fabsf(o), 2.38418579e-7f, 1e-18f * tmaxSeg) + 1e-30f;
         r.leftFirst = true;
@@ -449,17 +454,18 @@ struct WalkEnt {  // a subtree (block index or leaf reference) and the parameter
 HXR_HD bool ent_valid(const WalkEnt& e) { return e.lo <= e.hi && e.ref != HXR_KD_EMPTY; }
 
 // One block = a node and both its children: up to four grandchildren e0..e3, FRONT TO BACK (test ent_valid on each).
-HXR_HD void block_step(const KdBlock& B, const WalkRay& w, float tmin, float tmax, float tbest, WalkEnt& e0, WalkEnt& e1, WalkEnt& e2, WalkEnt& e3)
+template <bool PAR, class RAY>
+HXR_HD void block_step_t(const KdBlock& B, const RAY& w, float tmin, float tmax, float tbest, WalkEnt& e0, WalkEnt& e1, WalkEnt& e2, WalkEnt& e3)
 {
     const uint32_t a0 = B.meta & 3u, aL = (B.meta >> 2) & 3u, aR = (B.meta >> 4) & 3u;
     const float tE = fminf(tmax, tbest);
-    const PlaneX p0 = plane_cross(B.split[0], a0, w, tmax);
+    const PlaneX p0 = plane_cross<PAR>(B.split[0], a0, w, tmax);
     const float nHi = fminf(tE, p0.thi), fLo = fmaxf(tmin, p0.tlo);
     const float lLo = p0.leftFirst ? tmin : fLo, lHi = p0.leftFirst ? nHi : tE;
     const float rLo = p0.leftFirst ? fLo : tmin, rHi = p0.leftFirst ? tE : nHi;
     WalkEnt l0, l1, r0, r1;
     {
-        const PlaneX pl = plane_cross(B.split[1], aL, w, tmax);
+        const PlaneX pl = plane_cross<PAR>(B.split[1], aL, w, tmax);
         const bool leaf = aL == 3u;
         const bool lf = pl.leftFirst || leaf;
         l0.ref = lf ? B.ref[0] : B.ref[1];
@@ -468,7 +474,7 @@ HXR_HD void block_step(const KdBlock& B, const WalkRay& w, float tmin, float tma
         l1.lo = fmaxf(lLo, pl.tlo); l1.hi = lHi;
     }
     {
-        const PlaneX pr = plane_cross(B.split[2], aR, w, tmax);
+        const PlaneX pr = plane_cross<PAR>(B.split[2], aR, w, tmax);
         const bool leaf = aR == 3u;
         const bool lf = pr.leftFirst || leaf;
         r0.ref = lf ? B.ref[2] : B.ref[3];
@@ -477,6 +483,12 @@ HXR_HD void block_step(const KdBlock& B, const WalkRay& w, float tmin, float tma
         r1.lo = fmaxf(rLo, pr.tlo); r1.hi = rHi;
     }
     e0 = p0.leftFirst ? l0 : r0; e1 = p0.leftFirst ? l1 : r1; e2 = p0.leftFirst ? r0 : l0; e3 = p0.leftFirst ? r1 : l1;
+}
+template <class RAY>
+HXR_HD void block_step(const KdBlock& B, const RAY& w, float tmin, float tmax, float tbest, WalkEnt& e0, WalkEnt& e1, WalkEnt& e2, WalkEnt& e3)
+{
+    if (w.par) block_step_t<true>(B, w, tmin, tmax, tbest, e0, e1, e2, e3);  // rare: a direction component is (almost) zero
+    else block_step_t<false>(B, w, tmin, tmax, tbest, e0, e1, e2, e3);
 }
 
 // ---- the FP32 triangle filter
@@ -765,8 +777,11 @@ HXR_HD_NOINLINE bool geom_intersect(const DScene& sc, int gi, const Ray& ray, Hi
 }
 
 // ---------------------------------------------------------------- instancing + lights
-// world_limit: world-space distance beyond which a hit cannot matter (prunes mesh traversal only)
-template <bool COUNT>
+// world_limit: world-space distance beyond which a hit cannot matter (prunes mesh traversal only).
+// SIMPLE: the scene's inline nodes are only planes, spheres, cubes and brute-force meshes (DScene::simple_inline); the
+// kernels are compiled twice so that such scenes do not carry the CSG / heightfield / tree-walk code (its stack frame
+// and registers) through every ray.
+template <bool COUNT, bool SIMPLE>
 HXR_HD bool node_intersect(const DScene& sc, const hxr_node& nd, const Ray& ray, Hit& info, double world_limit, TravCounters* cnt)
 {
     Ray t;
@@ -775,13 +790,28 @@ HXR_HD bool node_intersect(const DScene& sc, const hxr_node& nd, const Ray& ray,
     t.d = normalize_f(dl);
     t.depth = ray.depth;
     t.flags = ray.flags;
-    double gamma_limit = HXR_INF;
-    if (world_limit < HXR_INF) {
-        // world distance of the object-space point o + g*d is g * |d * m|
-        const double k = length(mul_vm(t.d, nd.T.m));
-        gamma_limit = world_limit / k * (1.0 + 1e-9) + 1e-9;
+    bool hit;
+    if (SIMPLE) {
+        const hxr_geometry& g = sc.geoms[nd.geom];
+        if (g.type == HXR_GEOM_PLANE) hit = plane_intersect(g, nd.geom, t, info);
+        else if (g.type == HXR_GEOM_SPHERE) hit = sphere_intersect(g, nd.geom, t, info);
+        else if (g.type == HXR_GEOM_CUBE) hit = cube_intersect(g, nd.geom, t, info);
+        else {
+            const DMesh& M = sc.meshes[g.a];
+            MeshBest best;
+            hit = mesh_bruteforce(M, t, HXR_INF, best);
+            if (hit) mesh_fill_hit(M, nd.geom, t, best, info);
+        }
+    } else {
+        double gamma_limit = HXR_INF;
+        if (world_limit < HXR_INF) {
+            // world distance of the object-space point o + g*d is g * |d * m|
+            const double k = length(mul_vm(t.d, nd.T.m));
+            gamma_limit = world_limit / k * (1.0 + 1e-9) + 1e-9;
+        }
+        hit = geom_intersect<0, COUNT>(sc, nd.geom, t, info, gamma_limit, cnt);
     }
-    if (!geom_intersect<0, COUNT>(sc, nd.geom, t, info, gamma_limit, cnt)) return false;
+    if (!hit) return false;
     info.ip = mul_vm(info.ip, nd.T.m) + ld3(nd.T.offset);
     info.norm = normalize_m(mul_vm(info.norm, nd.T.inv_t));
     info.dist = distance3(ray.o, info.ip);

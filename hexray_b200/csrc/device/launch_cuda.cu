@@ -210,18 +210,18 @@ __global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, 
 #define HXR_WALK_STEPS 3  /* block steps per round of the walk loop */
 #endif
 
-template <bool COUNT>
+template <bool COUNT, bool SIMPLE>
 __global__ void __launch_bounds__(128) k_setup_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
                                                        TraceScratch ts, TravCounters* cnt)
 {
     const uint32_t n = min(*q_count, cap);
     const uint32_t stride = gridDim.x * blockDim.x;
     TravCounters local = {0, 0, 0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_closest_item<COUNT>(sc, task_ray(q[i]), i, ts, &local);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_closest_item<COUNT, SIMPLE>(sc, task_ray(q[i]), i, ts, &local);
     if (COUNT && local.mesh_queries) atomicAdd(&cnt->mesh_queries, local.mesh_queries);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool SIMPLE>
 __global__ void __launch_bounds__(128) k_finalize_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
                                                           TraceScratch ts, HitRec* __restrict__ hits, TravCounters* cnt)
 {
@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(128) k_finalize_closest(DScene sc, const RayTa
     TravCounters local = {0, 0, 0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         HitRec h;
-        finalize_closest_item<COUNT>(sc, task_ray(q[i]), i, ts, h, &local);
+        finalize_closest_item<COUNT, SIMPLE>(sc, task_ray(q[i]), i, ts, h, &local);
         hits[i] = h;
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, bool SIMPLE>
 __global__ void __launch_bounds__(128) k_setup_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap,
                                                       TraceScratch ts, TravCounters* cnt, unsigned long long* total)
 {
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128) k_setup_shadow(DScene sc, const ShadowTas
     const uint32_t stride = gridDim.x * blockDim.x;
     if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(total, (unsigned long long)n);
     TravCounters local = {0, 0, 0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_shadow_item<COUNT>(sc, shadow[i], i, ts, &local);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_shadow_item<COUNT, SIMPLE>(sc, shadow[i], i, ts, &local);
 }
 
 __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap, TraceScratch ts,
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
 #define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
 
 struct WalkShared {
-    float ray[6][HXR_WALK_BLOCK];
+    float ray[11][HXR_WALK_BLOCK];  // rows 0-2 origin, 4-6 1/direction, 8-10 direction (3 and 7: zero, read for leaf "axis 3")
     uint32_t tb[HXR_WALK_BLOCK];  // bits of the (non-negative) float bound; 0 = shadow ray certainly blocked
     uint32_t stRef[HXR_SSTACK][HXR_WALK_BLOCK];
     float stMin[HXR_SSTACK][HXR_WALK_BLOCK];
@@ -295,9 +295,16 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     uint32_t ovRef[HXR_KD_STACK - HXR_SSTACK];
     float ovMin[HXR_KD_STACK - HXR_SSTACK], ovMax[HXR_KD_STACK - HXR_SSTACK];
     bool active = false, drained = false;
-    WalkRay wr;
-    wr.ox = wr.oy = wr.oz = wr.ix = wr.iy = wr.iz = 0;
+    struct SharedRay {  // o(axis) / inv(axis) straight from this lane's shared-memory column: no selects, no registers
+        const float* col;
+        uint32_t par;
+        __device__ __forceinline__ float o(uint32_t axis) const { return col[axis * HXR_WALK_BLOCK]; }
+        __device__ __forceinline__ float inv(uint32_t axis) const { return col[(4 + axis) * HXR_WALK_BLOCK]; }
+    } wr;
+    wr.col = &sh.ray[0][tid];
     wr.par = 0;
+    sh.ray[3][tid] = 0.0f;
+    sh.ray[7][tid] = 0.0f;
     const KdBlock* blocks = nullptr;  // the current mesh
     const uint32_t* leafTris = nullptr;
     const TriF32* tris = nullptr;
@@ -340,9 +347,11 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         taskIdx = k;
                         const float ox = __uint_as_float(w0.z), oy = __uint_as_float(w0.w), oz = __uint_as_float(w1.x);
                         const float dx = __uint_as_float(w1.y), dy = __uint_as_float(w1.z), dz = __uint_as_float(w1.w);
-                        wr = walk_ray_f(ox, oy, oz, dx, dy, dz);
+                        const WalkRay w = walk_ray_f(ox, oy, oz, dx, dy, dz);
+                        wr.par = w.par;
                         sh.ray[0][tid] = ox; sh.ray[1][tid] = oy; sh.ray[2][tid] = oz;
-                        sh.ray[3][tid] = dx; sh.ray[4][tid] = dy; sh.ray[5][tid] = dz;
+                        sh.ray[4][tid] = w.ix; sh.ray[5][tid] = w.iy; sh.ray[6][tid] = w.iz;
+                        sh.ray[8][tid] = dx; sh.ray[9][tid] = dy; sh.ray[10][tid] = dz;
                         tmin = __uint_as_float(w2.x);
                         tmax = __uint_as_float(w2.y);
                         tbest = __uint_as_float(w2.z);
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 const unsigned ot = warpBase | (unsigned)o;
                 const float oBest = __uint_as_float(sh.tb[ot]);  // the freshest bound (other lanes may have lowered it this round)
                 float ghi;
-                const int cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[3][ot], sh.ray[4][ot], sh.ray[5][ot],
+                const int cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[8][ot], sh.ray[9][ot], sh.ray[10][ot],
                                            oErr, oBest, ghi);
                 if (cls == HXR_TF_CERTAIN) {
                     if (SHADOW && ghi < oOcc) atomicMin(&sh.tb[ot], 0u);  // certainly blocked: no exact test needed
@@ -583,8 +592,11 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
     cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
     const uint32_t nb = stage_grid(q_cap);
     int launches = 2;
-    if (cnt) k_setup_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, cnt);
-    else k_setup_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
+    // counting builds and scenes with CSG / heightfield / inline tree walks take the generic variant
+    const bool simple = sc.simple_inline && !cnt;
+    if (cnt) k_setup_closest<true, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, cnt);
+    else if (simple) k_setup_closest<false, true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
+    else k_setup_closest<false, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
     if (sc.n_big) {
         if (cnt) {
             if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
@@ -597,8 +609,9 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
         k_confirm_closest_b<<<nb, 256, 0, g_stream>>>(sc, ts);
         launches += 3;
     }
-    if (cnt) k_finalize_closest<true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
-    else k_finalize_closest<false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
+    if (cnt) k_finalize_closest<true, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
+    else if (simple) k_finalize_closest<false, true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
+    else k_finalize_closest<false, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
     g_launches[PROF_TRACE_CLOSEST] += launches - 1;
     return launches;
 }
@@ -623,8 +636,9 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
     cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
     const uint32_t nb = stage_grid(cap);
     int launches = 1;
-    if (cnt) k_setup_shadow<true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
-    else k_setup_shadow<false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
+    if (cnt) k_setup_shadow<true, false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
+    else if (sc.simple_inline) k_setup_shadow<false, true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
+    else k_setup_shadow<false, false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
     if (sc.n_big) {
         if (cnt) {
             if (!gridCount) gridCount = walk_grid(k_walk<true, true>);

@@ -98,6 +98,7 @@ struct DScene {
     // traversal kernel), -1 otherwise (analytic primitives, CSG, heightfields, meshes <= HXR_SMALL_MESH)
     const int32_t* node_slot;
     int32_t n_big;
+    int32_t simple_inline;  // every inline node is a plane, sphere, cube or brute-force mesh (selects the lean kernel variants)
     int32_t n_nodes, n_lights;
     int32_t has_env;
     int32_t env_images[6];

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <future>
 #include <thread>
 
@@ -44,6 +45,10 @@ struct Builder {
 
     explicit Builder(const hxr_mesh& m, const KdBuildParams& p) : mesh(m), P(p)
     {
+        // experiment knobs (defaults in kdtree.h)
+        if (const char* e = getenv("HXR_KD_INTERSECT_COST")) P.intersectCost = (float)atof(e);
+        if (const char* e = getenv("HXR_KD_MAX_LEAF")) P.maxLeafSize = atoi(e);
+        if (const char* e = getenv("HXR_KD_EMPTY_BONUS")) P.emptyBonus = (float)atof(e);
         const int n = m.n_triangles;
         tb.resize(n);
         for (int i = 0; i < n; i++) {

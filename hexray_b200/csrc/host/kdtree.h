@@ -21,9 +21,9 @@ struct KdTree {
 
 struct KdBuildParams {
     float traversalCost = 1.0f;
-    float intersectCost = 2.0f;
+    float intersectCost = 1.0f;  // a triangle costs the walk about one tree level: leaves are filtered 32 pairs at a time (k_walk)
     float emptyBonus = 0.2f;
-    int maxLeafSize = 4;
+    int maxLeafSize = 16;
     int maxDepth = -1;      // -1: 8 + 1.3 log2(N), capped at HXR_KD_MAX_DEPTH so the device stack cannot overflow
     int binnedAbove = 192;  // nodes with more triangles than this use 32-bin SAH, smaller ones an exact sweep
     int threads = 0;        // 0: hardware concurrency

@@ -252,6 +252,14 @@ int Renderer::uploadScene(const hxr_scene* sp)
         m_scene.node_slot = uploadArray(slot.data(), slot.size());
         if (!m_scene.node_slot) return oom();
         m_scene.n_big = m_nBig;
+        m_scene.simple_inline = 1;
+        for (int i = 0; i < s.n_nodes; i++) {
+            if (slot[i] >= 0) continue;
+            const hxr_geometry& g = s.geometries[s.nodes[i].geom];
+            const bool simple = g.type == HXR_GEOM_PLANE || g.type == HXR_GEOM_SPHERE || g.type == HXR_GEOM_CUBE ||
+                                (g.type == HXR_GEOM_MESH && dm[g.a].brute);
+            if (!simple) m_scene.simple_inline = 0;
+        }
     }
     m_scene.n_nodes = s.n_nodes;
     m_scene.n_lights = s.n_lights;

@@ -92,16 +92,19 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
     auto stage = [&](uint32_t m, auto f) {
         if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
     };
-    if (cnt) stage(n, [&](uint32_t i) { setup_closest_item<true>(sc, task_ray(q[i]), i, ts, cnt); });
-    else stage(n, [&](uint32_t i) { setup_closest_item<false>(sc, task_ray(q[i]), i, ts, nullptr); });
+    const bool simple = sc.simple_inline && !cnt;
+    if (cnt) stage(n, [&](uint32_t i) { setup_closest_item<true, false>(sc, task_ray(q[i]), i, ts, cnt); });
+    else if (simple) stage(n, [&](uint32_t i) { setup_closest_item<false, true>(sc, task_ray(q[i]), i, ts, nullptr); });
+    else stage(n, [&](uint32_t i) { setup_closest_item<false, false>(sc, task_ray(q[i]), i, ts, nullptr); });
     const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
     if (cnt) stage(nt, [&](uint32_t k) { walk_item<false, true>(sc, k, ts, cnt); });
     else stage(nt, [&](uint32_t k) { walk_item<false, false>(sc, k, ts, nullptr); });
     const uint32_t np = std::min(*ts.pair_count, ts.pair_cap);
     stage(np, [&](uint32_t i) { confirm_closest_a_item(sc, q, i, ts); });
     stage(np, [&](uint32_t i) { confirm_closest_b_item(sc, i, ts); });
-    if (cnt) stage(n, [&](uint32_t i) { finalize_closest_item<true>(sc, task_ray(q[i]), i, ts, hits[i], cnt); });
-    else stage(n, [&](uint32_t i) { finalize_closest_item<false>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
+    if (cnt) stage(n, [&](uint32_t i) { finalize_closest_item<true, false>(sc, task_ray(q[i]), i, ts, hits[i], cnt); });
+    else if (simple) stage(n, [&](uint32_t i) { finalize_closest_item<false, true>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
+    else stage(n, [&](uint32_t i) { finalize_closest_item<false, false>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
     g_launches[PROF_TRACE_CLOSEST] += 5;
     return 5;
 }
@@ -129,8 +132,9 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
     auto stage = [&](uint32_t m, auto f) {
         if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
     };
-    if (cnt) stage(n, [&](uint32_t i) { setup_shadow_item<true>(sc, shadow[i], i, ts, cnt); });
-    else stage(n, [&](uint32_t i) { setup_shadow_item<false>(sc, shadow[i], i, ts, nullptr); });
+    if (cnt) stage(n, [&](uint32_t i) { setup_shadow_item<true, false>(sc, shadow[i], i, ts, cnt); });
+    else if (sc.simple_inline) stage(n, [&](uint32_t i) { setup_shadow_item<false, true>(sc, shadow[i], i, ts, nullptr); });
+    else stage(n, [&](uint32_t i) { setup_shadow_item<false, false>(sc, shadow[i], i, ts, nullptr); });
     const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
     if (cnt) stage(nt, [&](uint32_t k) { walk_item<true, true>(sc, k, ts, cnt); });
     else stage(nt, [&](uint32_t k) { walk_item<true, false>(sc, k, ts, nullptr); });
