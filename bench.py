@@ -112,7 +112,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--ref-width", type=int, default=192, help="reference arm: bounded sample resolution")
     ap.add_argument("--ref-height", type=int, default=108)
-    ap.add_argument("--ref-spp", type=int, default=2)
+    ap.add_argument("--ref-spp", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--queue-capacity", type=int, default=16 << 20)
     return ap.parse_args()
@@ -290,8 +290,11 @@ def ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from hexray_b200 import distributed
+
     def step(i, to_host):
-        """one frame: this rank's sample passes -> (NCCL reduce) -> resolve [-> host]"""
+        """one frame: this rank's sample passes -> (NCCL reduce) -> resolve [-> host]. Returns (stats, device ms of the
+        part that runs on torch's stream: reduce + resolve + copy)."""
         if flush is not None:
             flush.zero_()
             torch.cuda.synchronize(dev)
@@ -299,8 +302,10 @@ def ours(a):
             r.set_camera(cam)  # the per-frame input of the C ABI (hxr_set_camera), host -> device
         if world == 1 and to_host:
             _, st = r.render(width=W, height=H, mode=mode, spp=spp_total, seed=i, out=host.numpy().reshape(H, W, 3))
-            return st
+            return st, 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=spp_total, seed=i, shard=(rank, world))
+        e0.record()
         if world > 1:
             dist.reduce(acc, dst=0)
             torch.cuda.synchronize(dev)  # NCCL runs on torch's stream, the resolve kernel on the library's
@@ -308,21 +313,23 @@ def ours(a):
                 r.resolve_device(acc.data_ptr(), W, H, spp_total)
         if to_host and rank == 0:
             host.copy_(acc, non_blocking=False)
+        e1.record()
         torch.cuda.synchronize(dev)
-        return st
+        return st, e0.elapsed_time(e1)
 
     def run(n, to_host, first_seed):
         rays = np.zeros(2, dtype=np.float64)
-        prof = {"trace_closest_ms": 0.0, "trace_shadow_ms": 0.0, "shade_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0,
-                "trace_closest_launches": 0, "trace_shadow_launches": 0, "kernel_launches": 0}
+        prof = {"trace_closest_ms": 0.0, "trace_shadow_ms": 0.0, "shade_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0, "walk_ms": 0.0,
+                "trace_closest_launches": 0, "trace_shadow_launches": 0, "walk_launches": 0, "kernel_launches": 0, "post_ms": 0.0}
         for i in range(n):
-            st = step(first_seed + i, to_host)
+            st, post_ms = step(first_seed + i, to_host)
             rays += (st["rays_closest"], st["rays_shadow"])
             for k in prof:
-                prof[k] += st[k]
+                prof[k] += post_ms if k == "post_ms" else st[k]
         return rays, prof
 
-    # ---- device-resident throughput ("value")
+    # ---- device-resident throughput ("value"): CUDA-event time of the frames (render on the library's stream +
+    # reduce/resolve on torch's), max over ranks; the wall clock around the same region is reported beside it
     r.set_profiling(True)
     run(a.warmup, False, 1000)
     barrier()
@@ -330,8 +337,10 @@ def ours(a):
         t0 = time.perf_counter()
         rays, prof = run(a.steps, False, 0)
         barrier()
-        dt = time.perf_counter() - t0
-    # ---- end to end through the C ABI with host buffers ("e2e")
+        dt_wall = time.perf_counter() - t0
+    dt = (prof["render_ms"] + prof["post_ms"]) * 1e-3
+    # ---- end to end through the C ABI with host buffers ("e2e"): wall clock around blocking calls that end with the
+    # frame in host memory
     run(min(a.warmup, 1), True, 2000)
     barrier()
     t0 = time.perf_counter()
@@ -355,6 +364,7 @@ def ours(a):
     rays = allsum(rays)
     rays_e = allsum(rays_e)
     dt = allmax(dt)
+    dt_wall = allmax(dt_wall)
     dt_e = allmax(dt_e)
 
     # ---- traversal counters (a separate, un-timed counting pass of the same workload at 1 spp per rank)
@@ -368,31 +378,40 @@ def ours(a):
         per_ray = {"inner": cst["kd_inner"] / max(1, n_rays_cnt), "tri": cst["tri_tests"] / max(1, n_rays_cnt),
                    "leaf": cst["kd_leaves"] / max(1, n_rays_cnt), "mesh_queries": cst["mesh_queries"] / max(1, n_rays_cnt)}
         b_ray = B_RECORD + B_INNER * per_ray["inner"] + B_TRI * per_ray["tri"] + B_LEAF * per_ray["leaf"]
-        trav_ms = prof["trace_closest_ms"] + prof["trace_shadow_ms"]
-        trav_launches = prof["trace_closest_launches"] + prof["trace_shadow_launches"]
+        walk_ms = prof["walk_ms"]
+        walk_launches = prof["walk_launches"]
         my_rays = total_rays / world  # rank 0's share (shards are equal)
-        achieved = my_rays * b_ray / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        achieved = my_rays * b_ray / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
         hbm_bound = geometry_bytes > (126 << 20)
         peak = peaks["hbm_gbs"] if hbm_bound else 23149.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "walk_traffic.json")  # written by tools/ncu_traffic.py from an `ncu --set full` capture
+        if os.path.exists(tp) and a.workload == "terrain":
+            with open(tp) as f:
+                traffic = json.load(f)
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32 walk + f64 exact tests", "data": "synthetic",
             "config": {"workload": workload_name(a), "width": W, "height": H, "spp_per_gpu": a.spp, "spp_total": spp_total,
                        "integrator": "path tracing (gi), maxTraceDepth 8", "sharding": "sample passes s %% N == rank, NCCL reduce of the sum buffer",
                        "l2": "geometry %.2f GB >> 126 MB L2" % (geometry_bytes / 1e9) if flush is None else "512 MB buffer written between timed iterations",
                        "rays_per_step": total_rays / a.steps, "setup_s": setup_s, "kd": accel},
-            "ms_per_frame": dt / a.steps * 1e3,
+            "ms_per_frame": dt / a.steps * 1e3, "wall_ms_per_step": dt_wall / a.steps * 1e3,
+            "timing": "CUDA events (render on the library's stream + reduce/resolve on torch's), max over ranks; wall clock beside it",
             "e2e": {"value": float(rays_e.sum()) / dt_e / 1e6, "unit": "Mrays/s", "ms_per_step": dt_e / a.steps * 1e3,
                     "h2d_bytes_per_step": 256, "d2h_bytes_per_step": W * H * 12},
             "gpu_launches": int(prof["kernel_launches"]),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm" if hbm_bound else "l2", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "k_trace_closest + k_trace_shadow (KD traversal)", "peak_source": peak_src if hbm_bound else "tools/microbench L2 read (profiles/microbench_r1.json)",
-                         "bytes_per_ray": b_ray, "per_ray": per_ray, "launches": int(trav_launches),
-                         "avg_launch_ms": trav_ms / max(1, trav_launches), "traversal_share_of_step": trav_ms / max(1e-9, prof["render_ms"])},
-            "kernel_ms_per_step": {k: prof[k] / a.steps for k in ("trace_closest_ms", "trace_shadow_ms", "shade_ms", "other_ms", "render_ms")},
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_source": traffic,
+                         "kernel": "k_walk (KD-tree walk: closest-hit + shadow launches)", "peak_source": peak_src if hbm_bound else "tools/microbench L2 read (profiles/microbench_r1.json)",
+                         "bytes_per_ray": b_ray, "bytes_per_launch": my_rays * b_ray / max(1, walk_launches), "per_ray": per_ray,
+                         "launches": int(walk_launches), "avg_launch_ms": walk_ms / max(1, walk_launches),
+                         "walk_share_of_step": walk_ms / max(1e-9, prof["render_ms"]),
+                         "traversal_share_of_step": (prof["trace_closest_ms"] + prof["trace_shadow_ms"]) / max(1e-9, prof["render_ms"])},
+            "kernel_ms_per_step": {k: prof[k] / a.steps for k in ("trace_closest_ms", "trace_shadow_ms", "walk_ms", "shade_ms", "other_ms", "render_ms")},
         }
         if world == 1 and not a.no_cpu_baseline:
             b = argparse.Namespace(**vars(a))

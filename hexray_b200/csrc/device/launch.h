@@ -33,7 +33,8 @@ double timer_ms(Timer*);               // blocks until the stop event has happen
 bool set_u32(uint32_t* p, uint32_t v);  // async, stream ordered
 
 // per-category device time of the launches below (CUDA events around every launch when enabled)
-enum ProfCat { PROF_TRACE_CLOSEST = 0, PROF_TRACE_SHADOW = 1, PROF_SHADE = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
+// PROF_WALK: the k_walk launches alone (they are also inside PROF_TRACE_CLOSEST / PROF_TRACE_SHADOW)
+enum ProfCat { PROF_TRACE_CLOSEST = 0, PROF_TRACE_SHADOW = 1, PROF_SHADE = 2, PROF_OTHER = 3, PROF_WALK = 4, PROF_NCAT = 5 };
 void prof_enable(bool on);
 void prof_reset();
 void prof_collect(double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);  // blocks; launches are counted even when disabled

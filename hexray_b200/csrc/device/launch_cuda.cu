@@ -34,7 +34,7 @@ static cudaStream_t g_stream = nullptr;
 static std::string g_err;
 static bool g_prof = false;
 // walk-loop tunables (uniform kernel arguments; HXR_WALK_STEPS / HXR_REFILL_MIN in the environment override the defaults)
-static int g_walkSteps = 3, g_refillMin = 8;
+static int g_walkSteps = 3, g_refillMin = 8, g_leafTrigger = 33;
 static uint64_t g_launches[PROF_NCAT];
 static std::vector<cudaEvent_t> g_evPool;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
@@ -68,6 +68,7 @@ bool init(int device, char* err, size_t errlen)
     g_device = device;
     g_sms = p.multiProcessorCount;
     if (const char* e = getenv("HXR_WALK_STEPS")) g_walkSteps = std::max(1, atoi(e));
+    if (const char* e = getenv("HXR_LEAF_TRIGGER")) g_leafTrigger = std::max(1, atoi(e));
     if (const char* e = getenv("HXR_REFILL_MIN")) g_refillMin = std::min(32, std::max(1, atoi(e)));
     if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
     return true;
@@ -286,7 +287,7 @@ struct WalkShared {
 
 template <bool SHADOW, bool COUNT>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, TraceScratch ts, TravCounters* cnt, int walkSteps,
-                                                                              int refillMin)
+                                                                              int refillMin, int leafTrigger)
 {
     __shared__ WalkShared sh;
     const unsigned FULL = 0xffffffffu;
@@ -409,7 +410,9 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 cur = c.ref; tmin = c.lo; tmax = c.hi;
             }
             if (stepping && active && (cur >> 31)) leafCnt = __ldg(leafTris + (cur & ~HXR_KD_LEAF));  // in flight while the others keep stepping
-            __syncwarp();
+            // enough leaves for full rounds of phase 2 (or nobody left to step): stop stepping early
+            const unsigned lm = __ballot_sync(FULL, active && (cur >> 31));
+            if (__popc(lm) >= leafTrigger) break;
         }
         // ---- phase 2: all (ray, triangle) pairs of the leaves held by this warp, dealt out over its 32 lanes
         const bool hasLeaf = active && (cur >> 31);
@@ -598,12 +601,15 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
     else if (simple) k_setup_closest<false, true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
     else k_setup_closest<false, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
     if (sc.n_big) {
-        if (cnt) {
-            if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
-            k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin);
-        } else {
-            if (!gridPlain) gridPlain = walk_grid(k_walk<false, false>);
-            k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin);
+        {
+            ProfScope pw(PROF_WALK);
+            if (cnt) {
+                if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
+                k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_leafTrigger);
+            } else {
+                if (!gridPlain) gridPlain = walk_grid(k_walk<false, false>);
+                k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin, g_leafTrigger);
+            }
         }
         k_confirm_closest_a<<<nb, 128, 0, g_stream>>>(sc, q, ts);
         k_confirm_closest_b<<<nb, 256, 0, g_stream>>>(sc, ts);
@@ -640,12 +646,15 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
     else if (sc.simple_inline) k_setup_shadow<false, true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
     else k_setup_shadow<false, false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
     if (sc.n_big) {
-        if (cnt) {
-            if (!gridCount) gridCount = walk_grid(k_walk<true, true>);
-            k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin);
-        } else {
-            if (!gridPlain) gridPlain = walk_grid(k_walk<true, false>);
-            k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin);
+        {
+            ProfScope pw(PROF_WALK);
+            if (cnt) {
+                if (!gridCount) gridCount = walk_grid(k_walk<true, true>);
+                k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_leafTrigger);
+            } else {
+                if (!gridPlain) gridPlain = walk_grid(k_walk<true, false>);
+                k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin, g_leafTrigger);
+            }
         }
         k_confirm_shadow<<<nb, 128, 0, g_stream>>>(sc, shadow, ts);
         launches += 2;

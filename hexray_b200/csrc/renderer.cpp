@@ -593,6 +593,8 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
         st.other_ms = ms[dev::PROF_OTHER];
         st.trace_closest_launches = ln[dev::PROF_TRACE_CLOSEST];
         st.trace_shadow_launches = ln[dev::PROF_TRACE_SHADOW];
+        st.walk_ms = ms[dev::PROF_WALK];
+        st.walk_launches = ln[dev::PROF_WALK];
     }
     if (stats) *stats = st;
     if (!dev::sync()) return fail(HXR_ERR_CUDA, dev::last_error());

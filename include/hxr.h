@@ -263,6 +263,8 @@ typedef struct hxr_stats {
     uint64_t trace_closest_launches, trace_shadow_launches;
     uint32_t spp_done;
     uint32_t aa_pixels;
+    double walk_ms;         /* device time of the KD-walk kernel launches alone (inside the two trace times above) */
+    uint64_t walk_launches;
 } hxr_stats;
 
 typedef struct hxr_ray {
