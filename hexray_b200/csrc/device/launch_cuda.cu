@@ -558,6 +558,11 @@ __global__ void k_add_into(float* dst, const float* __restrict__ src, size_t n)
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
 }
+__global__ void k_stereo_mix(float* out, const float* __restrict__ L, const float* __restrict__ R, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stereo_mix_item(out, L, R, i);
+}
 // ---- launchers --------------------------------------------------------------------------
 template <class K> static int persistent_grid(K kernel, int block)
 {
@@ -687,6 +692,12 @@ int add_into(float* dst, const float* src, size_t n)
 {
     ProfScope ps(PROF_OTHER);
     k_add_into<<<g_sms * 8, 256, 0, g_stream>>>(dst, src, n);
+    return 1;
+}
+int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels)
+{
+    ProfScope ps(PROF_OTHER);
+    k_stereo_mix<<<g_sms * 8, 256, 0, g_stream>>>(out, left, right, n_pixels);
     return 1;
 }
 }  // namespace dev

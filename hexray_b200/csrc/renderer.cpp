@@ -28,6 +28,8 @@ Renderer::~Renderer()
     dev::free_(m_aaList);
     dev::free_(m_aaMask);
     dev::free_(m_accum);
+    dev::free_(m_eye[0]);
+    dev::free_(m_eye[1]);
 }
 
 int Renderer::create(const hxr_config& cfg)
@@ -467,10 +469,29 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
         m_accumPixels = m_accum ? nPix : 0;
         if (!m_accum) { m_scene.settings = savedSettings; return fail(HXR_ERR_CUDA, std::string("framebuffer allocation failed: ") + dev::last_error()); }
     }
+    // stereo anaglyph (src/main.cpp:234-248): every sample is traced once per eye; the eyes accumulate separately
+    // and are mixed (a linear map) into the frame
+    const int eyes = m_scene.cam.stereo_separation != 0.0 ? 2 : 1;
+    float* eyeBuf[2] = {m_accum, nullptr};
+    if (eyes == 2) {
+        if (m_eyePixels < nPix) {
+            for (int e = 0; e < 2; e++) { dev::free_(m_eye[e]); m_eye[e] = (float*)dev::alloc(nPix * 3 * sizeof(float)); }
+            m_eyePixels = (m_eye[0] && m_eye[1]) ? nPix : 0;
+            if (!m_eyePixels) { m_scene.settings = savedSettings; return fail(HXR_ERR_CUDA, "stereo buffer allocation failed"); }
+        }
+        eyeBuf[0] = m_eye[0];
+        eyeBuf[1] = m_eye[1];
+    }
+    auto setEye = [&](int e) {
+        fp.stereo_offset = eyes == 2 ? (e == 0 ? -0.5f : 0.5f) : 0.0f;
+        fp.stream0 = 1u + (uint32_t)e;
+    };
+    setEye(0);
     dev::prof_reset();
     dev::Timer* tm = dev::timer_create();
     dev::timer_start(tm);
     dev::zero(m_accum, nPix * 3 * sizeof(float));
+    for (int e = 0; e < eyes && eyes == 2; e++) dev::zero(eyeBuf[e], nPix * 3 * sizeof(float));
     dev::set_u32(m_counters + C_OVERFLOW, 0);
     dev::zero(m_trav, sizeof(TravCounters) + 64);
     int ov = 0;
@@ -500,20 +521,27 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
                 const uint32_t k = std::min(sppPass, nMine - k0);
                 fp.sample_base = (uint32_t)shardIndex + k0 * (uint32_t)shardCount;
                 const uint32_t items = (uint32_t)(nPix * k);
-                st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, 0, items, k, m_q[0], m_counters + C_Q0);
-                ov = drain(fp, m_accum, items, st);
+                for (int e = 0; e < eyes && !ov; e++) {
+                    setEye(e);
+                    st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, 0, items, k, m_q[0], m_counters + C_Q0);
+                    ov = drain(fp, eyeBuf[e], items, st);
+                }
             }
         } else {
             for (uint32_t k0 = 0; k0 < nMine && !ov; k0++) {
                 fp.sample_base = (uint32_t)shardIndex + k0 * (uint32_t)shardCount;
                 for (size_t first = 0; first < nPix && !ov; first += primaryBatch) {
                     const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, nPix - first);
-                    st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)first, items, 1, m_q[0], m_counters + C_Q0);
-                    ov = drain(fp, m_accum, items, st);
+                    for (int e = 0; e < eyes && !ov; e++) {
+                        setEye(e);
+                        st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)first, items, 1, m_q[0], m_counters + C_Q0);
+                        ov = drain(fp, eyeBuf[e], items, st);
+                    }
                 }
             }
         }
         st.spp_done = nMine;
+        if (eyes == 2 && !ov) st.kernel_launches += dev::stereo_mix(m_accum, eyeBuf[0], eyeBuf[1], nPix);
         if (shardCount == 1) st.kernel_launches += dev::scale_all(m_accum, nPix * 3, 1.0f / (float)spp);
     } else {
         // pass 1: one ray through every pixel corner. Row shards own rows y with (y/16) % count == index
@@ -530,11 +558,15 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
             size_t first = (size_t)y * W, count = (size_t)(y1 - y) * W;
             for (size_t off = 0; off < count && !ov; off += primaryBatch) {
                 const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, count - off);
-                st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)(first + off), items, 1, m_q[0], m_counters + C_Q0);
-                ov = drain(fp, m_accum, items, st);
+                for (int e = 0; e < eyes && !ov; e++) {
+                    setEye(e);
+                    st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)(first + off), items, 1, m_q[0], m_counters + C_Q0);
+                    ov = drain(fp, eyeBuf[e], items, st);
+                }
             }
             y = y1;
         }
+        if (eyes == 2 && !ov) st.kernel_launches += dev::stereo_mix(m_accum, eyeBuf[0], eyeBuf[1], nPix);  // what detectAApixels looks at
         if (wantAA && !ov) {
             if (m_aaCap < nPix) {
                 dev::free_(m_aaList);
@@ -552,9 +584,13 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
             const uint32_t pixPerBatch = std::max<uint32_t>(1, primaryBatch / 4);
             for (uint32_t first = 0; first < nAA && !ov; first += pixPerBatch) {
                 const uint32_t np = std::min(pixPerBatch, nAA - first);
-                st.kernel_launches += dev::gen_primary(m_scene, fp, m_aaList + first, 0, np * 4, 4, m_q[0], m_counters + C_Q0);
-                ov = drain(fp, m_accum, np * 4, st);
+                for (int e = 0; e < eyes && !ov; e++) {
+                    setEye(e);
+                    st.kernel_launches += dev::gen_primary(m_scene, fp, m_aaList + first, 0, np * 4, 4, m_q[0], m_counters + C_Q0);
+                    ov = drain(fp, eyeBuf[e], np * 4, st);
+                }
             }
+            if (eyes == 2 && !ov) st.kernel_launches += dev::stereo_mix(m_accum, eyeBuf[0], eyeBuf[1], nPix);
             st.kernel_launches += dev::scale_listed(m_accum, m_aaList, m_counters + C_AA, (uint32_t)nPix, 1.0f / 5);
         }
         if (shardCount > 1) {

@@ -64,6 +64,8 @@ private:
     uint32_t* m_aaList = nullptr;
     uint8_t* m_aaMask = nullptr;
     float* m_accum = nullptr;
+    float* m_eye[2] = {nullptr, nullptr};  // per-eye accumulation of anaglyph frames
+    size_t m_eyePixels = 0;
     size_t m_accumPixels = 0;
     size_t m_aaCap = 0;
     bool m_countTraversal = false;

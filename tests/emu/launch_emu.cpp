@@ -182,5 +182,11 @@ int add_into(float* dst, const float* src, size_t n)
     g_launches[PROF_OTHER]++;
     return 1;
 }
+int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels)
+{
+    for (size_t i = 0; i < n_pixels; i++) stereo_mix_item(out, left, right, i);
+    g_launches[PROF_OTHER]++;
+    return 1;
+}
 }  // namespace dev
 }  // namespace hxr

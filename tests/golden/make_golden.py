@@ -169,8 +169,30 @@ def terrain(side=320):
     print("terrain", side, "rays", len(rays), "terrain hits", int(ok.sum()), "visible", float(vis.mean()), "img mean", float(img.mean()), info["best_ms"])
 
 
+def stereo():
+    """Anaglyph frames (camera.stereoSeparation != 0, src/main.cpp:234-248): no bundled scene uses the feature, so the
+    fixtures are bundled scenes with the property added (tests/hxr_testlib.py: stereo_scene)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hxr_testlib as T
+    tmp = "/tmp/hxr_golden.bin"
+    for name, W, H, spp in (("kdtree_test", 320, 240, 0), ("cornell_box", 96, 96, 4096)):
+        variant = T.stereo_scene(name, T.STEREO[name])
+        args = ["render", scene_path(variant), "--width", str(W), "--height", str(H), "--out", tmp]
+        if spp:
+            args += ["--spp", str(spp)]
+        info = run(args)
+        img = np.fromfile(tmp, dtype=np.float32).reshape(H, W, 3)
+        np.savez_compressed(os.path.join(HERE, "stereo_%s.npz" % tag(name)), img=img.astype(np.float16), spp=spp, separation=T.STEREO[name],
+                            cmd="hexray_ref render data/%s.hexray + stereoSeparation %g --width %d --height %d" % (name, T.STEREO[name], W, H),
+                            info=json.dumps(info))
+        print("stereo", name, img.shape, float(img.mean()), img.reshape(-1, 3).mean(0))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "terrain":
         terrain()
+    elif len(sys.argv) > 1 and sys.argv[1] == "stereo":
+        stereo()
     else:
         main()

@@ -49,6 +49,23 @@ def oracle_render(scene, W, H, spp=0, extra=()):
     return np.fromfile(out, dtype=np.float32).reshape(H, W, 3), info
 
 
+def stereo_scene(scene, separation):
+    """A copy of a bundled scene with `stereoSeparation` set on its camera (anaglyph frames, src/main.cpp:234-248),
+    written next to the original so that its asset paths keep resolving."""
+    src = scene_path(scene)
+    dst = os.path.join(os.path.dirname(src), "_stereo_%s.hexray" % os.path.basename(scene))
+    text = open(src).read()
+    i = text.index("Camera")
+    j = text.index("{", i)
+    text = text[:j + 1] + "\n\tstereoSeparation %g" % separation + text[j + 1:]
+    with open(dst, "w") as f:
+        f.write(text)
+    return os.path.relpath(dst, hx.data_root())[:-len(".hexray")]
+
+
+STEREO = {"kdtree_test": 12.0, "cornell_box": 40.0}  # scene -> stereoSeparation used by the fixtures
+
+
 class Session:
     """Caches loaded scenes per library so a test module pays the parse/upload once per scene."""
 
@@ -190,3 +207,25 @@ def check_terrain(api, queue_capacity=1 << 20, spp=64):
     finally:
         r.close()
         sf.close()
+
+
+def check_stereo(sess, scene, spp=0):
+    """Anaglyph frame of a bundled scene with stereoSeparation added, against the compiled reference's frame."""
+    g = golden("stereo", scene)
+    ref = g["img"].astype(np.float32)
+    H, W = ref.shape[:2]
+    r = sess.renderer(stereo_scene(scene, STEREO[scene]))
+    if spp == 0:
+        img, st = r.render(width=W, height=H)
+        d = np.abs(clamp01(img) - clamp01(ref)).max(axis=2)
+        frac = float((d <= PIXEL_TOL + 6e-4).mean())
+        assert frac >= PIXEL_FRACTION, "stereo %s: only %.4f%% of pixels within 1/255 (max diff %.4f)" % (scene, frac * 100, d.max())
+        return frac
+    a, st = r.render(width=W, height=H, spp=spp, seed=11)
+    b, _ = r.render(width=W, height=H, spp=spp, seed=22)
+    own = rmse(a, b) / np.sqrt(2.0)
+    err = rmse(a, ref)
+    mean_delta = np.abs(clamp01(a).mean(axis=(0, 1)) - clamp01(ref).mean(axis=(0, 1)))
+    assert err <= 1.25 * own + 0.004, "stereo %s: rmse vs converged reference %.4f, own noise %.4f" % (scene, err, own)
+    assert mean_delta.max() <= 0.004, "stereo %s: mean delta %s" % (scene, mean_delta)
+    return err

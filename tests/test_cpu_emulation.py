@@ -35,3 +35,9 @@ def test_montecarlo_parity(sess, scene, spp):
 def test_terrain_walk(emu_api):
     # the conservative FP32 block walk (host form) on the bench's terrain; its camera sits ON a split plane
     T.check_terrain(emu_api, spp=8)
+
+
+def test_stereo_anaglyph(sess):
+    # src/main.cpp:234-248: two traces per sample mixed into an anaglyph; Whitted + AA (deterministic) and GI
+    T.check_stereo(sess, "kdtree_test")
+    T.check_stereo(sess, "cornell_box", spp=32)

@@ -162,3 +162,9 @@ def test_walk_equals_brute_force(gpu_api, side):
     m = walk["status"] == 0
     assert np.array_equal(walk["dist"][m], brute["dist"][m]) and np.array_equal(walk["ip"][m], brute["ip"][m])
     assert np.array_equal(walk["norm"][m], brute["norm"][m])
+
+
+def test_stereo_anaglyph(sess):
+    # src/main.cpp:234-248: two traces per sample mixed into an anaglyph; Whitted + AA (deterministic) and GI
+    T.check_stereo(sess, "kdtree_test")
+    T.check_stereo(sess, "cornell_box", spp=256)
