@@ -562,14 +562,15 @@ HXR_HD void mesh_fill_hit(const DMesh& M, int gi, const Ray& ray, const MeshBest
     const TriAttr& ta = M.tri_attr[best.tri];
     info.dist = best.gamma;
     info.ip = ray.o + best.gamma * ray.d;
-    const d3 texA = ld3(M.uvs + 3 * ta.t[0]), texB = ld3(M.uvs + 3 * ta.t[1]), texC = ld3(M.uvs + 3 * ta.t[2]);
+    // uvs[t.t[k]] with the third coordinate dropped: only x and y are used (src/mesh.cpp:203-207)
+    const d3 texA = mk3(ta.uv[0][0], ta.uv[0][1], 0), texB = mk3(ta.uv[1][0], ta.uv[1][1], 0), texC = mk3(ta.uv[2][0], ta.uv[2][1], 0);
     const d3 tex = texA + (texB - texA) * best.l2 + (texC - texA) * best.l3;
     info.u = tex.x;
     info.v = tex.y;
     if (M.faceted) {
         info.norm = ld3(ta.gnormal);
     } else {
-        const d3 nA = ld3(M.normals + 3 * ta.n[0]), nB = ld3(M.normals + 3 * ta.n[1]), nC = ld3(M.normals + 3 * ta.n[2]);
+        const d3 nA = ld3(ta.nrm[0]), nB = ld3(ta.nrm[1]), nC = ld3(ta.nrm[2]);
         info.norm = normalize_m(nA + (nB - nA) * best.l2 + (nC - nA) * best.l3);
     }
     info.dNdx = ld3(ta.dNdx);

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128) k_setup_closest(DScene sc, const RayTask*
 }
 
 template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128) k_finalize_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
+__global__ void __launch_bounds__(128, SIMPLE ? 4 : 2) k_finalize_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
                                                           TraceScratch ts, HitRec* __restrict__ hits, TravCounters* cnt)
 {
     const uint32_t n = min(*q_count, cap);
@@ -518,13 +518,17 @@ __global__ void __launch_bounds__(128) k_confirm_shadow(DScene sc, const ShadowT
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) confirm_shadow_item(sc, shadows, i, ts);
 }
 
-__global__ void __launch_bounds__(HXR_SHADE_BLOCK) k_shade(DScene sc, FrameParams fp, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count,
-                                                           const HitRec* __restrict__ hits, uint32_t begin, uint32_t end, Sinks sinks)
+// GI (one path vertex) and Whitted (shader tree with its stacks) are separate compilations: the path-tracing vertex
+// needs far fewer registers than the tree walk, and occupancy is what hides this kernel's gather latency
+template <bool GI>
+__global__ void __launch_bounds__(HXR_SHADE_BLOCK, GI ? 5 : 3) k_shade(DScene sc, FrameParams fp, const RayTask* __restrict__ q,
+                                                                       const uint32_t* __restrict__ q_count, const HitRec* __restrict__ hits,
+                                                                       uint32_t begin, uint32_t end, Sinks sinks)
 {
     const uint32_t e = min(end, *q_count);
     const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= e) return;
-    if (fp.gi) shade_gi_item(sc, fp, q[i], hits[i], sinks);
+    if (GI) shade_gi_item(sc, fp, q[i], hits[i], sinks);
     else shade_whitted_item(sc, fp, q[i], hits[i], sinks);
 }
 
@@ -633,7 +637,8 @@ int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint3
     if (end <= begin) return 0;
     ProfScope ps(PROF_SHADE);
     const uint32_t blocks = (end - begin + HXR_SHADE_BLOCK - 1) / HXR_SHADE_BLOCK;
-    k_shade<<<blocks, HXR_SHADE_BLOCK, 0, g_stream>>>(sc, fp, q, q_count, hits, begin, end, sinks);
+    if (fp.gi) k_shade<true><<<blocks, HXR_SHADE_BLOCK, 0, g_stream>>>(sc, fp, q, q_count, hits, begin, end, sinks);
+    else k_shade<false><<<blocks, HXR_SHADE_BLOCK, 0, g_stream>>>(sc, fp, q, q_count, hits, begin, end, sinks);
     return 1;
 }
 

@@ -8,7 +8,7 @@
 //   TriF32   48 B  float copy of TriTest: what the walk's conservative triangle filter reads (3 x 128-bit loads)
 //   TriTest  96 B  the four vectors the reference's triangle test reads (A, AB, AC, AB^AC),
 //                  in double so the test is the reference's arithmetic (src/mesh.cpp:178-196)
-//   TriAttr  96 B  read once per ray for the winning triangle (normals/uv indices, dNdx/dNdy)
+//   TriAttr 192 B  read once per ray for the winning triangle: gnormal, dNdx/dNdy, the three vertex normals and uvs inline
 #pragma once
 #include "hd.h"
 #include "../../../include/hxr.h"
@@ -49,9 +49,10 @@ struct alignas(16) TriF32 {  // 48 B: the same four vectors rounded to float, fo
     float A[3], AB[3], AC[3], N[3];
 };
 
-struct TriAttr {
-    int32_t n[3], t[3];
+struct alignas(16) TriAttr {  // 192 B, self-contained: the winning triangle's shading data in ONE gather (no index -> vertex-array hop)
     double gnormal[3], dNdx[3], dNdy[3];
+    double nrm[3][3];  // the three vertex normals
+    double uv[3][2];   // the three texture coordinates
 };
 
 struct DMesh {
@@ -60,8 +61,6 @@ struct DMesh {
     const TriTest* tri_test;
     const TriF32* tri_f32;
     const TriAttr* tri_attr;
-    const double* normals;
-    const double* uvs;
     double bbmin[3], bbmax[3];
     int32_t faceted, backface;
     int32_t n_tris;

@@ -167,9 +167,9 @@ int Renderer::uploadScene(const hxr_scene* sp)
                 tf[t].AB[k] = (float)tt[t].AB[k];
                 tf[t].AC[k] = (float)tt[t].AC[k];
                 tf[t].N[k] = (float)tt[t].N[k];
-                ta[t].n[k] = T.n[k];
-                ta[t].t[k] = T.t[k];
                 ta[t].gnormal[k] = T.gnormal[k];
+                for (int c = 0; c < 3; c++) ta[t].nrm[k][c] = m.normals[3 * (size_t)T.n[k] + c];
+                for (int c = 0; c < 2; c++) ta[t].uv[k][c] = m.uvs[3 * (size_t)T.t[k] + c];
                 ta[t].dNdx[k] = T.dndx[k];
                 ta[t].dNdy[k] = T.dndy[k];
             }
@@ -181,9 +181,7 @@ int Renderer::uploadScene(const hxr_scene* sp)
         d.tri_test = uploadArray(tt.data(), tt.size());
         d.tri_f32 = uploadArray(tf.data(), tf.size());
         d.tri_attr = uploadArray(ta.data(), ta.size());
-        d.normals = uploadArray(m.normals, (size_t)m.n_normals * 3);
-        d.uvs = uploadArray(m.uvs, (size_t)m.n_uvs * 3);
-        if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_f32 || !d.tri_attr || !d.normals || !d.uvs) return oom();
+        if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_f32 || !d.tri_attr) return oom();
         double amax = 0;
         for (int k = 0; k < 3; k++) {
             d.bbmin[k] = m.bbox_min[k];

@@ -1,11 +1,11 @@
 #!/bin/bash
 # sweep SAH build parameters (intersect cost / max leaf size) in one gpurun job
-TAG=${1:-sweep2}
+TAG=${1:-sweep2}; shift
 mkdir -p gpurun_out
 : > gpurun_out/${TAG}.jsonl
-for cfg in "2.0 4" "1.0 4" "1.0 8" "0.5 8" "0.5 16" "0.3 16" "1.0 16"; do
+for cfg in "$@"; do
   set -- $cfg
-  HXR_KD_INTERSECT_COST=$1 HXR_KD_MAX_LEAF=$2 timeout 600 python bench.py --steps 2 --warmup 2 --spp 8 --no-cpu-baseline 2>/dev/null | python -c "
+  HXR_KD_INTERSECT_COST=$1 HXR_KD_MAX_LEAF=$2 timeout 600 python bench.py --steps 2 --warmup 2 --spp 16 --no-cpu-baseline 2>/dev/null | python -c "
 import sys,json
 j=json.loads(sys.stdin.read().strip().splitlines()[-1])
 kd=j['config']['kd']
