@@ -34,7 +34,7 @@ static cudaStream_t g_stream = nullptr;
 static std::string g_err;
 static bool g_prof = false;
 // walk-loop tunables (uniform kernel arguments; HXR_WALK_STEPS / HXR_REFILL_MIN in the environment override the defaults)
-static int g_walkSteps = 3, g_refillMin = 8, g_leafTrigger = 33;
+static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10;
 static uint64_t g_launches[PROF_NCAT];
 static std::vector<cudaEvent_t> g_evPool;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
@@ -68,7 +68,7 @@ bool init(int device, char* err, size_t errlen)
     g_device = device;
     g_sms = p.multiProcessorCount;
     if (const char* e = getenv("HXR_WALK_STEPS")) g_walkSteps = std::max(1, atoi(e));
-    if (const char* e = getenv("HXR_LEAF_TRIGGER")) g_leafTrigger = std::max(1, atoi(e));
+    if (const char* e = getenv("HXR_SSTACK")) g_sstack = atoi(e);
     if (const char* e = getenv("HXR_REFILL_MIN")) g_refillMin = std::min(32, std::max(1, atoi(e)));
     if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
     return true;
@@ -274,22 +274,24 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
 // State per lane in shared memory: the float ray (24 B), the best-hit bound (4 B, lowered with atomicMin by whichever
 // lane filters a certain hit) and the first HXR_SSTACK stack entries (12 B each); deeper entries overflow to local
 // memory (rare: the stack is shallow for almost all rays).
-#define HXR_SSTACK 10
 #define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
 
+template <int SSTACK>
 struct WalkShared {
     float ray[11][HXR_WALK_BLOCK];  // rows 0-2 origin, 4-6 1/direction, 8-10 direction (3 and 7: zero, read for leaf "axis 3")
     uint32_t tb[HXR_WALK_BLOCK];  // bits of the (non-negative) float bound; 0 = shadow ray certainly blocked
-    uint32_t stRef[HXR_SSTACK][HXR_WALK_BLOCK];
-    float stMin[HXR_SSTACK][HXR_WALK_BLOCK];
-    float stMax[HXR_SSTACK][HXR_WALK_BLOCK];
+    uint32_t stRef[SSTACK][HXR_WALK_BLOCK];
+    float stMin[SSTACK][HXR_WALK_BLOCK];
+    float stMax[SSTACK][HXR_WALK_BLOCK];
 };
 
-template <bool SHADOW, bool COUNT>
+// SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
+template <bool SHADOW, bool COUNT, int SSTACK>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, TraceScratch ts, TravCounters* cnt, int walkSteps,
-                                                                              int refillMin, int leafTrigger)
+                                                                              int refillMin)
 {
-    __shared__ WalkShared sh;
+    __shared__ WalkShared<SSTACK> sh;
+    constexpr int HXR_SSTACK = SSTACK;
     const unsigned FULL = 0xffffffffu;
     const uint32_t n = min(*ts.task_count, ts.task_cap);
     const unsigned tid = threadIdx.x, lane = tid & 31u, warpBase = tid & ~31u;
@@ -410,9 +412,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 cur = c.ref; tmin = c.lo; tmax = c.hi;
             }
             if (stepping && active && (cur >> 31)) leafCnt = __ldg(leafTris + (cur & ~HXR_KD_LEAF));  // in flight while the others keep stepping
-            // enough leaves for full rounds of phase 2 (or nobody left to step): stop stepping early
-            const unsigned lm = __ballot_sync(FULL, active && (cur >> 31));
-            if (__popc(lm) >= leafTrigger) break;
+            __syncwarp();
         }
         // ---- phase 2: all (ray, triangle) pairs of the leaves held by this warp, dealt out over its 32 lanes
         const bool hasLeaf = active && (cur >> 31);
@@ -594,11 +594,27 @@ template <class K> static int walk_grid(K kernel)
     return g_sms * perSm;
 }
 
+template <bool SHADOW, bool COUNT, int SSTACK> static void launch_walk_s(const DScene& sc, const TraceScratch& ts, TravCounters* cnt)
+{
+    static int grid = 0;
+    if (!grid) grid = walk_grid(k_walk<SHADOW, COUNT, SSTACK>);
+    k_walk<SHADOW, COUNT, SSTACK><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin);
+}
+template <bool SHADOW> static void launch_walk(const DScene& sc, const TraceScratch& ts, TravCounters* cnt)
+{
+    if (cnt) { launch_walk_s<SHADOW, true, 10>(sc, ts, cnt); return; }
+    switch (g_sstack) {
+        case 12: launch_walk_s<SHADOW, false, 12>(sc, ts, nullptr); break;
+        case 14: launch_walk_s<SHADOW, false, 14>(sc, ts, nullptr); break;
+        case 16: launch_walk_s<SHADOW, false, 16>(sc, ts, nullptr); break;
+        default: launch_walk_s<SHADOW, false, 10>(sc, ts, nullptr); break;
+    }
+}
+
 int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits, const TraceScratch& ts,
                   TravCounters* cnt)
 {
     ProfScope ps(PROF_TRACE_CLOSEST);
-    static int gridPlain = 0, gridCount = 0;
     cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
@@ -612,13 +628,7 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
     if (sc.n_big) {
         {
             ProfScope pw(PROF_WALK);
-            if (cnt) {
-                if (!gridCount) gridCount = walk_grid(k_walk<false, true>);
-                k_walk<false, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_leafTrigger);
-            } else {
-                if (!gridPlain) gridPlain = walk_grid(k_walk<false, false>);
-                k_walk<false, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin, g_leafTrigger);
-            }
+            launch_walk<false>(sc, ts, cnt);
         }
         k_confirm_closest_a<<<nb, 128, 0, g_stream>>>(sc, q, ts);
         k_confirm_closest_b<<<nb, 256, 0, g_stream>>>(sc, ts);
@@ -646,7 +656,6 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
                  TravCounters* cnt, unsigned long long* total)
 {
     ProfScope ps(PROF_TRACE_SHADOW);
-    static int gridPlain = 0, gridCount = 0;
     cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
@@ -658,13 +667,7 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
     if (sc.n_big) {
         {
             ProfScope pw(PROF_WALK);
-            if (cnt) {
-                if (!gridCount) gridCount = walk_grid(k_walk<true, true>);
-                k_walk<true, true><<<gridCount, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_leafTrigger);
-            } else {
-                if (!gridPlain) gridPlain = walk_grid(k_walk<true, false>);
-                k_walk<true, false><<<gridPlain, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, nullptr, g_walkSteps, g_refillMin, g_leafTrigger);
-            }
+            launch_walk<true>(sc, ts, cnt);
         }
         k_confirm_shadow<<<nb, 128, 0, g_stream>>>(sc, shadow, ts);
         launches += 2;
