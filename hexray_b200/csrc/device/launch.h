@@ -51,8 +51,9 @@ int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels,
 
 // closest hit for q[0 .. *q_count) (count read on the device) -> hits[i]. Three stages:
 // setup (inline nodes + queue big-mesh walks) -> walk (persistent KD traversal) -> finalize.
+// n_hint: a host-side upper bound of *q_count (sizes the grids; small waves do not pay for full-size launches)
 int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits,
-                  const TraceScratch& ts, TravCounters* cnt);
+                  const TraceScratch& ts, TravCounters* cnt, uint32_t n_hint);
 
 // shade q[begin .. min(end, *q_count)); gi selects pathtrace vs Whitted
 int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits,
@@ -61,7 +62,7 @@ int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint3
 // visible() for shadow[0 .. *count): ts.occluded[i] = 1 if blocked; when accum != nullptr the carried colour of
 // every unblocked task is added to its pixel. *total += *count (64-bit running total kept on the device).
 int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum,
-                 const TraceScratch& ts, TravCounters* cnt, unsigned long long* total);
+                 const TraceScratch& ts, TravCounters* cnt, unsigned long long* total, uint32_t n_hint);
 
 // needsAA flags -> compacted pixel list (order unspecified) ; *n_out = number of flagged pixels
 // rows restricted to y with ((y / HXR_ROW_BAND) % shard_count) == shard_index

@@ -585,7 +585,7 @@ int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels,
 }
 
 // per-item stage kernels are grid-stride loops over a count that only the device knows
-static uint32_t stage_grid(uint32_t cap) { return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)cap + 127) / 128, (uint64_t)g_sms * 16)); }
+static uint32_t stage_grid(uint32_t n) { return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)g_sms * 16)); }
 
 template <class K> static int walk_grid(K kernel)
 {
@@ -594,31 +594,35 @@ template <class K> static int walk_grid(K kernel)
     return g_sms * perSm;
 }
 
-template <bool SHADOW, bool COUNT, int SSTACK> static void launch_walk_s(const DScene& sc, const TraceScratch& ts, TravCounters* cnt)
+// max_tasks: host-side upper bound of the task count (a small wave gets a small grid: one lane per task at most)
+template <bool SHADOW, bool COUNT, int SSTACK> static void launch_walk_s(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
 {
-    static int grid = 0;
-    if (!grid) grid = walk_grid(k_walk<SHADOW, COUNT, SSTACK>);
+    static int full = 0;
+    if (!full) full = walk_grid(k_walk<SHADOW, COUNT, SSTACK>);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, (max_tasks + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
     k_walk<SHADOW, COUNT, SSTACK><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin);
 }
-template <bool SHADOW> static void launch_walk(const DScene& sc, const TraceScratch& ts, TravCounters* cnt)
+template <bool SHADOW> static void launch_walk(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
 {
-    if (cnt) { launch_walk_s<SHADOW, true, 10>(sc, ts, cnt); return; }
+    if (cnt) { launch_walk_s<SHADOW, true, 10>(sc, ts, cnt, max_tasks); return; }
     switch (g_sstack) {
-        case 12: launch_walk_s<SHADOW, false, 12>(sc, ts, nullptr); break;
-        case 14: launch_walk_s<SHADOW, false, 14>(sc, ts, nullptr); break;
-        case 16: launch_walk_s<SHADOW, false, 16>(sc, ts, nullptr); break;
-        default: launch_walk_s<SHADOW, false, 10>(sc, ts, nullptr); break;
+        case 12: launch_walk_s<SHADOW, false, 12>(sc, ts, nullptr, max_tasks); break;
+        case 14: launch_walk_s<SHADOW, false, 14>(sc, ts, nullptr, max_tasks); break;
+        case 16: launch_walk_s<SHADOW, false, 16>(sc, ts, nullptr, max_tasks); break;
+        default: launch_walk_s<SHADOW, false, 10>(sc, ts, nullptr, max_tasks); break;
     }
 }
 
 int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits, const TraceScratch& ts,
-                  TravCounters* cnt)
+                  TravCounters* cnt, uint32_t n_hint)
 {
     ProfScope ps(PROF_TRACE_CLOSEST);
     cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
-    const uint32_t nb = stage_grid(q_cap);
+    const uint32_t nb = stage_grid(std::min(q_cap, n_hint));
+    const uint64_t maxTasks = (uint64_t)std::min(q_cap, n_hint) * (uint64_t)std::max(1, sc.n_big);
+    const uint32_t nbPairs = stage_grid((uint32_t)std::min<uint64_t>(ts.pair_cap, maxTasks * 4));  // a ray rarely leaves more than a few pairs
     int launches = 2;
     // counting builds and scenes with CSG / heightfield / inline tree walks take the generic variant
     const bool simple = sc.simple_inline && !cnt;
@@ -628,10 +632,10 @@ int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, u
     if (sc.n_big) {
         {
             ProfScope pw(PROF_WALK);
-            launch_walk<false>(sc, ts, cnt);
+            launch_walk<false>(sc, ts, cnt, maxTasks);
         }
-        k_confirm_closest_a<<<nb, 128, 0, g_stream>>>(sc, q, ts);
-        k_confirm_closest_b<<<nb, 256, 0, g_stream>>>(sc, ts);
+        k_confirm_closest_a<<<nbPairs, 128, 0, g_stream>>>(sc, q, ts);
+        k_confirm_closest_b<<<nbPairs, 256, 0, g_stream>>>(sc, ts);
         launches += 3;
     }
     if (cnt) k_finalize_closest<true, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
@@ -653,13 +657,15 @@ int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint3
 }
 
 int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, const TraceScratch& ts,
-                 TravCounters* cnt, unsigned long long* total)
+                 TravCounters* cnt, unsigned long long* total, uint32_t n_hint)
 {
     ProfScope ps(PROF_TRACE_SHADOW);
     cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
     cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
-    const uint32_t nb = stage_grid(cap);
+    const uint32_t nb = stage_grid(std::min(cap, n_hint));
+    const uint64_t maxTasks = (uint64_t)std::min(cap, n_hint) * (uint64_t)std::max(1, sc.n_big);
+    const uint32_t nbPairs = stage_grid((uint32_t)std::min<uint64_t>(ts.pair_cap, maxTasks * 4));
     int launches = 1;
     if (cnt) k_setup_shadow<true, false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
     else if (sc.simple_inline) k_setup_shadow<false, true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
@@ -667,9 +673,9 @@ int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* cou
     if (sc.n_big) {
         {
             ProfScope pw(PROF_WALK);
-            launch_walk<true>(sc, ts, cnt);
+            launch_walk<true>(sc, ts, cnt, maxTasks);
         }
-        k_confirm_shadow<<<nb, 128, 0, g_stream>>>(sc, shadow, ts);
+        k_confirm_shadow<<<nbPairs, 128, 0, g_stream>>>(sc, shadow, ts);
         launches += 2;
     }
     if (accum) { k_accum_shadow<<<nb, 256, 0, g_stream>>>(shadow, count, cap, ts, accum); launches++; }

@@ -388,7 +388,7 @@ int Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_
     TravCounters* cnt = m_countTraversal ? m_trav : nullptr;
     for (int level = 0; n > 0 && level <= fp.max_depth + 2; level++) {
         if (n > m_cap) return 1;  // overflow
-        st.kernel_launches += dev::trace_closest(m_scene, m_q[cur], m_counters + cur, m_cap, m_hits, scratch(C_HEAD_A), cnt);
+        st.kernel_launches += dev::trace_closest(m_scene, m_q[cur], m_counters + cur, m_cap, m_hits, scratch(C_HEAD_A), cnt, n);
         st.rays_closest += n;
         dev::set_u32(m_counters + (1 - cur), 0);
         Sinks sk;
@@ -403,7 +403,8 @@ int Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_
         for (uint32_t b = 0; b < n; b += chunk) {
             dev::set_u32(m_counters + C_SHADOW, 0);
             st.kernel_launches += dev::shade(m_scene, fp, m_q[cur], m_counters + cur, m_hits, b, std::min<uint64_t>(n, (uint64_t)b + chunk), sk);
-            st.kernel_launches += dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, accum, scratch(C_HEAD_B), cnt, shadowTotalPtr(m_trav));
+            st.kernel_launches += dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, accum, scratch(C_HEAD_B), cnt, shadowTotalPtr(m_trav),
+                                                   (uint32_t)std::min<uint64_t>(m_shadowCap, (std::min<uint64_t>(n, (uint64_t)b + chunk) - b) * perHit));
         }
         n = readCount(m_counters + (1 - cur));
         cur = 1 - cur;
@@ -672,7 +673,7 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
         dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
         dev::set_u32(m_counters + C_Q0, m);
         dev::set_u32(m_counters + C_OVERFLOW, 0);
-        dev::trace_closest(m_scene, m_q[0], m_counters + C_Q0, m_cap, m_hits, scratch(C_HEAD_A), nullptr);
+        dev::trace_closest(m_scene, m_q[0], m_counters + C_Q0, m_cap, m_hits, scratch(C_HEAD_A), nullptr, m);
         if (!dev::download(recs.data(), m_hits, (size_t)m * sizeof(HitRec))) return fail(HXR_ERR_CUDA, dev::last_error());
         if (readCount(m_counters + C_OVERFLOW)) return fail(HXR_ERR_OVERFLOW, "trace_closest: traversal scratch overflow; raise hxr_config.queue_capacity");
         for (uint32_t i = 0; i < m; i++) {
@@ -712,7 +713,7 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
         dev::upload(m_shadow, tasks.data(), (size_t)m * sizeof(ShadowTask));
         dev::set_u32(m_counters + C_SHADOW, m);
         dev::set_u32(m_counters + C_OVERFLOW, 0);
-        dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, nullptr, scratch(C_HEAD_B), nullptr, nullptr);
+        dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, nullptr, scratch(C_HEAD_B), nullptr, nullptr, m);
         if (!dev::download(occ.data(), m_occluded, m)) return fail(HXR_ERR_CUDA, dev::last_error());
         if (readCount(m_counters + C_OVERFLOW)) return fail(HXR_ERR_OVERFLOW, "trace_visible: traversal scratch overflow; raise hxr_config.queue_capacity");
         for (uint32_t i = 0; i < m; i++) out[first + i] = occ[i] ? 0 : 1;

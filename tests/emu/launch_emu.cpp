@@ -84,7 +84,7 @@ int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels,
     return 1;
 }
 
-int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t, HitRec* hits, const TraceScratch& ts, TravCounters* cnt)
+int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t, HitRec* hits, const TraceScratch& ts, TravCounters* cnt, uint32_t)
 {
     const uint32_t n = *q_count;
     *ts.task_count = 0;
@@ -124,7 +124,7 @@ int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint3
 }
 
 int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, const TraceScratch& ts,
-                 TravCounters* cnt, unsigned long long* total)
+                 TravCounters* cnt, unsigned long long* total, uint32_t)
 {
     const uint32_t n = std::min(*count, cap);
     *ts.task_count = 0;
