@@ -5,6 +5,7 @@
 #include "../../include/hxr.h"
 #include "host/scene.h"
 #include "renderer.h"
+#include "device/isect.h"
 
 struct hxr_ctx {
     hxr::Renderer r;
@@ -89,6 +90,42 @@ int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits
 int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->r.traceVisible(seg, n, vis)) }
 int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { HXR_CTX_CALL(ctx->r.traceColor(rays, n, rgb)) }
 int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out) { HXR_CTX_CALL(ctx->r.accelInfo(mesh, out)) }
+
+int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out,
+                        float* ghi_out, int32_t* exact_out, double* gamma_out)
+{
+    if (n && (!rays || !tris || !tbest || !cls_out || !ghi_out || !exact_out || !gamma_out)) { g_lastError = "hxr_test_tri_filter: null argument"; return HXR_ERR_INVALID; }
+    using namespace hxr;
+    for (size_t i = 0; i < n; i++) {
+        const double* r = rays + 6 * i;
+        const double* v = tris + 9 * i;
+        TriTest tt;
+        TriF32 tf;
+        double amax = 0;
+        for (int k = 0; k < 3; k++) {
+            tt.A[k] = v[k];
+            tt.AB[k] = v[3 + k] - v[k];
+            tt.AC[k] = v[6 + k] - v[k];
+            for (int c = 0; c < 3; c++) amax = std::max(amax, std::fabs(v[3 * c + k]));
+        }
+        const d3 N = cross(ld3(tt.AB), ld3(tt.AC));
+        tt.N[0] = N.x; tt.N[1] = N.y; tt.N[2] = N.z;
+        for (int k = 0; k < 3; k++) { tf.A[k] = (float)tt.A[k]; tf.AB[k] = (float)tt.AB[k]; tf.AC[k] = (float)tt.AC[k]; tf.N[k] = (float)tt.N[k]; }
+        // what push_walk_task puts into a WalkTask (pipeline.h): float ray, error bound from |o| and the mesh extent
+        const double mo = std::max(std::fabs(r[0]), std::max(std::fabs(r[1]), std::fabs(r[2])));
+        const float err = f32_above((mo + (double)std::nextafter((float)amax, INFINITY)) * (1.01 / 8388608.0));
+        float ghi = 0;
+        cls_out[i] = tri_filter(&tf, backface != 0, (float)r[0], (float)r[1], (float)r[2], (float)r[3], (float)r[4], (float)r[5], err,
+                                f32_above(tbest[i]), ghi);
+        ghi_out[i] = ghi;
+        Ray ray;
+        ray.o = ld3(r); ray.d = ld3(r + 3); ray.depth = 0; ray.flags = 0;
+        double g = 0, l2, l3;
+        exact_out[i] = tri_core(&tt, backface != 0, ray, 0, tbest[i], -1, g, l2, l3) ? 1 : 0;
+        gamma_out[i] = g;
+    }
+    return HXR_OK;
+}
 
 // ---------------------------------------------------------------- host front-end
 int hxr_scene_load(const char* path, hxr_scene_file** out)

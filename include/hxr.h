@@ -316,6 +316,14 @@ int hxr_trace_visible(hxr_ctx* ctx, const double* segments /* n*6: A,B */, size_
 /* raytrace() (Whitted) colour for explicit rays: n*3 floats out */
 int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb);
 
+/* test hook (pure host code, no context): the walk's conservative FP32 triangle filter (csrc/device/isect.h: tri_filter)
+ * next to the reference's exact double test (tri_core) on n independent (ray, triangle) pairs.
+ *   rays: n*6 (origin, unit direction), tris: n*9 (vertices A, B, C), tbest: n (best parameter known so far)
+ *   cls_out: 0 MISS / 1 MAYBE / 2 CERTAIN, ghi_out: the filter's upper bound for CERTAIN, exact_out: 1 if the exact test
+ *   accepts the pair at a parameter <= tbest, gamma_out: that parameter */
+int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface_culling,
+                        int32_t* cls_out, float* ghi_out, int32_t* exact_out, double* gamma_out);
+
 /* acceleration-structure facts for reporting (per mesh): nodes, leaves, max depth, tri refs, build ms */
 typedef struct hxr_accel_info {
     uint64_t nodes, leaves, tri_refs, bytes_nodes, bytes_tris;
