@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, 
 #endif
 
 template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128) k_setup_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
+__global__ void __launch_bounds__(128, SIMPLE ? 6 : 1) k_setup_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
                                                        TraceScratch ts, TravCounters* cnt)
 {
     const uint32_t n = min(*q_count, cap);
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128, SIMPLE ? 4 : 2) k_finalize_closest(DScene
 }
 
 template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128) k_setup_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap,
+__global__ void __launch_bounds__(128, SIMPLE ? 6 : 1) k_setup_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap,
                                                       TraceScratch ts, TravCounters* cnt, unsigned long long* total)
 {
     const uint32_t n = min(*count, cap);
