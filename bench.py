@@ -105,7 +105,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="terrain", choices=["terrain", "cornell_box", "kdtree_test", "smallpt"])
+    ap.add_argument("--workload", default="terrain", choices=["terrain", "soup", "cornell_box", "kdtree_test", "smallpt"])
+    ap.add_argument("--soup-triangles", type=int, default=10000000, help="soup workload: random triangles in [-500,500]^3 (SURVEY.md 8d, worst-case incoherence)")
     ap.add_argument("--grid-side", type=int, default=2237, help="terrain vertices per side (2237 -> 9 999 392 triangles)")
     ap.add_argument("--spp", type=int, default=32, help="samples per pixel per GPU per step")
     ap.add_argument("--width", type=int, default=1920)
@@ -122,11 +123,19 @@ def workload_name(a):
     if a.workload == "terrain":
         ntri = 2 * (a.grid_side - 1) ** 2
         return "synthetic terrain %d triangles (grid %d^2, seed 0x5EED) in a 5-wall Lambert box, 1 RectLight 4x4, GI depth 8" % (ntri, a.grid_side)
+    if a.workload == "soup":
+        return "synthetic soup %d random triangles (seed 0x5EEE) in the same 5-wall Lambert box, 1 RectLight 4x4, GI depth 8" % a.soup_triangles
     return "data/%s.hexray" % a.workload
 
 
 def scene_text(a, mesh_file, W, H, spp):
     return TERRAIN_SCENE.format(W=W, H=H, spp=spp, mesh=mesh_file)
+
+
+def synthetic_mesh_name(a):
+    if getattr(a, "workload", "terrain") == "soup":
+        return "synthetic:soup:%d:0x5EEE" % a.soup_triangles
+    return "synthetic:terrain:%d:0x5EED" % a.grid_side
 
 
 def measured_peaks():
@@ -185,14 +194,15 @@ def run_reference_sample(a, workdir, threads=0, repeat=1):
     if not os.path.exists(ref):
         return None, {"unavailable": "oracle/_ref/hexray_ref_count not built (run `make -C oracle` where /root/reference exists)"}
     import hexray_b200 as hx
-    if a.workload == "terrain":
-        obj = os.path.join(workdir, "terrain_%d.obj" % a.grid_side)
-        scene = os.path.join(workdir, "terrain_ref_%d.hexray" % a.grid_side)
+    if a.workload in ("terrain", "soup"):
+        size = a.grid_side if a.workload == "terrain" else a.soup_triangles
+        obj = os.path.join(workdir, "%s_%d.obj" % (a.workload, size))
+        scene = os.path.join(workdir, "%s_ref_%d.hexray" % (a.workload, size))
         if not os.path.exists(obj):
             # the procedural mesh is produced by the host front-end (pure host code) and handed to the reference as an OBJ
-            gen = os.path.join(workdir, "terrain_gen_%d.hexray" % a.grid_side)
+            gen = os.path.join(workdir, "%s_gen_%d.hexray" % (a.workload, size))
             with open(gen, "w") as f:
-                f.write(scene_text(a, "synthetic:terrain:%d:0x5EED" % a.grid_side, a.ref_width, a.ref_height, a.ref_spp))
+                f.write(scene_text(a, synthetic_mesh_name(a), a.ref_width, a.ref_height, a.ref_spp))
             sf = hx.SceneFile(gen)
             sf.write_obj(0, obj + ".tmp")
             sf.close()
@@ -262,10 +272,10 @@ def ours(a):
 
     workdir = os.path.join(tempfile.gettempdir(), "hexray_b200_bench")
     os.makedirs(workdir, exist_ok=True)
-    if a.workload == "terrain":
-        path = os.path.join(workdir, "terrain_%d_rank%d.hexray" % (a.grid_side, rank))
+    if a.workload in ("terrain", "soup"):
+        path = os.path.join(workdir, "%s_%d_rank%d.hexray" % (a.workload, a.grid_side if a.workload == "terrain" else a.soup_triangles, rank))
         with open(path, "w") as f:
-            f.write(scene_text(a, "synthetic:terrain:%d:0x5EED" % a.grid_side, W, H, spp_total))
+            f.write(scene_text(a, synthetic_mesh_name(a), W, H, spp_total))
     else:
         path = os.path.join(hx.data_root(), a.workload + ".hexray")
     t0 = time.time()
@@ -386,7 +396,7 @@ def ours(a):
         peak = peaks["hbm_gbs"] if hbm_bound else 23149.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "walk_traffic.json")  # written by tools/ncu_traffic.py from an `ncu --set full` capture
-        if os.path.exists(tp) and a.workload == "terrain":
+        if os.path.exists(tp) and a.workload == "terrain" and a.grid_side == 2237:
             with open(tp) as f:
                 traffic = json.load(f)
         line = {
@@ -417,8 +427,11 @@ def ours(a):
             b = argparse.Namespace(**vars(a))
             note = ""
             if a.workload == "terrain" and a.grid_side > 709:
-                b.grid_side = 709  # the reference needs ~2 min to parse + build the 10 M mesh: that is what --impl reference times
+                b.grid_side = 709  # the reference needs ~1 min to parse + build the 10 M mesh: that is what --impl reference times
                 note = " (1 002 528-triangle variant of the terrain; the full mesh is timed by --impl reference)"
+            if a.workload == "soup" and a.soup_triangles > 1000000:
+                b.soup_triangles = 1000000
+                note = " (1 M-triangle variant of the soup; the full mesh is timed by --impl reference)"
             mr, info = run_reference_sample(b, workdir)
             if mr is None:
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": info["unavailable"]}
