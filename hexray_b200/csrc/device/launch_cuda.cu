@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
 
 template <int SSTACK>
 struct WalkShared {
-    float ray[11][HXR_WALK_BLOCK];  // rows 0-2 origin, 4-6 1/direction, 8-10 direction (3 and 7: zero, read for leaf "axis 3")
+    float ray[9][HXR_WALK_BLOCK];  // rows 0-2 origin, 3-5 1/direction, 6-8 direction (a leaf child's "axis 3" reads the next row: finite, unused)
     uint32_t tb[HXR_WALK_BLOCK];  // bits of the (non-negative) float bound; 0 = shadow ray certainly blocked
     uint32_t stRef[SSTACK][HXR_WALK_BLOCK];
     float stMin[SSTACK][HXR_WALK_BLOCK];
@@ -302,12 +302,11 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         const float* col;
         uint32_t par;
         __device__ __forceinline__ float o(uint32_t axis) const { return col[axis * HXR_WALK_BLOCK]; }
-        __device__ __forceinline__ float inv(uint32_t axis) const { return col[(4 + axis) * HXR_WALK_BLOCK]; }
+        __device__ __forceinline__ float inv(uint32_t axis) const { return col[(3 + axis) * HXR_WALK_BLOCK]; }
     } wr;
     wr.col = &sh.ray[0][tid];
     wr.par = 0;
-    sh.ray[3][tid] = 0.0f;
-    sh.ray[7][tid] = 0.0f;
+    for (int r = 0; r < 9; r++) sh.ray[r][tid] = 0.0f;
     const KdBlock* blocks = nullptr;  // the current mesh
     const uint32_t* leafTris = nullptr;
     const TriF32* tris = nullptr;
@@ -353,8 +352,8 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         const WalkRay w = walk_ray_f(ox, oy, oz, dx, dy, dz);
                         wr.par = w.par;
                         sh.ray[0][tid] = ox; sh.ray[1][tid] = oy; sh.ray[2][tid] = oz;
-                        sh.ray[4][tid] = w.ix; sh.ray[5][tid] = w.iy; sh.ray[6][tid] = w.iz;
-                        sh.ray[8][tid] = dx; sh.ray[9][tid] = dy; sh.ray[10][tid] = dz;
+                        sh.ray[3][tid] = w.ix; sh.ray[4][tid] = w.iy; sh.ray[5][tid] = w.iz;
+                        sh.ray[6][tid] = dx; sh.ray[7][tid] = dy; sh.ray[8][tid] = dz;
                         tmin = __uint_as_float(w2.x);
                         tmax = __uint_as_float(w2.y);
                         tbest = __uint_as_float(w2.z);
@@ -455,7 +454,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 const unsigned ot = warpBase | (unsigned)o;
                 const float oBest = __uint_as_float(sh.tb[ot]);  // the freshest bound (other lanes may have lowered it this round)
                 float ghi;
-                const int cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[8][ot], sh.ray[9][ot], sh.ray[10][ot],
+                const int cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot],
                                            oErr, oBest, ghi);
                 if (cls == HXR_TF_CERTAIN) {
                     if (SHADOW && ghi < oOcc) atomicMin(&sh.tb[ot], 0u);  // certainly blocked: no exact test needed
@@ -606,6 +605,7 @@ template <bool SHADOW> static void launch_walk(const DScene& sc, const TraceScra
 {
     if (cnt) { launch_walk_s<SHADOW, true, 10>(sc, ts, cnt, max_tasks); return; }
     switch (g_sstack) {
+        case 9: launch_walk_s<SHADOW, false, 9>(sc, ts, nullptr, max_tasks); break;
         case 12: launch_walk_s<SHADOW, false, 12>(sc, ts, nullptr, max_tasks); break;
         case 14: launch_walk_s<SHADOW, false, 14>(sc, ts, nullptr, max_tasks); break;
         case 16: launch_walk_s<SHADOW, false, 16>(sc, ts, nullptr, max_tasks); break;
