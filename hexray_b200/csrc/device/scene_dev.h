@@ -96,6 +96,10 @@ struct DScene {
     // per node: slot of its traversal results if its geometry is a "big" mesh (walked by the persistent
     // traversal kernel), -1 otherwise (analytic primitives, CSG, heightfields, meshes <= HXR_SMALL_MESH)
     const int32_t* node_slot;
+    // per node: conservative world-space box of its geometry (min xyz, max xyz; +-1e300 when unbounded or unknown): the
+    // node loops skip a node whose box the ray misses before paying for the object-space transform and intersector
+    const double* node_box;
+    int32_t use_node_box;
     int32_t n_big;
     int32_t simple_inline;  // every inline node is a plane, sphere, cube or brute-force mesh (selects the lean kernel variants)
     int32_t n_nodes, n_lights;

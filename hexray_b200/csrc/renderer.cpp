@@ -252,6 +252,46 @@ int Renderer::uploadScene(const hxr_scene* sp)
         m_scene.node_slot = uploadArray(slot.data(), slot.size());
         if (!m_scene.node_slot) return oom();
         m_scene.n_big = m_nBig;
+        // world boxes of the inline nodes' geometry: the 8 corners of the object-space box through the node transform
+        std::vector<double> box((size_t)std::max(1, s.n_nodes) * 6);
+        for (int i = 0; i < s.n_nodes; i++) {
+            double* b = &box[(size_t)i * 6];
+            for (int k = 0; k < 3; k++) { b[k] = -1e300; b[3 + k] = 1e300; }
+            const hxr_geometry& g = s.geometries[s.nodes[i].geom];
+            double lo[3], hi[3];
+            bool bounded = true;
+            switch (g.type) {
+                case HXR_GEOM_PLANE: lo[0] = lo[2] = -g.p[1]; hi[0] = hi[2] = g.p[1]; lo[1] = hi[1] = g.p[0]; break;
+                case HXR_GEOM_SPHERE: for (int k = 0; k < 3; k++) { lo[k] = g.p[k] - g.p[3]; hi[k] = g.p[k] + g.p[3]; } break;
+                case HXR_GEOM_CUBE: for (int k = 0; k < 3; k++) { lo[k] = g.p[k] - g.p[3]; hi[k] = g.p[k] + g.p[3]; } break;
+                case HXR_GEOM_MESH: for (int k = 0; k < 3; k++) { lo[k] = s.meshes[g.a].bbox_min[k]; hi[k] = s.meshes[g.a].bbox_max[k]; } break;
+                default: bounded = false; break;  // CSG, heightfield: always tested
+            }
+            for (int k = 0; k < 3 && bounded; k++) bounded = std::isfinite(lo[k]) && std::isfinite(hi[k]) && std::fabs(lo[k]) < 1e30 && std::fabs(hi[k]) < 1e30;
+            if (!bounded) continue;
+            const hxr_transform& T = s.nodes[i].T;
+            double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+            for (int c = 0; c < 8; c++) {
+                const double p[3] = {(c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]};
+                for (int k = 0; k < 3; k++) {
+                    const double w = p[0] * T.m[k] + p[1] * T.m[3 + k] + p[2] * T.m[6 + k] + T.offset[k];
+                    mn[k] = std::min(mn[k], w);
+                    mx[k] = std::max(mx[k], w);
+                }
+            }
+            for (int k = 0; k < 3; k++) {
+                // margin: the intersectors' own 1e-6 tolerances (scaled by the transform) plus rounding
+                const double mag = std::max(std::fabs(mn[k]), std::fabs(mx[k]));
+                double scale = 0;
+                for (int r = 0; r < 3; r++) scale += std::fabs(T.m[3 * r + k]);
+                const double pad = 1e-5 * (1.0 + scale) + 1e-9 * mag;
+                b[k] = mn[k] - pad;
+                b[3 + k] = mx[k] + pad;
+            }
+        }
+        m_scene.node_box = uploadArray(box.data(), box.size());
+        if (!m_scene.node_box) return oom();
+        m_scene.use_node_box = getenv("HXR_NO_NODE_BOX") ? 0 : 1;
         m_scene.simple_inline = 1;
         for (int i = 0; i < s.n_nodes; i++) {
             if (slot[i] >= 0) continue;
