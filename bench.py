@@ -111,9 +111,9 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=32, help="samples per pixel per GPU per step")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--ref-width", type=int, default=192, help="reference arm: bounded sample resolution")
-    ap.add_argument("--ref-height", type=int, default=108)
-    ap.add_argument("--ref-spp", type=int, default=8)
+    ap.add_argument("--ref-width", type=int, default=384, help="reference arm: bounded sample resolution")
+    ap.add_argument("--ref-height", type=int, default=216)
+    ap.add_argument("--ref-spp", type=int, default=8, help="reference arm: samples per pixel of the bounded sample (the cpu_baseline leg of our arm uses 4x)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--queue-capacity", type=int, default=16 << 20)
     return ap.parse_args()
@@ -425,6 +425,7 @@ def ours(a):
         }
         if world == 1 and not a.no_cpu_baseline:
             b = argparse.Namespace(**vars(a))
+            b.ref_spp = a.ref_spp * 4  # ~10 s of CPU rendering on the 1 M-triangle variant
             note = ""
             if a.workload == "terrain" and a.grid_side > 709:
                 b.grid_side = 709  # the reference needs ~1 min to parse + build the 10 M mesh: that is what --impl reference times
