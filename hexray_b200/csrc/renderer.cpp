@@ -192,7 +192,8 @@ int Renderer::uploadScene(const hxr_scene* sp)
         d.faceted = m.faceted;
         d.backface = m.backface_culling;
         d.n_tris = m.n_triangles;
-        d.brute = (m.n_triangles <= HXR_SMALL_MESH || (m_cfg.flags & HXR_CFG_BRUTE_FORCE_MESHES)) ? 1 : 0;
+        const int smallMesh = getenv("HXR_SMALL_MESH") ? atoi(getenv("HXR_SMALL_MESH")) : HXR_SMALL_MESH;
+        d.brute = (m.n_triangles <= smallMesh || (m_cfg.flags & HXR_CFG_BRUTE_FORCE_MESHES)) ? 1 : 0;
         hxr_accel_info& ai = m_accel[i];
         ai.nodes = kd.blocks.size();
         ai.leaves = kd.leaves;
