@@ -355,7 +355,9 @@ bool Renderer::ensureQueues()
 {
     const uint32_t cap = m_cfg.queue_capacity ? (uint32_t)std::min<uint64_t>(m_cfg.queue_capacity, 1u << 30) : (8u << 20);
     const uint32_t shadowCap = (uint32_t)std::min<uint64_t>(1u << 30, std::max<uint64_t>((uint64_t)cap * 2, (uint64_t)m_maxShadowPerHit * 4096));
-    const uint32_t taskCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)std::max(cap, shadowCap) * (uint64_t)std::max(1, m_nBig));
+    // a ray becomes a walk task only for the meshes whose box it enters: room for 8 per ray is plenty even with hundreds of
+    // meshes; if a wave ever needs more, the overflow flag makes render() redo the frame in smaller batches
+    const uint32_t taskCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)std::max(cap, shadowCap) * (uint64_t)std::min(8, std::max(1, m_nBig)));
     if (m_q[0] && cap == m_cap && shadowCap == m_shadowCap && taskCap == m_taskCap) return true;
     for (int i = 0; i < 2; i++) { dev::free_(m_q[i]); m_q[i] = nullptr; }
     dev::free_(m_hits); m_hits = nullptr;
