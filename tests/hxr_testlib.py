@@ -229,3 +229,40 @@ def check_stereo(sess, scene, spp=0):
     assert err <= 1.25 * own + 0.004, "stereo %s: rmse vs converged reference %.4f, own noise %.4f" % (scene, err, own)
     assert mean_delta.max() <= 0.004, "stereo %s: mean delta %s" % (scene, mean_delta)
     return err
+
+
+def many_meshes_scene(n_side=6):
+    """n_side^2 instanced little meshes (44-triangle dice, a 10-triangle box) over a floor: many big-mesh nodes per scene."""
+    path = os.path.join(hx.data_root(), "_many_meshes.hexray")
+    lines = ["GlobalSettings {\n\tframeWidth 160\n\tframeHeight 120\n\tambientLight (0.2, 0.2, 0.2)\n\tmaxTraceDepth 4\n}",
+             "Camera camera {\n\tpos (0, 60, -140)\n\taspectRatio 1.33333\n\tpitch -22\n\tfov 90\n}",
+             "PointLight l1 {\n\tpos (-60, 160, -80)\n\tcolor (1, 1, 1)\n\tpower 40000\n}",
+             "Plane floor {\n\ty 0\n\tlimit 400\n}", "Mesh dice {\n\tfile \"geom/truncated_cube.obj\"\n\tfaceted true\n}",
+             "Mesh box {\n\tfile \"cornell/tallblock.obj\"\n\tfaceted true\n}",
+             "Lambert grey {\n\tcolor (0.7, 0.7, 0.7)\n}", "Lambert red {\n\tcolor (0.8, 0.3, 0.2)\n}",
+             "Reflection mirror {\n\tmultiplier 0.8\n}", "Node nfloor {\n\tgeometry floor\n\tshader grey\n}"]
+    k = 0
+    for i in range(n_side):
+        for j in range(n_side):
+            geom, scale = ("dice", 6.0) if (i + j) % 2 == 0 else ("box", 0.05)
+            shader = ("red", "mirror", "grey")[k % 3]
+            lines.append("Node n%d {\n\tgeometry %s\n\tshader %s\n\tscale (%g, %g, %g)\n\trotate (%d, %d, 0)\n\ttranslate (%g, %g, %g)\n}" % (
+                k, geom, shader, scale, scale, scale, 17 * k % 360, 29 * k % 90, (i - n_side / 2) * 28.0, 10.0, (j - n_side / 2) * 28.0))
+            k += 1
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return "_many_meshes"
+
+
+def check_many_meshes(api):
+    """36 mesh nodes: the walk (with its per-ray task budget) against brute force over every triangle, bit for bit."""
+    scene = many_meshes_scene()
+    sf = hx.SceneFile(scene_path(scene), api_=api)
+    out = []
+    for flags in (0, hx.CFG_BRUTE_FORCE_MESHES):
+        r = hx.Renderer(api_=api, queue_capacity=1 << 16, flags=flags).load(sf)
+        out.append(r.render()[0].copy())
+        r.close()
+    sf.close()
+    assert float(out[0].mean()) > 0.02
+    assert np.abs(out[0] - out[1]).max() < 1e-5

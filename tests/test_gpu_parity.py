@@ -168,3 +168,7 @@ def test_stereo_anaglyph(sess):
     # src/main.cpp:234-248: two traces per sample mixed into an anaglyph; Whitted + AA (deterministic) and GI
     T.check_stereo(sess, "kdtree_test")
     T.check_stereo(sess, "cornell_box", spp=256)
+
+
+def test_many_mesh_nodes(gpu_api):
+    T.check_many_meshes(gpu_api)
