@@ -90,6 +90,7 @@ int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits
 int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->r.traceVisible(seg, n, vis)) }
 int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { HXR_CTX_CALL(ctx->r.traceColor(rays, n, rgb)) }
 int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out) { HXR_CTX_CALL(ctx->r.accelInfo(mesh, out)) }
+int hxr_save_frame_bmp(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->r.saveFrameBmp(d_rgb, w, h, path)) }
 
 int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out,
                         float* ghi_out, int32_t* exact_out, double* gamma_out)

@@ -74,6 +74,8 @@ int scale_listed(float* vfb, const uint32_t* list, const uint32_t* n, uint32_t c
 int scale_all(float* buf, size_t n, float mul);
 // dst[i] += src[i]
 int add_into(float* dst, const float* src, size_t n);
+// float RGB frame -> BMP pixel array (bottom-up BGR rows of rowsz bytes, padding zeroed) through the 4097-entry table `lut`
+int to_bmp_rows(const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out);
 // anaglyph mix of the two eyes' images into out (n_pixels RGB pixels)
 int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels);
 

@@ -566,6 +566,11 @@ __global__ void k_stereo_mix(float* out, const float* __restrict__ L, const floa
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stereo_mix_item(out, L, R, i);
 }
+__global__ void k_to_bmp_rows(const float* __restrict__ rgb, int W, int H, int rowsz, const uint8_t* __restrict__ lut, uint8_t* out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < W && y < H) bmp_pixel_item(rgb, W, H, rowsz, lut, out, x, y);
+}
 // ---- launchers --------------------------------------------------------------------------
 template <class K> static int persistent_grid(K kernel, int block)
 {
@@ -706,6 +711,14 @@ int add_into(float* dst, const float* src, size_t n)
 {
     ProfScope ps(PROF_OTHER);
     k_add_into<<<g_sms * 8, 256, 0, g_stream>>>(dst, src, n);
+    return 1;
+}
+int to_bmp_rows(const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out)
+{
+    ProfScope ps(PROF_OTHER);
+    cudaMemsetAsync(out, 0, (size_t)rowsz * H, g_stream);
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_to_bmp_rows<<<g, b, 0, g_stream>>>(rgb, W, H, rowsz, lut, out);
     return 1;
 }
 int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels)

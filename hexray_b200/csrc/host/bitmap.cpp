@@ -179,6 +179,18 @@ bool Bitmap::saveBMP(const char* filename) const
     return true;
 }
 
+bool writeBmpFile(const char* filename, int width, int height, int rowsz, const unsigned char* rows)
+{
+    FILE* fp = fopen(filename, "wb");
+    if (!fp) return false;
+    BmpFileHeader fh = {19778, rowsz * height + 54, 0, 54};
+    BmpInfoHeader ih = {40, width, height, 1, 24, 0, 0, 0, 0, 0, 0};
+    bool ok = fwrite(&fh, sizeof fh, 1, fp) == 1 && fwrite(&ih, sizeof ih, 1, fp) == 1;
+    ok = ok && fwrite(rows, (size_t)rowsz, (size_t)height, fp) == (size_t)height;
+    fclose(fp);
+    return ok;
+}
+
 bool Bitmap::loadEXR(const char* filename)
 {
     exr::Image img;

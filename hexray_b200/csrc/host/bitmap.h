@@ -14,6 +14,8 @@ namespace hxr {
 namespace host {
 
 unsigned convertTo8bit_sRGB(float x);         // color.h:36-47
+// header + an already converted pixel array (bottom-up BGR rows of rowsz bytes): what saveBMP writes (bitmap.cpp:202-240)
+bool writeBmpFile(const char* filename, int width, int height, int rowsz, const unsigned char* rows);
 unsigned convertTo8bit_sRGB_cached(float x);  // sdl.cpp:414-419
 float decompress_sRGB(float x);               // color.h:49-57
 std::string extensionUpper(const char* fileName);

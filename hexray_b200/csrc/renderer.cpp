@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include "host/bitmap.h"
 
 namespace hxr {
 
@@ -28,6 +29,7 @@ Renderer::~Renderer()
     dev::free_(m_aaList);
     dev::free_(m_aaMask);
     dev::free_(m_accum);
+    dev::free_(m_srgbLut);
     dev::free_(m_eye[0]);
     dev::free_(m_eye[1]);
 }
@@ -648,6 +650,8 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
     m_scene.settings = savedSettings;
     if (ov) { overflow = true; return HXR_OK; }
 
+    m_lastW = W;
+    m_lastH = H;
     bool ok = true;
     if (devOut) ok = ok && dev::copy_d2d(devOut, m_accum, nPix * 3 * sizeof(float));
     if (hostOut) ok = ok && dev::download(hostOut, m_accum, nPix * 3 * sizeof(float));
@@ -684,6 +688,33 @@ int Renderer::resolveDevice(void* d_rgb, int W, int H, int spp)
     if (!d_rgb || W <= 0 || H <= 0 || spp <= 0) return fail(HXR_ERR_INVALID, "resolve: bad arguments");
     dev::scale_all((float*)d_rgb, (size_t)W * H * 3, 1.0f / (float)spp);
     if (!dev::sync()) return fail(HXR_ERR_CUDA, dev::last_error());
+    return HXR_OK;
+}
+
+// The screenshot (takeScreenshot -> Bitmap::saveBMP, src/sdl.cpp:103-116, src/bitmap.cpp:202-240) straight from device
+// memory: the 8-bit conversion runs on the GPU and a quarter of the float frame's bytes cross PCIe.
+int Renderer::saveFrameBmp(const void* d_rgb, int W, int H, const char* path)
+{
+    if (!path) return fail(HXR_ERR_INVALID, "save_frame: null path");
+    if (!d_rgb) { d_rgb = m_accum; W = m_lastW; H = m_lastH; }
+    if (!d_rgb || W <= 0 || H <= 0) return fail(HXR_ERR_INVALID, "save_frame: no frame");
+    if (!m_srgbLut) {
+        uint8_t lut[4097];
+        for (int i = 0; i <= 4096; i++) lut[i] = (uint8_t)host::convertTo8bit_sRGB(i / 4096.0f);
+        m_srgbLut = (uint8_t*)dev::alloc(sizeof lut);
+        if (!m_srgbLut || !dev::upload(m_srgbLut, lut, sizeof lut)) return fail(HXR_ERR_CUDA, dev::last_error());
+    }
+    int rowsz = W * 3;
+    if (rowsz % 4) rowsz += 4 - (rowsz % 4);
+    const size_t bytes = (size_t)rowsz * H;
+    uint8_t* dout = (uint8_t*)dev::alloc(bytes);
+    if (!dout) return fail(HXR_ERR_CUDA, dev::last_error());
+    std::vector<uint8_t> rows(bytes);
+    dev::to_bmp_rows((const float*)d_rgb, W, H, rowsz, m_srgbLut, dout);
+    const bool ok = dev::download(rows.data(), dout, bytes);
+    dev::free_(dout);
+    if (!ok) return fail(HXR_ERR_CUDA, dev::last_error());
+    if (!host::writeBmpFile(path, W, H, rowsz, rows.data())) return fail(HXR_ERR_IO, std::string("cannot write ") + path);
     return HXR_OK;
 }
 

@@ -18,6 +18,7 @@ public:
     int setCamera(const hxr_camera* cam);
     int render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats);
     int resolveDevice(void* d_rgb, int W, int H, int spp);
+    int saveFrameBmp(const void* d_rgb, int W, int H, const char* path);
     int traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits);
     int traceVisible(const double* seg, size_t n, uint8_t* out);
     int traceColor(const hxr_ray* rays, size_t n, float* rgb);
@@ -64,6 +65,8 @@ private:
     uint32_t* m_aaList = nullptr;
     uint8_t* m_aaMask = nullptr;
     float* m_accum = nullptr;
+    int m_lastW = 0, m_lastH = 0;    // size of the frame m_accum holds
+    uint8_t* m_srgbLut = nullptr;    // the reference's 4097-entry sRGB table on the device
     float* m_eye[2] = {nullptr, nullptr};  // per-eye accumulation of anaglyph frames
     size_t m_eyePixels = 0;
     size_t m_accumPixels = 0;

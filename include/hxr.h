@@ -354,6 +354,12 @@ void hxr_scene_file_free(hxr_scene_file* sf);
  * src/sdl.cpp:404-419) or ".exr" (HALF RGBA, alpha 1). rgb: w*h*3 floats top-down. */
 int hxr_save_image(const char* path, const float* rgb, int32_t width, int32_t height);
 
+/* The screenshot straight from device memory (takeScreenshot -> Bitmap::saveBMP, src/sdl.cpp:103-116, src/bitmap.cpp:202-240):
+ * the sRGB-table conversion runs on the GPU, only the 8-bit pixel array is copied back. d_rgb: width*height*3 floats on the
+ * context's device, or NULL for the frame of the last hxr_render / hxr_render_device call (then width/height are ignored).
+ * The file is byte-identical to hxr_save_image(".bmp") of the same frame. */
+int hxr_save_frame_bmp(hxr_ctx* ctx, const void* d_rgb, int32_t width, int32_t height, const char* path);
+
 /* Bitmap::loadImage equivalent (".bmp" 8/24/32 bpp, ".exr" scan-line NONE/RLE/ZIPS/ZIP/PIZ): fills *width / *height;
  * when rgb_out is non-NULL and capacity_floats >= width*height*3 also the pixels (float RGB, top-down). */
 int hxr_load_image(const char* path, int32_t* width, int32_t* height, float* rgb_out, size_t capacity_floats);

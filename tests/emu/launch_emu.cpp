@@ -182,6 +182,14 @@ int add_into(float* dst, const float* src, size_t n)
     g_launches[PROF_OTHER]++;
     return 1;
 }
+int to_bmp_rows(const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out)
+{
+    memset(out, 0, (size_t)rowsz * H);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) bmp_pixel_item(rgb, W, H, rowsz, lut, out, x, y);
+    g_launches[PROF_OTHER]++;
+    return 1;
+}
 int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels)
 {
     for (size_t i = 0; i < n_pixels; i++) stereo_mix_item(out, left, right, i);

@@ -266,3 +266,13 @@ def check_many_meshes(api):
     sf.close()
     assert float(out[0].mean()) > 0.02
     assert np.abs(out[0] - out[1]).max() < 1e-5
+
+
+def check_screenshot(sess, tmp_path):
+    r = sess.renderer("simple")
+    img, _ = r.render(width=203, height=77)  # a row size that needs BMP padding
+    a, b = str(tmp_path / "device.bmp"), str(tmp_path / "host.bmp")
+    r.save_frame_bmp(a)
+    hx.save_image(b, img, api_=sess.api)
+    da, db = open(a, "rb").read(), open(b, "rb").read()
+    assert len(da) == 54 + 77 * 612 and da == db

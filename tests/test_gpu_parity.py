@@ -172,3 +172,8 @@ def test_stereo_anaglyph(sess):
 
 def test_many_mesh_nodes(gpu_api):
     T.check_many_meshes(gpu_api)
+
+
+def test_device_screenshot_equals_host_save(sess, tmp_path):
+    # hxr_save_frame_bmp (8-bit conversion on the GPU) writes the same bytes as hxr_save_image of the downloaded frame
+    T.check_screenshot(sess, tmp_path)
