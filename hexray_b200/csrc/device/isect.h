@@ -548,8 +548,10 @@ HXR_HD int tri_filter(const TriF32* p, bool backface, float ox, float oy, float 
 // used for meshes so small that a tree walk costs more than it saves
 HXR_HD bool mesh_bruteforce(const DMesh& M, const Ray& ray, double gamma_limit, MeshBest& best)
 {
+    // The box gate (src/mesh.cpp:249) never changes the answer - a hit lies inside the box - it only saves work; for a quad
+    // it costs more issue slots than the two triangle tests it guards, and it splits the warp
     double t0, t1;
-    if (!mesh_slab(M, ray, gamma_limit, t0, t1)) return false;
+    if (M.brute != 3 && !mesh_slab(M, ray, gamma_limit, t0, t1)) return false;
     best.gamma = gamma_limit;
     best.tri = -1;
     best.l2 = best.l3 = 0;

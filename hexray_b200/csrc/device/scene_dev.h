@@ -66,7 +66,7 @@ struct DMesh {
     int32_t n_tris;
     float abs_max;  // largest |coordinate| of the mesh box (error bound of the float filter)
     int32_t pad;
-    int32_t brute;  // test all triangles in index order (tiny meshes, or HXR_CFG_BRUTE_FORCE_MESHES) instead of walking the tree
+    int32_t brute;  // test all triangles in index order (tiny meshes, or HXR_CFG_BRUTE_FORCE_MESHES) instead of walking the tree; 3: and skip the box gate
 };
 
 struct DHeightfield {

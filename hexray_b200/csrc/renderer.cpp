@@ -196,6 +196,7 @@ int Renderer::uploadScene(const hxr_scene* sp)
         d.n_tris = m.n_triangles;
         const int smallMesh = getenv("HXR_SMALL_MESH") ? atoi(getenv("HXR_SMALL_MESH")) : HXR_SMALL_MESH;
         d.brute = (m.n_triangles <= smallMesh || (m_cfg.flags & HXR_CFG_BRUTE_FORCE_MESHES)) ? 1 : 0;
+        if (d.brute && m.n_triangles <= HXR_SMALL_MESH && !getenv("HXR_QUAD_SLAB")) d.brute = 3;  // tiny: no box gate either
         hxr_accel_info& ai = m_accel[i];
         ai.nodes = kd.blocks.size();
         ai.leaves = kd.leaves;
