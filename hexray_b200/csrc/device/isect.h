@@ -14,10 +14,12 @@
 //
 // Mesh traversal: the reference walks a median-split tree recursively and keeps a leaf hit only
 // if it lies inside the leaf box (mesh.cpp:221-245); the net result is the closest triangle hit
-// under the triangle test's own arithmetic. We get the same result from a SAH KD-tree walked
-// front to back with an explicit stack: every triangle whose (inflated) bounds overlap a leaf is
-// referenced by it, hits are accepted wherever they fall, and the walk stops only once the best
-// hit lies safely before the end of the current leaf segment.
+// under the triangle test's own arithmetic. We get the same result from a SAH KD-tree (two levels
+// per 32-byte block) walked front to back with an explicit stack: every triangle whose bounds
+// overlap a leaf is referenced by it, hits are accepted wherever they fall, and a pending subtree
+// is skipped only when its whole parameter range lies beyond the best hit. Two forms walk it:
+// mesh_closest (double planes, one ray: CSG children, CPU tests) and the conservative FP32 walk
+// (plane_cross / block_step / tri_filter below: what the GPU kernel runs).
 #pragma once
 #include "scene_dev.h"
 

@@ -1,22 +1,22 @@
 // launch_cuda.cu — the sm_100a kernels of the render hot path and their launchers
 // (implements device/launch.h; the only translation unit compiled by nvcc).
 //
-// Kernels (one per wavefront stage; per-item bodies live in pipeline.h):
-//   k_gen_primary     primary-ray generator (pixel jitter / AA offsets / DOF lens)     -> ray queue
-//   k_setup_closest   per ray: every inline node (analytic primitives, CSG, heightfield, tiny meshes) in scene
-//                     order; each big mesh whose box the ray enters becomes a (ray, node) walk task
-//   k_walk            the KD-tree walk: PERSISTENT warps running a per-lane state machine. A lane that
-//                     finishes its task takes a new one (idle lanes found with __ballot_sync, one
-//                     atomicAdd on the queue head by the first idle lane, broadcast with __shfl_sync), so
-//                     lanes stay busy although rays need very different numbers of steps. One step =
-//                     one inner node (a single 128-bit node load) or one triangle test (six 128-bit loads).
-//   k_finalize_closest winner across inline nodes and walks, IntersectionInfo, lights, environment, bump
-//   k_shade           Whitted shader tree or path-tracing vertex: pushes child/shadow tasks,
-//                     accumulates radiance with RED.ADD.F32
-//   k_setup_shadow / k_walk<shadow> / k_accum_shadow   visible() in the same three stages (any-hit walk)
-//   k_aa_detect / k_scale_* / k_add   frame-buffer passes
-// Grid sizing: persistent kernels launch (SM count x resident blocks/SM) blocks — 148 SMs on
-// B200 — so every SM holds its full complement of warps for the whole launch.
+// Kernels (one per wavefront stage; per-item bodies live in pipeline.h / isect.h / shade.h):
+//   k_gen_primary        primary-ray generator (pixel jitter / AA offsets / DOF lens / stereo eye)  -> ray queue
+//   k_setup_closest      per ray, in double: every inline node (analytic primitives, CSG, heightfield, quads) in scene
+//                        order; each mesh whose box the ray enters becomes a ready-to-walk float task
+//   k_walk               the KD-tree walk, FP32 only: PERSISTENT warps, idle lanes refilled with __ballot_sync + one
+//                        atomicAdd per warp + __shfl_sync; a bounded phase of block steps (32-byte block = two tree
+//                        levels) alternates with a warp-cooperative phase that filters the triangles of all leaves held
+//                        by the warp, 32 (ray, triangle) pairs at a time; undecided pairs go to a list
+//   k_confirm_closest_a/b, k_confirm_shadow   the exact (double) triangle test on the listed pairs
+//   k_finalize_closest   winner across inline nodes and walked meshes, IntersectionInfo, lights, environment, bump
+//   k_shade<GI>          Whitted shader tree or path-tracing vertex: pushes child/shadow tasks,
+//                        accumulates radiance with RED.ADD.F32
+//   k_setup_shadow / k_walk<shadow> / k_confirm_shadow / k_accum_shadow   visible() in the same stages (any-hit walk)
+//   k_aa_detect / k_scale_* / k_add_into / k_stereo_mix / k_to_bmp_rows   frame-buffer passes
+// Grid sizing: the persistent walk launches (SM count x resident blocks/SM) blocks - 148 SMs on B200 - the per-item
+// stage kernels are grid-stride loops over device-side counts, sized by a host-side upper bound of the count.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
