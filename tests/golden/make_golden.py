@@ -189,8 +189,34 @@ def stereo():
         print("stereo", name, img.shape, float(img.mean()), img.reshape(-1, 3).mean(0))
 
 
+def features():
+    """Scenes written for this repo that exercise what no bundled scene does (tests/hxr_testlib.py: FEATURES_*)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hxr_testlib as T
+    tmp = "/tmp/hxr_golden.bin"
+    name = T.feature_scene("whitted")
+    info = run(["render", scene_path(name), "--out", tmp])
+    img = np.fromfile(tmp, dtype=np.float32).reshape(240, 320, 3)
+    np.savez_compressed(os.path.join(HERE, "features_whitted.npz"), img=img.astype(np.float16), info=json.dumps(info),
+                        cmd="hexray_ref render <tests/hxr_testlib.py FEATURES_WHITTED>")
+    print("features whitted", float(img.mean()))
+    name = T.feature_scene("stochastic")
+    reps = 200  # glossy reflection and the DOF lens are stochastic at 16 samples per pixel: average frames
+    acc = np.zeros((120, 160, 3), dtype=np.float64)
+    for r in range(reps):
+        info = run(["render", scene_path(name), "--out", tmp])
+        acc += np.fromfile(tmp, dtype=np.float32).reshape(120, 160, 3)
+    img = (acc / reps).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "features_stochastic.npz"), img=img.astype(np.float16), reps=reps, info=json.dumps(info),
+                        cmd="hexray_ref render <tests/hxr_testlib.py FEATURES_STOCHASTIC> x %d frames averaged" % reps)
+    print("features stochastic", float(img.mean()))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "terrain":
+    if len(sys.argv) > 1 and sys.argv[1] == "features":
+        features()
+    elif len(sys.argv) > 1 and sys.argv[1] == "terrain":
         terrain()
     elif len(sys.argv) > 1 and sys.argv[1] == "stereo":
         stereo()

@@ -276,3 +276,229 @@ def check_screenshot(sess, tmp_path):
     hx.save_image(b, img, api_=sess.api)
     da, db = open(a, "rb").read(), open(b, "rb").read()
     assert len(da) == 54 + 77 * 612 and da == db
+
+
+# ---------------------------------------------------------------------------- features no bundled scene uses
+FEATURES_WHITTED = """GlobalSettings {
+	frameWidth 320
+	frameHeight 240
+	ambientLight (0.15, 0.15, 0.15)
+	maxTraceDepth 5
+	wantAA true
+}
+Camera camera {
+	pos (0, 70, -150)
+	aspectRatio 1.33333
+	pitch -20
+	fov 95
+}
+PointLight l1 {
+	pos (-60, 170, -110)
+	color (1, 1, 1)
+	power 45000
+}
+Plane floor {
+	y 0
+	limit 350
+}
+CheckerTexture checker {
+	color1 (0.9, 0.9, 0.9)
+	color2 (0.15, 0.25, 0.55)
+	scaling 0.1
+}
+CheckerTexture smallChecker {
+	color1 (0.95, 0.8, 0.2)
+	color2 (0.2, 0.6, 0.3)
+	scaling 0.125
+}
+Lambert floorShader {
+	color (1, 1, 1)
+	texture checker
+}
+Lambert sphereShader {
+	color (1, 1, 1)
+	texture smallChecker
+}
+Phong phong {
+	color (0.8, 0.25, 0.2)
+	specular (0.7, 0.7, 0.7)
+	exponent 40
+}
+Reflection mirror {
+	multiplier 0.85
+}
+Refraction glass {
+	ior 1.45
+	multiplier 0.9
+}
+Const emissive {
+	color (0.3, 0.9, 0.4)
+}
+Sphere uvSphere {
+	O (0, 0, 0)
+	R 16
+	uvscaling 6
+}
+Cube cubeA {
+	O (0, 0, 0)
+	side 26
+}
+Cube cubeB {
+	O (9, 9, -9)
+	side 22
+}
+Sphere ball {
+	O (0, 0, 0)
+	R 17
+}
+CSGUnion csgUnion {
+	left cubeA
+	right ball
+}
+CSGInter csgInter {
+	left cubeA
+	right ball
+}
+CSGDiff csgNested {
+	left csgUnion
+	right cubeB
+}
+Mesh culledDice {
+	file "geom/truncated_cube.obj"
+	faceted true
+	backfaceCulling true
+}
+Node nFloor {
+	geometry floor
+	shader floorShader
+}
+Node nSphere {
+	geometry uvSphere
+	shader sphereShader
+	translate (-70, 18, 10)
+}
+Node nUnion {
+	geometry csgUnion
+	shader phong
+	rotate (25, 15, 0)
+	translate (-25, 20, 30)
+}
+Node nInter {
+	geometry csgInter
+	shader mirror
+	rotate (40, 0, 10)
+	translate (25, 18, -10)
+}
+Node nNested {
+	geometry csgNested
+	shader glass
+	rotate (-30, 20, 0)
+	translate (70, 20, 35)
+}
+Node nDice {
+	geometry culledDice
+	shader emissive
+	scale (9, 9, 9)
+	rotate (33, 21, 0)
+	translate (0, 14, -55)
+}
+"""
+
+FEATURES_STOCHASTIC = """GlobalSettings {
+	frameWidth 160
+	frameHeight 120
+	ambientLight (0.2, 0.2, 0.2)
+	maxTraceDepth 4
+	wantAA false
+}
+Camera camera {
+	pos (0, 60, -140)
+	aspectRatio 1.33333
+	pitch -18
+	fov 90
+	dof true
+	autoFocus true
+	fNumber 4
+	numSamples 16
+}
+PointLight l1 {
+	pos (-60, 170, -110)
+	color (1, 1, 1)
+	power 45000
+}
+Plane floor {
+	y 0
+	limit 350
+}
+Lambert grey {
+	color (0.75, 0.75, 0.75)
+}
+Reflection glossy {
+	multiplier 0.9
+	glossiness 0.78
+	numSamples 6
+}
+Layered floorShader {
+	layer grey (1, 1, 1)
+	layer glossy (0.35, 0.35, 0.35)
+}
+Phong phong {
+	color (0.2, 0.5, 0.85)
+	specular (0.6, 0.6, 0.6)
+	exponent 25
+}
+Sphere ball {
+	O (0, 0, 0)
+	R 22
+}
+Cube box {
+	O (0, 0, 0)
+	side 30
+}
+Node nFloor {
+	geometry floor
+	shader floorShader
+}
+Node nBall {
+	geometry ball
+	shader phong
+	translate (-30, 22, 20)
+}
+Node nBox {
+	geometry box
+	shader glossy
+	rotate (30, 0, 0)
+	translate (35, 15, 0)
+}
+"""
+
+
+def feature_scene(kind):
+    text = FEATURES_WHITTED if kind == "whitted" else FEATURES_STOCHASTIC
+    path = os.path.join(hx.data_root(), "_features_%s.hexray" % kind)
+    with open(path, "w") as f:
+        f.write(text)
+    return "_features_%s" % kind
+
+
+def check_features(sess, frames=24):
+    """CSG union / intersection / nested CSG, Sphere uvscaling, backface culling, Const, Phong, Refraction (deterministic, per
+    pixel) and glossy Reflection + DOF with autoFocus (stochastic, averaged frames) against the compiled reference."""
+    g = golden("features", "whitted")
+    ref = g["img"].astype(np.float32)
+    H, W = ref.shape[:2]
+    img, st = sess.renderer(feature_scene("whitted")).render(width=W, height=H)
+    d = np.abs(clamp01(img) - clamp01(ref)).max(axis=2)
+    frac = float((d <= PIXEL_TOL + 6e-4).mean())
+    assert frac >= PIXEL_FRACTION, "features: only %.4f%% of pixels within 1/255 (max diff %.4f)" % (frac * 100, d.max())
+    g = golden("features", "stochastic")
+    ref = g["img"].astype(np.float32)
+    H, W = ref.shape[:2]
+    r = sess.renderer(feature_scene("stochastic"))
+    acc = np.zeros_like(ref)
+    for s in range(frames):
+        acc += r.render(width=W, height=H, seed=500 + s)[0]
+    acc /= frames
+    dd = np.abs(clamp01(acc) - clamp01(ref))
+    assert dd.mean() < 0.004 and np.sqrt((dd ** 2).mean()) < 0.012, (float(dd.mean()), float(np.sqrt((dd ** 2).mean())))
+    return frac

@@ -50,3 +50,7 @@ def test_many_mesh_nodes(emu_api):
 def test_device_screenshot_equals_host_save(sess, tmp_path):
     # hxr_save_frame_bmp (8-bit conversion on the device) writes the same bytes as hxr_save_image of the downloaded frame
     T.check_screenshot(sess, tmp_path)
+
+
+def test_features_no_bundled_scene_uses(sess):
+    T.check_features(sess, frames=12)

@@ -177,3 +177,8 @@ def test_many_mesh_nodes(gpu_api):
 def test_device_screenshot_equals_host_save(sess, tmp_path):
     # hxr_save_frame_bmp (8-bit conversion on the GPU) writes the same bytes as hxr_save_image of the downloaded frame
     T.check_screenshot(sess, tmp_path)
+
+
+def test_features_no_bundled_scene_uses(sess):
+    # CSG union / intersection / nesting, uvscaling, backface culling, Const, glossy Reflection, autoFocus vs the reference
+    T.check_features(sess, frames=48)
