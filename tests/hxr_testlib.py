@@ -502,3 +502,16 @@ def check_features(sess, frames=24):
     dd = np.abs(clamp01(acc) - clamp01(ref))
     assert dd.mean() < 0.004 and np.sqrt((dd ** 2).mean()) < 0.012, (float(dd.mean()), float(np.sqrt((dd ** 2).mean())))
     return frac
+
+
+def check_small_queue(api):
+    """A ray queue far smaller than the frame: the driver renders in batches (and redoes the frame in smaller ones when a
+    ray tree outgrows the queue); the image must not depend on the queue size."""
+    out = []
+    for qc in (1 << 20, 4096):
+        sf = hx.SceneFile(scene_path("meshes"), api_=api)
+        r = hx.Renderer(api_=api, queue_capacity=qc).load(sf)
+        out.append(r.render(width=200, height=150)[0].copy())
+        r.close()
+        sf.close()
+    assert np.abs(out[0] - out[1]).max() < 1e-4

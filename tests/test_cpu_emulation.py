@@ -54,3 +54,7 @@ def test_device_screenshot_equals_host_save(sess, tmp_path):
 
 def test_features_no_bundled_scene_uses(sess):
     T.check_features(sess, frames=12)
+
+
+def test_small_queue(emu_api):
+    T.check_small_queue(emu_api)

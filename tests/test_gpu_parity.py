@@ -182,3 +182,7 @@ def test_device_screenshot_equals_host_save(sess, tmp_path):
 def test_features_no_bundled_scene_uses(sess):
     # CSG union / intersection / nesting, uvscaling, backface culling, Const, glossy Reflection, autoFocus vs the reference
     T.check_features(sess, frames=48)
+
+
+def test_small_queue(gpu_api):
+    T.check_small_queue(gpu_api)
