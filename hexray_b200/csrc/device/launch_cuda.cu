@@ -34,7 +34,7 @@ static cudaStream_t g_stream = nullptr;
 static std::string g_err;
 static bool g_prof = false;
 // walk-loop tunables (uniform kernel arguments; HXR_WALK_STEPS / HXR_REFILL_MIN in the environment override the defaults)
-static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10;
+static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10, g_useMail = 1;
 static uint64_t g_launches[PROF_NCAT];
 static std::vector<cudaEvent_t> g_evPool;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
@@ -69,6 +69,7 @@ bool init(int device, char* err, size_t errlen)
     g_sms = p.multiProcessorCount;
     if (const char* e = getenv("HXR_WALK_STEPS")) g_walkSteps = std::max(1, atoi(e));
     if (const char* e = getenv("HXR_SSTACK")) g_sstack = atoi(e);
+    if (getenv("HXR_NO_MAILBOX")) g_useMail = 0;
     if (const char* e = getenv("HXR_REFILL_MIN")) g_refillMin = std::min(32, std::max(1, atoi(e)));
     if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
     return true;
@@ -280,6 +281,7 @@ template <int SSTACK>
 struct WalkShared {
     float ray[9][HXR_WALK_BLOCK];  // rows 0-2 origin, 3-5 1/direction, 6-8 direction (a leaf child's "axis 3" reads the next row: finite, unused)
     uint32_t tb[HXR_WALK_BLOCK];  // bits of the (non-negative) float bound; 0 = shadow ray certainly blocked
+    uint32_t mail[2][HXR_WALK_BLOCK];  // the last two triangles this task already put on the pair list (a triangle sits in several leaves)
     uint32_t stRef[SSTACK][HXR_WALK_BLOCK];
     float stMin[SSTACK][HXR_WALK_BLOCK];
     float stMax[SSTACK][HXR_WALK_BLOCK];
@@ -288,7 +290,7 @@ struct WalkShared {
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
 template <bool SHADOW, bool COUNT, int SSTACK>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, TraceScratch ts, TravCounters* cnt, int walkSteps,
-                                                                              int refillMin)
+                                                                              int refillMin, int useMail)
 {
     __shared__ WalkShared<SSTACK> sh;
     constexpr int HXR_SSTACK = SSTACK;
@@ -361,6 +363,8 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         err = __uint_as_float(w3.x);
                         meshIdx = (int)w3.y;
                         sh.tb[tid] = __float_as_uint(tbest);
+                        sh.mail[0][tid] = 0xFFFFFFFFu;
+                        sh.mail[1][tid] = 0xFFFFFFFFu;
                         const DMesh& M = sc.meshes[meshIdx];
                         blocks = M.blocks;
                         leafTris = M.leaf_tris;
@@ -453,9 +457,10 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 ti = __ldg(lt + oFirst + (pair - oExcl));
                 const unsigned ot = warpBase | (unsigned)o;
                 const float oBest = __uint_as_float(sh.tb[ot]);  // the freshest bound (other lanes may have lowered it this round)
-                float ghi;
-                const int cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot],
-                                           oErr, oBest, ghi);
+                float ghi = 0;
+                int cls = HXR_TF_MISS;
+                if (ti != sh.mail[0][ot] && ti != sh.mail[1][ot])  // not already on the list from a neighbouring leaf
+                    cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot], oErr, oBest, ghi);
                 if (cls == HXR_TF_CERTAIN) {
                     if (SHADOW && ghi < oOcc) atomicMin(&sh.tb[ot], 0u);  // certainly blocked: no exact test needed
                     else { atomicMin(&sh.tb[ot], __float_as_uint(ghi)); emit = true; }
@@ -471,6 +476,11 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 if ((int)lane == leader) pb = atomicAdd(ts.pair_count, (uint32_t)__popc(em));
                 pb = __shfl_sync(FULL, pb, leader);
                 if (emit) {
+                    const unsigned ot = warpBase | (unsigned)o;
+                    if (useMail) {
+                        sh.mail[1][ot] = sh.mail[0][ot];  // (lanes emitting for the same owner race here: any of their triangles is a valid entry)
+                        sh.mail[0][ot] = ti;
+                    }
                     const uint32_t k = pb + __popc(em & ((1u << lane) - 1u));
                     if (k < ts.pair_cap) { PairRec pr; pr.task = oTask; pr.tri = ti; ts.pairs[k] = pr; }
                     else atomicExch(ts.overflow, 1u);
@@ -604,7 +614,7 @@ template <bool SHADOW, bool COUNT, int SSTACK> static void launch_walk_s(const D
     static int full = 0;
     if (!full) full = walk_grid(k_walk<SHADOW, COUNT, SSTACK>);
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, (max_tasks + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin);
+    k_walk<SHADOW, COUNT, SSTACK><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_useMail);
 }
 template <bool SHADOW> static void launch_walk(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
 {
