@@ -92,8 +92,8 @@ int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { H
 int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out) { HXR_CTX_CALL(ctx->r.accelInfo(mesh, out)) }
 int hxr_save_frame_bmp(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->r.saveFrameBmp(d_rgb, w, h, path)) }
 
-int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out,
-                        float* ghi_out, int32_t* exact_out, double* gamma_out)
+static int test_tri_filter(bool packed, size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out,
+                           float* ghi_out, int32_t* exact_out, double* gamma_out)
 {
     if (n && (!rays || !tris || !tbest || !cls_out || !ghi_out || !exact_out || !gamma_out)) { g_lastError = "hxr_test_tri_filter: null argument"; return HXR_ERR_INVALID; }
     using namespace hxr;
@@ -116,8 +116,12 @@ int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const 
         const double mo = std::max(std::fabs(r[0]), std::max(std::fabs(r[1]), std::fabs(r[2])));
         const float err = f32_above((mo + (double)std::nextafter((float)amax, INFINITY)) * (1.01 / 8388608.0));
         float ghi = 0;
-        cls_out[i] = tri_filter(&tf, backface != 0, (float)r[0], (float)r[1], (float)r[2], (float)r[3], (float)r[4], (float)r[5], err,
-                                f32_above(tbest[i]), ghi);
+        TriPacked tp;
+        if (packed && !pack_tri(tt, tp)) { g_lastError = "hxr_test_tri_filter_packed: triangle does not fit the packed form"; return HXR_ERR_INVALID; }
+        cls_out[i] = packed ? tri_filter_packed(&tp, backface != 0, (float)r[0], (float)r[1], (float)r[2], (float)r[3], (float)r[4], (float)r[5], err,
+                                                f32_above(tbest[i]), ghi)
+                            : tri_filter(&tf, backface != 0, (float)r[0], (float)r[1], (float)r[2], (float)r[3], (float)r[4], (float)r[5], err,
+                                         f32_above(tbest[i]), ghi);
         ghi_out[i] = ghi;
         Ray ray;
         ray.o = ld3(r); ray.d = ld3(r + 3); ray.depth = 0; ray.flags = 0;
@@ -126,6 +130,17 @@ int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const 
         gamma_out[i] = g;
     }
     return HXR_OK;
+}
+
+int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out, float* ghi_out,
+                        int32_t* exact_out, double* gamma_out)
+{
+    return test_tri_filter(false, n, rays, tris, tbest, backface, cls_out, ghi_out, exact_out, gamma_out);
+}
+int hxr_test_tri_filter_packed(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out,
+                               float* ghi_out, int32_t* exact_out, double* gamma_out)
+{
+    return test_tri_filter(true, n, rays, tris, tbest, backface, cls_out, ghi_out, exact_out, gamma_out);
 }
 
 // ---------------------------------------------------------------- host front-end

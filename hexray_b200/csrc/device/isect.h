@@ -21,6 +21,8 @@
 // mesh_closest (double planes, one ray: CSG children, CPU tests) and the conservative FP32 walk
 // (plane_cross / block_step / tri_filter below: what the GPU kernel runs).
 #pragma once
+#include <cmath>
+#include <cstring>
 #include "scene_dev.h"
 
 namespace hxr {
@@ -506,18 +508,16 @@ HXR_HD void block_step(const KdBlock& B, const RAY& w, float tmin, float tmax, f
 #define HXR_TF_MAYBE 1
 #define HXR_TF_CERTAIN 2
 
-HXR_HD int tri_filter(const TriF32* p, bool backface, float ox, float oy, float oz, float dx, float dy, float dz, float err, float tbest,
-                      float& ghi)
+//   Packed triangles (TriPacked, PK = true): AB and AC are exact multiples of 2^e, off the true edges by at most
+//   qab = 2^(eAB-1), qac = 2^(eAC-1) per component, and N is rebuilt as fl(AB' x AC'):
+//     |d((H x AC).nd)| grows by 2 qac |H|_1, |d((AB x H).nd)| by 2 qab |H|_1,
+//     sum_i |dN_i| <= 2 qab |AC|_1 + 2 qac |AB|_1 + 4 eps |AB|_1 |AC|_1 =: dN  (edge error + rounding of the cross product),
+//     |d(N.nd)| grows by dN and |d(N.H)| by dN |H|_1.   (2.5 instead of 2 below: slack for the second-order terms.)
+template <bool PK>
+HXR_HD int tri_filter_core(float ax, float ay, float az, float abx, float aby, float abz, float acx, float acy, float acz, float nx, float ny,
+                           float nz, float qab, float qac, bool backface, float ox, float oy, float oz, float dx, float dy, float dz, float err,
+                           float tbest, float& ghi)
 {
-#if defined(__CUDA_ARCH__)
-    const float4 q0 = __ldg(reinterpret_cast<const float4*>(p)), q1 = __ldg(reinterpret_cast<const float4*>(p) + 1),
-                 q2 = __ldg(reinterpret_cast<const float4*>(p) + 2);
-    const float ax = q0.x, ay = q0.y, az = q0.z, abx = q0.w, aby = q1.x, abz = q1.y, acx = q1.z, acy = q1.w, acz = q2.x, nx = q2.y, ny = q2.z,
-                nz = q2.w;
-#else
-    const float ax = p->A[0], ay = p->A[1], az = p->A[2], abx = p->AB[0], aby = p->AB[1], abz = p->AB[2], acx = p->AC[0], acy = p->AC[1],
-                acz = p->AC[2], nx = p->N[0], ny = p->N[1], nz = p->N[2];
-#endif
     const float eps = 5.9604645e-8f;
     const float hx = ox - ax, hy = oy - ay, hz = oz - az;
     const float ex = -dx, ey = -dy, ez = -dz;
@@ -528,7 +528,14 @@ HXR_HD int tri_filter(const TriF32* p, bool backface, float ox, float oy, float 
     const float H1 = fabsf(hx) + fabsf(hy) + fabsf(hz);
     const float AC1 = fabsf(acx) + fabsf(acy) + fabsf(acz), AB1 = fabsf(abx) + fabsf(aby) + fabsf(abz), N1 = fabsf(nx) + fabsf(ny) + fabsf(nz);
     const float eh = 2.0f * err + 16.0f * eps * H1;
-    const float E2 = AC1 * eh, E3 = AB1 * eh, EG = N1 * eh, ED = 8.0f * eps * N1;
+    float E2 = AC1 * eh, E3 = AB1 * eh, EG = N1 * eh, ED = 8.0f * eps * N1;
+    if (PK) {
+        const float dN = 2.5f * (qab * AC1 + qac * AB1) + 4.0f * eps * (AB1 * AC1);
+        E2 += 2.5f * qac * H1;
+        E3 += 2.5f * qab * H1;
+        EG += dN * H1;
+        ED += dN;
+    }
     if (backface && Dcr < -ED) return HXR_TF_MISS;  // dot(d, N) = -Dcr is certainly positive: culled
     const float aD = fabsf(Dcr);
     if (!(aD > ED)) return HXR_TF_MAYBE;  // grazing (or a degenerate triangle): not even the sign is known
@@ -545,6 +552,90 @@ HXR_HD int tri_filter(const TriF32* p, bool backface, float ox, float oy, float 
     }
     return HXR_TF_MAYBE;
 }
+
+HXR_HD int tri_filter(const TriF32* p, bool backface, float ox, float oy, float oz, float dx, float dy, float dz, float err, float tbest,
+                      float& ghi)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(p)), q1 = __ldg(reinterpret_cast<const float4*>(p) + 1),
+                 q2 = __ldg(reinterpret_cast<const float4*>(p) + 2);
+    const float ax = q0.x, ay = q0.y, az = q0.z, abx = q0.w, aby = q1.x, abz = q1.y, acx = q1.z, acy = q1.w, acz = q2.x, nx = q2.y, ny = q2.z,
+                nz = q2.w;
+#else
+    const float ax = p->A[0], ay = p->A[1], az = p->A[2], abx = p->AB[0], aby = p->AB[1], abz = p->AB[2], acx = p->AC[0], acy = p->AC[1],
+                acz = p->AC[2], nx = p->N[0], ny = p->N[1], nz = p->N[2];
+#endif
+    return tri_filter_core<false>(ax, ay, az, abx, aby, abz, acx, acy, acz, nx, ny, nz, 0.0f, 0.0f, backface, ox, oy, oz, dx, dy, dz, err, tbest, ghi);
+}
+
+HXR_HD float f32_from_bits(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+HXR_HD float sext24f(uint32_t x) { return (float)((int32_t)(x << 8) >> 8); }  // low 24 bits as a signed integer, exactly, in float
+
+// the same filter on a 32-byte packed triangle: ONE sector per test instead of two
+HXR_HD int tri_filter_packed(const TriPacked* p, bool backface, float ox, float oy, float oz, float dx, float dy, float dz, float err, float tbest,
+                             float& ghi)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(p)), q1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    const float ax = __uint_as_float(q0.x), ay = __uint_as_float(q0.y), az = __uint_as_float(q0.z);
+    const uint32_t w0 = q0.w, w1 = q1.x, w2 = q1.y, w3 = q1.z, w4 = q1.w;
+#else
+    const float ax = p->A[0], ay = p->A[1], az = p->A[2];
+    const uint32_t w0 = p->w[0], w1 = p->w[1], w2 = p->w[2], w3 = p->w[3], w4 = p->w[4];
+#endif
+    const float sab = f32_from_bits(((w0 & 0xFFu) + 1u) << 23), sac = f32_from_bits((((w0 >> 8) & 0xFFu) + 1u) << 23);  // 2^e: e + 127 = byte + 1
+    const float abx = sext24f((w0 >> 16) | (w1 << 16)) * sab, aby = (float)((int32_t)w1 >> 8) * sab, abz = sext24f(w2) * sab;
+    const float acx = sext24f((w2 >> 24) | (w3 << 8)) * sac, acy = sext24f((w3 >> 16) | (w4 << 16)) * sac, acz = (float)((int32_t)w4 >> 8) * sac;
+    const float nx = aby * acz - abz * acy, ny = abz * acx - abx * acz, nz = abx * acy - aby * acx;
+    return tri_filter_core<true>(ax, ay, az, abx, aby, abz, acx, acy, acz, nx, ny, nz, 0.5f * sab, 0.5f * sac, backface, ox, oy, oz, dx, dy, dz, err,
+                                 tbest, ghi);
+}
+
+#if !defined(__CUDA_ARCH__)
+// host: pack one vector as m_i * 2^e, e in [-126, 127], |m_i| < 2^23; false if it does not fit (not finite or >= 2^150)
+inline bool pack_vec24(const double v[3], int32_t m[3], uint32_t& ebyte)
+{
+    const double mx = std::fmax(std::fabs(v[0]), std::fmax(std::fabs(v[1]), std::fabs(v[2])));
+    if (!(mx < 1e300)) return false;
+    int e = -126;
+    if (mx > 0) {
+        int ex;
+        std::frexp(mx, &ex);  // mx < 2^ex
+        e = ex - 23;          // mx / 2^e in [2^22, 2^23)
+        if (e < -126) e = -126;
+        if (std::nearbyint(std::ldexp(mx, -e)) >= 8388608.0) e++;
+        if (e > 127) return false;
+    }
+    for (int k = 0; k < 3; k++) m[k] = (int32_t)std::nearbyint(std::ldexp(v[k], -e));
+    ebyte = (uint32_t)(e + 126);
+    return true;
+}
+inline bool pack_tri(const TriTest& t, TriPacked& o)
+{
+    int32_t a[3], c[3];
+    uint32_t ea, ec;
+    if (!pack_vec24(t.AB, a, ea) || !pack_vec24(t.AC, c, ec)) return false;
+    const uint32_t M = 0xFFFFFFu;
+    const uint32_t m0 = (uint32_t)a[0] & M, m1 = (uint32_t)a[1] & M, m2 = (uint32_t)a[2] & M, m3 = (uint32_t)c[0] & M, m4 = (uint32_t)c[1] & M,
+                   m5 = (uint32_t)c[2] & M;
+    for (int k = 0; k < 3; k++) o.A[k] = (float)t.A[k];
+    o.w[0] = ea | (ec << 8) | ((m0 & 0xFFFFu) << 16);
+    o.w[1] = (m0 >> 16) | (m1 << 8);
+    o.w[2] = m2 | ((m3 & 0xFFu) << 24);
+    o.w[3] = (m3 >> 8) | ((m4 & 0xFFFFu) << 16);
+    o.w[4] = (m4 >> 16) | (m5 << 8);
+    return true;
+}
+#endif
 
 // all triangles in index order: exactly the reference's brute-force path (src/mesh.cpp:255-262);
 // used for meshes so small that a tree walk costs more than it saves

@@ -34,7 +34,8 @@ static cudaStream_t g_stream = nullptr;
 static std::string g_err;
 static bool g_prof = false;
 // walk-loop tunables (uniform kernel arguments; HXR_WALK_STEPS / HXR_REFILL_MIN in the environment override the defaults)
-static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10, g_useMail = 1;
+#define HXR_PAIR_CHUNK 64 /* pair-list slots a warp of k_walk reserves per atomic (0: one atomic per append) */
+static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10, g_useMail = 1, g_pairChunk = HXR_PAIR_CHUNK;
 static uint64_t g_launches[PROF_NCAT];
 static std::vector<cudaEvent_t> g_evPool;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
@@ -70,6 +71,7 @@ bool init(int device, char* err, size_t errlen)
     if (const char* e = getenv("HXR_WALK_STEPS")) g_walkSteps = std::max(1, atoi(e));
     if (const char* e = getenv("HXR_SSTACK")) g_sstack = atoi(e);
     if (getenv("HXR_NO_MAILBOX")) g_useMail = 0;
+    if (const char* e = getenv("HXR_PAIR_CHUNK")) g_pairChunk = std::min(1024, std::max(0, atoi(e)));
     if (const char* e = getenv("HXR_REFILL_MIN")) g_refillMin = std::min(32, std::max(1, atoi(e)));
     if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
     return true;
@@ -288,9 +290,9 @@ struct WalkShared {
 };
 
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
-template <bool SHADOW, bool COUNT, int SSTACK>
+template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, TraceScratch ts, TravCounters* cnt, int walkSteps,
-                                                                              int refillMin, int useMail)
+                                                                              int refillMin, int useMail, int pairChunk)
 {
     __shared__ WalkShared<SSTACK> sh;
     constexpr int HXR_SSTACK = SSTACK;
@@ -311,13 +313,14 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     for (int r = 0; r < 9; r++) sh.ray[r][tid] = 0.0f;
     const KdBlock* blocks = nullptr;  // the current mesh
     const uint32_t* leafTris = nullptr;
-    const TriF32* tris = nullptr;
+    const void* tris = nullptr;  // TriPacked (32 B) or TriF32 (48 B) records of the current mesh
     bool backface = false;
     int meshIdx = -1;
     uint32_t cur = HXR_POP, leafCnt = 0;
     float tmin = 0, tmax = 0, tbest = 0, err = 0, occ = 0;
     int sp = 0;
     uint32_t taskIdx = 0, taskRay = 0;
+    uint32_t pkBase = 0, pkLeft = 0;  // this warp's reserved slots of the pair list (warp-uniform)
     TravCounters local = {0, 0, 0, 0};
 
     auto push = [&](const WalkEnt& e) {
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         const DMesh& M = sc.meshes[meshIdx];
                         blocks = M.blocks;
                         leafTris = M.leaf_tris;
-                        tris = M.tri_f32;
+                        tris = PACKED ? (const void*)M.tri_pk : (const void*)M.tri_f32;
                         backface = M.backface != 0;
                         sp = 0;
                         cur = 0;
@@ -448,19 +451,21 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             uint32_t ti = 0;
             if (pair < total) {
                 const uint32_t* lt = leafTris;
-                const TriF32* tt = tris;
+                const void* tt = tris;
                 bool bf = backface;
                 if (oMesh != meshIdx) {
                     const DMesh& M = sc.meshes[oMesh];
-                    lt = M.leaf_tris; tt = M.tri_f32; bf = M.backface != 0;
+                    lt = M.leaf_tris; tt = PACKED ? (const void*)M.tri_pk : (const void*)M.tri_f32; bf = M.backface != 0;
                 }
                 ti = __ldg(lt + oFirst + (pair - oExcl));
                 const unsigned ot = warpBase | (unsigned)o;
                 const float oBest = __uint_as_float(sh.tb[ot]);  // the freshest bound (other lanes may have lowered it this round)
                 float ghi = 0;
                 int cls = HXR_TF_MISS;
-                if (ti != sh.mail[0][ot] && ti != sh.mail[1][ot])  // not already on the list from a neighbouring leaf
-                    cls = tri_filter(tt + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot], oErr, oBest, ghi);
+                if (ti != sh.mail[0][ot] && ti != sh.mail[1][ot]) {  // not already on the list from a neighbouring leaf
+                    if (PACKED) cls = tri_filter_packed(static_cast<const TriPacked*>(tt) + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot], oErr, oBest, ghi);
+                    else cls = tri_filter(static_cast<const TriF32*>(tt) + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot], oErr, oBest, ghi);
+                }
                 if (cls == HXR_TF_CERTAIN) {
                     if (SHADOW && ghi < oOcc) atomicMin(&sh.tb[ot], 0u);  // certainly blocked: no exact test needed
                     else { atomicMin(&sh.tb[ot], __float_as_uint(ghi)); emit = true; }
@@ -468,13 +473,24 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                     emit = true;
                 }
             }
-            // append the surviving pairs to the confirmation list, one atomic per warp
+            // append the surviving pairs to the confirmation list. Every warp of the GPU appends all the time: one atomic per
+            // append on the single list counter serialises in L2 (measured: 20 % of this kernel's stall samples sat here), so
+            // a warp reserves HXR_PAIR_CHUNK slots at a time and hands them out itself; slots it does not use are marked
+            // invalid (task = HXR_PAIR_NONE) and skipped by the confirmation kernels
             const unsigned em = __ballot_sync(FULL, emit);
             if (em) {
-                const int leader = __ffs(em) - 1;
-                uint32_t pb = 0;
-                if ((int)lane == leader) pb = atomicAdd(ts.pair_count, (uint32_t)__popc(em));
-                pb = __shfl_sync(FULL, pb, leader);
+                const uint32_t need = (uint32_t)__popc(em);
+                if (need > pkLeft) {
+                    if (lane < pkLeft && pkBase + lane < ts.pair_cap) ts.pairs[pkBase + lane].task = HXR_PAIR_NONE;  // pkLeft < need <= 32
+                    uint32_t nb = 0;
+                    const uint32_t take = pairChunk ? (uint32_t)pairChunk : need;  // 0: one atomic per append (A/B)
+                    if (lane == 0) nb = atomicAdd(ts.pair_count, take);
+                    pkBase = __shfl_sync(FULL, nb, 0);
+                    pkLeft = take;
+                }
+                const uint32_t pb = pkBase;
+                pkBase += need;
+                pkLeft -= need;
                 if (emit) {
                     const unsigned ot = warpBase | (unsigned)o;
                     if (useMail) {
@@ -499,6 +515,8 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             }
         }
     }
+    for (uint32_t i = lane; i < pkLeft; i += 32u)  // the unused tail of this warp's last chunk
+        if (pkBase + i < ts.pair_cap) ts.pairs[pkBase + i].task = HXR_PAIR_NONE;
     if (COUNT) {
         atomicAdd(&cnt->kd_inner, local.kd_inner);
         atomicAdd(&cnt->kd_leaves, local.kd_leaves);
@@ -609,23 +627,25 @@ template <class K> static int walk_grid(K kernel)
 }
 
 // max_tasks: host-side upper bound of the task count (a small wave gets a small grid: one lane per task at most)
-template <bool SHADOW, bool COUNT, int SSTACK> static void launch_walk_s(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
+template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED> static void launch_walk_s(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
 {
     static int full = 0;
-    if (!full) full = walk_grid(k_walk<SHADOW, COUNT, SSTACK>);
+    if (!full) full = walk_grid(k_walk<SHADOW, COUNT, SSTACK, PACKED>);
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, (max_tasks + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_useMail);
+    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_useMail, g_pairChunk);
+}
+template <bool SHADOW, bool PACKED> static void launch_walk_p(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
+{
+    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(sc, ts, cnt, max_tasks); return; }
+    switch (g_sstack) {
+        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(sc, ts, nullptr, max_tasks); break;
+        default: launch_walk_s<SHADOW, false, 10, PACKED>(sc, ts, nullptr, max_tasks); break;
+    }
 }
 template <bool SHADOW> static void launch_walk(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
 {
-    if (cnt) { launch_walk_s<SHADOW, true, 10>(sc, ts, cnt, max_tasks); return; }
-    switch (g_sstack) {
-        case 9: launch_walk_s<SHADOW, false, 9>(sc, ts, nullptr, max_tasks); break;
-        case 12: launch_walk_s<SHADOW, false, 12>(sc, ts, nullptr, max_tasks); break;
-        case 14: launch_walk_s<SHADOW, false, 14>(sc, ts, nullptr, max_tasks); break;
-        case 16: launch_walk_s<SHADOW, false, 16>(sc, ts, nullptr, max_tasks); break;
-        default: launch_walk_s<SHADOW, false, 10>(sc, ts, nullptr, max_tasks); break;
-    }
+    if (sc.walk_packed) launch_walk_p<SHADOW, true>(sc, ts, cnt, max_tasks);
+    else launch_walk_p<SHADOW, false>(sc, ts, cnt, max_tasks);
 }
 
 int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits, const TraceScratch& ts,

@@ -6,6 +6,10 @@
 //                  (two 128-bit loads) decides up to four grandchildren; leaves are not nodes at all but
 //                  tagged references into leaf_tris
 //   TriF32   48 B  float copy of TriTest: what the walk's conservative triangle filter reads (3 x 128-bit loads)
+//   TriPacked 32 B ONE sector: A in float, AB and AC as block floating point (one exponent byte + three signed 24-bit
+//                  mantissas per vector); the filter rebuilds AB x AC itself. The walk saturates the GPU's RANDOM-access
+//                  DRAM rate (tools/microbench.cu: ~31 G sectors/s whatever the record size), so sectors per triangle
+//                  are what the walk pays for
 //   TriTest  96 B  the four vectors the reference's triangle test reads (A, AB, AC, AB^AC),
 //                  in double so the test is the reference's arithmetic (src/mesh.cpp:178-196)
 //   TriAttr 192 B  read once per ray for the winning triangle: gnormal, dNdx/dNdy, the three vertex normals and uvs inline
@@ -49,6 +53,14 @@ struct alignas(16) TriF32 {  // 48 B: the same four vectors rounded to float, fo
     float A[3], AB[3], AC[3], N[3];
 };
 
+// 32 B: A rounded to float; AB, AC as v_i = m_i * 2^e with one exponent per vector (|v_i - m_i 2^e| <= 2^(e-1)).
+//   w[0] = (eAB + 126) | (eAC + 126) << 8 | m0 low 16 << 16;  w[1] = m0 high 8 | m1 << 8;  w[2] = m2 | m3 low 8 << 24;
+//   w[3] = m3 high 16 | m4 low 16 << 16;  w[4] = m4 high 8 | m5 << 8      (m0..2 = AB, m3..5 = AC, two's complement)
+struct alignas(32) TriPacked {
+    float A[3];
+    uint32_t w[5];
+};
+
 struct alignas(16) TriAttr {  // 192 B, self-contained: the winning triangle's shading data in ONE gather (no index -> vertex-array hop)
     double gnormal[3], dNdx[3], dNdy[3];
     double nrm[3][3];  // the three vertex normals
@@ -60,6 +72,7 @@ struct DMesh {
     const uint32_t* leaf_tris;
     const TriTest* tri_test;
     const TriF32* tri_f32;
+    const TriPacked* tri_pk;  // null when an edge of the mesh does not fit the packed form (the walk then reads tri_f32)
     const TriAttr* tri_attr;
     double bbmin[3], bbmax[3];
     int32_t faceted, backface;
@@ -100,6 +113,7 @@ struct DScene {
     // node loops skip a node whose box the ray misses before paying for the object-space transform and intersector
     const double* node_box;
     int32_t use_node_box;
+    int32_t walk_packed;  // every walked mesh has tri_pk: the walk filters 32-byte packed triangles
     int32_t n_big;
     int32_t simple_inline;  // every inline node is a plane, sphere, cube or brute-force mesh (selects the lean kernel variants)
     int32_t n_nodes, n_lights;

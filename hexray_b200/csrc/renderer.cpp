@@ -176,8 +176,16 @@ int Renderer::uploadScene(const hxr_scene* sp)
                 ta[t].dNdy[k] = T.dndy[k];
             }
         }
+        // the walk's 32-byte form of the same triangles (one sector per test); a mesh with an edge that does not fit keeps tri_f32 only
+        std::vector<TriPacked> tp(getenv("HXR_NO_TRI_PACK") ? 0 : m.n_triangles);
+        for (size_t t = 0; t < tp.size(); t++)
+            if (!pack_tri(tt[t], tp[t])) { tp.clear(); break; }
         DMesh& d = dm[i];
         memset(&d, 0, sizeof d);
+        if (!tp.empty()) {
+            d.tri_pk = uploadArray(tp.data(), tp.size());
+            if (!d.tri_pk) return oom();
+        }
         d.blocks = uploadArray(kd.blocks.data(), kd.blocks.size());
         d.leaf_tris = uploadArray(kd.leafTris.data(), kd.leafTris.size());
         d.tri_test = uploadArray(tt.data(), tt.size());
@@ -202,7 +210,7 @@ int Renderer::uploadScene(const hxr_scene* sp)
         ai.leaves = kd.leaves;
         ai.tri_refs = kd.leafTris.size();
         ai.bytes_nodes = kd.blocks.size() * sizeof(KdBlock);
-        ai.bytes_tris = kd.leafTris.size() * sizeof(uint32_t) + tf.size() * sizeof(TriF32) + tt.size() * sizeof(TriTest);
+        ai.bytes_tris = kd.leafTris.size() * sizeof(uint32_t) + (tp.empty() ? tf.size() * sizeof(TriF32) : tp.size() * sizeof(TriPacked)) + tt.size() * sizeof(TriTest);
         ai.max_depth = kd.maxDepth;
         ai.n_triangles = (uint32_t)m.n_triangles;
         ai.build_ms = kd.buildMs;
@@ -305,6 +313,9 @@ int Renderer::uploadScene(const hxr_scene* sp)
             if (!simple) m_scene.simple_inline = 0;
         }
     }
+    m_scene.walk_packed = s.n_meshes > 0 ? 1 : 0;
+    for (int i = 0; i < s.n_meshes; i++)
+        if (!dm[i].tri_pk) m_scene.walk_packed = 0;
     m_scene.n_nodes = s.n_nodes;
     m_scene.n_lights = s.n_lights;
     m_scene.has_env = s.has_environment;
@@ -377,7 +388,8 @@ bool Renderer::ensureQueues()
     m_pre = (RayPre*)dev::alloc((size_t)cap * sizeof(RayPre));
     m_tasks = (WalkTask*)dev::alloc((size_t)taskCap * sizeof(WalkTask));
     // (task, triangle) pairs the FP32 filter leaves for the exact test: about one per task (the hit itself) plus near misses
-    m_pairCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)taskCap * 2 + 4096);
+    // (+ the slots the walk's warps reserve in chunks and may leave unused: 64 per resident warp, a few hundred thousand)
+    m_pairCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)taskCap * 2 + (1u << 20));
     m_pairs = (PairRec*)dev::alloc((size_t)m_pairCap * sizeof(PairRec));
     m_pairGamma = (double*)dev::alloc((size_t)m_pairCap * sizeof(double));
     m_res = (MeshRes*)dev::alloc((size_t)cap * std::max(1, m_nBig) * sizeof(MeshRes));

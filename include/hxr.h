@@ -323,6 +323,9 @@ int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb);
  *   accepts the pair at a parameter <= tbest, gamma_out: that parameter */
 int hxr_test_tri_filter(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface_culling,
                         int32_t* cls_out, float* ghi_out, int32_t* exact_out, double* gamma_out);
+/* the same through the 32-byte packed triangle record the walk reads by default (tri_filter_packed) */
+int hxr_test_tri_filter_packed(size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface_culling,
+                               int32_t* cls_out, float* ghi_out, int32_t* exact_out, double* gamma_out);
 
 /* acceleration-structure facts for reporting (per mesh): nodes, leaves, max depth, tri refs, build ms */
 typedef struct hxr_accel_info {

@@ -12,7 +12,7 @@ from hexray_b200 import capi
 MISS, MAYBE, CERTAIN = 0, 1, 2
 
 
-def run_filter(api, rays, tris, tbest, backface=0):
+def run_filter(api, rays, tris, tbest, backface=0, packed=False):
     n = len(rays)
     rays = np.ascontiguousarray(rays, dtype=np.float64)
     tris = np.ascontiguousarray(tris, dtype=np.float64)
@@ -21,8 +21,9 @@ def run_filter(api, rays, tris, tbest, backface=0):
     ghi = np.zeros(n, dtype=np.float32)
     exact = np.zeros(n, dtype=np.int32)
     gamma = np.zeros(n, dtype=np.float64)
-    st = api.lib.hxr_test_tri_filter(n, rays.ctypes.data, tris.ctypes.data, tbest.ctypes.data, backface, cls.ctypes.data, ghi.ctypes.data,
-                                     exact.ctypes.data, gamma.ctypes.data)
+    fn = api.lib.hxr_test_tri_filter_packed if packed else api.lib.hxr_test_tri_filter
+    st = fn(n, rays.ctypes.data, tris.ctypes.data, tbest.ctypes.data, backface, cls.ctypes.data, ghi.ctypes.data,
+            exact.ctypes.data, gamma.ctypes.data)
     assert st == capi.HXR_OK
     return cls, ghi, exact.astype(bool), gamma
 
@@ -65,9 +66,11 @@ def make_pairs(rng, n, world, size, dist, aim, graze_fraction=0.25):
     return rays, tris, t[:, 0]
 
 
+@pytest.mark.parametrize("packed", [False, True], ids=["f32", "packed32B"])
 @pytest.mark.parametrize("world,size,dist", [(1.0, 0.3, 3.0), (500.0, 0.5, 300.0), (500.0, 0.5, 2.0), (1000.0, 1e-3, 50.0), (5.0, 5.0, 1e-3),
                                              (1e4, 30.0, 1e4), (0.0, 1e-4, 1e-2)])
-def test_filter_is_conservative(emu_api, world, size, dist):
+def test_filter_is_conservative(emu_api, world, size, dist, packed):
+    # both forms of the record: TriF32 (48 B) and TriPacked (32 B: block-floating-point edges, N rebuilt in the filter)
     rng = np.random.default_rng(int(world * 7 + size * 1e4 + dist * 13) % (2 ** 31))
     n = 120000
     seen = np.zeros(3, dtype=np.int64)
@@ -75,7 +78,7 @@ def test_filter_is_conservative(emu_api, world, size, dist):
         rays, tris, t = make_pairs(rng, n, world, size, dist, aim)
         for tb in (np.full(n, 1e99), t * (1 + rng.normal(0, 1e-7, n)), t * rng.uniform(0.2, 3.0, n)):
             for backface in (0, 1):
-                cls, ghi, exact, gamma = run_filter(emu_api, rays, tris, tb, backface)
+                cls, ghi, exact, gamma = run_filter(emu_api, rays, tris, tb, backface, packed)
                 assert not (exact & (cls == MISS)).any(), "filter said MISS for %d pairs the exact test accepts (%s)" % ((exact & (cls == MISS)).sum(), aim)
                 c = cls == CERTAIN
                 # CERTAIN promises a triangle hit at gamma <= ghi; the exact test may still reject it for lying beyond tbest
@@ -86,10 +89,11 @@ def test_filter_is_conservative(emu_api, world, size, dist):
     assert seen[MISS] > 0 and seen[CERTAIN] > 0  # the adversarial mix still leaves both verdicts in play
 
 
-def test_filter_decides_typical_pairs(emu_api):
+@pytest.mark.parametrize("packed", [False, True], ids=["f32", "packed32B"])
+def test_filter_decides_typical_pairs(emu_api, packed):
     # the bench's regime (coordinates ~500, edges ~0.5, rays from a few hundred units): nearly everything is decided in float
     rng = np.random.default_rng(5)
     rays, tris, t = make_pairs(rng, 200000, 500.0, 0.5, 200.0, "any", graze_fraction=0.0)
-    cls, ghi, exact, gamma = run_filter(emu_api, rays, tris, np.full(len(rays), 1e99))
+    cls, ghi, exact, gamma = run_filter(emu_api, rays, tris, np.full(len(rays), 1e99), packed=packed)
     assert (cls == MAYBE).mean() < 0.02
     assert not (exact & (cls == MISS)).any()

@@ -41,6 +41,36 @@ __global__ void k_chase(const uint4* __restrict__ p, uint32_t mask, int steps, u
     if (idx == 0xffffffffu) out[0] = idx;
 }
 
+// independent random CHUNK-byte reads (hashed addresses, 4 in flight per lane): the cost of a random DRAM access as a
+// function of its size -- what a KD walk pays per tree block / triangle record that misses L2
+template <int CHUNK>
+__global__ void k_gather(const uint4* __restrict__ p, uint32_t chunkMask, int steps, uint32_t* out)
+{
+    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t acc = 0;
+    for (int s = 0; s < steps; s++) {
+        h = h * 1664525u + 1013904223u;
+        const uint4* q = p + (size_t)((h >> 4) & chunkMask) * (CHUNK / 16);
+#pragma unroll
+        for (int k = 0; k < CHUNK / 16; k++) acc ^= __ldg(q + k).x;
+    }
+    if (acc == 0x12345u) out[0] = acc;
+}
+
+template <int CHUNK>
+static double gather_rate(const uint4* buf, size_t bytes, int sms, uint32_t* o32, cudaEvent_t a, cudaEvent_t b)
+{
+    const int steps = 64, threads = sms * 2048;
+    const uint32_t mask = (uint32_t)(bytes / CHUNK) - 1;
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(a); k_gather<CHUNK><<<threads / 256, 256>>>(buf, mask, steps, o32); cudaEventRecord(b);
+        float ms; cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+        if (r && ms < best) best = ms;
+    }
+    return (double)threads * steps / (best * 1e-3) / 1e9;
+}
+
 static float timeit(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int main()
@@ -86,6 +116,28 @@ int main()
         float ms = timeit(a, b); if (r && ms < chL2) chL2 = ms;
         cudaEventRecord(a); k_chase<<<cthreads / 256, 256>>>(buf, (1u << 27) - 1, steps, o32); cudaEventRecord(b);
         ms = timeit(a, b); if (r && ms < chHbm) chHbm = ms;
+    }
+    // random access cost by size and by the L2 fetch granularity limit (2 GB table)
+    {
+        const int grans[3] = {32, 64, 128};
+        printf("{\"random_gather_G_per_s\": {");
+        for (int g = 0; g < 3; g++) {
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, grans[g]);
+            size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+            const size_t B = (size_t)2 << 30;
+            printf("%s\"l2gran%d(got %zu)\": {\"16B\": %.2f, \"32B\": %.2f, \"64B\": %.2f, \"128B\": %.2f, \"256B\": %.2f, \"chase16B\": ", g ? ", " : "", grans[g], got,
+                   gather_rate<16>(buf, B, p.multiProcessorCount, o32, a, b), gather_rate<32>(buf, B, p.multiProcessorCount, o32, a, b),
+                   gather_rate<64>(buf, B, p.multiProcessorCount, o32, a, b), gather_rate<128>(buf, B, p.multiProcessorCount, o32, a, b),
+                   gather_rate<256>(buf, B, p.multiProcessorCount, o32, a, b));
+            float ch = 1e30f;
+            for (int r = 0; r < 3; r++) {
+                cudaEventRecord(a); k_chase<<<cthreads / 256, 256>>>(buf, (1u << 27) - 1, steps, o32); cudaEventRecord(b);
+                float ms = timeit(a, b); if (r && ms < ch) ch = ms;
+            }
+            printf("%.2f}", (double)cthreads * steps / (ch * 1e-3) / 1e9);
+        }
+        printf("}}\n");
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 64);
     }
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp32_tfma_per_s\": %.3f, \"fp64_tfma_per_s\": %.3f, \"l2_read_gbs\": %.1f, "
            "\"hbm_read_gbs\": %.1f, \"random16B_loads_L2_G_per_s\": %.3f, \"random16B_loads_HBM_G_per_s\": %.3f, \"cuda_err\": \"%s\"}\n",
