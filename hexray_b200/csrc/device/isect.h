@@ -653,24 +653,31 @@ HXR_HD bool mesh_bruteforce(const DMesh& M, const Ray& ray, double gamma_limit, 
     return best.tri >= 0;
 }
 
-HXR_HD void mesh_fill_hit(const DMesh& M, int gi, const Ray& ray, const MeshBest& best, Hit& info)
+// lean: the caller knows that nobody reads u, v, dNdx, dNdy of this hit (DScene::node_lean): skip their gather
+HXR_HD void mesh_fill_hit(const DMesh& M, int gi, const Ray& ray, const MeshBest& best, Hit& info, bool lean = false)
 {
     const TriAttr& ta = M.tri_attr[best.tri];
     info.dist = best.gamma;
     info.ip = ray.o + best.gamma * ray.d;
-    // uvs[t.t[k]] with the third coordinate dropped: only x and y are used (src/mesh.cpp:203-207)
-    const d3 texA = mk3(ta.uv[0][0], ta.uv[0][1], 0), texB = mk3(ta.uv[1][0], ta.uv[1][1], 0), texC = mk3(ta.uv[2][0], ta.uv[2][1], 0);
-    const d3 tex = texA + (texB - texA) * best.l2 + (texC - texA) * best.l3;
-    info.u = tex.x;
-    info.v = tex.y;
+    if (lean) {
+        info.u = info.v = 0;
+        info.dNdx = info.dNdy = mk3(0, 0, 0);
+    } else {
+        const TriAttrUv& tu = M.tri_attr_uv[best.tri];
+        // uvs[t.t[k]] with the third coordinate dropped: only x and y are used (src/mesh.cpp:203-207)
+        const d3 texA = mk3(tu.uv[0][0], tu.uv[0][1], 0), texB = mk3(tu.uv[1][0], tu.uv[1][1], 0), texC = mk3(tu.uv[2][0], tu.uv[2][1], 0);
+        const d3 tex = texA + (texB - texA) * best.l2 + (texC - texA) * best.l3;
+        info.u = tex.x;
+        info.v = tex.y;
+        info.dNdx = ld3(tu.dNdx);
+        info.dNdy = ld3(tu.dNdy);
+    }
     if (M.faceted) {
         info.norm = ld3(ta.gnormal);
     } else {
         const d3 nA = ld3(ta.nrm[0]), nB = ld3(ta.nrm[1]), nC = ld3(ta.nrm[2]);
         info.norm = normalize_m(nA + (nB - nA) * best.l2 + (nC - nA) * best.l3);
     }
-    info.dNdx = ld3(ta.dNdx);
-    info.dNdy = ld3(ta.dNdy);
     info.geom = gi;
 }
 

@@ -12,7 +12,7 @@
 //                  are what the walk pays for
 //   TriTest  96 B  the four vectors the reference's triangle test reads (A, AB, AC, AB^AC),
 //                  in double so the test is the reference's arithmetic (src/mesh.cpp:178-196)
-//   TriAttr 192 B  read once per ray for the winning triangle: gnormal, dNdx/dNdy, the three vertex normals and uvs inline
+//   TriAttr 96 B + TriAttrUv 96 B  read once per ray for the winning triangle: normals / uvs and dNdx, dNdy inline
 #pragma once
 #include "hd.h"
 #include "../../../include/hxr.h"
@@ -61,10 +61,16 @@ struct alignas(32) TriPacked {
     uint32_t w[5];
 };
 
-struct alignas(16) TriAttr {  // 192 B, self-contained: the winning triangle's shading data in ONE gather (no index -> vertex-array hop)
-    double gnormal[3], dNdx[3], dNdy[3];
+// The winning triangle's shading data, read once per ray by finalize. Two 96-byte records (3 sectors each): every hit needs
+// the normals; the texture coordinates and dNdx/dNdy only matter to textured or bump-mapped nodes (DScene::node_lean), so an
+// untextured mesh costs 3 random sectors per hit instead of 6 (random sectors are what a gather pays for, see TriPacked)
+struct alignas(32) TriAttr {
+    double gnormal[3];
     double nrm[3][3];  // the three vertex normals
-    double uv[3][2];   // the three texture coordinates
+};
+struct alignas(32) TriAttrUv {
+    double uv[3][2];  // the three texture coordinates
+    double dNdx[3], dNdy[3];
 };
 
 struct DMesh {
@@ -74,6 +80,7 @@ struct DMesh {
     const TriF32* tri_f32;
     const TriPacked* tri_pk;  // null when an edge of the mesh does not fit the packed form (the walk then reads tri_f32)
     const TriAttr* tri_attr;
+    const TriAttrUv* tri_attr_uv;
     double bbmin[3], bbmax[3];
     int32_t faceted, backface;
     int32_t n_tris;
@@ -112,6 +119,10 @@ struct DScene {
     // per node: conservative world-space box of its geometry (min xyz, max xyz; +-1e300 when unbounded or unknown): the
     // node loops skip a node whose box the ray misses before paying for the object-space transform and intersector
     const double* node_box;
+    // per node: 1 if nothing downstream reads u, v, dNdx, dNdy of a hit on it (no texture anywhere in its shader, no bump map):
+    // finalize then skips the TriAttrUv gather and leaves those fields zero. full_attr = 1 overrides (the trace_closest hook).
+    const int32_t* node_lean;
+    int32_t full_attr;
     int32_t use_node_box;
     int32_t walk_packed;  // every walked mesh has tri_pk: the walk filters 32-byte packed triangles
     int32_t n_big;

@@ -151,12 +151,16 @@ int Renderer::uploadScene(const hxr_scene* sp)
     // meshes: build the KD-tree on the host, split triangles into test / attribute records
     std::vector<DMesh> dm(s.n_meshes);
     m_accel.resize(s.n_meshes);
+    size_t filterBytes = 0;
+    for (int i = 0; i < s.n_meshes; i++) filterBytes += (size_t)s.meshes[i].n_triangles * sizeof(TriF32);
+    const bool wantPack = getenv("HXR_TRI_PACK") ? atoi(getenv("HXR_TRI_PACK")) != 0 : filterBytes > ((size_t)64 << 20);
     for (int i = 0; i < s.n_meshes; i++) {
         const hxr_mesh& m = s.meshes[i];
         host::KdTree kd;
         host::buildKdTree(m, host::KdBuildParams(), kd);
         std::vector<TriTest> tt(m.n_triangles);
         std::vector<TriAttr> ta(m.n_triangles);
+        std::vector<TriAttrUv> tu(m.n_triangles);
         std::vector<TriF32> tf(m.n_triangles);
         for (int t = 0; t < m.n_triangles; t++) {
             const hxr_triangle& T = m.triangles[t];
@@ -171,13 +175,16 @@ int Renderer::uploadScene(const hxr_scene* sp)
                 tf[t].N[k] = (float)tt[t].N[k];
                 ta[t].gnormal[k] = T.gnormal[k];
                 for (int c = 0; c < 3; c++) ta[t].nrm[k][c] = m.normals[3 * (size_t)T.n[k] + c];
-                for (int c = 0; c < 2; c++) ta[t].uv[k][c] = m.uvs[3 * (size_t)T.t[k] + c];
-                ta[t].dNdx[k] = T.dndx[k];
-                ta[t].dNdy[k] = T.dndy[k];
+                for (int c = 0; c < 2; c++) tu[t].uv[k][c] = m.uvs[3 * (size_t)T.t[k] + c];
+                tu[t].dNdx[k] = T.dndx[k];
+                tu[t].dNdy[k] = T.dndy[k];
             }
         }
-        // the walk's 32-byte form of the same triangles (one sector per test); a mesh with an edge that does not fit keeps tri_f32 only
-        std::vector<TriPacked> tp(getenv("HXR_NO_TRI_PACK") ? 0 : m.n_triangles);
+        // the walk's 32-byte form of the same triangles: one sector per test instead of 1.5-2, at ~35 more instructions per test.
+        // Measured (profiles/README.md): on terrain-10M (triangles >> L2, walk bound by memory) k_walk -2.7 %; on cornell_box (36
+        // triangles, walk bound by issue slots) k_walk +12 %. So: packed when the scene's filter triangles outgrow the L2
+        // (HXR_TRI_PACK=0/1 overrides). A mesh with an edge that does not fit the format keeps the scene on tri_f32.
+        std::vector<TriPacked> tp(wantPack ? m.n_triangles : 0);
         for (size_t t = 0; t < tp.size(); t++)
             if (!pack_tri(tt[t], tp[t])) { tp.clear(); break; }
         DMesh& d = dm[i];
@@ -191,7 +198,8 @@ int Renderer::uploadScene(const hxr_scene* sp)
         d.tri_test = uploadArray(tt.data(), tt.size());
         d.tri_f32 = uploadArray(tf.data(), tf.size());
         d.tri_attr = uploadArray(ta.data(), ta.size());
-        if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_f32 || !d.tri_attr) return oom();
+        d.tri_attr_uv = uploadArray(tu.data(), tu.size());
+        if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_f32 || !d.tri_attr || !d.tri_attr_uv) return oom();
         double amax = 0;
         for (int k = 0; k < 3; k++) {
             d.bbmin[k] = m.bbox_min[k];
@@ -263,6 +271,20 @@ int Renderer::uploadScene(const hxr_scene* sp)
         }
         m_scene.node_slot = uploadArray(slot.data(), slot.size());
         if (!m_scene.node_slot) return oom();
+        // nodes on which nothing reads a hit's u, v, dNdx, dNdy: no bump map and no texture anywhere in the shader tree
+        std::function<bool(int, int)> textured = [&](int si, int depth) -> bool {
+            if (si < 0 || si >= s.n_shaders || depth > 16) return true;  // unknown: assume it reads them
+            const hxr_shader& sh = s.shaders[si];
+            if (sh.tex >= 0) return true;
+            if (sh.type == HXR_SHADER_LAYERED)
+                for (int l = sh.first_layer; l < sh.first_layer + sh.n_layers; l++)
+                    if (s.layers[l].tex >= 0 || textured(s.layers[l].shader, depth + 1)) return true;
+            return false;
+        };
+        std::vector<int32_t> lean(std::max(1, s.n_nodes), 0);
+        for (int i = 0; i < s.n_nodes; i++) lean[i] = (s.nodes[i].bump_tex < 0 && !textured(s.nodes[i].shader, 0) && !getenv("HXR_FULL_ATTR")) ? 1 : 0;
+        m_scene.node_lean = uploadArray(lean.data(), lean.size());
+        if (!m_scene.node_lean) return oom();
         m_scene.n_big = m_nBig;
         // world boxes of the inline nodes' geometry: the 8 corners of the object-space box through the node transform
         std::vector<double> box((size_t)std::max(1, s.n_nodes) * 6);
@@ -760,7 +782,9 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
         dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
         dev::set_u32(m_counters + C_Q0, m);
         dev::set_u32(m_counters + C_OVERFLOW, 0);
-        dev::trace_closest(m_scene, m_q[0], m_counters + C_Q0, m_cap, m_hits, scratch(C_HEAD_A), nullptr, m);
+        DScene full = m_scene;
+        full.full_attr = 1;  // the hook reports u, v, dNdx, dNdy of every hit, whatever the node's shader reads
+        dev::trace_closest(full, m_q[0], m_counters + C_Q0, m_cap, m_hits, scratch(C_HEAD_A), nullptr, m);
         if (!dev::download(recs.data(), m_hits, (size_t)m * sizeof(HitRec))) return fail(HXR_ERR_CUDA, dev::last_error());
         if (readCount(m_counters + C_OVERFLOW)) return fail(HXR_ERR_OVERFLOW, "trace_closest: traversal scratch overflow; raise hxr_config.queue_capacity");
         for (uint32_t i = 0; i < m; i++) {

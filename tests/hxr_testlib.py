@@ -209,6 +209,36 @@ def check_terrain(api, queue_capacity=1 << 20, spp=64):
         sf.close()
 
 
+def check_layout_switches(api, side=320, queue_capacity=1 << 20):
+    """The optional data layouts change what is FETCHED, never the result: the 32-byte packed triangle record (HXR_TRI_PACK,
+    filter decisions differ, the exact test decides the same winner) and the full-attribute gather on untextured nodes
+    (HXR_FULL_ATTR) must give bit-identical hit records, shadow answers and frames."""
+    g = np.load(os.path.join(GOLDEN, "terrain_320.npz"))
+    W, H = int(g["W"]), int(g["H"])
+    rays = np.concatenate([g["rays"], np.zeros((len(g["rays"]), 2))], axis=1)
+    out = []
+    for env in ({}, {"HXR_TRI_PACK": "1"}, {"HXR_FULL_ATTR": "1"}):
+        os.environ.update(env)
+        try:
+            sf = terrain_scene_file(api, side, W, H)
+            r = hx.Renderer(api_=api, queue_capacity=queue_capacity).load(sf)
+        finally:
+            for k in env:
+                del os.environ[k]
+        hits = r.trace_closest(rays).copy()
+        vis = r.trace_visible(g["seg"]).copy()
+        img, st = r.render(width=W, height=H, spp=4, seed=9)
+        out.append((hits, vis, img.copy()))
+        r.close()
+        sf.close()
+    for hits, vis, img in out[1:]:
+        for f in ("status", "node", "dist", "ip", "norm", "u", "v"):
+            assert np.array_equal(hits[f], out[0][0][f]), f
+        assert np.array_equal(vis, out[0][1])
+        # (radiance is summed per pixel with atomic float adds: the order, hence the last bits, varies from run to run)
+        assert np.allclose(img, out[0][2], rtol=2e-5, atol=1e-6), float(np.abs(img - out[0][2]).max())
+
+
 def check_stereo(sess, scene, spp=0):
     """Anaglyph frame of a bundled scene with stereoSeparation added, against the compiled reference's frame."""
     g = golden("stereo", scene)

@@ -37,6 +37,10 @@ def test_terrain_walk(emu_api):
     T.check_terrain(emu_api, spp=8)
 
 
+def test_layout_switches_do_not_change_results(emu_api):
+    T.check_layout_switches(emu_api)
+
+
 def test_stereo_anaglyph(sess):
     # src/main.cpp:234-248: two traces per sample mixed into an anaglyph; Whitted + AA (deterministic) and GI
     T.check_stereo(sess, "kdtree_test")

@@ -164,6 +164,10 @@ def test_walk_equals_brute_force(gpu_api, side):
     assert np.array_equal(walk["norm"][m], brute["norm"][m])
 
 
+def test_layout_switches_do_not_change_results(gpu_api):
+    T.check_layout_switches(gpu_api)
+
+
 def test_stereo_anaglyph(sess):
     # src/main.cpp:234-248: two traces per sample mixed into an anaglyph; Whitted + AA (deterministic) and GI
     T.check_stereo(sess, "kdtree_test")
