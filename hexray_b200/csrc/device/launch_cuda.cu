@@ -35,7 +35,7 @@ static std::string g_err;
 static bool g_prof = false;
 // walk-loop tunables (uniform kernel arguments; HXR_WALK_STEPS / HXR_REFILL_MIN in the environment override the defaults)
 #define HXR_PAIR_CHUNK 64 /* pair-list slots a warp of k_walk reserves per atomic (0: one atomic per append) */
-static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10, g_useMail = 1, g_pairChunk = HXR_PAIR_CHUNK;
+static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10, g_useMail = 1, g_pairChunk = HXR_PAIR_CHUNK, g_bfPush = 1, g_walkCarveout = -1, g_walkBlocksPerSm = 0;
 static uint64_t g_launches[PROF_NCAT];
 static std::vector<cudaEvent_t> g_evPool;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
@@ -71,6 +71,9 @@ bool init(int device, char* err, size_t errlen)
     if (const char* e = getenv("HXR_WALK_STEPS")) g_walkSteps = std::max(1, atoi(e));
     if (const char* e = getenv("HXR_SSTACK")) g_sstack = atoi(e);
     if (getenv("HXR_NO_MAILBOX")) g_useMail = 0;
+    if (getenv("HXR_BRANCHY_PUSH")) g_bfPush = 0;
+    if (const char* e = getenv("HXR_WALK_CARVEOUT")) g_walkCarveout = std::min(100, std::max(0, atoi(e)));
+    if (const char* e = getenv("HXR_WALK_BLOCKS_PER_SM")) g_walkBlocksPerSm = std::max(1, atoi(e));
     if (const char* e = getenv("HXR_PAIR_CHUNK")) g_pairChunk = std::min(1024, std::max(0, atoi(e)));
     if (const char* e = getenv("HXR_REFILL_MIN")) g_refillMin = std::min(32, std::max(1, atoi(e)));
     if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
@@ -292,7 +295,7 @@ struct WalkShared {
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, TraceScratch ts, TravCounters* cnt, int walkSteps,
-                                                                              int refillMin, int useMail, int pairChunk)
+                                                                              int refillMin, int useMail, int pairChunk, int branchFreePush)
 {
     __shared__ WalkShared<SSTACK> sh;
     constexpr int HXR_SSTACK = SSTACK;
@@ -407,15 +410,36 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 const KdBlock B = load_block(blocks + cur);
                 WalkEnt e0, e1, e2, e3;
                 block_step(B, wr, tmin, tmax, tbest, e0, e1, e2, e3);
-                // nearest valid entry becomes the cursor, the others are pushed far-to-near
-                WalkEnt c;
-                c.ref = HXR_POP; c.lo = 0; c.hi = 0;
-                bool have = false;
-                if (ent_valid(e3)) { c = e3; have = true; }
-                if (ent_valid(e2)) { if (have) push(c); c = e2; have = true; }
-                if (ent_valid(e1)) { if (have) push(c); c = e1; have = true; }
-                if (ent_valid(e0)) { if (have) push(c); c = e0; have = true; }
-                cur = c.ref; tmin = c.lo; tmax = c.hi;
+                // nearest valid entry becomes the cursor, the others are pushed far-to-near. Branch-free: an entry is pushed iff it
+                // is valid and a nearer one is too; its slot follows from the pushes before it; the three stores are predicated.
+                // (The chained "if valid { if have push; c = e }" form compiled to ~75 issue slots per step at 2-6 active lanes.)
+                const bool v0 = ent_valid(e0), v1 = ent_valid(e1), v2 = ent_valid(e2), v3 = ent_valid(e3);
+                if (branchFreePush) {
+                    const bool p3 = v3 && (v0 || v1 || v2), p2 = v2 && (v0 || v1), p1 = v1 && v0;
+                    const int s3 = sp, s2 = s3 + (p3 ? 1 : 0), s1 = s2 + (p2 ? 1 : 0);
+                    sp = s1 + (p1 ? 1 : 0);
+                    if (p3 && s3 < HXR_SSTACK) { sh.stRef[s3][tid] = e3.ref; sh.stMin[s3][tid] = e3.lo; sh.stMax[s3][tid] = e3.hi; }
+                    if (p2 && s2 < HXR_SSTACK) { sh.stRef[s2][tid] = e2.ref; sh.stMin[s2][tid] = e2.lo; sh.stMax[s2][tid] = e2.hi; }
+                    if (p1 && s1 < HXR_SSTACK) { sh.stRef[s1][tid] = e1.ref; sh.stMin[s1][tid] = e1.lo; sh.stMax[s1][tid] = e1.hi; }
+                    if (sp > HXR_SSTACK) {  // rare: some of them belong to the overflow part of the stack (local memory)
+                        if (p3 && s3 >= HXR_SSTACK && s3 < HXR_KD_STACK) { ovRef[s3 - HXR_SSTACK] = e3.ref; ovMin[s3 - HXR_SSTACK] = e3.lo; ovMax[s3 - HXR_SSTACK] = e3.hi; }
+                        if (p2 && s2 >= HXR_SSTACK && s2 < HXR_KD_STACK) { ovRef[s2 - HXR_SSTACK] = e2.ref; ovMin[s2 - HXR_SSTACK] = e2.lo; ovMax[s2 - HXR_SSTACK] = e2.hi; }
+                        if (p1 && s1 >= HXR_SSTACK && s1 < HXR_KD_STACK) { ovRef[s1 - HXR_SSTACK] = e1.ref; ovMin[s1 - HXR_SSTACK] = e1.lo; ovMax[s1 - HXR_SSTACK] = e1.hi; }
+                        if (sp > HXR_KD_STACK) sp = HXR_KD_STACK;  // unreachable: the build caps the depth (see push)
+                    }
+                    cur = v0 ? e0.ref : v1 ? e1.ref : v2 ? e2.ref : v3 ? e3.ref : HXR_POP;
+                    tmin = v0 ? e0.lo : v1 ? e1.lo : v2 ? e2.lo : e3.lo;
+                    tmax = v0 ? e0.hi : v1 ? e1.hi : v2 ? e2.hi : e3.hi;
+                } else {
+                    WalkEnt c;
+                    c.ref = HXR_POP; c.lo = 0; c.hi = 0;
+                    bool have = false;
+                    if (v3) { c = e3; have = true; }
+                    if (v2) { if (have) push(c); c = e2; have = true; }
+                    if (v1) { if (have) push(c); c = e1; have = true; }
+                    if (v0) { if (have) push(c); c = e0; have = true; }
+                    cur = c.ref; tmin = c.lo; tmax = c.hi;
+                }
             }
             if (stepping && active && (cur >> 31)) leafCnt = __ldg(leafTris + (cur & ~HXR_KD_LEAF));  // in flight while the others keep stepping
             __syncwarp();
@@ -630,14 +654,20 @@ template <class K> static int walk_grid(K kernel)
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED> static void launch_walk_s(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
 {
     static int full = 0;
-    if (!full) full = walk_grid(k_walk<SHADOW, COUNT, SSTACK, PACKED>);
+    if (!full) {
+        // fewer resident blocks than fit + a smaller shared-memory carve-out leave the L1 more room for the top of the tree
+        if (g_walkCarveout >= 0) cudaFuncSetAttribute(k_walk<SHADOW, COUNT, SSTACK, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout, g_walkCarveout);
+        full = walk_grid(k_walk<SHADOW, COUNT, SSTACK, PACKED>);
+        if (g_walkBlocksPerSm > 0) full = std::min(full, g_sms * g_walkBlocksPerSm);
+    }
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, (max_tasks + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_useMail, g_pairChunk);
+    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_useMail, g_pairChunk, g_bfPush);
 }
 template <bool SHADOW, bool PACKED> static void launch_walk_p(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
 {
     if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(sc, ts, cnt, max_tasks); return; }
     switch (g_sstack) {
+        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(sc, ts, nullptr, max_tasks); break;
         case 12: launch_walk_s<SHADOW, false, 12, PACKED>(sc, ts, nullptr, max_tasks); break;
         default: launch_walk_s<SHADOW, false, 10, PACKED>(sc, ts, nullptr, max_tasks); break;
     }
