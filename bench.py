@@ -399,6 +399,19 @@ def ours(a):
         if os.path.exists(tp) and a.workload == "terrain" and a.grid_side == 2237:
             with open(tp) as f:
                 traffic = json.load(f)
+        # context for the roofline: what this GPU delivers to RANDOM gathers (tools/microbench.cu, profiles/microbench_r1_v12.json) --
+        # the copy bandwidth in `peak` is not reachable by a tree walk, whatever the record size
+        gather = None
+        mp = os.path.join(ROOT, "profiles", "microbench_r1_v12.json")
+        if os.path.exists(mp):
+            try:
+                with open(mp) as f:
+                    g = json.loads(f.readline())["random_gather_G_per_s"]["l2gran64(got 64)"]
+                gather = {"sectors32B_G_per_s": g["32B"], "gbs_64B_records": g["64B"] * 64.0, "source": "profiles/microbench_r1_v12.json"}
+                if traffic and walk_ms > 0:
+                    gather["walk_dram_gbs"] = traffic["dram_bytes_per_launch"] / (walk_ms / max(1, walk_launches) * 1e-3) / 1e9
+            except Exception:
+                gather = None
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -419,6 +432,7 @@ def ours(a):
                          "kernel": "k_walk (KD-tree walk: closest-hit + shadow launches)", "peak_source": peak_src if hbm_bound else "tools/microbench L2 read (profiles/microbench_r1.json)",
                          "bytes_per_ray": b_ray, "bytes_per_launch": my_rays * b_ray / max(1, walk_launches), "per_ray": per_ray,
                          "launches": int(walk_launches), "avg_launch_ms": walk_ms / max(1, walk_launches),
+                         "random_gather": gather,
                          "walk_share_of_step": walk_ms / max(1e-9, prof["render_ms"]),
                          "traversal_share_of_step": (prof["trace_closest_ms"] + prof["trace_shadow_ms"]) / max(1e-9, prof["render_ms"])},
             "kernel_ms_per_step": {k: prof[k] / a.steps for k in ("trace_closest_ms", "trace_shadow_ms", "walk_ms", "shade_ms", "other_ms", "render_ms")},
