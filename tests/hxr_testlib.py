@@ -177,6 +177,43 @@ def terrain_scene_file(api, side, W=96, H=54, spp=16, tmpdir="/tmp"):
     return hx.SceneFile(path, api_=api)
 
 
+def soup_scene_file(api, n_tris, W=96, H=54, spp=16, tmpdir="/tmp"):
+    """bench.py's soup workload: n_tris random triangles in [-500, 500]^3 (overlapping, incoherent: deep stacks, many leaves per ray)."""
+    import argparse
+    import bench
+    path = os.path.join(tmpdir, "hxr_soup_%d_%d.hexray" % (n_tris, os.getpid()))
+    with open(path, "w") as f:
+        f.write(bench.scene_text(argparse.Namespace(grid_side=0, workload="soup", soup_triangles=n_tris), "synthetic:soup:%d:0x5EEE" % n_tris, W, H, spp))
+    return hx.SceneFile(path, api_=api)
+
+
+def check_soup_walk_equals_brute_force(api, n_tris, n_rays, queue_capacity=1 << 20):
+    """The KD walk against testing every triangle in index order (the reference's useKDTree=false path) on the soup: rays
+    cross hundreds of leaves, the traversal stack overflows its shared-memory part, triangles overlap and intersect each other."""
+    rng = np.random.default_rng(n_tris)
+    o = rng.uniform(-480, 480, (n_rays, 3))
+    d = rng.normal(size=(n_rays, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.zeros((n_rays, 2))], axis=1)
+    seg = np.concatenate([o, o + d * rng.uniform(5, 400, (n_rays, 1))], axis=1)
+    sf = soup_scene_file(api, n_tris)
+    out = []
+    for flags in (0, hx.CFG_BRUTE_FORCE_MESHES):
+        r = hx.Renderer(api_=api, queue_capacity=queue_capacity, flags=flags).load(sf)
+        out.append((r.trace_closest(rays).copy(), r.trace_visible(seg).copy()))
+        r.close()
+    sf.close()
+    (walk, wvis), (brute, bvis) = out
+    assert (walk["node"] == brute["node"]).all() and (walk["status"] == brute["status"]).all()
+    m = walk["status"] == 0
+    hit_soup = int((walk["node"][m] == 0).sum())  # sparse soups are mostly missed: optical depth ~ n_tris * 1.7 * 500 / 1e9
+    assert hit_soup >= min(n_rays // 4, max(3, int(n_rays * n_tris * 1e-7))), hit_soup
+    for f in ("dist", "ip", "norm", "u", "v"):
+        assert np.array_equal(walk[f][m], brute[f][m]), f
+    assert np.array_equal(wvis, bvis)
+    assert 0 < wvis.sum() <= n_rays
+
+
 def check_terrain(api, queue_capacity=1 << 20, spp=64):
     """Explicit rays / shadow segments / a GI frame on the 203k-triangle terrain against the compiled reference."""
     g = np.load(os.path.join(GOLDEN, "terrain_320.npz"))

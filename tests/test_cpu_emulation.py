@@ -37,6 +37,10 @@ def test_terrain_walk(emu_api):
     T.check_terrain(emu_api, spp=8)
 
 
+def test_soup_walk_equals_brute_force(emu_api):
+    T.check_soup_walk_equals_brute_force(emu_api, 100000, 1500)
+
+
 def test_layout_switches_do_not_change_results(emu_api):
     T.check_layout_switches(emu_api)
 

@@ -164,6 +164,12 @@ def test_walk_equals_brute_force(gpu_api, side):
     assert np.array_equal(walk["norm"][m], brute["norm"][m])
 
 
+@pytest.mark.parametrize("n_tris", [20000, 2000000])
+def test_soup_walk_equals_brute_force(gpu_api, n_tris):
+    # 2 M triangles exceed the 64 MB threshold: the walk reads the 32-byte packed records there
+    T.check_soup_walk_equals_brute_force(gpu_api, n_tris, 4096 if n_tris <= 20000 else 512)
+
+
 def test_layout_switches_do_not_change_results(gpu_api):
     T.check_layout_switches(gpu_api)
 
