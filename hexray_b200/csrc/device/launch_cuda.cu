@@ -207,6 +207,16 @@ __global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, 
 }
 
 #define HXR_WALK_BLOCK 128
+// resident blocks per SM of the lean per-ray kernels (register caps 65536 / (128 * blocks)); A/B-ed on B200, see profiles/README.md
+#ifndef HXR_SETUP_BLOCKS
+#define HXR_SETUP_BLOCKS 6
+#endif
+#ifndef HXR_FIN_BLOCKS
+#define HXR_FIN_BLOCKS 4
+#endif
+#ifndef HXR_SHADE_GI_BLOCKS
+#define HXR_SHADE_GI_BLOCKS 5
+#endif
 #ifndef HXR_WALK_MIN_BLOCKS
 #define HXR_WALK_MIN_BLOCKS 8
 #endif
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, 
 #endif
 
 template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, SIMPLE ? 6 : 1) k_setup_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
+__global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
                                                        TraceScratch ts, TravCounters* cnt)
 {
     const uint32_t n = min(*q_count, cap);
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(128, SIMPLE ? 6 : 1) k_setup_closest(DScene sc
 }
 
 template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, SIMPLE ? 4 : 2) k_finalize_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
+__global__ void __launch_bounds__(128, SIMPLE ? HXR_FIN_BLOCKS : 2) k_finalize_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
                                                           TraceScratch ts, HitRec* __restrict__ hits, TravCounters* cnt)
 {
     const uint32_t n = min(*q_count, cap);
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(128, SIMPLE ? 4 : 2) k_finalize_closest(DScene
 }
 
 template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, SIMPLE ? 6 : 1) k_setup_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap,
+__global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap,
                                                       TraceScratch ts, TravCounters* cnt, unsigned long long* total)
 {
     const uint32_t n = min(*count, cap);
@@ -572,7 +582,7 @@ __global__ void __launch_bounds__(128) k_confirm_shadow(DScene sc, const ShadowT
 // GI (one path vertex) and Whitted (shader tree with its stacks) are separate compilations: the path-tracing vertex
 // needs far fewer registers than the tree walk, and occupancy is what hides this kernel's gather latency
 template <bool GI>
-__global__ void __launch_bounds__(HXR_SHADE_BLOCK, GI ? 5 : 3) k_shade(DScene sc, FrameParams fp, const RayTask* __restrict__ q,
+__global__ void __launch_bounds__(HXR_SHADE_BLOCK, GI ? HXR_SHADE_GI_BLOCKS : 3) k_shade(DScene sc, FrameParams fp, const RayTask* __restrict__ q,
                                                                        const uint32_t* __restrict__ q_count, const HitRec* __restrict__ hits,
                                                                        uint32_t begin, uint32_t end, Sinks sinks)
 {

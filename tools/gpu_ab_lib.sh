@@ -4,7 +4,7 @@ TAG=$1; SPP=${2:-16}; shift 2
 mkdir -p gpurun_out; : > gpurun_out/${TAG}.jsonl
 LIB=hexray_b200/libhexray_b200.so
 cp $LIB /tmp/tree.so
-for v in "$@" "$@"; do
+for v in "$@"; do
   if [ "$v" = "tree" ]; then cp /tmp/tree.so $LIB; else cp $v $LIB; fi
   timeout 600 python bench.py --steps 2 --warmup 2 --spp $SPP --no-cpu-baseline ${HXR_AB_ARGS} 2>/dev/null | python -c "
 import sys,json
