@@ -8,7 +8,8 @@
 //   k_walk               the KD-tree walk, FP32 only: PERSISTENT warps, idle lanes refilled with __ballot_sync + one
 //                        atomicAdd per warp + __shfl_sync; a bounded phase of block steps (32-byte block = two tree
 //                        levels) alternates with a warp-cooperative phase that filters the triangles of all leaves held
-//                        by the warp, 32 (ray, triangle) pairs at a time; undecided pairs go to a list
+//                        by the warp, 32 (ray, triangle) pairs at a time; undecided pairs go to a list (slots reserved 64
+//                        per warp: one same-address atomic per append serialised in L2)
 //   k_confirm_closest_a/b, k_confirm_shadow   the exact (double) triangle test on the listed pairs
 //   k_finalize_closest   winner across inline nodes and walked meshes, IntersectionInfo, lights, environment, bump
 //   k_shade<GI>          Whitted shader tree or path-tracing vertex: pushes child/shadow tasks,
@@ -33,7 +34,8 @@ static int g_sms = 0;
 static cudaStream_t g_stream = nullptr;
 static std::string g_err;
 static bool g_prof = false;
-// walk-loop tunables (uniform kernel arguments; HXR_WALK_STEPS / HXR_REFILL_MIN in the environment override the defaults)
+// walk-loop tunables (uniform kernel arguments; environment overrides for A/B runs: HXR_WALK_STEPS, HXR_REFILL_MIN, HXR_SSTACK,
+// HXR_PAIR_CHUNK, HXR_NO_MAILBOX, HXR_BRANCHY_PUSH, HXR_WALK_CARVEOUT, HXR_WALK_BLOCKS_PER_SM; measured optima are the defaults)
 #define HXR_PAIR_CHUNK 64 /* pair-list slots a warp of k_walk reserves per atomic (0: one atomic per append) */
 static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10, g_useMail = 1, g_pairChunk = HXR_PAIR_CHUNK, g_bfPush = 1, g_walkCarveout = -1, g_walkBlocksPerSm = 0;
 static uint64_t g_launches[PROF_NCAT];
@@ -285,7 +287,8 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
 // The kernel is FP32 only: conservative plane arithmetic (isect.h: block_step) and the conservative triangle
 // filter (tri_filter). Pairs the filter cannot rule out are appended to a list for the exact double test
 // (k_confirm_*); certain hits shorten the walk. No double arithmetic keeps the kernel at <= 64 registers
-// (8 blocks = 1024 lanes per SM) and halves the triangle bytes (48 B instead of 96 B).
+// (8 blocks = 1024 lanes per SM; A/B: 9 or 10 blocks at 55 / 48 registers and 5-7 blocks are all slower) and cuts the
+// triangle bytes (48-byte TriF32, or 32-byte TriPacked on scenes whose triangles outgrow the L2, instead of 96 B).
 //
 // State per lane in shared memory: the float ray (24 B), the best-hit bound (4 B, lowered with atomicMin by whichever
 // lane filters a certain hit) and the first HXR_SSTACK stack entries (12 B each); deeper entries overflow to local
