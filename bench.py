@@ -115,7 +115,8 @@ def parse_args():
     ap.add_argument("--ref-height", type=int, default=216)
     ap.add_argument("--ref-spp", type=int, default=8, help="reference arm: samples per pixel of the bounded sample (the cpu_baseline leg of our arm uses 4x)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--queue-capacity", type=int, default=16 << 20)
+    ap.add_argument("--queue-capacity", type=int, default=64 << 20,
+                    help="rays per wave of the wavefront renderer: 64 Mi holds one whole 1080p x 32 spp pass (measured: 1475 -> 1542 Mrays/s against 16 Mi; ~45 GB of the 180 GB HBM)")
     return ap.parse_args()
 
 

@@ -13,9 +13,10 @@ def main():
             hdr, start = r, i + 1
             break
     ki, mi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    ni = hdr.index("Metric Name") if "Metric Name" in hdr else -1
     agg = collections.OrderedDict()
     for r in rows[start:]:
-        if len(r) <= mi:
+        if len(r) <= mi or (ni >= 0 and r[ni] != "gpu__time_duration.sum"):  # the list may carry other metrics per launch too
             continue
         name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("hxr::dev::", "")
         try:
