@@ -177,6 +177,10 @@ class Renderer:
         """takeScreenshot: the last rendered frame (or the device frame at `dptr`) as a BMP, converted to 8 bits on the GPU."""
         self._check(self.api.lib.hxr_save_frame_bmp(self.ctx, C.c_void_p(dptr) if dptr else None, width, height, path.encode()))
 
+    def save_frame_exr(self, path, dptr=None, width=0, height=0):
+        """Bitmap::saveEXR of the last rendered frame (or the device frame at `dptr`): float -> half on the GPU."""
+        self._check(self.api.lib.hxr_save_frame_exr(self.ctx, C.c_void_p(dptr) if dptr else None, width, height, path.encode()))
+
     def set_profiling(self, on):
         self._check(self.api.lib.hxr_set_profiling(self.ctx, 1 if on else 0))
 

@@ -116,7 +116,8 @@ class Stats(C.Structure):
                 ("tri_tests", c_u64), ("mesh_queries", c_u64), ("kernel_launches", c_u64), ("render_ms", c_f64),
                 ("trace_closest_ms", c_f64), ("trace_shadow_ms", c_f64), ("shade_ms", c_f64), ("other_ms", c_f64),
                 ("trace_closest_launches", c_u64), ("trace_shadow_launches", c_u64), ("spp_done", c_u32),
-                ("aa_pixels", c_u32), ("walk_ms", c_f64), ("walk_launches", c_u64)]
+                ("aa_pixels", c_u32), ("walk_ms", c_f64), ("walk_launches", c_u64), ("cand_overflow", c_u64),
+                ("shadow_resolve_ms", c_f64), ("gen_ms", c_f64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -140,7 +141,7 @@ SYMBOLS = ["hxr_create", "hxr_destroy", "hxr_last_error", "hxr_upload_scene", "h
            "hxr_render_device", "hxr_resolve_device", "hxr_trace_closest", "hxr_trace_visible", "hxr_trace_color",
            "hxr_get_accel_info", "hxr_set_profiling", "hxr_scene_load", "hxr_scene_file_scene", "hxr_scene_file_camera",
            "hxr_scene_file_set_synthetic_mesh", "hxr_scene_file_write_obj", "hxr_scene_file_free", "hxr_save_image", "hxr_load_image",
-           "hxr_test_tri_filter", "hxr_test_tri_filter_packed", "hxr_save_frame_bmp"]
+           "hxr_test_tri_filter", "hxr_test_tri_filter_packed", "hxr_save_frame_bmp", "hxr_save_frame_exr"]
 
 
 class Api:
@@ -178,6 +179,7 @@ class Api:
         L.hxr_scene_file_free.restype = None
         L.hxr_save_image.argtypes = [C.c_char_p, C.POINTER(c_f32), c_i32, c_i32]
         L.hxr_save_frame_bmp.argtypes = [vp, vp, c_i32, c_i32, C.c_char_p]
+        L.hxr_save_frame_exr.argtypes = [vp, vp, c_i32, c_i32, C.c_char_p]
         L.hxr_test_tri_filter.argtypes = [C.c_size_t, vp, vp, vp, c_i32, vp, vp, vp, vp]
         L.hxr_test_tri_filter_packed.argtypes = [C.c_size_t, vp, vp, vp, c_i32, vp, vp, vp, vp]
         L.hxr_load_image.argtypes = [C.c_char_p, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_f32), C.c_size_t]

@@ -44,7 +44,7 @@ int hxr_create(const hxr_config* cfg, hxr_ctx** out)
     memset(&c, 0, sizeof c);
     if (cfg) c = *cfg;
     std::unique_ptr<hxr_ctx> ctx(new hxr_ctx);
-    int rc = ctx->r.create(c);
+    int rc = ctx->r.create(c, c.device);
     if (rc != HXR_OK) { g_lastError = ctx->r.error(); return rc; }
     *out = ctx.release();
     return HXR_OK;
@@ -85,12 +85,13 @@ int hxr_render_device(hxr_ctx* ctx, const hxr_render_params* p, void* d_rgb, hxr
     HXR_CTX_CALL(ctx->r.render(*p, nullptr, d_rgb, stats))
 }
 int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t w, int32_t h, int32_t spp) { HXR_CTX_CALL(ctx->r.resolveDevice(d_rgb, w, h, spp)) }
-int hxr_set_profiling(hxr_ctx* ctx, int32_t on) { HXR_CTX_CALL((hxr::dev::prof_enable(on != 0), HXR_OK)) }
+int hxr_set_profiling(hxr_ctx* ctx, int32_t on) { HXR_CTX_CALL((ctx->r.setProfiling(on != 0), HXR_OK)) }
 int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits) { HXR_CTX_CALL(ctx->r.traceClosest(rays, n, hits)) }
 int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->r.traceVisible(seg, n, vis)) }
 int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { HXR_CTX_CALL(ctx->r.traceColor(rays, n, rgb)) }
 int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out) { HXR_CTX_CALL(ctx->r.accelInfo(mesh, out)) }
 int hxr_save_frame_bmp(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->r.saveFrameBmp(d_rgb, w, h, path)) }
+int hxr_save_frame_exr(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->r.saveFrameExr(d_rgb, w, h, path)) }
 
 static int test_tri_filter(bool packed, size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out,
                            float* ghi_out, int32_t* exact_out, double* gamma_out)

@@ -2,82 +2,112 @@
 // device. The product implements it in launch_cuda.cu (sm_100a kernels, CUDA streams/events).
 // tests/emu/launch_emu.cpp implements the same interface as plain host loops over the SAME
 // per-item functions (pipeline.h) — test infrastructure for the CPU tier, never shipped.
+//
+// Everything goes through a Context: one per GPU, holding the device ordinal, its stream, its error state and its
+// profiling events. A process may hold any number of contexts on any number of devices (the multi-GPU renderer of
+// multi.cpp drives one per device from one host thread each); there is no process-wide device state.
 #pragma once
 #include "pipeline.h"
 
 namespace hxr {
 namespace dev {
 
+struct Context;
+
 // ---- device lifetime / memory -------------------------------------------------------
-// returns false and fills err if no usable device (product: no CUDA device => hard failure)
-bool init(int device, char* err, size_t errlen);
+// nullptr (and err filled) if the device is unusable (product: no CUDA device => hard failure, there is no CPU fallback)
+Context* create(int device, char* err, size_t errlen);
+void destroy(Context*);
+int device_count();                    // usable devices in this process (0 if none)
+int device_of(const Context*);
+void* stream_of(const Context*);       // cudaStream_t of the context (nullptr in the emulation)
 const char* backend_name();
-void* alloc(size_t bytes);             // nullptr on failure
-void free_(void* p);
-bool upload(void* dst, const void* src, size_t bytes);
-bool download(void* dst, const void* src, size_t bytes);       // blocking
-bool upload_pinned_async(void* dst, const void* src, size_t bytes);
-bool zero(void* p, size_t bytes);
-bool copy_d2d(void* dst, const void* src, size_t bytes);
-bool sync();
-const char* last_error();              // text of the last failed call ("" if none)
+void* alloc(Context*, size_t bytes);   // nullptr on failure
+void free_(Context*, void* p);
+void* alloc_pinned(Context*, size_t bytes);  // page-locked host memory (plain malloc in the emulation)
+void free_pinned(Context*, void* p);
+bool upload(Context*, void* dst, const void* src, size_t bytes);
+bool download(Context*, void* dst, const void* src, size_t bytes);       // blocking
+bool download_async(Context*, void* dst, const void* src, size_t bytes); // stream ordered; dst should be pinned
+bool zero(Context*, void* p, size_t bytes);
+bool copy_d2d(Context*, void* dst, const void* src, size_t bytes);
+bool sync(Context*);
+// text of the first failed call or kernel launch since the last clear_error ("" if none): launches are asynchronous, so
+// the frame driver checks this once per frame instead of after every launch
+const char* last_error(const Context*);
+bool failed(const Context*);
+void clear_error(Context*);
 
 // timers on the context's stream (CUDA events in the product)
 struct Timer;
-Timer* timer_create();
-void timer_destroy(Timer*);
-void timer_start(Timer*);
-void timer_stop(Timer*);
-double timer_ms(Timer*);               // blocks until the stop event has happened
-
-bool set_u32(uint32_t* p, uint32_t v);  // async, stream ordered
+Timer* timer_create(Context*);
+void timer_destroy(Context*, Timer*);
+void timer_start(Context*, Timer*);
+void timer_stop(Context*, Timer*);
+double timer_ms(Context*, Timer*);     // blocks until the stop event has happened
 
 // per-category device time of the launches below (CUDA events around every launch when enabled)
-// PROF_WALK: the k_walk launches alone (they are also inside PROF_TRACE_CLOSEST / PROF_TRACE_SHADOW)
-enum ProfCat { PROF_TRACE_CLOSEST = 0, PROF_TRACE_SHADOW = 1, PROF_SHADE = 2, PROF_OTHER = 3, PROF_WALK = 4, PROF_NCAT = 5 };
-void prof_enable(bool on);
-void prof_reset();
-void prof_collect(double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);  // blocks; launches are counted even when disabled
+enum ProfCat { PROF_WALK_CLOSEST = 0, PROF_WALK_SHADOW = 1, PROF_SHADE = 2, PROF_SHADOW_RESOLVE = 3, PROF_GEN = 4, PROF_OTHER = 5, PROF_NCAT = 6 };
+void prof_enable(Context*, bool on);
+void prof_reset(Context*);
+void prof_collect(Context*, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);  // blocks; launches are counted even when disabled
+
+// device-side totals of one frame (64-bit, accumulated by the kernels)
+struct FrameTotals {
+    unsigned long long rays_closest;   // closest-hit queries past the depth guard
+    unsigned long long rays_shadow;    // visible() queries
+    unsigned long long cand_overflow;  // rays redone with the exact walk because their candidate record overflowed
+    unsigned long long pad;
+};
 
 // ---- kernels -------------------------------------------------------------------------
-// Every launcher returns the number of kernel launches it issued.
+// Every launcher returns the number of kernel launches it issued. Counts live on the device; n_hint is a host-side upper
+// bound of the count that only sizes the grid (a small wave does not pay for a full-size launch).
 
-// primary rays for `n_items` (pixel, sample) pairs:
+// primary rays for `n_items` (pixel, sample) pairs, written to q[0 .. n_items) with their inline part decided; *q.count = n_items
 //   item i -> pixel = pixels ? pixels[i / spp_pass] : first_pixel + i / spp_pass,
 //             sample = fp.sample_base + (i % spp_pass) * fp.sample_stride
-// written to q[0 .. n_items); *q_count is set to n_items.
-int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels, uint32_t first_pixel,
-                uint32_t n_items, uint32_t spp_pass, RayTask* q, uint32_t* q_count);
+// pixels_count (device, may be null): when given, only the first *pixels_count * spp_pass items exist
+int gen_primary(Context*, const DScene& sc, const FrameParams& fp, const uint32_t* pixels, const uint32_t* pixels_count, uint32_t first_pixel,
+                uint32_t n_items, uint32_t spp_pass, const RayQueue& q);
 
-// closest hit for q[0 .. *q_count) (count read on the device) -> hits[i]. Three stages:
-// setup (inline nodes + queue big-mesh walks) -> walk (persistent KD traversal) -> finalize.
-// n_hint: a host-side upper bound of *q_count (sizes the grids; small waves do not pay for full-size launches)
-int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits,
-                  const TraceScratch& ts, TravCounters* cnt, uint32_t n_hint);
+// explicit rays (test hooks): rays[i] -> q slot i with its inline part decided; *q.count = n
+int setup_rays(Context*, const DScene& sc, const hxr_ray* rays, uint32_t n, const RayQueue& q);
+// explicit segments (test hook): seg[6 i .. 6 i + 5] = A, B -> shadow ray i (pre = -2 when an inline node or light blocks it)
+int setup_segments(Context*, const DScene& sc, const double* seg, uint32_t n, const ShadowQueue& q);
 
-// shade q[begin .. min(end, *q_count)); gi selects pathtrace vs Whitted
-int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits,
-          uint32_t begin, uint32_t end, const Sinks& sinks);
+// the KD walk of the big meshes for geom[0 .. *count): one candidate record per ray. head: work-fetch cursor (zeroed by the caller)
+int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+         TravCounters* cnt, uint32_t n_hint);
 
-// visible() for shadow[0 .. *count): ts.occluded[i] = 1 if blocked; when accum != nullptr the carried colour of
-// every unblocked task is added to its pixel. *total += *count (64-bit running total kept on the device).
-int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum,
-                 const TraceScratch& ts, TravCounters* cnt, unsigned long long* total, uint32_t n_hint);
+// shade q[begin .. min(end, *q.count)): exact test of the candidates, winner, shading; pushes child rays and shadow rays.
+// totals->rays_closest += the rays shaded, totals->rays_shadow += the visible() queries issued
+int shade(Context*, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,
+          FrameTotals* totals, TravCounters* cnt);
+
+// shadow rays after their walk: exact test of undecided pairs, then accum[pixel] += colour of every unblocked ray;
+// visible (may be null): visible[i] = 1 / 0 (test hook)
+int resolve_shadow(Context*, const DScene& sc, const ShadowQueue& q, const CandRec* cand, float* accum, uint8_t* visible, FrameTotals* totals,
+                   TravCounters* cnt, uint32_t n_hint);
+
+// raycast() records for q[0 .. *q.count) (test hook)
+int hit_records(Context*, const DScene& sc, const RayQueue& q, const CandRec* cand, HitRec* hits, uint32_t n_hint);
 
 // needsAA flags -> compacted pixel list (order unspecified) ; *n_out = number of flagged pixels
 // rows restricted to y with ((y / HXR_ROW_BAND) % shard_count) == shard_index
-int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out,
-              uint8_t* mask);
+int aa_detect(Context*, const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask);
 // vfb[p] *= mul for every flagged pixel in list[0..*n)
-int scale_listed(float* vfb, const uint32_t* list, const uint32_t* n, uint32_t cap, float mul);
+int scale_listed(Context*, float* vfb, const uint32_t* list, const uint32_t* n, uint32_t cap, float mul);
 // buf[i] *= mul, i < n
-int scale_all(float* buf, size_t n, float mul);
+int scale_all(Context*, float* buf, size_t n, float mul);
 // dst[i] += src[i]
-int add_into(float* dst, const float* src, size_t n);
+int add_into(Context*, float* dst, const float* src, size_t n);
 // float RGB frame -> BMP pixel array (bottom-up BGR rows of rowsz bytes, padding zeroed) through the 4097-entry table `lut`
-int to_bmp_rows(const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out);
+int to_bmp_rows(Context*, const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out);
+// float RGB frame -> half RGBA scan lines as an uncompressed EXR stores them (per row: all A, all B, all G, all R halves)
+int to_exr_rows(Context*, const float* rgb, int W, int H, uint16_t* out);
 // anaglyph mix of the two eyes' images into out (n_pixels RGB pixels)
-int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels);
+int stereo_mix(Context*, float* out, const float* left, const float* right, size_t n_pixels);
 
 }  // namespace dev
 }  // namespace hxr

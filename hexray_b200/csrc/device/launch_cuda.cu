@@ -1,23 +1,25 @@
 // launch_cuda.cu — the sm_100a kernels of the render hot path and their launchers
 // (implements device/launch.h; the only translation unit compiled by nvcc).
 //
-// Kernels (one per wavefront stage; per-item bodies live in pipeline.h / isect.h / shade.h):
-//   k_gen_primary        primary-ray generator (pixel jitter / AA offsets / DOF lens / stereo eye)  -> ray queue
-//   k_setup_closest      per ray, in double: every inline node (analytic primitives, CSG, heightfield, quads) in scene
-//                        order; each mesh whose box the ray enters becomes a ready-to-walk float task
-//   k_walk               the KD-tree walk, FP32 only: PERSISTENT warps, idle lanes refilled with __ballot_sync + one
-//                        atomicAdd per warp + __shfl_sync; a bounded phase of block steps (32-byte block = two tree
+// One bounce of the wavefront is FOUR kernels; a ray lives in a 64-byte geometry record + a 24-byte payload between them:
+//   k_walk<closest>      the KD-tree walk, FP32 only: PERSISTENT warps; a lane owns one RAY and walks, one after the other,
+//                        every big mesh whose box the ray enters (the world -> object transform of the ray is the only double
+//                        arithmetic here, done once per (ray, mesh) at refill); idle lanes are refilled with __ballot_sync +
+//                        one atomicAdd per warp + __shfl_sync; a bounded phase of block steps (32-byte block = two tree
 //                        levels) alternates with a warp-cooperative phase that filters the triangles of all leaves held
-//                        by the warp, 32 (ray, triangle) pairs at a time; undecided pairs go to a list (slots reserved 64
-//                        per warp: one same-address atomic per append serialised in L2)
-//   k_confirm_closest_a/b, k_confirm_shadow   the exact (double) triangle test on the listed pairs
-//   k_finalize_closest   winner across inline nodes and walked meshes, IntersectionInfo, lights, environment, bump
-//   k_shade<GI>          Whitted shader tree or path-tracing vertex: pushes child/shadow tasks,
-//                        accumulates radiance with RED.ADD.F32
-//   k_setup_shadow / k_walk<shadow> / k_confirm_shadow / k_accum_shadow   visible() in the same stages (any-hit walk)
-//   k_aa_detect / k_scale_* / k_add_into / k_stereo_mix / k_to_bmp_rows   frame-buffer passes
+//                        by the warp, 32 (ray, triangle) pairs at a time; pairs the filter cannot rule out are collected
+//                        in the owner's shared-memory slots and leave the kernel as ONE 16-byte candidate record per ray
+//   k_shade<GI>          per ray: exact (double) test of its candidates, winner across inline nodes and meshes,
+//                        IntersectionInfo, lights, environment, bump, then the Whitted shader tree or the path-tracing vertex;
+//                        every ray it creates gets its inline part (analytic nodes, CSG, heightfields, quads, in double)
+//                        decided on the spot and is pushed ready to walk; radiance lands with RED.ADD.F32
+//   k_walk<shadow>       any-hit form of the same walk
+//   k_resolve_shadow     exact test of the undecided shadow pairs, then the carried colour
+// plus k_gen_primary (camera rays with their inline part), the test-hook kernels (k_setup_rays, k_setup_segments,
+// k_hit_records) and the frame-buffer passes (k_aa_detect, k_scale_*, k_add_into, k_stereo_mix, k_to_bmp_rows, k_to_exr_rows).
 // Grid sizing: the persistent walk launches (SM count x resident blocks/SM) blocks - 148 SMs on B200 - the per-item
-// stage kernels are grid-stride loops over device-side counts, sized by a host-side upper bound of the count.
+// kernels are grid-stride loops over device-side counts, sized by a host-side upper bound of the count: the host never
+// reads a count back between bounces.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
@@ -29,33 +31,41 @@
 namespace hxr {
 namespace dev {
 
-static int g_device = -1;
-static int g_sms = 0;
-static cudaStream_t g_stream = nullptr;
-static std::string g_err;
-static bool g_prof = false;
-// walk-loop tunables (uniform kernel arguments; environment overrides for A/B runs: HXR_WALK_STEPS, HXR_REFILL_MIN, HXR_SSTACK,
-// HXR_PAIR_CHUNK, HXR_NO_MAILBOX, HXR_BRANCHY_PUSH, HXR_WALK_CARVEOUT, HXR_WALK_BLOCKS_PER_SM; measured optima are the defaults)
-#define HXR_PAIR_CHUNK 64 /* pair-list slots a warp of k_walk reserves per atomic (0: one atomic per append) */
-static int g_walkSteps = 3, g_refillMin = 8, g_sstack = 10, g_useMail = 1, g_pairChunk = HXR_PAIR_CHUNK, g_bfPush = 1, g_walkCarveout = -1, g_walkBlocksPerSm = 0;
-static uint64_t g_launches[PROF_NCAT];
-static std::vector<cudaEvent_t> g_evPool;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_evPairs[PROF_NCAT];
+struct Context {
+    int device = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;  // first failure since clear_error
+    bool prof = false;
+    // walk-loop tunables (uniform kernel arguments; environment overrides for A/B runs: HXR_WALK_STEPS, HXR_REFILL_MIN, HXR_SSTACK,
+    // HXR_NO_MAILBOX, HXR_BRANCHY_PUSH, HXR_WALK_CARVEOUT, HXR_WALK_BLOCKS_PER_SM; measured optima are the defaults)
+    int walkSteps = 3, refillMin = 8, sstack = 10, useMail = 1, bfPush = 1, walkCarveout = -1, walkBlocksPerSm = 0;
+    uint64_t launches[PROF_NCAT] = {};
+    std::vector<cudaEvent_t> evPool;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPairs[PROF_NCAT];
+    int walkGrid[2][2][3][2] = {};  // cached occupancy-derived grid per k_walk instantiation
+};
 
-static bool ck(cudaError_t e, const char* what)
+static bool ck(Context* c, cudaError_t e, const char* what)
 {
     if (e == cudaSuccess) return true;
-    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    if (c->err.empty()) c->err = std::string(what) + ": " + cudaGetErrorString(e);
     return false;
 }
-static bool use() { return g_device >= 0 && ck(cudaSetDevice(g_device), "cudaSetDevice"); }
+static bool use(Context* c) { return c && c->device >= 0 && ck(c, cudaSetDevice(c->device), "cudaSetDevice"); }
 
-bool init(int device, char* err, size_t errlen)
+int device_count()
 {
-    auto fail = [&](const std::string& m) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+Context* create(int device, char* err, size_t errlen)
+{
+    auto fail = [&](const std::string& m) -> Context* {
         snprintf(err, errlen, "%s", m.c_str());
-        g_err = m;
-        return false;
+        return nullptr;
     };
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -63,219 +73,281 @@ bool init(int device, char* err, size_t errlen)
         return fail(std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
                     "); hexray_b200 has no CPU fallback");
     if (device < 0 || device >= n) return fail("CUDA device ordinal out of range");
-    if (g_device >= 0 && g_device != device) return fail("this process is already bound to another device (one process per GPU)");
     if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
     if (p.major < 10) return fail(std::string("device '") + p.name + "' is not Blackwell (sm_100a code only)");
-    g_device = device;
-    g_sms = p.multiProcessorCount;
-    if (const char* e = getenv("HXR_WALK_STEPS")) g_walkSteps = std::max(1, atoi(e));
-    if (const char* e = getenv("HXR_SSTACK")) g_sstack = atoi(e);
-    if (getenv("HXR_NO_MAILBOX")) g_useMail = 0;
-    if (getenv("HXR_BRANCHY_PUSH")) g_bfPush = 0;
-    if (const char* e = getenv("HXR_WALK_CARVEOUT")) g_walkCarveout = std::min(100, std::max(0, atoi(e)));
-    if (const char* e = getenv("HXR_WALK_BLOCKS_PER_SM")) g_walkBlocksPerSm = std::max(1, atoi(e));
-    if (const char* e = getenv("HXR_PAIR_CHUNK")) g_pairChunk = std::min(1024, std::max(0, atoi(e)));
-    if (const char* e = getenv("HXR_REFILL_MIN")) g_refillMin = std::min(32, std::max(1, atoi(e)));
-    if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
-    return true;
+    Context* c = new Context;
+    c->device = device;
+    c->sms = p.multiProcessorCount;
+    if (const char* v = getenv("HXR_WALK_STEPS")) c->walkSteps = std::max(1, atoi(v));
+    if (const char* v = getenv("HXR_SSTACK")) c->sstack = atoi(v);
+    if (getenv("HXR_NO_MAILBOX")) c->useMail = 0;
+    if (getenv("HXR_BRANCHY_PUSH")) c->bfPush = 0;
+    if (const char* v = getenv("HXR_WALK_CARVEOUT")) c->walkCarveout = std::min(100, std::max(0, atoi(v)));
+    if (const char* v = getenv("HXR_WALK_BLOCKS_PER_SM")) c->walkBlocksPerSm = std::max(1, atoi(v));
+    if (const char* v = getenv("HXR_REFILL_MIN")) c->refillMin = std::min(32, std::max(1, atoi(v)));
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail("cudaStreamCreate failed");
+    }
+    return c;
 }
-const char* backend_name() { return "cuda sm_100a"; }
-const char* last_error() { return g_err.c_str(); }
-
-void* alloc(size_t bytes)
+void destroy(Context* c)
 {
-    if (!use()) return nullptr;
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < PROF_NCAT; k++)
+        for (auto& pr : c->evPairs[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+int device_of(const Context* c) { return c->device; }
+void* stream_of(const Context* c) { return (void*)c->stream; }
+const char* backend_name() { return "cuda sm_100a"; }
+const char* last_error(const Context* c) { return c->err.c_str(); }
+bool failed(const Context* c) { return !c->err.empty(); }
+void clear_error(Context* c) { c->err.clear(); }
+
+void* alloc(Context* c, size_t bytes)
+{
+    if (!use(c)) return nullptr;
     void* p = nullptr;
-    if (!ck(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) return nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // an allocation failure is reported to the caller, it does not poison the context
+        return nullptr;
+    }
     return p;
 }
-void free_(void* p)
+void free_(Context* c, void* p)
 {
-    if (p && use()) cudaFree(p);
+    if (p && use(c)) cudaFree(p);
 }
-bool upload(void* d, const void* s, size_t n)
+void* alloc_pinned(Context* c, size_t bytes)
 {
-    return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, g_stream), "H2D copy") && ck(cudaStreamSynchronize(g_stream), "H2D sync");
+    if (!use(c)) return nullptr;
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
 }
-bool upload_pinned_async(void* d, const void* s, size_t n) { return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, g_stream), "H2D copy"); }
-bool download(void* d, const void* s, size_t n)
+void free_pinned(Context* c, void* p)
 {
-    return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, g_stream), "D2H copy") && ck(cudaStreamSynchronize(g_stream), "D2H sync");
+    if (p && use(c)) cudaFreeHost(p);
 }
-bool zero(void* p, size_t n) { return use() && ck(cudaMemsetAsync(p, 0, n, g_stream), "memset"); }
-bool copy_d2d(void* d, const void* s, size_t n) { return use() && ck(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, g_stream), "D2D copy"); }
-bool sync() { return use() && ck(cudaStreamSynchronize(g_stream), "stream sync"); }
+bool upload(Context* c, void* d, const void* s, size_t n)
+{
+    return use(c) && ck(c, cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, c->stream), "H2D copy") && ck(c, cudaStreamSynchronize(c->stream), "H2D sync");
+}
+bool download(Context* c, void* d, const void* s, size_t n)
+{
+    return use(c) && ck(c, cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream), "D2H copy") && ck(c, cudaStreamSynchronize(c->stream), "D2H sync");
+}
+bool download_async(Context* c, void* d, const void* s, size_t n) { return use(c) && ck(c, cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream), "D2H copy"); }
+bool zero(Context* c, void* p, size_t n) { return use(c) && ck(c, cudaMemsetAsync(p, 0, n, c->stream), "memset"); }
+bool copy_d2d(Context* c, void* d, const void* s, size_t n) { return use(c) && ck(c, cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream), "D2D copy"); }
+bool sync(Context* c) { return use(c) && ck(c, cudaStreamSynchronize(c->stream), "stream sync"); }
 
 struct Timer { cudaEvent_t a, b; };
-Timer* timer_create()
+Timer* timer_create(Context* c)
 {
-    use();
+    use(c);
     Timer* t = new Timer;
     cudaEventCreate(&t->a);
     cudaEventCreate(&t->b);
     return t;
 }
-void timer_destroy(Timer* t)
+void timer_destroy(Context* c, Timer* t)
 {
     if (!t) return;
+    use(c);
     cudaEventDestroy(t->a);
     cudaEventDestroy(t->b);
     delete t;
 }
-void timer_start(Timer* t) { cudaEventRecord(t->a, g_stream); }
-void timer_stop(Timer* t) { cudaEventRecord(t->b, g_stream); }
-double timer_ms(Timer* t)
+void timer_start(Context* c, Timer* t) { use(c); cudaEventRecord(t->a, c->stream); }
+void timer_stop(Context* c, Timer* t) { use(c); cudaEventRecord(t->b, c->stream); }
+double timer_ms(Context* c, Timer* t)
 {
     float ms = 0;
+    use(c);
     cudaEventSynchronize(t->b);
     cudaEventElapsedTime(&ms, t->a, t->b);
     return ms;
 }
 
 // ---- per-launch profiling -------------------------------------------------------------
-void prof_enable(bool on) { g_prof = on; }
-static cudaEvent_t ev_get()
+void prof_enable(Context* c, bool on) { c->prof = on; }
+static cudaEvent_t ev_get(Context* c)
 {
-    if (!g_evPool.empty()) { cudaEvent_t e = g_evPool.back(); g_evPool.pop_back(); return e; }
+    if (!c->evPool.empty()) { cudaEvent_t e = c->evPool.back(); c->evPool.pop_back(); return e; }
     cudaEvent_t e;
     cudaEventCreate(&e);
     return e;
 }
-void prof_reset()
+void prof_reset(Context* c)
 {
-    for (int c = 0; c < PROF_NCAT; c++) {
-        g_launches[c] = 0;
-        for (auto& pr : g_evPairs[c]) { g_evPool.push_back(pr.first); g_evPool.push_back(pr.second); }
-        g_evPairs[c].clear();
+    for (int k = 0; k < PROF_NCAT; k++) {
+        c->launches[k] = 0;
+        for (auto& pr : c->evPairs[k]) { c->evPool.push_back(pr.first); c->evPool.push_back(pr.second); }
+        c->evPairs[k].clear();
     }
 }
-void prof_collect(double ms[PROF_NCAT], uint64_t launches[PROF_NCAT])
+void prof_collect(Context* c, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT])
 {
-    cudaStreamSynchronize(g_stream);
-    for (int c = 0; c < PROF_NCAT; c++) {
+    use(c);
+    cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < PROF_NCAT; k++) {
         double s = 0;
-        for (auto& pr : g_evPairs[c]) {
+        for (auto& pr : c->evPairs[k]) {
             float m = 0;
             cudaEventElapsedTime(&m, pr.first, pr.second);
             s += m;
         }
-        ms[c] = s;
-        launches[c] = g_launches[c];
+        ms[k] = s;
+        launches[k] = c->launches[k];
     }
 }
-struct ProfScope {
+// brackets one launch: counts it, times it when profiling is on, and records a launch failure in the context (sticky)
+struct LaunchScope {
+    Context* c;
     int cat;
     cudaEvent_t a = nullptr, b = nullptr;
-    explicit ProfScope(int c) : cat(c)
+    LaunchScope(Context* ctx, int category) : c(ctx), cat(category)
     {
-        use();
-        g_launches[c]++;
-        if (g_prof) { a = ev_get(); b = ev_get(); cudaEventRecord(a, g_stream); }
+        use(c);
+        c->launches[cat]++;
+        if (c->prof) { a = ev_get(c); b = ev_get(c); cudaEventRecord(a, c->stream); }
     }
-    ~ProfScope()
+    ~LaunchScope()
     {
-        if (g_prof) { cudaEventRecord(b, g_stream); g_evPairs[cat].emplace_back(a, b); }
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) g_err = std::string("kernel launch: ") + cudaGetErrorString(e);
+        if (c->prof) { cudaEventRecord(b, c->stream); c->evPairs[cat].emplace_back(a, b); }
+        ck(c, cudaGetLastError(), "kernel launch");
     }
 };
 
-// ---- kernels ----------------------------------------------------------------------------
-#define HXR_TRACE_BLOCK 128
-#define HXR_SHADE_BLOCK 128
-
-__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
-
-bool set_u32(uint32_t* p, uint32_t v)
+// ---- small device helpers ------------------------------------------------------------------
+__device__ __forceinline__ RayGeom load_geom(const RayGeom* p)
 {
-    if (!use()) return false;
-    if (v == 0) return ck(cudaMemsetAsync(p, 0, sizeof(uint32_t), g_stream), "memset");
-    k_set_u32<<<1, 1, 0, g_stream>>>(p, v);
-    return true;
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    RayGeom g;
+    g.o[0] = a.x; g.o[1] = a.y; g.o[2] = b.x;
+    g.d[0] = b.y; g.d[1] = c.x; g.d[2] = c.y;
+    g.limit = d.x;
+    const long long t = __double_as_longlong(d.y);
+    g.pre = (int32_t)(uint32_t)(t & 0xFFFFFFFFll);
+    g.depth_flags = (uint32_t)((unsigned long long)t >> 32);
+    return g;
 }
-
-__global__ void __launch_bounds__(128) k_gen_primary(DScene sc, FrameParams fp, const uint32_t* __restrict__ pixels, uint32_t first_pixel,
-                                                     uint32_t n_items, uint32_t spp_pass, RayTask* __restrict__ q, uint32_t* q_count)
+__device__ __forceinline__ RayAux load_aux(const RayAux* p)
 {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
-        const uint32_t pi = i / spp_pass;
-        const uint32_t pixel = pixels ? pixels[pi] : first_pixel + pi;
-        q[i] = gen_primary_item(sc, fp, pixel, fp.sample_base + (i % spp_pass) * fp.sample_stride);
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    const uint2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    RayAux x;
+    x.w[0] = __uint_as_float(a.x); x.w[1] = __uint_as_float(a.y); x.w[2] = __uint_as_float(b.x);
+    x.pixel = b.y; x.sample = c.x; x.stream = c.y;
+    return x;
+}
+__device__ __forceinline__ CandRec load_cand(const CandRec* p)
+{
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    CandRec c;
+    c.tri[0] = u.x; c.tri[1] = u.y; c.tri[2] = u.z; c.meta = u.w;
+    return c;
+}
+// per-thread tallies -> one atomic per warp (all threads of the block reach this together, after their grid-stride loop)
+__device__ __forceinline__ void flush_totals(FrameTotals* totals, const EmitCounters& ec)
+{
+    if (!totals) return;
+    __syncwarp();
+    const unsigned s = __reduce_add_sync(0xffffffffu, ec.shadow_rays), o = __reduce_add_sync(0xffffffffu, ec.cand_overflow);
+    if ((threadIdx.x & 31u) == 0) {
+        if (s) atomicAdd(&totals->rays_shadow, (unsigned long long)s);
+        if (o) atomicAdd(&totals->cand_overflow, (unsigned long long)o);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *q_count = n_items;
+}
+__device__ __forceinline__ void flush_trav(TravCounters* cnt, const TravCounters& local)
+{
+    if (!cnt) return;
+    if (local.kd_inner) atomicAdd(&cnt->kd_inner, local.kd_inner);
+    if (local.kd_leaves) atomicAdd(&cnt->kd_leaves, local.kd_leaves);
+    if (local.tri_tests) atomicAdd(&cnt->tri_tests, local.tri_tests);
+    if (local.mesh_queries) atomicAdd(&cnt->mesh_queries, local.mesh_queries);
 }
 
+// ---- kernels ----------------------------------------------------------------------------
 #define HXR_WALK_BLOCK 128
-// resident blocks per SM of the lean per-ray kernels (register caps 65536 / (128 * blocks)); A/B-ed on B200, see profiles/README.md
-#ifndef HXR_SETUP_BLOCKS
-#define HXR_SETUP_BLOCKS 6
-#endif
-#ifndef HXR_FIN_BLOCKS
-#define HXR_FIN_BLOCKS 4
+// resident blocks per SM of the per-ray kernels (register caps 65536 / (128 * blocks)); A/B-ed on B200, see profiles/README.md
+#ifndef HXR_GEN_BLOCKS
+#define HXR_GEN_BLOCKS 5
 #endif
 #ifndef HXR_SHADE_GI_BLOCKS
-#define HXR_SHADE_GI_BLOCKS 5
+#define HXR_SHADE_GI_BLOCKS 4
+#endif
+#ifndef HXR_SHADE_WH_BLOCKS
+#define HXR_SHADE_WH_BLOCKS 3
 #endif
 #ifndef HXR_WALK_MIN_BLOCKS
 #define HXR_WALK_MIN_BLOCKS 8
 #endif
-#ifndef HXR_REFILL_MIN
-#define HXR_REFILL_MIN 8  /* refill as soon as this many lanes of a warp are idle */
-#endif
-#ifndef HXR_WALK_STEPS
-#define HXR_WALK_STEPS 3  /* block steps per round of the walk loop */
-#endif
 
-template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
-                                                       TraceScratch ts, TravCounters* cnt)
+template <bool SIMPLE>
+__global__ void __launch_bounds__(128, SIMPLE ? HXR_GEN_BLOCKS : 1) k_gen_primary(DScene sc, FrameParams fp, const uint32_t* __restrict__ pixels,
+                                                                                  const uint32_t* __restrict__ pixels_count, uint32_t first_pixel,
+                                                                                  uint32_t n_items, uint32_t spp_pass, RayQueue q)
 {
-    const uint32_t n = min(*q_count, cap);
+    if (pixels_count) n_items = min(n_items, *pixels_count * spp_pass);
     const uint32_t stride = gridDim.x * blockDim.x;
-    TravCounters local = {0, 0, 0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_closest_item<COUNT, SIMPLE>(sc, task_ray(q[i]), i, ts, &local);
-    if (COUNT && local.mesh_queries) atomicAdd(&cnt->mesh_queries, local.mesh_queries);
-}
-
-template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, SIMPLE ? HXR_FIN_BLOCKS : 2) k_finalize_closest(DScene sc, const RayTask* __restrict__ q, const uint32_t* __restrict__ q_count, uint32_t cap,
-                                                          TraceScratch ts, HitRec* __restrict__ hits, TravCounters* cnt)
-{
-    const uint32_t n = min(*q_count, cap);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    TravCounters local = {0, 0, 0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        HitRec h;
-        finalize_closest_item<COUNT, SIMPLE>(sc, task_ray(q[i]), i, ts, h, &local);
-        hits[i] = h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
+        const uint32_t pi = i / spp_pass;
+        const uint32_t pixel = pixels ? pixels[pi] : first_pixel + pi;
+        gen_primary_item<SIMPLE>(sc, fp, pixel, fp.sample_base + (i % spp_pass) * fp.sample_stride, q.geom, q.aux, i);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = n_items;
 }
 
-template <bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup_shadow(DScene sc, const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap,
-                                                      TraceScratch ts, TravCounters* cnt, unsigned long long* total)
+__global__ void __launch_bounds__(128, 1) k_setup_rays(DScene sc, const hxr_ray* __restrict__ rays, uint32_t n, RayQueue q)
 {
-    const uint32_t n = min(*count, cap);
     const uint32_t stride = gridDim.x * blockDim.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(total, (unsigned long long)n);
-    TravCounters local = {0, 0, 0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) setup_shadow_item<COUNT, SIMPLE>(sc, shadow[i], i, ts, &local);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const hxr_ray r = rays[i];
+        Ray ray;
+        ray.o = ld3(r.start);
+        ray.d = ld3(r.dir);
+        ray.depth = r.depth;
+        ray.flags = r.flags;
+        place_ray<false, false>(sc, q.geom, q.aux, i, ray, mkc(1, 1, 1), i, 0u, 1u, nullptr);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = n;
 }
 
-__global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restrict__ shadow, const uint32_t* __restrict__ count, uint32_t cap, TraceScratch ts,
-                                                      float* accum)
+__global__ void __launch_bounds__(128, 1) k_setup_segments(DScene sc, const double* __restrict__ seg, uint32_t n, ShadowQueue q)
 {
-    const uint32_t n = min(*count, cap);
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) accumulate_shadow_item(shadow[i], i, ts, accum);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double D;
+        const Ray ray = shadow_ray(ld3(seg + 6 * (size_t)i), ld3(seg + 6 * (size_t)i + 3), D);
+        q.geom[i] = shadow_geom(ray, D, inline_blocked<false, false>(sc, ray, D, nullptr));
+        ShadowAux a;
+        a.c[0] = a.c[1] = a.c[2] = 0;
+        a.pixel = i;
+        q.aux[i] = a;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = n;
 }
 
 // ---- the KD walk -------------------------------------------------------------------------------------
-// One lane = one walk task (a ray inside one big mesh); lanes that run out of work are refilled from the task queue
-// (__ballot_sync finds idle lanes, one atomicAdd per warp, __shfl_sync broadcast). Each round of the loop has two phases:
+// One lane = one ray; the lane walks the big meshes the ray enters one after the other. Lanes that run out of work are
+// refilled from the ray queue (__ballot_sync finds them, one atomicAdd per warp, __shfl_sync broadcast). Each round has:
+//   0. refill (only when enough lanes are idle): finished rays write their candidate record, empty lanes take new rays,
+//      lanes between two meshes transform their ray into the next mesh whose box it enters (the kernel's only double
+//      arithmetic: the reference's Node::intersect transform, rounded to float together with its error bound);
 //   1. `walkSteps` block steps: every lane whose cursor is a tree block pops / steps (block_step: one 32-byte
 //      fetch = two tree levels, up to four grandchildren front to back, the far ones pushed on the stack);
 //   2. the leaves reached so far are filtered WARP-COOPERATIVELY: the (ray, triangle) pairs of all lanes' leaves are
@@ -284,22 +356,22 @@ __global__ void __launch_bounds__(256) k_accum_shadow(const ShadowTask* __restri
 // Bounding phase 1 keeps lanes from idling while one ray of the warp descends a long path (the measured SIMD
 // efficiency of an unbounded while-while loop on incoherent GI rays was 20 %).
 //
-// The kernel is FP32 only: conservative plane arithmetic (isect.h: block_step) and the conservative triangle
-// filter (tri_filter). Pairs the filter cannot rule out are appended to a list for the exact double test
-// (k_confirm_*); certain hits shorten the walk. No double arithmetic keeps the kernel at <= 64 registers
-// (8 blocks = 1024 lanes per SM; A/B: 9 or 10 blocks at 55 / 48 registers and 5-7 blocks are all slower) and cuts the
-// triangle bytes (48-byte TriF32, or 32-byte TriPacked on scenes whose triangles outgrow the L2, instead of 96 B).
+// The walk itself is FP32 only: conservative plane arithmetic (isect.h: block_step) and the conservative triangle
+// filter (tri_filter). Pairs the filter cannot rule out are the ray's CANDIDATES for the exact double test, which runs
+// in the kernel that consumes the ray (k_shade / k_resolve_shadow); certain hits shorten the walk.
 //
-// State per lane in shared memory: the float ray (24 B), the best-hit bound (4 B, lowered with atomicMin by whichever
-// lane filters a certain hit) and the first HXR_SSTACK stack entries (12 B each); deeper entries overflow to local
-// memory (rare: the stack is shallow for almost all rays).
+// State per lane in shared memory: the float ray (36 B), the best-hit bound (4 B, lowered with atomicMin by whichever
+// lane filters a certain hit), the candidate slots (3 x 4 B + count/slot word), a two-entry mailbox and the first HXR_SSTACK
+// stack entries (12 B each); deeper entries overflow to local memory (rare: the stack is shallow for almost all rays).
 #define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
 
 template <int SSTACK>
 struct WalkShared {
     float ray[9][HXR_WALK_BLOCK];  // rows 0-2 origin, 3-5 1/direction, 6-8 direction (a leaf child's "axis 3" reads the next row: finite, unused)
     uint32_t tb[HXR_WALK_BLOCK];  // bits of the (non-negative) float bound; 0 = shadow ray certainly blocked
-    uint32_t mail[2][HXR_WALK_BLOCK];  // the last two triangles this task already put on the pair list (a triangle sits in several leaves)
+    uint32_t mail[2][HXR_WALK_BLOCK];  // the last two triangles of the current mesh already among the candidates (a triangle sits in several leaves)
+    uint32_t cand[HXR_CAND_MAX][HXR_WALK_BLOCK];
+    uint32_t meta[HXR_WALK_BLOCK];  // CandRec::meta under construction
     uint32_t stRef[SSTACK][HXR_WALK_BLOCK];
     float stMin[SSTACK][HXR_WALK_BLOCK];
     float stMax[SSTACK][HXR_WALK_BLOCK];
@@ -307,17 +379,19 @@ struct WalkShared {
 
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
-__global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, TraceScratch ts, TravCounters* cnt, int walkSteps,
-                                                                              int refillMin, int useMail, int pairChunk, int branchFreePush)
+__global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayGeom* __restrict__ geom, const uint32_t* __restrict__ count,
+                                                                              uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, TravCounters* cnt,
+                                                                              int walkSteps, int refillMin, int useMail, int branchFreePush)
 {
     __shared__ WalkShared<SSTACK> sh;
     constexpr int HXR_SSTACK = SSTACK;
     const unsigned FULL = 0xffffffffu;
-    const uint32_t n = min(*ts.task_count, ts.task_cap);
+    const uint32_t n = min(*count, cap);
+    const int nBig = sc.n_big;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warpBase = tid & ~31u;
     uint32_t ovRef[HXR_KD_STACK - HXR_SSTACK];
     float ovMin[HXR_KD_STACK - HXR_SSTACK], ovMax[HXR_KD_STACK - HXR_SSTACK];
-    bool active = false, drained = false;
+    bool active = false, hasRay = false, drained = false;
     struct SharedRay {  // o(axis) / inv(axis) straight from this lane's shared-memory column: no selects, no registers
         const float* col;
         uint32_t par;
@@ -334,9 +408,10 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     int meshIdx = -1;
     uint32_t cur = HXR_POP, leafCnt = 0;
     float tmin = 0, tmax = 0, tbest = 0, err = 0, occ = 0;
+    float wcap = 0, kup = 0;  // world-distance cap of this ray (tightened by certain hits), world distance per unit parameter of the current mesh
     int sp = 0;
-    uint32_t taskIdx = 0, taskRay = 0;
-    uint32_t pkBase = 0, pkLeft = 0;  // this warp's reserved slots of the pair list (warp-uniform)
+    uint32_t rayIdx = 0;
+    int slot = 0;  // next walked-mesh slot this ray has to try (the mesh being walked is slot - 1)
     TravCounters local = {0, 0, 0, 0};
 
     auto push = [&](const WalkEnt& e) {
@@ -345,42 +420,74 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         } else if (sp < HXR_KD_STACK) {
             ovRef[sp - HXR_SSTACK] = e.ref; ovMin[sp - HXR_SSTACK] = e.lo; ovMax[sp - HXR_SSTACK] = e.hi;
         } else {
-            return;  // unreachable: the build caps the depth at HXR_KD_MAX_DEPTH (<= 1.5 pushes per level)
+            return;  // the build caps the depth at HXR_KD_MAX_DEPTH (<= 1.5 pushes per level): never reached
         }
         sp++;
     };
 
     for (;;) {
-        // ---- refill: idle lanes take new tasks
+        // ---- phase 0: refill
         const unsigned idle = __ballot_sync(FULL, !active);
-        if (!drained && (idle == FULL || __popc(idle) >= refillMin)) {
-            const int c = __popc(idle);
-            const int leader = __ffs(idle) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(ts.head, (uint32_t)c);
-            base = __shfl_sync(FULL, base, leader);
-            if (base + (uint32_t)c >= n) drained = true;
-            if (!active) {
-                const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
-                if (k < n) {
-                    const uint4* tp = reinterpret_cast<const uint4*>(ts.tasks + k);
-                    const uint4 w0 = __ldg(tp), w1 = __ldg(tp + 1), w2 = __ldg(tp + 2), w3 = __ldg(tp + 3);
-                    taskRay = w0.x;
-                    if (!(SHADOW && ts.occluded[taskRay])) {
-                        taskIdx = k;
-                        const float ox = __uint_as_float(w0.z), oy = __uint_as_float(w0.w), oz = __uint_as_float(w1.x);
-                        const float dx = __uint_as_float(w1.y), dy = __uint_as_float(w1.z), dz = __uint_as_float(w1.w);
-                        const WalkRay w = walk_ray_f(ox, oy, oz, dx, dy, dz);
+        if (idle == FULL || __popc(idle) >= refillMin) {
+            // rays that have tried all their meshes leave their candidate record
+            if (!active && hasRay && slot >= nBig) {
+                reinterpret_cast<uint4*>(cand)[rayIdx] = make_uint4(sh.cand[0][tid], sh.cand[1][tid], sh.cand[2][tid], sh.meta[tid]);
+                hasRay = false;
+            }
+            // empty lanes take new rays
+            const unsigned empty = __ballot_sync(FULL, !active && !hasRay);
+            if (!drained && empty) {
+                const int c = __popc(empty);
+                const int leader = __ffs(empty) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(head, (uint32_t)c);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + (uint32_t)c >= n) drained = true;
+                if (!active && !hasRay) {
+                    const uint32_t k = base + __popc(empty & ((1u << lane) - 1u));
+                    if (k < n) {
+                        const uint4 w3 = __ldg(reinterpret_cast<const uint4*>(geom + k) + 3);
+                        if ((int32_t)w3.z == -2) {  // past the depth guard / already blocked: nothing to walk
+                            reinterpret_cast<uint4*>(cand)[k] = make_uint4(0u, 0u, 0u, SHADOW ? HXR_CAND_BLOCKED : 0u);
+                        } else {
+                            rayIdx = k;
+                            hasRay = true;
+                            slot = 0;
+                            const double lim = __hiloint2double((int)w3.y, (int)w3.x);
+                            wcap = __double2float_ru(fmin(lim, 3e38));
+                            sh.meta[tid] = 0u;
+                            sh.cand[0][tid] = 0u; sh.cand[1][tid] = 0u; sh.cand[2][tid] = 0u;
+                        }
+                    }
+                }
+            }
+            // lanes between two meshes: into the next mesh whose box the ray enters
+            if (!active && hasRay) {
+                const RayGeom g = load_geom(geom + rayIdx);
+                {
+                    const float of[3] = {(float)g.o[0], (float)g.o[1], (float)g.o[2]}, df[3] = {(float)g.d[0], (float)g.d[1], (float)g.d[2]};
+                    while (slot < nBig && box_certainly_missed(sc.big_box + 6 * slot, of, df, wcap)) slot++;
+                }
+                if (slot < nBig) {
+                    Ray ray;
+                    ray.o = ld3(g.o);
+                    ray.d = ld3(g.d);
+                    ray.depth = 0;
+                    ray.flags = 0;
+                    MeshEntry e;
+                    if (enter_mesh<SHADOW>(sc, slot, ray, fmin(g.limit, (double)wcap), e)) {
+                        const WalkRay w = walk_ray_f(e.ox, e.oy, e.oz, e.dx, e.dy, e.dz);
                         wr.par = w.par;
-                        sh.ray[0][tid] = ox; sh.ray[1][tid] = oy; sh.ray[2][tid] = oz;
+                        sh.ray[0][tid] = e.ox; sh.ray[1][tid] = e.oy; sh.ray[2][tid] = e.oz;
                         sh.ray[3][tid] = w.ix; sh.ray[4][tid] = w.iy; sh.ray[5][tid] = w.iz;
-                        sh.ray[6][tid] = dx; sh.ray[7][tid] = dy; sh.ray[8][tid] = dz;
-                        tmin = __uint_as_float(w2.x);
-                        tmax = __uint_as_float(w2.y);
-                        tbest = __uint_as_float(w2.z);
-                        occ = __uint_as_float(w2.w);
-                        err = __uint_as_float(w3.x);
-                        meshIdx = (int)w3.y;
+                        sh.ray[6][tid] = e.dx; sh.ray[7][tid] = e.dy; sh.ray[8][tid] = e.dz;
+                        tmin = e.tmin;
+                        tmax = e.tmax;
+                        tbest = e.tlimit;
+                        occ = e.occ;
+                        err = e.err;
+                        kup = e.kup;
+                        meshIdx = e.mesh;
                         sh.tb[tid] = __float_as_uint(tbest);
                         sh.mail[0][tid] = 0xFFFFFFFFu;
                         sh.mail[1][tid] = 0xFFFFFFFFu;
@@ -394,11 +501,12 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         active = true;
                         if (COUNT) local.mesh_queries++;
                     }
+                    slot++;
                 }
             }
         }
         if (__ballot_sync(FULL, active) == 0) {
-            if (drained) break;
+            if (drained && __ballot_sync(FULL, hasRay) == 0) break;
             continue;
         }
         // ---- phase 1: a few block steps for every lane whose cursor is not a leaf
@@ -407,7 +515,10 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             const bool stepping = active && !(cur >> 31);
             if (stepping && cur == HXR_POP) {
                 if (sp == 0) {
-                    active = false;  // nothing left: this task is done (its hits are in the pair list)
+                    // this mesh is done: a certain hit at parameter <= tbest lies within world distance tbest * kup, the
+                    // ray's later meshes need not look farther (without a certain hit the product is >= the cap: no change)
+                    active = false;
+                    wcap = fminf(wcap, tbest * kup);
                 } else {
                     sp--;
                     WalkEnt e;
@@ -438,7 +549,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         if (p3 && s3 >= HXR_SSTACK && s3 < HXR_KD_STACK) { ovRef[s3 - HXR_SSTACK] = e3.ref; ovMin[s3 - HXR_SSTACK] = e3.lo; ovMax[s3 - HXR_SSTACK] = e3.hi; }
                         if (p2 && s2 >= HXR_SSTACK && s2 < HXR_KD_STACK) { ovRef[s2 - HXR_SSTACK] = e2.ref; ovMin[s2 - HXR_SSTACK] = e2.lo; ovMax[s2 - HXR_SSTACK] = e2.hi; }
                         if (p1 && s1 >= HXR_SSTACK && s1 < HXR_KD_STACK) { ovRef[s1 - HXR_SSTACK] = e1.ref; ovMin[s1 - HXR_SSTACK] = e1.lo; ovMax[s1 - HXR_SSTACK] = e1.hi; }
-                        if (sp > HXR_KD_STACK) sp = HXR_KD_STACK;  // unreachable: the build caps the depth (see push)
+                        if (sp > HXR_KD_STACK) sp = HXR_KD_STACK;  // never reached: the build caps the depth (see push)
                     }
                     cur = v0 ? e0.ref : v1 ? e1.ref : v2 ? e2.ref : v3 ? e3.ref : HXR_POP;
                     tmin = v0 ? e0.lo : v1 ? e1.lo : v2 ? e2.lo : e3.lo;
@@ -482,10 +593,8 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             const uint32_t oFirst = __shfl_sync(FULL, myFirst, o);
             const int oMesh = __shfl_sync(FULL, meshIdx, o);
             const float oErr = __shfl_sync(FULL, err, o);
-            const uint32_t oTask = __shfl_sync(FULL, taskIdx, o);
+            const int oSlot = __shfl_sync(FULL, slot, o) - 1;
             const float oOcc = SHADOW ? __shfl_sync(FULL, occ, o) : 0.0f;
-            bool emit = false;
-            uint32_t ti = 0;
             if (pair < total) {
                 const uint32_t* lt = leafTris;
                 const void* tt = tris;
@@ -494,49 +603,36 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                     const DMesh& M = sc.meshes[oMesh];
                     lt = M.leaf_tris; tt = PACKED ? (const void*)M.tri_pk : (const void*)M.tri_f32; bf = M.backface != 0;
                 }
-                ti = __ldg(lt + oFirst + (pair - oExcl));
+                const uint32_t ti = __ldg(lt + oFirst + (pair - oExcl));
                 const unsigned ot = warpBase | (unsigned)o;
                 const float oBest = __uint_as_float(sh.tb[ot]);  // the freshest bound (other lanes may have lowered it this round)
                 float ghi = 0;
                 int cls = HXR_TF_MISS;
-                if (ti != sh.mail[0][ot] && ti != sh.mail[1][ot]) {  // not already on the list from a neighbouring leaf
+                if (ti != sh.mail[0][ot] && ti != sh.mail[1][ot]) {  // not already a candidate from a neighbouring leaf
                     if (PACKED) cls = tri_filter_packed(static_cast<const TriPacked*>(tt) + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot], oErr, oBest, ghi);
                     else cls = tri_filter(static_cast<const TriF32*>(tt) + ti, bf, sh.ray[0][ot], sh.ray[1][ot], sh.ray[2][ot], sh.ray[6][ot], sh.ray[7][ot], sh.ray[8][ot], oErr, oBest, ghi);
                 }
+                bool emit = false;
                 if (cls == HXR_TF_CERTAIN) {
                     if (SHADOW && ghi < oOcc) atomicMin(&sh.tb[ot], 0u);  // certainly blocked: no exact test needed
                     else { atomicMin(&sh.tb[ot], __float_as_uint(ghi)); emit = true; }
                 } else if (cls == HXR_TF_MAYBE) {
                     emit = true;
                 }
-            }
-            // append the surviving pairs to the confirmation list. Every warp of the GPU appends all the time: one atomic per
-            // append on the single list counter serialises in L2 (measured: 20 % of this kernel's stall samples sat here), so
-            // a warp reserves HXR_PAIR_CHUNK slots at a time and hands them out itself; slots it does not use are marked
-            // invalid (task = HXR_PAIR_NONE) and skipped by the confirmation kernels
-            const unsigned em = __ballot_sync(FULL, emit);
-            if (em) {
-                const uint32_t need = (uint32_t)__popc(em);
-                if (need > pkLeft) {
-                    if (lane < pkLeft && pkBase + lane < ts.pair_cap) ts.pairs[pkBase + lane].task = HXR_PAIR_NONE;  // pkLeft < need <= 32
-                    uint32_t nb = 0;
-                    const uint32_t take = pairChunk ? (uint32_t)pairChunk : need;  // 0: one atomic per append (A/B)
-                    if (lane == 0) nb = atomicAdd(ts.pair_count, take);
-                    pkBase = __shfl_sync(FULL, nb, 0);
-                    pkLeft = take;
-                }
-                const uint32_t pb = pkBase;
-                pkBase += need;
-                pkLeft -= need;
+                // a surviving pair becomes a candidate of its owner's ray: a slot in the owner's shared-memory record (lanes
+                // serving the same owner take different slots through the atomic; the count saturates far below its 8-bit field)
                 if (emit) {
-                    const unsigned ot = warpBase | (unsigned)o;
+                    if ((sh.meta[ot] & 0xFFu) < 100u) {
+                        const uint32_t pos = atomicAdd(&sh.meta[ot], 1u) & 0xFFu;
+                        if (pos < HXR_CAND_MAX) {
+                            sh.cand[pos][ot] = ti;
+                            if (oSlot) atomicOr(&sh.meta[ot], (uint32_t)oSlot << (8u + 8u * pos));
+                        }
+                    }
                     if (useMail) {
                         sh.mail[1][ot] = sh.mail[0][ot];  // (lanes emitting for the same owner race here: any of their triangles is a valid entry)
                         sh.mail[0][ot] = ti;
                     }
-                    const uint32_t k = pb + __popc(em & ((1u << lane) - 1u));
-                    if (k < ts.pair_cap) { PairRec pr; pr.task = oTask; pr.tri = ti; ts.pairs[k] = pr; }
-                    else atomicExch(ts.overflow, 1u);
                 }
             }
         }
@@ -546,54 +642,74 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             cur = HXR_POP;
             const uint32_t tb = sh.tb[tid];
             tbest = __uint_as_float(tb);
-            if (SHADOW && tb == 0u) {
-                ts.occluded[taskRay] = 1;
+            if (SHADOW && tb == 0u) {  // certainly blocked: the ray is finished
+                sh.meta[tid] = HXR_CAND_BLOCKED;
                 active = false;
+                slot = nBig;
+            } else if ((sh.meta[tid] & 0xFFu) > HXR_CAND_MAX) {  // the record overflowed: its consumer redoes this ray exactly, stop here
+                active = false;
+                slot = nBig;
             }
         }
     }
-    for (uint32_t i = lane; i < pkLeft; i += 32u)  // the unused tail of this warp's last chunk
-        if (pkBase + i < ts.pair_cap) ts.pairs[pkBase + i].task = HXR_PAIR_NONE;
-    if (COUNT) {
-        atomicAdd(&cnt->kd_inner, local.kd_inner);
-        atomicAdd(&cnt->kd_leaves, local.kd_leaves);
-        atomicAdd(&cnt->tri_tests, local.tri_tests);
-        atomicAdd(&cnt->mesh_queries, local.mesh_queries);
+    if (COUNT) flush_trav(cnt, local);
+}
+
+// GI (one path vertex) and Whitted (shader tree with its stacks) are separate compilations, and so are scenes whose inline
+// nodes are only planes / spheres / cubes / quads (SIMPLE: no CSG, heightfield or inline tree-walk code, no stack frame)
+template <bool GI, bool COUNT, bool SIMPLE>
+__global__ void __launch_bounds__(128, SIMPLE ? (GI ? HXR_SHADE_GI_BLOCKS : HXR_SHADE_WH_BLOCKS) : 1)
+    k_shade(DScene sc, FrameParams fp, RayQueue q, const CandRec* __restrict__ cand, uint32_t begin, uint32_t end, Sinks sinks, FrameTotals* totals,
+            TravCounters* cnt)
+{
+    const uint32_t e = min(end, min(*q.count, q.cap));
+    const uint32_t stride = gridDim.x * blockDim.x;
+    EmitCounters ec = {0, 0};
+    TravCounters local = {0, 0, 0, 0};
+    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
+        const RayGeom g = load_geom(q.geom + i);
+        const RayAux a = load_aux(q.aux + i);
+        CandRec cr;
+        cr.meta = 0;
+        if (sc.n_big) cr = load_cand(cand + i);
+        shade_item<GI, COUNT, SIMPLE>(sc, fp, g, a, cr, sinks, ec, COUNT ? &local : nullptr);
     }
+    flush_totals(totals, ec);
+    if (totals && blockIdx.x == 0 && threadIdx.x == 0 && e > begin) atomicAdd(&totals->rays_closest, (unsigned long long)(e - begin));
+    if (COUNT) flush_trav(cnt, local);
 }
 
-// the exact test of the pairs the walk left undecided (one thread per pair; the count lives on the device)
-__global__ void __launch_bounds__(128) k_confirm_closest_a(DScene sc, const RayTask* __restrict__ q, TraceScratch ts)
+template <bool COUNT>
+__global__ void __launch_bounds__(128, COUNT ? 1 : 4) k_resolve_shadow(DScene sc, ShadowQueue q, const CandRec* __restrict__ cand, float* accum, uint8_t* visible,
+                                                                       FrameTotals* totals, TravCounters* cnt)
 {
-    const uint32_t n = min(*ts.pair_count, ts.pair_cap);
+    const uint32_t n = min(*q.count, q.cap);
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) confirm_closest_a_item(sc, q, i, ts);
-}
-__global__ void __launch_bounds__(256) k_confirm_closest_b(DScene sc, TraceScratch ts)
-{
-    const uint32_t n = min(*ts.pair_count, ts.pair_cap);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) confirm_closest_b_item(sc, i, ts);
-}
-__global__ void __launch_bounds__(128) k_confirm_shadow(DScene sc, const ShadowTask* __restrict__ shadows, TraceScratch ts)
-{
-    const uint32_t n = min(*ts.pair_count, ts.pair_cap);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) confirm_shadow_item(sc, shadows, i, ts);
+    EmitCounters ec = {0, 0};
+    TravCounters local = {0, 0, 0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        CandRec cr;
+        cr.meta = 0;
+        if (sc.n_big) cr = load_cand(cand + i);
+        if (visible) visible[i] = resolve_visible<COUNT>(sc, q.geom + i, cr, ec, COUNT ? &local : nullptr) ? 1 : 0;
+        else resolve_shadow_item<COUNT>(sc, q.geom + i, q.aux + i, cr, accum, ec, COUNT ? &local : nullptr);
+    }
+    flush_totals(totals, ec);
+    if (COUNT) flush_trav(cnt, local);
 }
 
-// GI (one path vertex) and Whitted (shader tree with its stacks) are separate compilations: the path-tracing vertex
-// needs far fewer registers than the tree walk, and occupancy is what hides this kernel's gather latency
-template <bool GI>
-__global__ void __launch_bounds__(HXR_SHADE_BLOCK, GI ? HXR_SHADE_GI_BLOCKS : 3) k_shade(DScene sc, FrameParams fp, const RayTask* __restrict__ q,
-                                                                       const uint32_t* __restrict__ q_count, const HitRec* __restrict__ hits,
-                                                                       uint32_t begin, uint32_t end, Sinks sinks)
+__global__ void __launch_bounds__(128, 1) k_hit_records(DScene sc, RayQueue q, const CandRec* __restrict__ cand, HitRec* __restrict__ hits)
 {
-    const uint32_t e = min(end, *q_count);
-    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= e) return;
-    if (GI) shade_gi_item(sc, fp, q[i], hits[i], sinks);
-    else shade_whitted_item(sc, fp, q[i], hits[i], sinks);
+    const uint32_t n = min(*q.count, q.cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        CandRec cr;
+        cr.meta = 0;
+        if (sc.n_big) cr = load_cand(cand + i);
+        HitRec h;
+        hit_record_item<false, false>(sc, load_geom(q.geom + i), cr, h, nullptr);
+        hits[i] = h;
+    }
 }
 
 __global__ void k_aa_detect(const float* __restrict__ vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out,
@@ -636,168 +752,165 @@ __global__ void k_to_bmp_rows(const float* __restrict__ rgb, int W, int H, int r
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x < W && y < H) bmp_pixel_item(rgb, W, H, rowsz, lut, out, x, y);
 }
-// ---- launchers --------------------------------------------------------------------------
-template <class K> static int persistent_grid(K kernel, int block)
+__global__ void k_to_exr_rows(const float* __restrict__ rgb, int W, int H, uint16_t* out)
 {
-    int perSm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, block, 0) != cudaSuccess || perSm < 1) perSm = 1;
-    return g_sms * perSm;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < W && y < H) exr_pixel_item(rgb, W, out, x, y);
 }
 
-int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels, uint32_t first_pixel, uint32_t n_items,
-                uint32_t spp_pass, RayTask* q, uint32_t* q_count)
+// ---- launchers --------------------------------------------------------------------------
+// per-item kernels are grid-stride loops over a count that only the device knows
+static uint32_t stage_grid(const Context* c, uint32_t n, int perSm = 16)
 {
-    ProfScope ps(PROF_OTHER);
-    const uint32_t blocks = n_items ? (uint32_t)std::min<uint64_t>(((uint64_t)n_items + 127) / 128, (uint64_t)g_sms * 32) : 1;
-    k_gen_primary<<<blocks, 128, 0, g_stream>>>(sc, fp, pixels, first_pixel, n_items, spp_pass, q, q_count);
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)c->sms * perSm));
+}
+
+int gen_primary(Context* c, const DScene& sc, const FrameParams& fp, const uint32_t* pixels, const uint32_t* pixels_count, uint32_t first_pixel,
+                uint32_t n_items, uint32_t spp_pass, const RayQueue& q)
+{
+    LaunchScope ls(c, PROF_GEN);
+    const uint32_t blocks = stage_grid(c, n_items, 32);
+    if (sc.simple_inline) k_gen_primary<true><<<blocks, 128, 0, c->stream>>>(sc, fp, pixels, pixels_count, first_pixel, n_items, spp_pass, q);
+    else k_gen_primary<false><<<blocks, 128, 0, c->stream>>>(sc, fp, pixels, pixels_count, first_pixel, n_items, spp_pass, q);
     return 1;
 }
 
-// per-item stage kernels are grid-stride loops over a count that only the device knows
-static uint32_t stage_grid(uint32_t n) { return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)g_sms * 16)); }
-
-template <class K> static int walk_grid(K kernel)
+int setup_rays(Context* c, const DScene& sc, const hxr_ray* rays, uint32_t n, const RayQueue& q)
 {
-    int perSm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, HXR_WALK_BLOCK, 0) != cudaSuccess || perSm < 1) perSm = 1;
-    return g_sms * perSm;
+    LaunchScope ls(c, PROF_OTHER);
+    k_setup_rays<<<stage_grid(c, n), 128, 0, c->stream>>>(sc, rays, n, q);
+    return 1;
+}
+int setup_segments(Context* c, const DScene& sc, const double* seg, uint32_t n, const ShadowQueue& q)
+{
+    LaunchScope ls(c, PROF_OTHER);
+    k_setup_segments<<<stage_grid(c, n), 128, 0, c->stream>>>(sc, seg, n, q);
+    return 1;
 }
 
-// max_tasks: host-side upper bound of the task count (a small wave gets a small grid: one lane per task at most)
-template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED> static void launch_walk_s(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
+template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
+static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+                          TravCounters* cnt, uint32_t n_hint)
 {
-    static int full = 0;
+    int& full = c->walkGrid[SHADOW][COUNT][SSTACK == 9 ? 0 : (SSTACK == 12 ? 2 : 1)][PACKED];
     if (!full) {
         // fewer resident blocks than fit + a smaller shared-memory carve-out leave the L1 more room for the top of the tree
-        if (g_walkCarveout >= 0) cudaFuncSetAttribute(k_walk<SHADOW, COUNT, SSTACK, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout, g_walkCarveout);
-        full = walk_grid(k_walk<SHADOW, COUNT, SSTACK, PACKED>);
-        if (g_walkBlocksPerSm > 0) full = std::min(full, g_sms * g_walkBlocksPerSm);
+        if (c->walkCarveout >= 0) cudaFuncSetAttribute(k_walk<SHADOW, COUNT, SSTACK, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout, c->walkCarveout);
+        int perSm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_walk<SHADOW, COUNT, SSTACK, PACKED>, HXR_WALK_BLOCK, 0) != cudaSuccess || perSm < 1) perSm = 1;
+        full = c->sms * perSm;
+        if (c->walkBlocksPerSm > 0) full = std::min(full, c->sms * c->walkBlocksPerSm);
     }
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, (max_tasks + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, g_stream>>>(sc, ts, cnt, g_walkSteps, g_refillMin, g_useMail, g_pairChunk, g_bfPush);
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, ((uint64_t)n_hint + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
+    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, cand, head, cnt, c->walkSteps, c->refillMin, c->useMail, c->bfPush);
 }
-template <bool SHADOW, bool PACKED> static void launch_walk_p(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
+template <bool SHADOW, bool PACKED>
+static void launch_walk_p(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+                          TravCounters* cnt, uint32_t n_hint)
 {
-    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(sc, ts, cnt, max_tasks); return; }
-    switch (g_sstack) {
-        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(sc, ts, nullptr, max_tasks); break;
-        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(sc, ts, nullptr, max_tasks); break;
-        default: launch_walk_s<SHADOW, false, 10, PACKED>(sc, ts, nullptr, max_tasks); break;
+    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(c, sc, geom, count, cap, cand, head, cnt, n_hint); return; }
+    switch (c->sstack) {
+        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(c, sc, geom, count, cap, cand, head, nullptr, n_hint); break;
+        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(c, sc, geom, count, cap, cand, head, nullptr, n_hint); break;
+        default: launch_walk_s<SHADOW, false, 10, PACKED>(c, sc, geom, count, cap, cand, head, nullptr, n_hint); break;
     }
-}
-template <bool SHADOW> static void launch_walk(const DScene& sc, const TraceScratch& ts, TravCounters* cnt, uint64_t max_tasks)
-{
-    if (sc.walk_packed) launch_walk_p<SHADOW, true>(sc, ts, cnt, max_tasks);
-    else launch_walk_p<SHADOW, false>(sc, ts, cnt, max_tasks);
 }
 
-int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t q_cap, HitRec* hits, const TraceScratch& ts,
-                  TravCounters* cnt, uint32_t n_hint)
+int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+         TravCounters* cnt, uint32_t n_hint)
 {
-    ProfScope ps(PROF_TRACE_CLOSEST);
-    cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
-    cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
-    cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
-    const uint32_t nb = stage_grid(std::min(q_cap, n_hint));
-    const uint64_t maxTasks = (uint64_t)std::min(q_cap, n_hint) * (uint64_t)std::max(1, sc.n_big);
-    const uint32_t nbPairs = stage_grid((uint32_t)std::min<uint64_t>(ts.pair_cap, maxTasks * 4));  // a ray rarely leaves more than a few pairs
-    int launches = 2;
-    // counting builds and scenes with CSG / heightfield / inline tree walks take the generic variant
-    const bool simple = sc.simple_inline && !cnt;
-    if (cnt) k_setup_closest<true, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, cnt);
-    else if (simple) k_setup_closest<false, true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
-    else k_setup_closest<false, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, nullptr);
-    if (sc.n_big) {
-        {
-            ProfScope pw(PROF_WALK);
-            launch_walk<false>(sc, ts, cnt, maxTasks);
-        }
-        k_confirm_closest_a<<<nbPairs, 128, 0, g_stream>>>(sc, q, ts);
-        k_confirm_closest_b<<<nbPairs, 256, 0, g_stream>>>(sc, ts);
-        launches += 3;
+    if (sc.n_big == 0) return 0;
+    LaunchScope ls(c, shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST);
+    if (shadow) {
+        if (sc.walk_packed) launch_walk_p<true, true>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
+        else launch_walk_p<true, false>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
+    } else {
+        if (sc.walk_packed) launch_walk_p<false, true>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
+        else launch_walk_p<false, false>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
     }
-    if (cnt) k_finalize_closest<true, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, cnt);
-    else if (simple) k_finalize_closest<false, true><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
-    else k_finalize_closest<false, false><<<nb, 128, 0, g_stream>>>(sc, q, q_count, q_cap, ts, hits, nullptr);
-    g_launches[PROF_TRACE_CLOSEST] += launches - 1;
-    return launches;
+    return 1;
 }
 
-int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits, uint32_t begin,
-          uint32_t end, const Sinks& sinks)
+int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,
+          FrameTotals* totals, TravCounters* cnt)
 {
     if (end <= begin) return 0;
-    ProfScope ps(PROF_SHADE);
-    const uint32_t blocks = (end - begin + HXR_SHADE_BLOCK - 1) / HXR_SHADE_BLOCK;
-    if (fp.gi) k_shade<true><<<blocks, HXR_SHADE_BLOCK, 0, g_stream>>>(sc, fp, q, q_count, hits, begin, end, sinks);
-    else k_shade<false><<<blocks, HXR_SHADE_BLOCK, 0, g_stream>>>(sc, fp, q, q_count, hits, begin, end, sinks);
-    return 1;
-}
-
-int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, const TraceScratch& ts,
-                 TravCounters* cnt, unsigned long long* total, uint32_t n_hint)
-{
-    ProfScope ps(PROF_TRACE_SHADOW);
-    cudaMemsetAsync(ts.task_count, 0, sizeof(uint32_t), g_stream);
-    cudaMemsetAsync(ts.head, 0, sizeof(uint32_t), g_stream);
-    cudaMemsetAsync(ts.pair_count, 0, sizeof(uint32_t), g_stream);
-    const uint32_t nb = stage_grid(std::min(cap, n_hint));
-    const uint64_t maxTasks = (uint64_t)std::min(cap, n_hint) * (uint64_t)std::max(1, sc.n_big);
-    const uint32_t nbPairs = stage_grid((uint32_t)std::min<uint64_t>(ts.pair_cap, maxTasks * 4));
-    int launches = 1;
-    if (cnt) k_setup_shadow<true, false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, cnt, total);
-    else if (sc.simple_inline) k_setup_shadow<false, true><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
-    else k_setup_shadow<false, false><<<nb, 128, 0, g_stream>>>(sc, shadow, count, cap, ts, nullptr, total);
-    if (sc.n_big) {
-        {
-            ProfScope pw(PROF_WALK);
-            launch_walk<true>(sc, ts, cnt, maxTasks);
-        }
-        k_confirm_shadow<<<nbPairs, 128, 0, g_stream>>>(sc, shadow, ts);
-        launches += 2;
+    LaunchScope ls(c, PROF_SHADE);
+    const uint32_t blocks = stage_grid(c, end - begin);
+    // counting builds and scenes with CSG / heightfield / inline tree walks take the generic variant
+    if (fp.gi) {
+        if (cnt) k_shade<true, true, false><<<blocks, 128, 0, c->stream>>>(sc, fp, q, cand, begin, end, sinks, totals, cnt);
+        else if (sc.simple_inline) k_shade<true, false, true><<<blocks, 128, 0, c->stream>>>(sc, fp, q, cand, begin, end, sinks, totals, nullptr);
+        else k_shade<true, false, false><<<blocks, 128, 0, c->stream>>>(sc, fp, q, cand, begin, end, sinks, totals, nullptr);
+    } else {
+        if (cnt) k_shade<false, true, false><<<blocks, 128, 0, c->stream>>>(sc, fp, q, cand, begin, end, sinks, totals, cnt);
+        else if (sc.simple_inline) k_shade<false, false, true><<<blocks, 128, 0, c->stream>>>(sc, fp, q, cand, begin, end, sinks, totals, nullptr);
+        else k_shade<false, false, false><<<blocks, 128, 0, c->stream>>>(sc, fp, q, cand, begin, end, sinks, totals, nullptr);
     }
-    if (accum) { k_accum_shadow<<<nb, 256, 0, g_stream>>>(shadow, count, cap, ts, accum); launches++; }
-    g_launches[PROF_TRACE_SHADOW] += launches - 1;
-    return launches;
+    return 1;
 }
 
-int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
+int resolve_shadow(Context* c, const DScene& sc, const ShadowQueue& q, const CandRec* cand, float* accum, uint8_t* visible, FrameTotals* totals,
+                   TravCounters* cnt, uint32_t n_hint)
 {
-    ProfScope ps(PROF_OTHER);
+    LaunchScope ls(c, PROF_SHADOW_RESOLVE);
+    const uint32_t blocks = stage_grid(c, n_hint);
+    if (cnt) k_resolve_shadow<true><<<blocks, 128, 0, c->stream>>>(sc, q, cand, accum, visible, totals, cnt);
+    else k_resolve_shadow<false><<<blocks, 128, 0, c->stream>>>(sc, q, cand, accum, visible, totals, nullptr);
+    return 1;
+}
+
+int hit_records(Context* c, const DScene& sc, const RayQueue& q, const CandRec* cand, HitRec* hits, uint32_t n_hint)
+{
+    LaunchScope ls(c, PROF_OTHER);
+    k_hit_records<<<stage_grid(c, n_hint), 128, 0, c->stream>>>(sc, q, cand, hits);
+    return 1;
+}
+
+int aa_detect(Context* c, const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
+{
+    LaunchScope ls(c, PROF_OTHER);
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    k_aa_detect<<<g, b, 0, g_stream>>>(vfb, W, H, shard_index, shard_count, list, n_out, mask);
+    k_aa_detect<<<g, b, 0, c->stream>>>(vfb, W, H, shard_index, shard_count, list, n_out, mask);
     return 1;
 }
-int scale_listed(float* vfb, const uint32_t* list, const uint32_t* n, uint32_t cap, float mul)
+int scale_listed(Context* c, float* vfb, const uint32_t* list, const uint32_t* n, uint32_t cap, float mul)
 {
-    ProfScope ps(PROF_OTHER);
-    k_scale_listed<<<g_sms * 4, 256, 0, g_stream>>>(vfb, list, n, cap, mul);
+    LaunchScope ls(c, PROF_OTHER);
+    k_scale_listed<<<c->sms * 4, 256, 0, c->stream>>>(vfb, list, n, cap, mul);
     return 1;
 }
-int scale_all(float* buf, size_t n, float mul)
+int scale_all(Context* c, float* buf, size_t n, float mul)
 {
-    ProfScope ps(PROF_OTHER);
-    k_scale_all<<<g_sms * 8, 256, 0, g_stream>>>(buf, n, mul);
+    LaunchScope ls(c, PROF_OTHER);
+    k_scale_all<<<c->sms * 8, 256, 0, c->stream>>>(buf, n, mul);
     return 1;
 }
-int add_into(float* dst, const float* src, size_t n)
+int add_into(Context* c, float* dst, const float* src, size_t n)
 {
-    ProfScope ps(PROF_OTHER);
-    k_add_into<<<g_sms * 8, 256, 0, g_stream>>>(dst, src, n);
+    LaunchScope ls(c, PROF_OTHER);
+    k_add_into<<<c->sms * 8, 256, 0, c->stream>>>(dst, src, n);
     return 1;
 }
-int to_bmp_rows(const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out)
+int to_bmp_rows(Context* c, const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out)
 {
-    ProfScope ps(PROF_OTHER);
-    cudaMemsetAsync(out, 0, (size_t)rowsz * H, g_stream);
+    LaunchScope ls(c, PROF_OTHER);
+    cudaMemsetAsync(out, 0, (size_t)rowsz * H, c->stream);
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    k_to_bmp_rows<<<g, b, 0, g_stream>>>(rgb, W, H, rowsz, lut, out);
+    k_to_bmp_rows<<<g, b, 0, c->stream>>>(rgb, W, H, rowsz, lut, out);
     return 1;
 }
-int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels)
+int to_exr_rows(Context* c, const float* rgb, int W, int H, uint16_t* out)
 {
-    ProfScope ps(PROF_OTHER);
-    k_stereo_mix<<<g_sms * 8, 256, 0, g_stream>>>(out, left, right, n_pixels);
+    LaunchScope ls(c, PROF_OTHER);
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_to_exr_rows<<<g, b, 0, c->stream>>>(rgb, W, H, out);
+    return 1;
+}
+int stereo_mix(Context* c, float* out, const float* left, const float* right, size_t n_pixels)
+{
+    LaunchScope ls(c, PROF_OTHER);
+    k_stereo_mix<<<c->sms * 8, 256, 0, c->stream>>>(out, left, right, n_pixels);
     return 1;
 }
 }  // namespace dev

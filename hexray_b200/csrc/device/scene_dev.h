@@ -116,6 +116,10 @@ struct DScene {
     // per node: slot of its traversal results if its geometry is a "big" mesh (walked by the persistent
     // traversal kernel), -1 otherwise (analytic primitives, CSG, heightfields, meshes <= HXR_SMALL_MESH)
     const int32_t* node_slot;
+    // walked nodes in scene order: big_nodes[slot] = node index; big_box[6 * slot] = float copy of that node's world box,
+    // rounded outward (the walk kernel skips a mesh whose box the ray certainly misses before paying for the double transform)
+    const int32_t* big_nodes;
+    const float* big_box;
     // per node: conservative world-space box of its geometry (min xyz, max xyz; +-1e300 when unbounded or unknown): the
     // node loops skip a node whose box the ray misses before paying for the object-space transform and intersector
     const double* node_box;
@@ -126,6 +130,7 @@ struct DScene {
     int32_t use_node_box;
     int32_t walk_packed;  // every walked mesh has tri_pk: the walk filters 32-byte packed triangles
     int32_t n_big;
+    int32_t n_inline;  // nodes handled inline (n_nodes - n_big)
     int32_t simple_inline;  // every inline node is a plane, sphere, cube or brute-force mesh (selects the lean kernel variants)
     int32_t n_nodes, n_lights;
     int32_t has_env;

@@ -531,7 +531,8 @@ inline bool load(const char* filename, Image& img, std::string* err = nullptr)
 }
 
 // ---------------------------------------------------------------- writer
-inline bool save_half_rgba(const char* filename, int W, int H, const float* rgb, int stride_floats)
+// rows: when non-null, the already converted scan lines (per row: W halves of A, then B, G, R) are written as they are
+inline bool save_half_impl(const char* filename, int W, int H, const float* rgb, int stride_floats, const uint16_t* rows)
 {
     FILE* f = fopen(filename, "wb");
     if (!f) return false;
@@ -573,8 +574,9 @@ inline bool save_half_rgba(const char* filename, int W, int H, const float* rgb,
     bool ok = fwrite(hdr.data(), 1, hdr.size(), f) == hdr.size();
     std::vector<uint16_t> line((size_t)W * 4);
     for (int y = 0; y < H && ok; y++) {
-        const float* src = rgb + (size_t)y * W * stride_floats;
-        for (int x = 0; x < W; x++) {
+        const float* src = rows ? nullptr : rgb + (size_t)y * W * stride_floats;
+        if (rows) memcpy(line.data(), rows + (size_t)y * W * 4, lineBytes);
+        for (int x = 0; x < W && !rows; x++) {
             line[x] = float_to_half(1.0f);
             line[W + x] = float_to_half(src[x * stride_floats + 2]);
             line[2 * W + x] = float_to_half(src[x * stride_floats + 1]);
@@ -586,6 +588,12 @@ inline bool save_half_rgba(const char* filename, int W, int H, const float* rgb,
     fclose(f);
     return ok;
 }
+
+inline bool save_half_rgba(const char* filename, int W, int H, const float* rgb, int stride_floats)
+{
+    return save_half_impl(filename, W, H, rgb, stride_floats, nullptr);
+}
+inline bool save_half_rows(const char* filename, int W, int H, const uint16_t* rows) { return save_half_impl(filename, W, H, nullptr, 0, rows); }
 
 }  // namespace exr
 }  // namespace hxr

@@ -6,46 +6,44 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <thread>
 #include "host/bitmap.h"
+#include "host/exr_codec.h"
 
 namespace hxr {
 
-enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_OVERFLOW = 3, C_HEAD_A = 4, C_HEAD_B = 5, C_AA = 6, C_TASKS = 7, C_PAIRS = 8, C_NCOUNTERS = 16 };
+// device counters (uint32): queue counts, the shadow queue's count, the work-fetch cursors of the two walks, flags
+enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_HEAD_A = 3, C_HEAD_B = 4, C_OVERFLOW = 5, C_AA = 6, C_NCOUNTERS = 16 };
 
 Renderer::~Renderer()
 {
+    if (!m_dev) return;
     freeScene();
-    for (int i = 0; i < 2; i++) dev::free_(m_q[i]);
-    dev::free_(m_hits);
-    dev::free_(m_shadow);
-    dev::free_(m_counters);
-    dev::free_(m_trav);
-    dev::free_(m_pre);
-    dev::free_(m_tasks);
-    dev::free_(m_pairs);
-    dev::free_(m_pairGamma);
-    dev::free_(m_res);
-    dev::free_(m_occluded);
-    dev::free_(m_aaList);
-    dev::free_(m_aaMask);
-    dev::free_(m_accum);
-    dev::free_(m_srgbLut);
-    dev::free_(m_eye[0]);
-    dev::free_(m_eye[1]);
+    freeQueues();
+    dev::free_(m_dev, m_counters);
+    dev::free_(m_dev, m_totals);
+    dev::free_(m_dev, m_trav);
+    dev::free_(m_dev, m_aaList);
+    dev::free_(m_dev, m_aaMask);
+    dev::free_(m_dev, m_accum);
+    dev::free_(m_dev, m_srgbLut);
+    dev::free_(m_dev, m_eye[0]);
+    dev::free_(m_dev, m_eye[1]);
+    dev::destroy(m_dev);
 }
 
-int Renderer::create(const hxr_config& cfg)
+int Renderer::create(const hxr_config& cfg, int device)
 {
     m_cfg = cfg;
     char err[256] = "";
-    if (!dev::init(cfg.device, err, sizeof err)) return fail(HXR_ERR_NO_DEVICE, err);
-    m_created = true;
+    m_dev = dev::create(device, err, sizeof err);
+    if (!m_dev) return fail(HXR_ERR_NO_DEVICE, err);
     return HXR_OK;
 }
 
 void Renderer::freeScene()
 {
-    for (void* p : m_sceneAllocs) dev::free_(p);
+    for (void* p : m_sceneAllocs) dev::free_(m_dev, p);
     m_sceneAllocs.clear();
     m_haveScene = false;
     m_accel.clear();
@@ -54,8 +52,8 @@ void Renderer::freeScene()
 template <class T> T* Renderer::uploadArray(const T* src, size_t n)
 {
     // a 1-element allocation keeps device pointers non-null for empty tables
-    T* d = (T*)keep(dev::alloc(std::max<size_t>(n, 1) * sizeof(T)));
-    if (d && n && !dev::upload(d, src, n * sizeof(T))) return nullptr;
+    T* d = (T*)keep(dev::alloc(m_dev, std::max<size_t>(n, 1) * sizeof(T)));
+    if (d && n && !dev::upload(m_dev, d, src, n * sizeof(T))) return nullptr;
     return d;
 }
 
@@ -138,67 +136,105 @@ static bool validateScene(const hxr_scene& s, std::string& why)
     return true;
 }
 
-int Renderer::uploadScene(const hxr_scene* sp)
-{
-    if (!m_created) return fail(HXR_ERR_INVALID, "context not created");
-    if (!sp) return fail(HXR_ERR_INVALID, "null scene");
-    const hxr_scene& s = *sp;
-    std::string why;
-    if (!validateScene(s, why)) return fail(HXR_ERR_INVALID, "invalid scene: " + why);
-    freeScene();
-    auto oom = [&]() { freeScene(); return fail(HXR_ERR_CUDA, std::string("scene upload failed: ") + dev::last_error()); };
 
-    // meshes: build the KD-tree on the host, split triangles into test / attribute records
-    std::vector<DMesh> dm(s.n_meshes);
-    m_accel.resize(s.n_meshes);
+// ---- the device-independent part of a scene upload: KD-trees and flattened triangle records
+bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& out, std::string& why)
+{
+    (void)cfg;
+    if (!validateScene(s, why)) return false;
+    out.meshes.clear();
+    out.meshes.resize(s.n_meshes);
+    out.build_ms = 0;
     size_t filterBytes = 0;
     for (int i = 0; i < s.n_meshes; i++) filterBytes += (size_t)s.meshes[i].n_triangles * sizeof(TriF32);
+    // the walk's 32-byte form of the triangles: one sector per test instead of 1.5-2, at ~35 more instructions per test.
+    // Measured (profiles/README.md): on terrain-10M (triangles >> L2, walk bound by memory) k_walk -2.7 %; on cornell_box (36
+    // triangles, walk bound by issue slots) k_walk +12 %. So: packed when the scene's filter triangles outgrow the L2
+    // (HXR_TRI_PACK=0/1 overrides). A mesh with an edge that does not fit the format keeps the scene on tri_f32.
     const bool wantPack = getenv("HXR_TRI_PACK") ? atoi(getenv("HXR_TRI_PACK")) != 0 : filterBytes > ((size_t)64 << 20);
     for (int i = 0; i < s.n_meshes; i++) {
         const hxr_mesh& m = s.meshes[i];
-        host::KdTree kd;
-        host::buildKdTree(m, host::KdBuildParams(), kd);
-        std::vector<TriTest> tt(m.n_triangles);
-        std::vector<TriAttr> ta(m.n_triangles);
-        std::vector<TriAttrUv> tu(m.n_triangles);
-        std::vector<TriF32> tf(m.n_triangles);
-        for (int t = 0; t < m.n_triangles; t++) {
-            const hxr_triangle& T = m.triangles[t];
-            for (int k = 0; k < 3; k++) {
-                tt[t].A[k] = m.vertices[3 * (size_t)T.v[0] + k];
-                tt[t].AB[k] = T.ab[k];
-                tt[t].AC[k] = T.ac[k];
-                tt[t].N[k] = T.ab_cross_ac[k];
-                tf[t].A[k] = (float)tt[t].A[k];
-                tf[t].AB[k] = (float)tt[t].AB[k];
-                tf[t].AC[k] = (float)tt[t].AC[k];
-                tf[t].N[k] = (float)tt[t].N[k];
-                ta[t].gnormal[k] = T.gnormal[k];
-                for (int c = 0; c < 3; c++) ta[t].nrm[k][c] = m.normals[3 * (size_t)T.n[k] + c];
-                for (int c = 0; c < 2; c++) tu[t].uv[k][c] = m.uvs[3 * (size_t)T.t[k] + c];
-                tu[t].dNdx[k] = T.dndx[k];
-                tu[t].dNdy[k] = T.dndy[k];
+        MeshTables& M = out.meshes[i];
+        host::buildKdTree(m, host::KdBuildParams(), M.kd);
+        out.build_ms += M.kd.buildMs;
+        const size_t nt = (size_t)m.n_triangles;
+        M.tt.resize(nt);
+        M.ta.resize(nt);
+        M.tu.resize(nt);
+        M.tf.resize(nt);
+        auto fill = [&](size_t t0, size_t t1) {
+            for (size_t t = t0; t < t1; t++) {
+                const hxr_triangle& T = m.triangles[t];
+                for (int k = 0; k < 3; k++) {
+                    M.tt[t].A[k] = m.vertices[3 * (size_t)T.v[0] + k];
+                    M.tt[t].AB[k] = T.ab[k];
+                    M.tt[t].AC[k] = T.ac[k];
+                    M.tt[t].N[k] = T.ab_cross_ac[k];
+                    M.tf[t].A[k] = (float)M.tt[t].A[k];
+                    M.tf[t].AB[k] = (float)M.tt[t].AB[k];
+                    M.tf[t].AC[k] = (float)M.tt[t].AC[k];
+                    M.tf[t].N[k] = (float)M.tt[t].N[k];
+                    M.ta[t].gnormal[k] = T.gnormal[k];
+                    for (int c = 0; c < 3; c++) M.ta[t].nrm[k][c] = m.normals[3 * (size_t)T.n[k] + c];
+                    for (int c = 0; c < 2; c++) M.tu[t].uv[k][c] = m.uvs[3 * (size_t)T.t[k] + c];
+                    M.tu[t].dNdx[k] = T.dndx[k];
+                    M.tu[t].dNdy[k] = T.dndy[k];
+                }
             }
+        };
+        // big meshes: the record fill is a pure streaming pass, split over the host threads
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t nth = nt > (1u << 18) ? std::min<size_t>(hw, 32) : 1;
+        if (nth <= 1) fill(0, nt);
+        else {
+            std::vector<std::thread> th;
+            for (size_t k = 0; k < nth; k++) th.emplace_back(fill, nt * k / nth, nt * (k + 1) / nth);
+            for (auto& x : th) x.join();
         }
-        // the walk's 32-byte form of the same triangles: one sector per test instead of 1.5-2, at ~35 more instructions per test.
-        // Measured (profiles/README.md): on terrain-10M (triangles >> L2, walk bound by memory) k_walk -2.7 %; on cornell_box (36
-        // triangles, walk bound by issue slots) k_walk +12 %. So: packed when the scene's filter triangles outgrow the L2
-        // (HXR_TRI_PACK=0/1 overrides). A mesh with an edge that does not fit the format keeps the scene on tri_f32.
-        std::vector<TriPacked> tp(wantPack ? m.n_triangles : 0);
-        for (size_t t = 0; t < tp.size(); t++)
-            if (!pack_tri(tt[t], tp[t])) { tp.clear(); break; }
+        M.tp.clear();
+        if (wantPack) {
+            M.tp.resize(nt);
+            for (size_t t = 0; t < nt; t++)
+                if (!pack_tri(M.tt[t], M.tp[t])) { M.tp.clear(); break; }
+        }
+    }
+    return true;
+}
+
+int Renderer::uploadScene(const hxr_scene* sp)
+{
+    if (!m_dev) return fail(HXR_ERR_INVALID, "context not created");
+    if (!sp) return fail(HXR_ERR_INVALID, "null scene");
+    SceneTables tab;
+    std::string why;
+    if (!buildSceneTables(*sp, m_cfg, tab, why)) return fail(HXR_ERR_INVALID, "invalid scene: " + why);
+    return uploadScene(*sp, tab);
+}
+
+int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
+{
+    if (!m_dev) return fail(HXR_ERR_INVALID, "context not created");
+    if ((int)tab.meshes.size() != s.n_meshes) return fail(HXR_ERR_INVALID, "scene tables do not match the scene");
+    freeScene();
+    auto oom = [&]() { freeScene(); return fail(HXR_ERR_CUDA, std::string("scene upload failed: ") + dev::last_error(m_dev)); };
+
+    std::vector<DMesh> dm(s.n_meshes);
+    m_accel.resize(s.n_meshes);
+    for (int i = 0; i < s.n_meshes; i++) {
+        const hxr_mesh& m = s.meshes[i];
+        const MeshTables& M = tab.meshes[i];
         DMesh& d = dm[i];
         memset(&d, 0, sizeof d);
-        if (!tp.empty()) {
-            d.tri_pk = uploadArray(tp.data(), tp.size());
+        if (!M.tp.empty()) {
+            d.tri_pk = uploadArray(M.tp.data(), M.tp.size());
             if (!d.tri_pk) return oom();
         }
-        d.blocks = uploadArray(kd.blocks.data(), kd.blocks.size());
-        d.leaf_tris = uploadArray(kd.leafTris.data(), kd.leafTris.size());
-        d.tri_test = uploadArray(tt.data(), tt.size());
-        d.tri_f32 = uploadArray(tf.data(), tf.size());
-        d.tri_attr = uploadArray(ta.data(), ta.size());
-        d.tri_attr_uv = uploadArray(tu.data(), tu.size());
+        d.blocks = uploadArray(M.kd.blocks.data(), M.kd.blocks.size());
+        d.leaf_tris = uploadArray(M.kd.leafTris.data(), M.kd.leafTris.size());
+        d.tri_test = uploadArray(M.tt.data(), M.tt.size());
+        d.tri_f32 = uploadArray(M.tf.data(), M.tf.size());
+        d.tri_attr = uploadArray(M.ta.data(), M.ta.size());
+        d.tri_attr_uv = uploadArray(M.tu.data(), M.tu.size());
         if (!d.blocks || !d.leaf_tris || !d.tri_test || !d.tri_f32 || !d.tri_attr || !d.tri_attr_uv) return oom();
         double amax = 0;
         for (int k = 0; k < 3; k++) {
@@ -214,14 +250,14 @@ int Renderer::uploadScene(const hxr_scene* sp)
         d.brute = (m.n_triangles <= smallMesh || (m_cfg.flags & HXR_CFG_BRUTE_FORCE_MESHES)) ? 1 : 0;
         if (d.brute && m.n_triangles <= HXR_SMALL_MESH && !getenv("HXR_QUAD_SLAB")) d.brute = 3;  // tiny: no box gate either
         hxr_accel_info& ai = m_accel[i];
-        ai.nodes = kd.blocks.size();
-        ai.leaves = kd.leaves;
-        ai.tri_refs = kd.leafTris.size();
-        ai.bytes_nodes = kd.blocks.size() * sizeof(KdBlock);
-        ai.bytes_tris = kd.leafTris.size() * sizeof(uint32_t) + (tp.empty() ? tf.size() * sizeof(TriF32) : tp.size() * sizeof(TriPacked)) + tt.size() * sizeof(TriTest);
-        ai.max_depth = kd.maxDepth;
+        ai.nodes = M.kd.blocks.size();
+        ai.leaves = M.kd.leaves;
+        ai.tri_refs = M.kd.leafTris.size();
+        ai.bytes_nodes = M.kd.blocks.size() * sizeof(KdBlock);
+        ai.bytes_tris = M.kd.leafTris.size() * sizeof(uint32_t) + (M.tp.empty() ? M.tf.size() * sizeof(TriF32) : M.tp.size() * sizeof(TriPacked)) + M.tt.size() * sizeof(TriTest);
+        ai.max_depth = M.kd.maxDepth;
         ai.n_triangles = (uint32_t)m.n_triangles;
-        ai.build_ms = kd.buildMs;
+        ai.build_ms = M.kd.buildMs;
     }
     std::vector<DHeightfield> dh(s.n_heightfields);
     for (int i = 0; i < s.n_heightfields; i++) {
@@ -263,14 +299,21 @@ int Renderer::uploadScene(const hxr_scene* sp)
         return oom();
     {
         // nodes whose geometry is a mesh too big for the inline brute-force test get a result slot
+        // (at most HXR_MAX_WALKED_NODES of them: a candidate record names the slot in 8 bits; further mesh nodes are
+        // intersected inline with the double walk)
         std::vector<int32_t> slot(std::max(1, s.n_nodes), -1);
+        std::vector<int32_t> bigNodes;
         m_nBig = 0;
         for (int i = 0; i < s.n_nodes; i++) {
             const hxr_geometry& g = s.geometries[s.nodes[i].geom];
-            if (g.type == HXR_GEOM_MESH && !dm[g.a].brute) slot[i] = m_nBig++;
+            if (g.type == HXR_GEOM_MESH && !dm[g.a].brute && m_nBig < HXR_MAX_WALKED_NODES) {
+                slot[i] = m_nBig++;
+                bigNodes.push_back(i);
+            }
         }
         m_scene.node_slot = uploadArray(slot.data(), slot.size());
-        if (!m_scene.node_slot) return oom();
+        m_scene.big_nodes = uploadArray(bigNodes.data(), bigNodes.size());
+        if (!m_scene.node_slot || !m_scene.big_nodes) return oom();
         // nodes on which nothing reads a hit's u, v, dNdx, dNdy: no bump map and no texture anywhere in the shader tree
         std::function<bool(int, int)> textured = [&](int si, int depth) -> bool {
             if (si < 0 || si >= s.n_shaders || depth > 16) return true;  // unknown: assume it reads them
@@ -325,6 +368,19 @@ int Renderer::uploadScene(const hxr_scene* sp)
         }
         m_scene.node_box = uploadArray(box.data(), box.size());
         if (!m_scene.node_box) return oom();
+        {
+            // float copies of the walked nodes' boxes, rounded outward (the walk kernel's pre-test)
+            std::vector<float> fb((size_t)std::max(1, m_nBig) * 6, 0.0f);
+            for (int sl = 0; sl < m_nBig; sl++)
+                for (int k = 0; k < 3; k++) {
+                    const double lo = box[(size_t)bigNodes[sl] * 6 + k], hi = box[(size_t)bigNodes[sl] * 6 + 3 + k];
+                    fb[(size_t)sl * 6 + k] = lo < -3e38 ? -INFINITY : std::nextafter((float)lo, -INFINITY);
+                    fb[(size_t)sl * 6 + 3 + k] = hi > 3e38 ? INFINITY : std::nextafter((float)hi, INFINITY);
+                }
+            m_scene.big_box = uploadArray(fb.data(), fb.size());
+            if (!m_scene.big_box) return oom();
+        }
+        m_scene.n_inline = s.n_nodes - m_nBig;
         m_scene.use_node_box = getenv("HXR_NO_NODE_BOX") ? 0 : 1;
         m_scene.simple_inline = 1;
         for (int i = 0; i < s.n_nodes; i++) {
@@ -387,109 +443,125 @@ int Renderer::accelInfo(int mesh, hxr_accel_info* out) const
 }
 
 // ------------------------------------------------------------------------------ queues
+void Renderer::freeQueues()
+{
+    for (int i = 0; i < 2; i++) {
+        dev::free_(m_dev, m_qg[i]); m_qg[i] = nullptr;
+        dev::free_(m_dev, m_qa[i]); m_qa[i] = nullptr;
+    }
+    dev::free_(m_dev, m_sg); m_sg = nullptr;
+    dev::free_(m_dev, m_sa); m_sa = nullptr;
+    dev::free_(m_dev, m_cand); m_cand = nullptr;
+    dev::free_(m_dev, m_scand); m_scand = nullptr;
+    dev::free_(m_dev, m_hits); m_hits = nullptr;
+    dev::free_(m_dev, m_visible); m_visible = nullptr;
+    m_cap = m_shadowCap = 0;
+}
+
+// Per ray in flight: 2 x (64 + 24) B of ray queues, 64 + 16 B of shadow queue, 16 B of candidate record (one buffer serves
+// the closest-hit walk and, after its rays are shaded, the shadow walk). Nothing here scales with the number of meshes.
 bool Renderer::ensureQueues()
 {
     const uint32_t cap = m_cfg.queue_capacity ? (uint32_t)std::min<uint64_t>(m_cfg.queue_capacity, 1u << 30) : (8u << 20);
-    const uint32_t shadowCap = (uint32_t)std::min<uint64_t>(1u << 30, std::max<uint64_t>((uint64_t)cap * 2, (uint64_t)m_maxShadowPerHit * 4096));
-    // a ray becomes a walk task only for the meshes whose box it enters: room for 8 per ray is plenty even with hundreds of
-    // meshes; if a wave ever needs more, the overflow flag makes render() redo the frame in smaller batches
-    const uint32_t taskCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)std::max(cap, shadowCap) * (uint64_t)std::min(8, std::max(1, m_nBig)));
-    if (m_q[0] && cap == m_cap && shadowCap == m_shadowCap && taskCap == m_taskCap) return true;
-    for (int i = 0; i < 2; i++) { dev::free_(m_q[i]); m_q[i] = nullptr; }
-    dev::free_(m_hits); m_hits = nullptr;
-    dev::free_(m_shadow); m_shadow = nullptr;
-    dev::free_(m_pre); m_pre = nullptr;
-    dev::free_(m_tasks); m_tasks = nullptr;
-    dev::free_(m_pairs); m_pairs = nullptr;
-    dev::free_(m_pairGamma); m_pairGamma = nullptr;
-    dev::free_(m_res); m_res = nullptr;
-    dev::free_(m_occluded); m_occluded = nullptr;
+    // path tracing issues at most one shadow ray per hit; a Whitted hit issues one per light sample and shader layer
+    // (a shade launch is cut into chunks whose shadow rays fit)
+    const uint64_t wantShadow = m_scene.settings.gi ? cap : std::max<uint64_t>((uint64_t)cap * 2, (uint64_t)m_maxShadowPerHit * 4096);
+    const uint32_t shadowCap = (uint32_t)std::min<uint64_t>(1u << 30, std::max<uint64_t>(wantShadow, (uint64_t)m_maxShadowPerHit));
+    if (m_qg[0] && cap == m_cap && shadowCap == m_shadowCap) return true;
+    freeQueues();
     m_cap = cap;
     m_shadowCap = shadowCap;
-    m_taskCap = taskCap;
-    m_pre = (RayPre*)dev::alloc((size_t)cap * sizeof(RayPre));
-    m_tasks = (WalkTask*)dev::alloc((size_t)taskCap * sizeof(WalkTask));
-    // (task, triangle) pairs the FP32 filter leaves for the exact test: about one per task (the hit itself) plus near misses
-    // (+ the slots the walk's warps reserve in chunks and may leave unused: 64 per resident warp, a few hundred thousand)
-    m_pairCap = (uint32_t)std::min<uint64_t>(1u << 31, (uint64_t)taskCap * 2 + (1u << 20));
-    m_pairs = (PairRec*)dev::alloc((size_t)m_pairCap * sizeof(PairRec));
-    m_pairGamma = (double*)dev::alloc((size_t)m_pairCap * sizeof(double));
-    m_res = (MeshRes*)dev::alloc((size_t)cap * std::max(1, m_nBig) * sizeof(MeshRes));
-    m_occluded = (uint8_t*)dev::alloc((size_t)shadowCap);
-    for (int i = 0; i < 2; i++) m_q[i] = (RayTask*)dev::alloc((size_t)cap * sizeof(RayTask));
-    m_hits = (HitRec*)dev::alloc((size_t)cap * sizeof(HitRec));
-    m_shadow = (ShadowTask*)dev::alloc((size_t)shadowCap * sizeof(ShadowTask));
-    if (!m_counters) m_counters = (uint32_t*)dev::alloc(C_NCOUNTERS * sizeof(uint32_t));
-    if (!m_trav) m_trav = (TravCounters*)dev::alloc(sizeof(TravCounters) + 64);
-    if (!m_q[0] || !m_q[1] || !m_hits || !m_shadow || !m_counters || !m_trav || !m_pre || !m_tasks || !m_res || !m_occluded || !m_pairs || !m_pairGamma) {
-        m_err = std::string("queue allocation failed: ") + dev::last_error();
+    for (int i = 0; i < 2; i++) {
+        m_qg[i] = (RayGeom*)dev::alloc(m_dev, (size_t)cap * sizeof(RayGeom));
+        m_qa[i] = (RayAux*)dev::alloc(m_dev, (size_t)cap * sizeof(RayAux));
+    }
+    m_sg = (RayGeom*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(RayGeom));
+    m_sa = (ShadowAux*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(ShadowAux));
+    m_cand = (CandRec*)dev::alloc(m_dev, (size_t)std::max(cap, shadowCap) * sizeof(CandRec));
+    if (!m_counters) m_counters = (uint32_t*)dev::alloc(m_dev, C_NCOUNTERS * sizeof(uint32_t));
+    if (!m_totals) m_totals = (dev::FrameTotals*)dev::alloc(m_dev, sizeof(dev::FrameTotals));
+    if (!m_trav) m_trav = (TravCounters*)dev::alloc(m_dev, sizeof(TravCounters));
+    if (!m_qg[0] || !m_qg[1] || !m_qa[0] || !m_qa[1] || !m_sg || !m_sa || !m_cand || !m_counters || !m_totals || !m_trav) {
+        m_err = "queue allocation failed (out of device memory: lower hxr_config.queue_capacity)";
+        freeQueues();
         return false;
     }
-    dev::zero(m_counters, C_NCOUNTERS * sizeof(uint32_t));
-    dev::zero(m_trav, sizeof(TravCounters) + 64);
+    dev::zero(m_dev, m_counters, C_NCOUNTERS * sizeof(uint32_t));
+    dev::zero(m_dev, m_totals, sizeof(dev::FrameTotals));
+    dev::zero(m_dev, m_trav, sizeof(TravCounters));
     return true;
 }
 
-TraceScratch Renderer::scratch(uint32_t headCounter) const
+RayQueue Renderer::queue(int i) const
 {
-    TraceScratch ts;
-    ts.pre = m_pre;
-    ts.tasks = m_tasks;
-    ts.task_count = m_counters + C_TASKS;
-    ts.task_cap = m_taskCap;
-    ts.res = m_res;
-    ts.res_stride = m_cap;
-    ts.occluded = m_occluded;
-    ts.head = m_counters + headCounter;
-    ts.pairs = m_pairs;
-    ts.pair_gamma = m_pairGamma;
-    ts.pair_count = m_counters + C_PAIRS;
-    ts.pair_cap = m_pairCap;
-    ts.overflow = m_counters + C_OVERFLOW;
-    return ts;
+    RayQueue q;
+    q.geom = m_qg[i];
+    q.aux = m_qa[i];
+    q.count = m_counters + (i ? C_Q1 : C_Q0);
+    q.cap = m_cap;
+    return q;
+}
+ShadowQueue Renderer::shadowQueue() const
+{
+    ShadowQueue q;
+    q.geom = m_sg;
+    q.aux = m_sa;
+    q.count = m_counters + C_SHADOW;
+    q.cap = m_shadowCap;
+    return q;
 }
 
 uint32_t Renderer::readCount(const uint32_t* dptr)
 {
     uint32_t v = 0;
-    dev::download(&v, dptr, sizeof v);
+    dev::download(m_dev, &v, dptr, sizeof v);
     return v;
 }
 
-// the tail of m_trav holds a 64-bit shadow-ray total maintained by the shadow kernel
-static unsigned long long* shadowTotalPtr(TravCounters* t) { return (unsigned long long*)(t + 1); }
-
-int Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st)
+// One bounce = walk(closest) -> shade -> walk(shadow) -> resolve(shadow). The counts stay on the device: the host
+// enqueues max_depth + 1 bounces (a ray's depth grows by one per bounce and the guard stops it at max_depth) with grids
+// sized from an upper bound of each level's population; levels that turn out empty cost four near-empty launches.
+void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st)
 {
     int cur = 0;
-    uint32_t n = nPrimary;
     const uint32_t perHit = fp.gi ? 1u : (uint32_t)m_maxShadowPerHit;
     const uint32_t chunk = std::max<uint32_t>(1, m_shadowCap / perHit);
+    const uint64_t fan = fp.gi ? 1u : (uint64_t)std::max(1, m_maxChildrenPerHit);
     TravCounters* cnt = m_countTraversal ? m_trav : nullptr;
-    for (int level = 0; n > 0 && level <= fp.max_depth + 2; level++) {
-        if (n > m_cap) return 1;  // overflow
-        st.kernel_launches += dev::trace_closest(m_scene, m_q[cur], m_counters + cur, m_cap, m_hits, scratch(C_HEAD_A), cnt, n);
-        st.rays_closest += n;
-        dev::set_u32(m_counters + (1 - cur), 0);
+    uint64_t hint = nPrimary;
+    for (int level = 0; level <= fp.max_depth && hint > 0; level++) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(hint, m_cap);
+        const RayQueue q = queue(cur);
+        dev::zero(m_dev, m_counters + (cur ? C_Q0 : C_Q1), sizeof(uint32_t));
+        dev::zero(m_dev, m_counters + C_SHADOW, 3 * sizeof(uint32_t));  // shadow count + both walk cursors
+        st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.count, q.cap, m_cand, m_counters + C_HEAD_A, cnt, n);
         Sinks sk;
-        sk.next = m_q[1 - cur];
-        sk.next_count = m_counters + (1 - cur);
-        sk.next_cap = m_cap;
-        sk.shadow = m_shadow;
-        sk.shadow_count = m_counters + C_SHADOW;
-        sk.shadow_cap = m_shadowCap;
+        sk.next = queue(1 - cur);
+        sk.shadow = shadowQueue();
         sk.accum = accum;
         sk.overflow = m_counters + C_OVERFLOW;
-        for (uint32_t b = 0; b < n; b += chunk) {
-            dev::set_u32(m_counters + C_SHADOW, 0);
-            st.kernel_launches += dev::shade(m_scene, fp, m_q[cur], m_counters + cur, m_hits, b, std::min<uint64_t>(n, (uint64_t)b + chunk), sk);
-            st.kernel_launches += dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, accum, scratch(C_HEAD_B), cnt, shadowTotalPtr(m_trav),
-                                                   (uint32_t)std::min<uint64_t>(m_shadowCap, (std::min<uint64_t>(n, (uint64_t)b + chunk) - b) * perHit));
+        // The candidate buffer serves both walks when the whole level is shaded by one launch (path tracing: always): every
+        // closest-hit record has been consumed before the shadow walk writes its own. A level shaded in chunks (Whitted
+        // hits with many light samples) needs the shadow records elsewhere.
+        CandRec* scand = m_cand;
+        if (n > chunk && m_scene.n_big) {
+            if (!m_scand) m_scand = (CandRec*)dev::alloc(m_dev, (size_t)m_shadowCap * sizeof(CandRec));
+            if (!m_scand) { m_err = "shadow candidate buffer allocation failed"; m_allocFailed = true; return; }
+            scand = m_scand;
         }
-        n = readCount(m_counters + (1 - cur));
+        for (uint32_t b = 0; b < n; b += chunk) {
+            const uint32_t e = (uint32_t)std::min<uint64_t>(n, (uint64_t)b + chunk);
+            if (b) dev::zero(m_dev, m_counters + C_SHADOW, 3 * sizeof(uint32_t));
+            st.kernel_launches += dev::shade(m_dev, m_scene, fp, q, m_cand, b, e, sk, m_totals, cnt);
+            if (m_scene.n_big) {
+                const uint32_t ns = (uint32_t)std::min<uint64_t>(m_shadowCap, (uint64_t)(e - b) * perHit);
+                st.kernel_launches += dev::walk(m_dev, m_scene, true, m_sg, m_counters + C_SHADOW, m_shadowCap, scand, m_counters + C_HEAD_B, cnt, ns);
+                st.kernel_launches += dev::resolve_shadow(m_dev, m_scene, sk.shadow, scand, accum, nullptr, m_totals, cnt, ns);
+            }
+        }
+        hint = std::min<uint64_t>(hint * fan, m_cap);
         cur = 1 - cur;
     }
-    return 0;
 }
 
 // ------------------------------------------------------------------------------ frames
@@ -532,6 +604,8 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
     const hxr_settings savedSettings = m_scene.settings;
     if (p.max_depth >= 0) m_scene.settings.max_trace_depth = p.max_depth;
     m_countTraversal = (p.flags & HXR_RENDER_COUNT_TRAVERSAL) != 0;
+    dev::clear_error(m_dev);
+    m_allocFailed = false;
 
     FrameParams fp;
     memset(&fp, 0, sizeof fp);
@@ -543,10 +617,10 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
     fp.seed = p.seed;
 
     if (m_accumPixels < nPix) {
-        dev::free_(m_accum);
-        m_accum = (float*)dev::alloc(nPix * 3 * sizeof(float));
+        dev::free_(m_dev, m_accum);
+        m_accum = (float*)dev::alloc(m_dev, nPix * 3 * sizeof(float));
         m_accumPixels = m_accum ? nPix : 0;
-        if (!m_accum) { m_scene.settings = savedSettings; return fail(HXR_ERR_CUDA, std::string("framebuffer allocation failed: ") + dev::last_error()); }
+        if (!m_accum) { m_scene.settings = savedSettings; return fail(HXR_ERR_CUDA, "framebuffer allocation failed"); }
     }
     // stereo anaglyph (src/main.cpp:234-248): every sample is traced once per eye; the eyes accumulate separately
     // and are mixed (a linear map) into the frame
@@ -554,7 +628,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
     float* eyeBuf[2] = {m_accum, nullptr};
     if (eyes == 2) {
         if (m_eyePixels < nPix) {
-            for (int e = 0; e < 2; e++) { dev::free_(m_eye[e]); m_eye[e] = (float*)dev::alloc(nPix * 3 * sizeof(float)); }
+            for (int e = 0; e < 2; e++) { dev::free_(m_dev, m_eye[e]); m_eye[e] = (float*)dev::alloc(m_dev, nPix * 3 * sizeof(float)); }
             m_eyePixels = (m_eye[0] && m_eye[1]) ? nPix : 0;
             if (!m_eyePixels) { m_scene.settings = savedSettings; return fail(HXR_ERR_CUDA, "stereo buffer allocation failed"); }
         }
@@ -566,62 +640,62 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
         fp.stream0 = 1u + (uint32_t)e;
     };
     setEye(0);
-    dev::prof_reset();
-    dev::Timer* tm = dev::timer_create();
-    dev::timer_start(tm);
-    dev::zero(m_accum, nPix * 3 * sizeof(float));
-    for (int e = 0; e < eyes && eyes == 2; e++) dev::zero(eyeBuf[e], nPix * 3 * sizeof(float));
-    dev::set_u32(m_counters + C_OVERFLOW, 0);
-    dev::zero(m_trav, sizeof(TravCounters) + 64);
-    int ov = 0;
+    if (mc && m_scene.cam.dof && m_scene.cam.auto_focus) {
+        // autofocus: distance of the closest NODE along the centre ray (src/main.cpp:350-362)
+        hxr_ray r;
+        Ray cr;
+        {
+            hxr_camera c = m_scene.cam;
+            c.dof = 0;
+            cr = camera_ray(c, W, H, W * 0.5, H * 0.5, 0, 0, 0);
+        }
+        r.start[0] = cr.o.x; r.start[1] = cr.o.y; r.start[2] = cr.o.z;
+        r.dir[0] = cr.d.x; r.dir[1] = cr.d.y; r.dir[2] = cr.d.z;
+        r.depth = 0; r.flags = 0;
+        hxr_hit h;
+        // note: like raycast, this also sees lights; a light in front of the geometry hides it
+        if (traceClosest(&r, 1, &h) == HXR_OK && h.status == 0) m_scene.cam.focal_plane_dist = h.dist;
+    }
+    dev::prof_reset(m_dev);
+    dev::Timer* tm = dev::timer_create(m_dev);
+    dev::timer_start(m_dev, tm);
+    dev::zero(m_dev, m_accum, nPix * 3 * sizeof(float));
+    for (int e = 0; e < eyes && eyes == 2; e++) dev::zero(m_dev, eyeBuf[e], nPix * 3 * sizeof(float));
+    dev::zero(m_dev, m_counters + C_OVERFLOW, sizeof(uint32_t));
+    dev::zero(m_dev, m_totals, sizeof(dev::FrameTotals));
+    dev::zero(m_dev, m_trav, sizeof(TravCounters));
 
     if (mc) {
-        if (m_scene.cam.dof && m_scene.cam.auto_focus) {
-            // autofocus: distance of the closest NODE along the centre ray (src/main.cpp:350-362)
-            hxr_ray r;
-            Ray cr;
-            {
-                hxr_camera c = m_scene.cam;
-                c.dof = 0;
-                cr = camera_ray(c, W, H, W * 0.5, H * 0.5, 0, 0, 0);
-            }
-            r.start[0] = cr.o.x; r.start[1] = cr.o.y; r.start[2] = cr.o.z;
-            r.dir[0] = cr.d.x; r.dir[1] = cr.d.y; r.dir[2] = cr.d.z;
-            r.depth = 0; r.flags = 0;
-            hxr_hit h;
-            // note: like raycast, this also sees lights; a light in front of the geometry hides it
-            if (traceClosest(&r, 1, &h) == HXR_OK && h.status == 0) m_scene.cam.focal_plane_dist = h.dist;
-        }
         const uint32_t nMine = (uint32_t)((spp - shardIndex + shardCount - 1) / shardCount);
         fp.sample_stride = (uint32_t)shardCount;
         if (nPix <= primaryBatch) {
             const uint32_t sppPass = std::max<uint32_t>(1, (uint32_t)(primaryBatch / nPix));
-            for (uint32_t k0 = 0; k0 < nMine && !ov; k0 += sppPass) {
+            for (uint32_t k0 = 0; k0 < nMine; k0 += sppPass) {
                 const uint32_t k = std::min(sppPass, nMine - k0);
                 fp.sample_base = (uint32_t)shardIndex + k0 * (uint32_t)shardCount;
                 const uint32_t items = (uint32_t)(nPix * k);
-                for (int e = 0; e < eyes && !ov; e++) {
+                for (int e = 0; e < eyes; e++) {
                     setEye(e);
-                    st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, 0, items, k, m_q[0], m_counters + C_Q0);
-                    ov = drain(fp, eyeBuf[e], items, st);
+                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, 0, items, k, queue(0));
+                    drain(fp, eyeBuf[e], items, st);
                 }
             }
         } else {
-            for (uint32_t k0 = 0; k0 < nMine && !ov; k0++) {
+            for (uint32_t k0 = 0; k0 < nMine; k0++) {
                 fp.sample_base = (uint32_t)shardIndex + k0 * (uint32_t)shardCount;
-                for (size_t first = 0; first < nPix && !ov; first += primaryBatch) {
+                for (size_t first = 0; first < nPix; first += primaryBatch) {
                     const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, nPix - first);
-                    for (int e = 0; e < eyes && !ov; e++) {
+                    for (int e = 0; e < eyes; e++) {
                         setEye(e);
-                        st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)first, items, 1, m_q[0], m_counters + C_Q0);
-                        ov = drain(fp, eyeBuf[e], items, st);
+                        st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, (uint32_t)first, items, 1, queue(0));
+                        drain(fp, eyeBuf[e], items, st);
                     }
                 }
             }
         }
         st.spp_done = nMine;
-        if (eyes == 2 && !ov) st.kernel_launches += dev::stereo_mix(m_accum, eyeBuf[0], eyeBuf[1], nPix);
-        if (shardCount == 1) st.kernel_launches += dev::scale_all(m_accum, nPix * 3, 1.0f / (float)spp);
+        if (eyes == 2) st.kernel_launches += dev::stereo_mix(m_dev, m_accum, eyeBuf[0], eyeBuf[1], nPix);
+        if (shardCount == 1) st.kernel_launches += dev::scale_all(m_dev, m_accum, nPix * 3, 1.0f / (float)spp);
     } else {
         // pass 1: one ray through every pixel corner. Row shards own rows y with (y/16) % count == index
         // and also render a one-row halo around each owned band so that pass 2 sees all 8 neighbours.
@@ -630,99 +704,105 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
         auto owned = [&](int y) { return shardCount == 1 || ((y / HXR_ROW_BAND) % shardCount) == shardIndex; };
         auto needed = [&](int y) { return owned(y) || (y > 0 && owned(y - 1)) || (y + 1 < H && owned(y + 1)); };
         int y = 0;
-        while (y < H && !ov) {
+        while (y < H) {
             if (!needed(y)) { y++; continue; }
             int y1 = y;
             while (y1 < H && needed(y1) && (size_t)(y1 - y + 1) * W <= std::max<size_t>(primaryBatch, W)) y1++;
             size_t first = (size_t)y * W, count = (size_t)(y1 - y) * W;
-            for (size_t off = 0; off < count && !ov; off += primaryBatch) {
+            for (size_t off = 0; off < count; off += primaryBatch) {
                 const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, count - off);
-                for (int e = 0; e < eyes && !ov; e++) {
+                for (int e = 0; e < eyes; e++) {
                     setEye(e);
-                    st.kernel_launches += dev::gen_primary(m_scene, fp, nullptr, (uint32_t)(first + off), items, 1, m_q[0], m_counters + C_Q0);
-                    ov = drain(fp, eyeBuf[e], items, st);
+                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, (uint32_t)(first + off), items, 1, queue(0));
+                    drain(fp, eyeBuf[e], items, st);
                 }
             }
             y = y1;
         }
-        if (eyes == 2 && !ov) st.kernel_launches += dev::stereo_mix(m_accum, eyeBuf[0], eyeBuf[1], nPix);  // what detectAApixels looks at
-        if (wantAA && !ov) {
+        if (eyes == 2) st.kernel_launches += dev::stereo_mix(m_dev, m_accum, eyeBuf[0], eyeBuf[1], nPix);  // what detectAApixels looks at
+        if (wantAA) {
             if (m_aaCap < nPix) {
-                dev::free_(m_aaList);
-                dev::free_(m_aaMask);
-                m_aaList = (uint32_t*)dev::alloc(nPix * sizeof(uint32_t));
-                m_aaMask = (uint8_t*)dev::alloc(nPix);
+                dev::free_(m_dev, m_aaList);
+                dev::free_(m_dev, m_aaMask);
+                m_aaList = (uint32_t*)dev::alloc(m_dev, nPix * sizeof(uint32_t));
+                m_aaMask = (uint8_t*)dev::alloc(m_dev, nPix);
                 m_aaCap = (m_aaList && m_aaMask) ? nPix : 0;
-                if (!m_aaCap) { m_scene.settings = savedSettings; dev::timer_destroy(tm); return fail(HXR_ERR_CUDA, "AA buffer allocation failed"); }
+                if (!m_aaCap) { m_scene.settings = savedSettings; dev::timer_destroy(m_dev, tm); return fail(HXR_ERR_CUDA, "AA buffer allocation failed"); }
             }
-            dev::set_u32(m_counters + C_AA, 0);
-            st.kernel_launches += dev::aa_detect(m_accum, W, H, shardIndex, shardCount, m_aaList, m_counters + C_AA, m_aaMask);
-            const uint32_t nAA = readCount(m_counters + C_AA);
+            dev::zero(m_dev, m_counters + C_AA, sizeof(uint32_t));
+            st.kernel_launches += dev::aa_detect(m_dev, m_accum, W, H, shardIndex, shardCount, m_aaList, m_counters + C_AA, m_aaMask);
+            const uint32_t nAA = readCount(m_counters + C_AA);  // the frame's one host read-back: sizes the second pass
             st.aa_pixels = nAA;
             fp.sample_base = 1;
             const uint32_t pixPerBatch = std::max<uint32_t>(1, primaryBatch / 4);
-            for (uint32_t first = 0; first < nAA && !ov; first += pixPerBatch) {
+            for (uint32_t first = 0; first < nAA; first += pixPerBatch) {
                 const uint32_t np = std::min(pixPerBatch, nAA - first);
-                for (int e = 0; e < eyes && !ov; e++) {
+                for (int e = 0; e < eyes; e++) {
                     setEye(e);
-                    st.kernel_launches += dev::gen_primary(m_scene, fp, m_aaList + first, 0, np * 4, 4, m_q[0], m_counters + C_Q0);
-                    ov = drain(fp, eyeBuf[e], np * 4, st);
+                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, m_aaList + first, nullptr, 0, np * 4, 4, queue(0));
+                    drain(fp, eyeBuf[e], np * 4, st);
                 }
             }
-            if (eyes == 2 && !ov) st.kernel_launches += dev::stereo_mix(m_accum, eyeBuf[0], eyeBuf[1], nPix);
-            st.kernel_launches += dev::scale_listed(m_accum, m_aaList, m_counters + C_AA, (uint32_t)nPix, 1.0f / 5);
+            if (eyes == 2) st.kernel_launches += dev::stereo_mix(m_dev, m_accum, eyeBuf[0], eyeBuf[1], nPix);
+            st.kernel_launches += dev::scale_listed(m_dev, m_accum, m_aaList, m_counters + C_AA, (uint32_t)nPix, 1.0f / 5);
         }
         if (shardCount > 1) {
             // drop the halo rows: the caller sums the shards
             for (int yy = 0; yy < H; yy++)
-                if (!owned(yy) && needed(yy)) dev::zero(m_accum + (size_t)yy * W * 3, (size_t)W * 3 * sizeof(float));
+                if (!owned(yy) && needed(yy)) dev::zero(m_dev, m_accum + (size_t)yy * W * 3, (size_t)W * 3 * sizeof(float));
         }
     }
-    dev::timer_stop(tm);
-    if (!ov) ov = readCount(m_counters + C_OVERFLOW) ? 1 : 0;
-    st.render_ms = dev::timer_ms(tm);
-    dev::timer_destroy(tm);
+    dev::timer_stop(m_dev, tm);
+    const bool ov = readCount(m_counters + C_OVERFLOW) != 0;
+    st.render_ms = dev::timer_ms(m_dev, tm);
+    dev::timer_destroy(m_dev, tm);
     m_scene.settings = savedSettings;
+    if (m_allocFailed) return HXR_ERR_CUDA;
+    if (dev::failed(m_dev)) return fail(HXR_ERR_CUDA, std::string("render failed: ") + dev::last_error(m_dev));
     if (ov) { overflow = true; return HXR_OK; }
 
     m_lastW = W;
     m_lastH = H;
     bool ok = true;
-    if (devOut) ok = ok && dev::copy_d2d(devOut, m_accum, nPix * 3 * sizeof(float));
-    if (hostOut) ok = ok && dev::download(hostOut, m_accum, nPix * 3 * sizeof(float));
-    if (!ok) return fail(HXR_ERR_CUDA, std::string("result copy failed: ") + dev::last_error());
+    if (devOut) ok = ok && dev::copy_d2d(m_dev, devOut, m_accum, nPix * 3 * sizeof(float));
+    if (hostOut) ok = ok && dev::download(m_dev, hostOut, m_accum, nPix * 3 * sizeof(float));
+    if (!ok) return fail(HXR_ERR_CUDA, std::string("result copy failed: ") + dev::last_error(m_dev));
     {
-        unsigned long long sh = 0;
+        dev::FrameTotals ft;
         TravCounters tc;
-        dev::download(&tc, m_trav, sizeof tc);
-        dev::download(&sh, shadowTotalPtr(m_trav), sizeof sh);
-        st.rays_shadow = sh;
+        dev::download(m_dev, &ft, m_totals, sizeof ft);
+        dev::download(m_dev, &tc, m_trav, sizeof tc);
+        st.rays_closest = ft.rays_closest;
+        st.rays_shadow = ft.rays_shadow;
+        st.cand_overflow = ft.cand_overflow;
         st.kd_inner = tc.kd_inner;
         st.kd_leaves = tc.kd_leaves;
         st.tri_tests = tc.tri_tests;
         st.mesh_queries = tc.mesh_queries;
         double ms[dev::PROF_NCAT];
         uint64_t ln[dev::PROF_NCAT];
-        dev::prof_collect(ms, ln);
-        st.trace_closest_ms = ms[dev::PROF_TRACE_CLOSEST];
-        st.trace_shadow_ms = ms[dev::PROF_TRACE_SHADOW];
+        dev::prof_collect(m_dev, ms, ln);
+        st.trace_closest_ms = ms[dev::PROF_WALK_CLOSEST];
+        st.trace_shadow_ms = ms[dev::PROF_WALK_SHADOW] + ms[dev::PROF_SHADOW_RESOLVE];
         st.shade_ms = ms[dev::PROF_SHADE];
-        st.other_ms = ms[dev::PROF_OTHER];
-        st.trace_closest_launches = ln[dev::PROF_TRACE_CLOSEST];
-        st.trace_shadow_launches = ln[dev::PROF_TRACE_SHADOW];
-        st.walk_ms = ms[dev::PROF_WALK];
-        st.walk_launches = ln[dev::PROF_WALK];
+        st.other_ms = ms[dev::PROF_OTHER] + ms[dev::PROF_GEN];
+        st.trace_closest_launches = ln[dev::PROF_WALK_CLOSEST];
+        st.trace_shadow_launches = ln[dev::PROF_WALK_SHADOW] + ln[dev::PROF_SHADOW_RESOLVE];
+        st.walk_ms = ms[dev::PROF_WALK_CLOSEST] + ms[dev::PROF_WALK_SHADOW];
+        st.walk_launches = ln[dev::PROF_WALK_CLOSEST] + ln[dev::PROF_WALK_SHADOW];
+        st.shadow_resolve_ms = ms[dev::PROF_SHADOW_RESOLVE];
+        st.gen_ms = ms[dev::PROF_GEN];
     }
     if (stats) *stats = st;
-    if (!dev::sync()) return fail(HXR_ERR_CUDA, dev::last_error());
+    if (!dev::sync(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
     return HXR_OK;
 }
 
 int Renderer::resolveDevice(void* d_rgb, int W, int H, int spp)
 {
     if (!d_rgb || W <= 0 || H <= 0 || spp <= 0) return fail(HXR_ERR_INVALID, "resolve: bad arguments");
-    dev::scale_all((float*)d_rgb, (size_t)W * H * 3, 1.0f / (float)spp);
-    if (!dev::sync()) return fail(HXR_ERR_CUDA, dev::last_error());
+    dev::scale_all(m_dev, (float*)d_rgb, (size_t)W * H * 3, 1.0f / (float)spp);
+    if (!dev::sync(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
     return HXR_OK;
 }
 
@@ -736,57 +816,66 @@ int Renderer::saveFrameBmp(const void* d_rgb, int W, int H, const char* path)
     if (!m_srgbLut) {
         uint8_t lut[4097];
         for (int i = 0; i <= 4096; i++) lut[i] = (uint8_t)host::convertTo8bit_sRGB(i / 4096.0f);
-        m_srgbLut = (uint8_t*)dev::alloc(sizeof lut);
-        if (!m_srgbLut || !dev::upload(m_srgbLut, lut, sizeof lut)) return fail(HXR_ERR_CUDA, dev::last_error());
+        m_srgbLut = (uint8_t*)dev::alloc(m_dev, sizeof lut);
+        if (!m_srgbLut || !dev::upload(m_dev, m_srgbLut, lut, sizeof lut)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
     }
     int rowsz = W * 3;
     if (rowsz % 4) rowsz += 4 - (rowsz % 4);
     const size_t bytes = (size_t)rowsz * H;
-    uint8_t* dout = (uint8_t*)dev::alloc(bytes);
-    if (!dout) return fail(HXR_ERR_CUDA, dev::last_error());
+    uint8_t* dout = (uint8_t*)dev::alloc(m_dev, bytes);
+    if (!dout) return fail(HXR_ERR_CUDA, "save_frame: out of device memory");
     std::vector<uint8_t> rows(bytes);
-    dev::to_bmp_rows((const float*)d_rgb, W, H, rowsz, m_srgbLut, dout);
-    const bool ok = dev::download(rows.data(), dout, bytes);
-    dev::free_(dout);
-    if (!ok) return fail(HXR_ERR_CUDA, dev::last_error());
+    dev::to_bmp_rows(m_dev, (const float*)d_rgb, W, H, rowsz, m_srgbLut, dout);
+    const bool ok = dev::download(m_dev, rows.data(), dout, bytes);
+    dev::free_(m_dev, dout);
+    if (!ok) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
     if (!host::writeBmpFile(path, W, H, rowsz, rows.data())) return fail(HXR_ERR_IO, std::string("cannot write ") + path);
     return HXR_OK;
 }
 
-// ------------------------------------------------------------------------------ test hooks
-static RayTask taskFromRay(const hxr_ray& r, uint32_t pixel)
+// The EXR screenshot (Bitmap::saveEXR, src/bitmap.cpp:270-288: HALF RGBA, alpha 1): float -> half on the GPU, two thirds of
+// the float frame's bytes cross PCIe; the file is byte-identical to hxr_save_image(".exr") of the same frame.
+int Renderer::saveFrameExr(const void* d_rgb, int W, int H, const char* path)
 {
-    RayTask t;
-    memset(&t, 0, sizeof t);
-    for (int k = 0; k < 3; k++) { t.o[k] = r.start[k]; t.d[k] = r.dir[k]; t.w[k] = 1.0f; }
-    t.pixel = pixel;
-    t.sample = 0;
-    t.stream = 1;
-    t.depth = r.depth;
-    t.flags = r.flags;
-    return t;
+    if (!path) return fail(HXR_ERR_INVALID, "save_frame: null path");
+    if (!d_rgb) { d_rgb = m_accum; W = m_lastW; H = m_lastH; }
+    if (!d_rgb || W <= 0 || H <= 0) return fail(HXR_ERR_INVALID, "save_frame: no frame");
+    const size_t halves = (size_t)W * H * 4;
+    uint16_t* dout = (uint16_t*)dev::alloc(m_dev, halves * sizeof(uint16_t));
+    if (!dout) return fail(HXR_ERR_CUDA, "save_frame: out of device memory");
+    std::vector<uint16_t> rows(halves);
+    dev::to_exr_rows(m_dev, (const float*)d_rgb, W, H, dout);
+    const bool ok = dev::download(m_dev, rows.data(), dout, halves * sizeof(uint16_t));
+    dev::free_(m_dev, dout);
+    if (!ok) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
+    if (!exr::save_half_rows(path, W, H, rows.data())) return fail(HXR_ERR_IO, std::string("cannot write ") + path);
+    return HXR_OK;
 }
 
+// ------------------------------------------------------------------------------ test hooks
 int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
 {
     if (!m_haveScene) return fail(HXR_ERR_INVALID, "trace: no scene");
     if (n && (!rays || !hits)) return fail(HXR_ERR_INVALID, "trace: null buffer");
     if (!ensureQueues()) return HXR_ERR_CUDA;
-    std::vector<RayTask> tasks;
+    if (!m_hits) m_hits = (HitRec*)dev::alloc(m_dev, (size_t)m_cap * sizeof(HitRec));
+    if (!m_hits) return fail(HXR_ERR_CUDA, "trace_closest: out of device memory");
+    dev::clear_error(m_dev);
     std::vector<HitRec> recs;
+    static_assert(sizeof(hxr_ray) <= sizeof(RayGeom), "the explicit rays are staged in the second ray queue");
     for (size_t first = 0; first < n; first += m_cap) {
         const uint32_t m = (uint32_t)std::min<size_t>(m_cap, n - first);
-        tasks.resize(m);
         recs.resize(m);
-        for (uint32_t i = 0; i < m; i++) tasks[i] = taskFromRay(rays[first + i], i);
-        dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
-        dev::set_u32(m_counters + C_Q0, m);
-        dev::set_u32(m_counters + C_OVERFLOW, 0);
+        hxr_ray* staged = (hxr_ray*)m_qg[1];
+        dev::upload(m_dev, staged, rays + first, (size_t)m * sizeof(hxr_ray));
         DScene full = m_scene;
         full.full_attr = 1;  // the hook reports u, v, dNdx, dNdy of every hit, whatever the node's shader reads
-        dev::trace_closest(full, m_q[0], m_counters + C_Q0, m_cap, m_hits, scratch(C_HEAD_A), nullptr, m);
-        if (!dev::download(recs.data(), m_hits, (size_t)m * sizeof(HitRec))) return fail(HXR_ERR_CUDA, dev::last_error());
-        if (readCount(m_counters + C_OVERFLOW)) return fail(HXR_ERR_OVERFLOW, "trace_closest: traversal scratch overflow; raise hxr_config.queue_capacity");
+        const RayQueue q = queue(0);
+        dev::setup_rays(m_dev, full, staged, m, q);
+        dev::zero(m_dev, m_counters + C_HEAD_A, sizeof(uint32_t));
+        dev::walk(m_dev, full, false, q.geom, q.count, q.cap, m_cand, m_counters + C_HEAD_A, nullptr, m);
+        dev::hit_records(m_dev, full, q, m_cand, m_hits, m);
+        if (!dev::download(m_dev, recs.data(), m_hits, (size_t)m * sizeof(HitRec)) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
         for (uint32_t i = 0; i < m; i++) {
             const HitRec& h = recs[i];
             hxr_hit& o = hits[first + i];
@@ -811,23 +900,21 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
     if (!m_haveScene) return fail(HXR_ERR_INVALID, "trace: no scene");
     if (n && (!seg || !out)) return fail(HXR_ERR_INVALID, "trace: null buffer");
     if (!ensureQueues()) return HXR_ERR_CUDA;
-    std::vector<ShadowTask> tasks;
-    std::vector<uint8_t> occ;
-    for (size_t first = 0; first < n; first += m_shadowCap) {
-        const uint32_t m = (uint32_t)std::min<size_t>(m_shadowCap, n - first);
-        tasks.resize(m);
-        occ.resize(m);
-        for (uint32_t i = 0; i < m; i++) {
-            memset(&tasks[i], 0, sizeof(ShadowTask));
-            for (int k = 0; k < 3; k++) { tasks[i].a[k] = seg[(first + i) * 6 + k]; tasks[i].b[k] = seg[(first + i) * 6 + 3 + k]; }
-        }
-        dev::upload(m_shadow, tasks.data(), (size_t)m * sizeof(ShadowTask));
-        dev::set_u32(m_counters + C_SHADOW, m);
-        dev::set_u32(m_counters + C_OVERFLOW, 0);
-        dev::trace_shadow(m_scene, m_shadow, m_counters + C_SHADOW, m_shadowCap, nullptr, scratch(C_HEAD_B), nullptr, nullptr, m);
-        if (!dev::download(occ.data(), m_occluded, m)) return fail(HXR_ERR_CUDA, dev::last_error());
-        if (readCount(m_counters + C_OVERFLOW)) return fail(HXR_ERR_OVERFLOW, "trace_visible: traversal scratch overflow; raise hxr_config.queue_capacity");
-        for (uint32_t i = 0; i < m; i++) out[first + i] = occ[i] ? 0 : 1;
+    if (!m_visible) m_visible = (uint8_t*)dev::alloc(m_dev, (size_t)m_shadowCap);
+    if (!m_visible) return fail(HXR_ERR_CUDA, "trace_visible: out of device memory");
+    dev::clear_error(m_dev);
+    static_assert(6 * sizeof(double) <= sizeof(RayGeom), "the explicit segments are staged in a ray queue");
+    const uint32_t batchCap = std::min(m_shadowCap, m_cap);
+    for (size_t first = 0; first < n; first += batchCap) {
+        const uint32_t m = (uint32_t)std::min<size_t>(batchCap, n - first);
+        double* staged = (double*)m_qg[1];
+        dev::upload(m_dev, staged, seg + first * 6, (size_t)m * 6 * sizeof(double));
+        const ShadowQueue q = shadowQueue();
+        dev::setup_segments(m_dev, m_scene, staged, m, q);
+        dev::zero(m_dev, m_counters + C_HEAD_B, sizeof(uint32_t));
+        dev::walk(m_dev, m_scene, true, q.geom, q.count, q.cap, m_cand, m_counters + C_HEAD_B, nullptr, m);
+        dev::resolve_shadow(m_dev, m_scene, q, m_cand, nullptr, m_visible, nullptr, nullptr, m);
+        if (!dev::download(m_dev, out + first, m_visible, m) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
     }
     return HXR_OK;
 }
@@ -838,31 +925,33 @@ int Renderer::traceColor(const hxr_ray* rays, size_t n, float* rgb)
     if (n && (!rays || !rgb)) return fail(HXR_ERR_INVALID, "trace: null buffer");
     if (!ensureQueues()) return HXR_ERR_CUDA;
     const uint32_t batch = std::max<uint32_t>(1024, m_cap / 8);
-    float* acc = (float*)dev::alloc((size_t)batch * 3 * sizeof(float));
-    if (!acc) return fail(HXR_ERR_CUDA, dev::last_error());
+    float* acc = (float*)dev::alloc(m_dev, (size_t)batch * 3 * sizeof(float));
+    if (!acc) return fail(HXR_ERR_CUDA, "trace_color: out of device memory");
+    dev::clear_error(m_dev);
     FrameParams fp;
     memset(&fp, 0, sizeof fp);
     fp.W = (int)batch;
     fp.H = 1;
     fp.max_depth = m_scene.settings.max_trace_depth;
     fp.sample_stride = 1;
-    std::vector<RayTask> tasks;
     hxr_stats st;
     memset(&st, 0, sizeof st);
     int rc = HXR_OK;
     m_countTraversal = false;
-    dev::set_u32(m_counters + C_OVERFLOW, 0);
+    m_allocFailed = false;
+    dev::zero(m_dev, m_counters + C_OVERFLOW, sizeof(uint32_t));
     for (size_t first = 0; first < n && rc == HXR_OK; first += batch) {
         const uint32_t m = (uint32_t)std::min<size_t>(batch, n - first);
-        tasks.resize(m);
-        for (uint32_t i = 0; i < m; i++) tasks[i] = taskFromRay(rays[first + i], i);
-        dev::zero(acc, (size_t)batch * 3 * sizeof(float));
-        dev::upload(m_q[0], tasks.data(), (size_t)m * sizeof(RayTask));
-        dev::set_u32(m_counters + C_Q0, m);
-        if (drain(fp, acc, m, st) || readCount(m_counters + C_OVERFLOW)) rc = fail(HXR_ERR_OVERFLOW, "trace_color: queue overflow");
-        else if (!dev::download(rgb + first * 3, acc, (size_t)m * 3 * sizeof(float))) rc = fail(HXR_ERR_CUDA, dev::last_error());
+        dev::zero(m_dev, acc, (size_t)batch * 3 * sizeof(float));
+        hxr_ray* staged = (hxr_ray*)m_qg[1];
+        dev::upload(m_dev, staged, rays + first, (size_t)m * sizeof(hxr_ray));
+        dev::setup_rays(m_dev, m_scene, staged, m, queue(0));  // pixel = index in the batch, weight 1
+        drain(fp, acc, m, st);
+        if (m_allocFailed) rc = HXR_ERR_CUDA;
+        else if (readCount(m_counters + C_OVERFLOW)) rc = fail(HXR_ERR_OVERFLOW, "trace_color: queue overflow");
+        else if (!dev::download(m_dev, rgb + first * 3, acc, (size_t)m * 3 * sizeof(float)) || dev::failed(m_dev)) rc = fail(HXR_ERR_CUDA, dev::last_error(m_dev));
     }
-    dev::free_(acc);
+    dev::free_(m_dev, acc);
     return rc;
 }
 

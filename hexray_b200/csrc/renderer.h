@@ -1,4 +1,4 @@
-// renderer.h — host-side frame driver of the wavefront renderer (one context = one GPU).
+// renderer.h — host-side frame driver of the wavefront renderer (one Renderer = one GPU; multi.h drives several).
 // Replaces the reference's frame driver (render / renderWithoutMonteCarlo / renderWithMonteCarlo,
 // src/main.cpp:253-426) and its thread pool (src/threading.cpp): the per-pixel loops become
 // kernel launches over ray queues, the bucket cursor becomes the queues' atomic heads.
@@ -10,58 +10,83 @@
 
 namespace hxr {
 
+// the host-side product of hxr_upload_scene that does not depend on the device: per mesh, the KD-tree and the flattened
+// triangle records. Built once and shared by every device of a multi-GPU context (the tree is never built twice).
+struct MeshTables {
+    host::KdTree kd;
+    std::vector<TriTest> tt;
+    std::vector<TriAttr> ta;
+    std::vector<TriAttrUv> tu;
+    std::vector<TriF32> tf;
+    std::vector<TriPacked> tp;  // empty: the scene walks tri_f32
+};
+struct SceneTables {
+    std::vector<MeshTables> meshes;
+    double build_ms = 0;
+};
+// validates the scene and builds its host tables (KD-trees with all host threads); false + why on an invalid scene
+bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& out, std::string& why);
+
 class Renderer {
 public:
     ~Renderer();
-    int create(const hxr_config& cfg);
-    int uploadScene(const hxr_scene* sc);
+    int create(const hxr_config& cfg, int device);
+    int uploadScene(const hxr_scene* sc);                          // builds the tables itself
+    int uploadScene(const hxr_scene& sc, const SceneTables& tab);  // tables built by the caller (shared across devices)
     int setCamera(const hxr_camera* cam);
     int render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats);
     int resolveDevice(void* d_rgb, int W, int H, int spp);
     int saveFrameBmp(const void* d_rgb, int W, int H, const char* path);
+    int saveFrameExr(const void* d_rgb, int W, int H, const char* path);
     int traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits);
     int traceVisible(const double* seg, size_t n, uint8_t* out);
     int traceColor(const hxr_ray* rays, size_t n, float* rgb);
     int accelInfo(int mesh, hxr_accel_info* out) const;
+    void setProfiling(bool on) { if (m_dev) dev::prof_enable(m_dev, on); }
     const std::string& error() const { return m_err; }
+    dev::Context* device() const { return m_dev; }
+    float* frame() const { return m_accum; }  // the frame of the last render (device memory, W*H*3 floats)
+    int frameWidth() const { return m_lastW; }
+    int frameHeight() const { return m_lastH; }
 
 private:
     int fail(int code, const std::string& msg) { m_err = msg; return code; }
     bool ensureQueues();
+    void freeQueues();
     void freeScene();
     void* keep(void* p) { if (p) m_sceneAllocs.push_back(p); return p; }
     template <class T> T* uploadArray(const T* src, size_t n);
-    // run the wavefront until the current queue drains; `gi` selects the integrator
-    int drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st);
+    // run the wavefront on the rays in queue 0 until the ray tree is exhausted (no host read-back between bounces)
+    void drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st);
     int renderOnce(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, uint32_t primaryBatch, bool& overflow);
     uint32_t readCount(const uint32_t* dptr);
+    RayQueue queue(int i) const;
+    ShadowQueue shadowQueue() const;
 
     std::string m_err;
     hxr_config m_cfg{};
-    bool m_created = false, m_haveScene = false, m_haveCamera = false;
+    dev::Context* m_dev = nullptr;
+    bool m_haveScene = false, m_haveCamera = false;
     DScene m_scene{};
     std::vector<void*> m_sceneAllocs;
     std::vector<hxr_accel_info> m_accel;
     int m_maxShadowPerHit = 1, m_maxChildrenPerHit = 1;
 
-    // queues
+    // queues: two ray queues (ping-pong per bounce), one shadow queue, one candidate buffer shared by both walks
     uint32_t m_cap = 0, m_shadowCap = 0;
-    RayTask* m_q[2] = {nullptr, nullptr};
-    HitRec* m_hits = nullptr;
-    ShadowTask* m_shadow = nullptr;
-    uint32_t* m_counters = nullptr;  // [0],[1] queue counts, [2] shadow count, [3] overflow, [4] work head A, [5] work head B, [6] aa count
+    RayGeom* m_qg[2] = {nullptr, nullptr};
+    RayAux* m_qa[2] = {nullptr, nullptr};
+    RayGeom* m_sg = nullptr;
+    ShadowAux* m_sa = nullptr;
+    CandRec* m_cand = nullptr;
+    CandRec* m_scand = nullptr;      // shadow candidates of levels shaded in chunks (allocated on first use)
+    bool m_allocFailed = false;
+    HitRec* m_hits = nullptr;        // test hook only, allocated on first use
+    uint8_t* m_visible = nullptr;    // test hook only
+    uint32_t* m_counters = nullptr;  // see renderer.cpp (C_*)
+    dev::FrameTotals* m_totals = nullptr;
     TravCounters* m_trav = nullptr;
-    // traversal scratch (device/pipeline.h: TraceScratch)
-    RayPre* m_pre = nullptr;
-    WalkTask* m_tasks = nullptr;
-    PairRec* m_pairs = nullptr;
-    double* m_pairGamma = nullptr;
-    uint32_t m_pairCap = 0;
-    MeshRes* m_res = nullptr;
-    uint8_t* m_occluded = nullptr;
-    uint32_t m_taskCap = 0;
     int m_nBig = 0;
-    TraceScratch scratch(uint32_t headCounter) const;
     uint32_t* m_aaList = nullptr;
     uint8_t* m_aaMask = nullptr;
     float* m_accum = nullptr;

@@ -259,12 +259,15 @@ typedef struct hxr_stats {
     uint64_t kd_inner, kd_leaves, tri_tests, mesh_queries; /* only with HXR_RENDER_COUNT_TRAVERSAL */
     uint64_t kernel_launches;
     double render_ms;       /* CUDA-event time of the whole render on the context's stream */
+    /* with profiling on: closest-hit walk / shadow walk + shadow resolve / shade (exact tests + shading + emission) / the rest */
     double trace_closest_ms, trace_shadow_ms, shade_ms, other_ms;
     uint64_t trace_closest_launches, trace_shadow_launches;
     uint32_t spp_done;
     uint32_t aa_pixels;
-    double walk_ms;         /* device time of the KD-walk kernel launches alone (inside the two trace times above) */
+    double walk_ms;         /* device time of the KD-walk kernel launches (closest-hit + shadow) */
     uint64_t walk_launches;
+    uint64_t cand_overflow; /* rays whose walk left more candidates than a record holds (redone with the exact double walk) */
+    double shadow_resolve_ms, gen_ms; /* with profiling on: the shadow-resolve and primary-ray kernels */
 } hxr_stats;
 
 typedef struct hxr_ray {
@@ -362,6 +365,8 @@ int hxr_save_image(const char* path, const float* rgb, int32_t width, int32_t he
  * context's device, or NULL for the frame of the last hxr_render / hxr_render_device call (then width/height are ignored).
  * The file is byte-identical to hxr_save_image(".bmp") of the same frame. */
 int hxr_save_frame_bmp(hxr_ctx* ctx, const void* d_rgb, int32_t width, int32_t height, const char* path);
+/* the same for Bitmap::saveEXR (src/bitmap.cpp:270-288): float -> half on the GPU; byte-identical to hxr_save_image(".exr") */
+int hxr_save_frame_exr(hxr_ctx* ctx, const void* d_rgb, int32_t width, int32_t height, const char* path);
 
 /* Bitmap::loadImage equivalent (".bmp" 8/24/32 bpp, ".exr" scan-line NONE/RLE/ZIPS/ZIP/PIZ): fills *width / *height;
  * when rgb_out is non-NULL and capacity_floats >= width*height*3 also the pixels (float RGB, top-down). */

@@ -7,6 +7,7 @@
 // in libhexray_b200.so fails with HXR_ERR_NO_DEVICE when CUDA is unavailable.
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -16,13 +17,16 @@
 namespace hxr {
 namespace dev {
 
-static int g_threads = 8;
-static uint64_t g_launches[PROF_NCAT];
+struct Context {
+    int device = 0;
+    int threads = 8;
+    uint64_t launches[PROF_NCAT] = {};
+};
 
-template <class F> static void parallel_for(uint32_t n, F f)
+template <class F> static void parallel_for(Context* c, uint32_t n, F f, bool serial = false)
 {
     if (n == 0) return;
-    const int nt = (int)std::min<uint32_t>((uint32_t)g_threads, (n + 63) / 64);
+    const int nt = serial ? 1 : (int)std::min<uint32_t>((uint32_t)c->threads, (n + 63) / 64);
     if (nt <= 1) { for (uint32_t i = 0; i < n; i++) f(i); return; }
     std::atomic<uint32_t> next{0};
     std::vector<std::thread> th;
@@ -38,115 +42,178 @@ template <class F> static void parallel_for(uint32_t n, F f)
     for (auto& x : th) x.join();
 }
 
-bool init(int, char*, size_t)
+int device_count() { return getenv("HXR_EMU_DEVICES") ? std::max(1, atoi(getenv("HXR_EMU_DEVICES"))) : 2; }
+Context* create(int device, char* err, size_t errlen)
 {
+    if (device < 0 || device >= device_count()) { snprintf(err, errlen, "device ordinal out of range"); return nullptr; }
+    Context* c = new Context;
+    c->device = device;
     unsigned hc = std::thread::hardware_concurrency();
-    g_threads = hc ? (int)hc : 4;
-    if (const char* e = getenv("HXR_EMU_THREADS")) g_threads = std::max(1, atoi(e));
-    return true;
+    c->threads = hc ? (int)hc : 4;
+    if (const char* e = getenv("HXR_EMU_THREADS")) c->threads = std::max(1, atoi(e));
+    return c;
 }
+void destroy(Context* c) { delete c; }
+int device_of(const Context* c) { return c->device; }
+void* stream_of(const Context*) { return nullptr; }
 const char* backend_name() { return "host-emulation (tests only)"; }
-void* alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
-void free_(void* p) { free(p); }
-bool upload(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
-bool download(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
-bool upload_pinned_async(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
-bool zero(void* p, size_t n) { memset(p, 0, n); return true; }
-bool copy_d2d(void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
-bool sync() { return true; }
-const char* last_error() { return ""; }
-bool set_u32(uint32_t* p, uint32_t v) { *p = v; return true; }
+void* alloc(Context*, size_t bytes) { return calloc(1, bytes ? bytes : 1); }
+void free_(Context*, void* p) { free(p); }
+void* alloc_pinned(Context*, size_t bytes) { return calloc(1, bytes ? bytes : 1); }
+void free_pinned(Context*, void* p) { free(p); }
+bool upload(Context*, void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
+bool download(Context*, void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
+bool download_async(Context*, void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
+bool zero(Context*, void* p, size_t n) { memset(p, 0, n); return true; }
+bool copy_d2d(Context*, void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
+bool sync(Context*) { return true; }
+const char* last_error(const Context*) { return ""; }
+bool failed(const Context*) { return false; }
+void clear_error(Context*) {}
 
 struct Timer { std::chrono::steady_clock::time_point a, b; };
-Timer* timer_create() { return new Timer; }
-void timer_destroy(Timer* t) { delete t; }
-void timer_start(Timer* t) { t->a = std::chrono::steady_clock::now(); }
-void timer_stop(Timer* t) { t->b = std::chrono::steady_clock::now(); }
-double timer_ms(Timer* t) { return std::chrono::duration<double, std::milli>(t->b - t->a).count(); }
+Timer* timer_create(Context*) { return new Timer; }
+void timer_destroy(Context*, Timer* t) { delete t; }
+void timer_start(Context*, Timer* t) { t->a = std::chrono::steady_clock::now(); }
+void timer_stop(Context*, Timer* t) { t->b = std::chrono::steady_clock::now(); }
+double timer_ms(Context*, Timer* t) { return std::chrono::duration<double, std::milli>(t->b - t->a).count(); }
 
-void prof_enable(bool) {}
-void prof_reset() { memset(g_launches, 0, sizeof g_launches); }
-void prof_collect(double ms[PROF_NCAT], uint64_t launches[PROF_NCAT])
+void prof_enable(Context*, bool) {}
+void prof_reset(Context* c) { memset(c->launches, 0, sizeof c->launches); }
+void prof_collect(Context* c, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT])
 {
-    for (int i = 0; i < PROF_NCAT; i++) { ms[i] = 0; launches[i] = g_launches[i]; }
+    for (int i = 0; i < PROF_NCAT; i++) { ms[i] = 0; launches[i] = c->launches[i]; }
 }
 
-int gen_primary(const DScene& sc, const FrameParams& fp, const uint32_t* pixels, uint32_t first_pixel, uint32_t n_items,
-                uint32_t spp_pass, RayTask* q, uint32_t* q_count)
+int gen_primary(Context* c, const DScene& sc, const FrameParams& fp, const uint32_t* pixels, const uint32_t* pixels_count, uint32_t first_pixel,
+                uint32_t n_items, uint32_t spp_pass, const RayQueue& q)
 {
-    parallel_for(n_items, [&](uint32_t i) {
+    if (pixels_count) n_items = std::min(n_items, *pixels_count * spp_pass);
+    parallel_for(c, n_items, [&](uint32_t i) {
         const uint32_t pi = i / spp_pass;
         const uint32_t pixel = pixels ? pixels[pi] : first_pixel + pi;
-        q[i] = gen_primary_item(sc, fp, pixel, fp.sample_base + (i % spp_pass) * fp.sample_stride);
+        const uint32_t sample = fp.sample_base + (i % spp_pass) * fp.sample_stride;
+        if (sc.simple_inline) gen_primary_item<true>(sc, fp, pixel, sample, q.geom, q.aux, i);
+        else gen_primary_item<false>(sc, fp, pixel, sample, q.geom, q.aux, i);
     });
-    *q_count = n_items;
-    g_launches[PROF_OTHER]++;
+    *q.count = n_items;
+    c->launches[PROF_GEN]++;
     return 1;
 }
 
-int trace_closest(const DScene& sc, const RayTask* q, const uint32_t* q_count, uint32_t, HitRec* hits, const TraceScratch& ts, TravCounters* cnt, uint32_t)
+int setup_rays(Context* c, const DScene& sc, const hxr_ray* rays, uint32_t n, const RayQueue& q)
 {
-    const uint32_t n = *q_count;
-    *ts.task_count = 0;
-    *ts.pair_count = 0;
-    auto stage = [&](uint32_t m, auto f) {
-        if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
-    };
-    const bool simple = sc.simple_inline && !cnt;
-    if (cnt) stage(n, [&](uint32_t i) { setup_closest_item<true, false>(sc, task_ray(q[i]), i, ts, cnt); });
-    else if (simple) stage(n, [&](uint32_t i) { setup_closest_item<false, true>(sc, task_ray(q[i]), i, ts, nullptr); });
-    else stage(n, [&](uint32_t i) { setup_closest_item<false, false>(sc, task_ray(q[i]), i, ts, nullptr); });
-    const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
-    if (cnt) stage(nt, [&](uint32_t k) { walk_item<false, true>(sc, k, ts, cnt); });
-    else stage(nt, [&](uint32_t k) { walk_item<false, false>(sc, k, ts, nullptr); });
-    const uint32_t np = std::min(*ts.pair_count, ts.pair_cap);
-    stage(np, [&](uint32_t i) { confirm_closest_a_item(sc, q, i, ts); });
-    stage(np, [&](uint32_t i) { confirm_closest_b_item(sc, i, ts); });
-    if (cnt) stage(n, [&](uint32_t i) { finalize_closest_item<true, false>(sc, task_ray(q[i]), i, ts, hits[i], cnt); });
-    else if (simple) stage(n, [&](uint32_t i) { finalize_closest_item<false, true>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
-    else stage(n, [&](uint32_t i) { finalize_closest_item<false, false>(sc, task_ray(q[i]), i, ts, hits[i], nullptr); });
-    g_launches[PROF_TRACE_CLOSEST] += 5;
-    return 5;
-}
-
-int shade(const DScene& sc, const FrameParams& fp, const RayTask* q, const uint32_t* q_count, const HitRec* hits, uint32_t begin,
-          uint32_t end, const Sinks& sinks)
-{
-    const uint32_t e = std::min(end, *q_count);
-    if (e > begin)
-        parallel_for(e - begin, [&](uint32_t k) {
-            const uint32_t i = begin + k;
-            if (fp.gi) shade_gi_item(sc, fp, q[i], hits[i], sinks);
-            else shade_whitted_item(sc, fp, q[i], hits[i], sinks);
-        });
-    g_launches[PROF_SHADE]++;
+    parallel_for(c, n, [&](uint32_t i) {
+        const hxr_ray r = rays[i];
+        Ray ray;
+        ray.o = ld3(r.start);
+        ray.d = ld3(r.dir);
+        ray.depth = r.depth;
+        ray.flags = r.flags;
+        place_ray<false, false>(sc, q.geom, q.aux, i, ray, mkc(1, 1, 1), i, 0u, 1u, nullptr);
+    });
+    *q.count = n;
+    c->launches[PROF_OTHER]++;
     return 1;
 }
 
-int trace_shadow(const DScene& sc, const ShadowTask* shadow, const uint32_t* count, uint32_t cap, float* accum, const TraceScratch& ts,
-                 TravCounters* cnt, unsigned long long* total, uint32_t)
+int setup_segments(Context* c, const DScene& sc, const double* seg, uint32_t n, const ShadowQueue& q)
 {
+    parallel_for(c, n, [&](uint32_t i) {
+        double D;
+        const Ray ray = shadow_ray(ld3(seg + 6 * (size_t)i), ld3(seg + 6 * (size_t)i + 3), D);
+        q.geom[i] = shadow_geom(ray, D, inline_blocked<false, false>(sc, ray, D, nullptr));
+        ShadowAux a;
+        a.c[0] = a.c[1] = a.c[2] = 0;
+        a.pixel = i;
+        q.aux[i] = a;
+    });
+    *q.count = n;
+    c->launches[PROF_OTHER]++;
+    return 1;
+}
+
+int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t*,
+         TravCounters* cnt, uint32_t)
+{
+    if (sc.n_big == 0) return 0;
     const uint32_t n = std::min(*count, cap);
-    *ts.task_count = 0;
-    *ts.pair_count = 0;
-    auto stage = [&](uint32_t m, auto f) {
-        if (cnt) { for (uint32_t i = 0; i < m; i++) f(i); } else parallel_for(m, f);
-    };
-    if (cnt) stage(n, [&](uint32_t i) { setup_shadow_item<true, false>(sc, shadow[i], i, ts, cnt); });
-    else if (sc.simple_inline) stage(n, [&](uint32_t i) { setup_shadow_item<false, true>(sc, shadow[i], i, ts, nullptr); });
-    else stage(n, [&](uint32_t i) { setup_shadow_item<false, false>(sc, shadow[i], i, ts, nullptr); });
-    const uint32_t nt = std::min(*ts.task_count, ts.task_cap);
-    if (cnt) stage(nt, [&](uint32_t k) { walk_item<true, true>(sc, k, ts, cnt); });
-    else stage(nt, [&](uint32_t k) { walk_item<true, false>(sc, k, ts, nullptr); });
-    const uint32_t np = std::min(*ts.pair_count, ts.pair_cap);
-    stage(np, [&](uint32_t i) { confirm_shadow_item(sc, shadow, i, ts); });
-    if (accum) stage(n, [&](uint32_t i) { accumulate_shadow_item(shadow[i], i, ts, accum); });
-    if (total) *total += n;
-    g_launches[PROF_TRACE_SHADOW] += 4;
-    return 4;
+    parallel_for(c, n, [&](uint32_t i) {
+        if (shadow) cand[i] = cnt ? walk_ray_item<true, true>(sc, geom[i], cnt) : walk_ray_item<true, false>(sc, geom[i], nullptr);
+        else cand[i] = cnt ? walk_ray_item<false, true>(sc, geom[i], cnt) : walk_ray_item<false, false>(sc, geom[i], nullptr);
+    }, cnt != nullptr);
+    c->launches[shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST]++;
+    return 1;
 }
 
-int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
+static std::atomic<unsigned long long>* as_atomic(unsigned long long* p) { return reinterpret_cast<std::atomic<unsigned long long>*>(p); }
+
+int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,
+          FrameTotals* totals, TravCounters* cnt)
+{
+    const uint32_t e = std::min(end, std::min(*q.count, q.cap));
+    if (e > begin) {
+        parallel_for(c, e - begin, [&](uint32_t k) {
+            const uint32_t i = begin + k;
+            EmitCounters ec = {0, 0};
+            CandRec cr;
+            cr.tri[0] = cr.tri[1] = cr.tri[2] = 0;
+            cr.meta = 0;
+            if (sc.n_big) cr = cand[i];
+            if (fp.gi) {
+                if (cnt) shade_item<true, true, false>(sc, fp, q.geom[i], q.aux[i], cr, sinks, ec, cnt);
+                else if (sc.simple_inline) shade_item<true, false, true>(sc, fp, q.geom[i], q.aux[i], cr, sinks, ec, nullptr);
+                else shade_item<true, false, false>(sc, fp, q.geom[i], q.aux[i], cr, sinks, ec, nullptr);
+            } else {
+                if (cnt) shade_item<false, true, false>(sc, fp, q.geom[i], q.aux[i], cr, sinks, ec, cnt);
+                else if (sc.simple_inline) shade_item<false, false, true>(sc, fp, q.geom[i], q.aux[i], cr, sinks, ec, nullptr);
+                else shade_item<false, false, false>(sc, fp, q.geom[i], q.aux[i], cr, sinks, ec, nullptr);
+            }
+            if (totals) {
+                if (ec.shadow_rays) as_atomic(&totals->rays_shadow)->fetch_add(ec.shadow_rays);
+                if (ec.cand_overflow) as_atomic(&totals->cand_overflow)->fetch_add(ec.cand_overflow);
+            }
+        }, cnt != nullptr);
+        if (totals) totals->rays_closest += e - begin;
+    }
+    c->launches[PROF_SHADE]++;
+    return 1;
+}
+
+int resolve_shadow(Context* c, const DScene& sc, const ShadowQueue& q, const CandRec* cand, float* accum, uint8_t* visible, FrameTotals* totals,
+                   TravCounters* cnt, uint32_t)
+{
+    const uint32_t n = std::min(*q.count, q.cap);
+    parallel_for(c, n, [&](uint32_t i) {
+        EmitCounters ec = {0, 0};
+        CandRec cr;
+        cr.tri[0] = cr.tri[1] = cr.tri[2] = 0;
+        cr.meta = 0;
+        if (sc.n_big) cr = cand[i];
+        if (visible) visible[i] = (cnt ? resolve_visible<true>(sc, q.geom + i, cr, ec, cnt) : resolve_visible<false>(sc, q.geom + i, cr, ec, nullptr)) ? 1 : 0;
+        else if (cnt) resolve_shadow_item<true>(sc, q.geom + i, q.aux + i, cr, accum, ec, cnt);
+        else resolve_shadow_item<false>(sc, q.geom + i, q.aux + i, cr, accum, ec, nullptr);
+        if (totals && ec.cand_overflow) as_atomic(&totals->cand_overflow)->fetch_add(ec.cand_overflow);
+    }, cnt != nullptr);
+    c->launches[PROF_SHADOW_RESOLVE]++;
+    return 1;
+}
+
+int hit_records(Context* c, const DScene& sc, const RayQueue& q, const CandRec* cand, HitRec* hits, uint32_t)
+{
+    const uint32_t n = std::min(*q.count, q.cap);
+    parallel_for(c, n, [&](uint32_t i) {
+        CandRec cr;
+        cr.tri[0] = cr.tri[1] = cr.tri[2] = 0;
+        cr.meta = 0;
+        if (sc.n_big) cr = cand[i];
+        hit_record_item<false, false>(sc, q.geom[i], cr, hits[i], nullptr);
+    });
+    c->launches[PROF_OTHER]++;
+    return 1;
+}
+
+int aa_detect(Context* c, const float* vfb, int W, int H, int shard_index, int shard_count, uint32_t* list, uint32_t* n_out, uint8_t* mask)
 {
     uint32_t n = 0;
     for (int y = 0; y < H; y++) {
@@ -158,42 +225,49 @@ int aa_detect(const float* vfb, int W, int H, int shard_index, int shard_count, 
         }
     }
     *n_out = n;
-    g_launches[PROF_OTHER]++;
+    c->launches[PROF_OTHER]++;
     return 1;
 }
 
-int scale_listed(float* vfb, const uint32_t* list, const uint32_t* n, uint32_t cap, float mul)
+int scale_listed(Context* c, float* vfb, const uint32_t* list, const uint32_t* n, uint32_t cap, float mul)
 {
     const uint32_t m = std::min(*n, cap);
     for (uint32_t i = 0; i < m; i++)
-        for (int c = 0; c < 3; c++) vfb[3 * (size_t)list[i] + c] *= mul;
-    g_launches[PROF_OTHER]++;
+        for (int k = 0; k < 3; k++) vfb[3 * (size_t)list[i] + k] *= mul;
+    c->launches[PROF_OTHER]++;
     return 1;
 }
-int scale_all(float* buf, size_t n, float mul)
+int scale_all(Context* c, float* buf, size_t n, float mul)
 {
     for (size_t i = 0; i < n; i++) buf[i] *= mul;
-    g_launches[PROF_OTHER]++;
+    c->launches[PROF_OTHER]++;
     return 1;
 }
-int add_into(float* dst, const float* src, size_t n)
+int add_into(Context* c, float* dst, const float* src, size_t n)
 {
     for (size_t i = 0; i < n; i++) dst[i] += src[i];
-    g_launches[PROF_OTHER]++;
+    c->launches[PROF_OTHER]++;
     return 1;
 }
-int to_bmp_rows(const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out)
+int to_bmp_rows(Context* c, const float* rgb, int W, int H, int rowsz, const uint8_t* lut, uint8_t* out)
 {
     memset(out, 0, (size_t)rowsz * H);
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) bmp_pixel_item(rgb, W, H, rowsz, lut, out, x, y);
-    g_launches[PROF_OTHER]++;
+    c->launches[PROF_OTHER]++;
     return 1;
 }
-int stereo_mix(float* out, const float* left, const float* right, size_t n_pixels)
+int to_exr_rows(Context* c, const float* rgb, int W, int H, uint16_t* out)
+{
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) exr_pixel_item(rgb, W, out, x, y);
+    c->launches[PROF_OTHER]++;
+    return 1;
+}
+int stereo_mix(Context* c, float* out, const float* left, const float* right, size_t n_pixels)
 {
     for (size_t i = 0; i < n_pixels; i++) stereo_mix_item(out, left, right, i);
-    g_launches[PROF_OTHER]++;
+    c->launches[PROF_OTHER]++;
     return 1;
 }
 }  // namespace dev
