@@ -32,7 +32,20 @@ def _all_inputs():
     return inputs
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: A/B builds of the kernels with other compile-time knobs (tools/build_variants.sh), e.g.
+    build(out="build_ab/gi3.so", defines=["HXR_SHADE_GI_BLOCKS=3"]); objects of a variant build go to a private directory."""
+    global OUT, OBJ
+    if out is not None:
+        saved = (OUT, OBJ)
+        OUT, OBJ = os.path.abspath(out), os.path.abspath(out) + ".obj"
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        try:
+            NVCC_FLAGS.extend("-D" + d for d in defines)
+            return build(force=True, verbose=verbose)
+        finally:
+            del NVCC_FLAGS[len(NVCC_FLAGS) - len(defines):]
+            OUT, OBJ = saved
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest(_all_inputs()):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -68,4 +81,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--out" in sys.argv:  # python -m hexray_b200.build --out build_ab/x.so -DNAME=VALUE ...
+        print(build(out=sys.argv[sys.argv.index("--out") + 1], defines=[a[2:] for a in sys.argv if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -47,7 +47,7 @@ void timer_stop(Context*, Timer*);
 double timer_ms(Context*, Timer*);     // blocks until the stop event has happened
 
 // per-category device time of the launches below (CUDA events around every launch when enabled)
-enum ProfCat { PROF_WALK_CLOSEST = 0, PROF_WALK_SHADOW = 1, PROF_SHADE = 2, PROF_SHADOW_RESOLVE = 3, PROF_GEN = 4, PROF_OTHER = 5, PROF_NCAT = 6 };
+enum ProfCat { PROF_WALK_CLOSEST = 0, PROF_WALK_SHADOW = 1, PROF_SHADE = 2, PROF_SHADOW_RESOLVE = 3, PROF_GEN = 4, PROF_OTHER = 5, PROF_SETUP = 6, PROF_NCAT = 7 };
 void prof_enable(Context*, bool on);
 void prof_reset(Context*);
 void prof_collect(Context*, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);  // blocks; launches are counted even when disabled
@@ -71,16 +71,17 @@ struct FrameTotals {
 int gen_primary(Context*, const DScene& sc, const FrameParams& fp, const uint32_t* pixels, const uint32_t* pixels_count, uint32_t first_pixel,
                 uint32_t n_items, uint32_t spp_pass, const RayQueue& q);
 
-// explicit rays (test hooks): rays[i] -> q slot i with its inline part decided; *q.count = n
-int setup_rays(Context*, const DScene& sc, const hxr_ray* rays, uint32_t n, const RayQueue& q);
-// explicit segments (test hook): seg[6 i .. 6 i + 5] = A, B -> shadow ray i (pre = -2 when an inline node or light blocks it)
-int setup_segments(Context*, const DScene& sc, const double* seg, uint32_t n, const ShadowQueue& q);
+// the inline part of queued rays, in place: geom[i].limit / .pre for closest-hit rays (every inline node in scene order: analytic
+// primitives, CSG, heightfields, quads, in double), geom[i].pre = -2 for shadow rays an inline node or a light blocks
+int setup_closest(Context*, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint);
+int setup_shadow(Context*, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint);
 
 // the KD walk of the big meshes for geom[0 .. *count): one candidate record per ray. head: work-fetch cursor (zeroed by the caller)
 int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
          TravCounters* cnt, uint32_t n_hint);
 
-// shade q[begin .. min(end, *q.count)): exact test of the candidates, winner, shading; pushes child rays and shadow rays.
+// shade q[begin .. min(end, *q.count)): exact test of the candidates, winner, shading; pushes child rays and shadow rays
+// (raw: their inline part is decided by setup_closest / setup_shadow).
 // totals->rays_closest += the rays shaded, totals->rays_shadow += the visible() queries issued
 int shade(Context*, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,
           FrameTotals* totals, TravCounters* cnt);

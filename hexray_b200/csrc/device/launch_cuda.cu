@@ -1,7 +1,9 @@
 // launch_cuda.cu — the sm_100a kernels of the render hot path and their launchers
 // (implements device/launch.h; the only translation unit compiled by nvcc).
 //
-// One bounce of the wavefront is FOUR kernels; a ray lives in a 64-byte geometry record + a 24-byte payload between them:
+// One bounce of the wavefront is SIX launches; a ray lives in a 64-byte geometry record + a 24-byte payload between them:
+//   k_setup<closest>     the inline part of raycast(), in place on the queue: depth guard + every inline node (analytic
+//                        primitives, CSG, heightfields, quads) in scene order, in double; reads 64 B, writes back 16 B
 //   k_walk<closest>      the KD-tree walk, FP32 only: PERSISTENT warps; a lane owns one RAY and walks, one after the other,
 //                        every big mesh whose box the ray enters (the world -> object transform of the ray is the only double
 //                        arithmetic here, done once per (ray, mesh) at refill); idle lanes are refilled with __ballot_sync +
@@ -11,12 +13,14 @@
 //                        in the owner's shared-memory slots and leave the kernel as ONE 16-byte candidate record per ray
 //   k_shade<GI>          per ray: exact (double) test of its candidates, winner across inline nodes and meshes,
 //                        IntersectionInfo, lights, environment, bump, then the Whitted shader tree or the path-tracing vertex;
-//                        every ray it creates gets its inline part (analytic nodes, CSG, heightfields, quads, in double)
-//                        decided on the spot and is pushed ready to walk; radiance lands with RED.ADD.F32
+//                        pushes child rays and shadow rays; radiance lands with RED.ADD.F32
+//   k_setup<shadow>      the inline part of visible(): inline nodes and lights, marks blocked rays
 //   k_walk<shadow>       any-hit form of the same walk
 //   k_resolve_shadow     exact test of the undecided shadow pairs, then the carried colour
-// plus k_gen_primary (camera rays with their inline part), the test-hook kernels (k_setup_rays, k_setup_segments,
-// k_hit_records) and the frame-buffer passes (k_aa_detect, k_scale_*, k_add_into, k_stereo_mix, k_to_bmp_rows, k_to_exr_rows).
+// (Round 2 first fused the two setup kernels into k_shade: the result ran at 7.7 of 32 lanes per instruction and stalled on
+// instruction fetch - profiles/ncu_fused_shade_r2_v1.txt - so the inline part is its own lean, convergent kernel again.)
+// plus k_gen_primary (camera rays with their inline part), k_hit_records (test hook) and the frame-buffer passes
+// (k_aa_detect, k_scale_*, k_add_into, k_stereo_mix, k_to_bmp_rows, k_to_exr_rows).
 // Grid sizing: the persistent walk launches (SM count x resident blocks/SM) blocks - 148 SMs on B200 - the per-item
 // kernels are grid-stride loops over device-side counts, sized by a host-side upper bound of the count: the host never
 // reads a count back between bounces.
@@ -245,6 +249,20 @@ __device__ __forceinline__ RayGeom load_geom(const RayGeom* p)
     g.depth_flags = (uint32_t)((unsigned long long)t >> 32);
     return g;
 }
+// same with plain (coherent) loads: for the kernel that updates the record in place
+__device__ __forceinline__ RayGeom load_geom_rw(const RayGeom* p)
+{
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+    RayGeom g;
+    g.o[0] = a.x; g.o[1] = a.y; g.o[2] = b.x;
+    g.d[0] = b.y; g.d[1] = c.x; g.d[2] = c.y;
+    g.limit = d.x;
+    const long long t = __double_as_longlong(d.y);
+    g.pre = (int32_t)(uint32_t)(t & 0xFFFFFFFFll);
+    g.depth_flags = (uint32_t)((unsigned long long)t >> 32);
+    return g;
+}
 __device__ __forceinline__ RayAux load_aux(const RayAux* p)
 {
     const uint2* q = reinterpret_cast<const uint2*>(p);
@@ -287,6 +305,9 @@ __device__ __forceinline__ void flush_trav(TravCounters* cnt, const TravCounters
 #ifndef HXR_GEN_BLOCKS
 #define HXR_GEN_BLOCKS 5
 #endif
+#ifndef HXR_SETUP_BLOCKS
+#define HXR_SETUP_BLOCKS 6
+#endif
 #ifndef HXR_SHADE_GI_BLOCKS
 #define HXR_SHADE_GI_BLOCKS 4
 #endif
@@ -312,34 +333,29 @@ __global__ void __launch_bounds__(128, SIMPLE ? HXR_GEN_BLOCKS : 1) k_gen_primar
     if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = n_items;
 }
 
-__global__ void __launch_bounds__(128, 1) k_setup_rays(DScene sc, const hxr_ray* __restrict__ rays, uint32_t n, RayQueue q)
+// the inline part of queued rays, in place: reads the 64-byte record, writes back its last 16 bytes
+template <bool SHADOW, bool COUNT, bool SIMPLE>
+__global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup(DScene sc, RayGeom* geom, const uint32_t* __restrict__ count, uint32_t cap,
+                                                                              TravCounters* cnt)
 {
+    const uint32_t n = min(*count, cap);
     const uint32_t stride = gridDim.x * blockDim.x;
+    TravCounters local = {0, 0, 0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const hxr_ray r = rays[i];
-        Ray ray;
-        ray.o = ld3(r.start);
-        ray.d = ld3(r.dir);
-        ray.depth = r.depth;
-        ray.flags = r.flags;
-        place_ray<false, false>(sc, q.geom, q.aux, i, ray, mkc(1, 1, 1), i, 0u, 1u, nullptr);
+        RayGeom g = load_geom_rw(geom + i);
+        if (SHADOW) {
+            if (g.pre == -2) continue;
+            setup_shadow_geom<COUNT, SIMPLE>(sc, g, COUNT ? &local : nullptr);
+            if (g.pre != -2) continue;  // not blocked: nothing to write
+        } else {
+            setup_closest_geom<COUNT, SIMPLE>(sc, g, COUNT ? &local : nullptr);
+        }
+        double2 tail;
+        tail.x = g.limit;
+        tail.y = __longlong_as_double((long long)(((unsigned long long)g.depth_flags << 32) | (unsigned long long)(uint32_t)g.pre));
+        reinterpret_cast<double2*>(geom + i)[3] = tail;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = n;
-}
-
-__global__ void __launch_bounds__(128, 1) k_setup_segments(DScene sc, const double* __restrict__ seg, uint32_t n, ShadowQueue q)
-{
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        double D;
-        const Ray ray = shadow_ray(ld3(seg + 6 * (size_t)i), ld3(seg + 6 * (size_t)i + 3), D);
-        q.geom[i] = shadow_geom(ray, D, inline_blocked<false, false>(sc, ray, D, nullptr));
-        ShadowAux a;
-        a.c[0] = a.c[1] = a.c[2] = 0;
-        a.pixel = i;
-        q.aux[i] = a;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = n;
+    if (COUNT) flush_trav(cnt, local);
 }
 
 // ---- the KD walk -------------------------------------------------------------------------------------
@@ -775,16 +791,29 @@ int gen_primary(Context* c, const DScene& sc, const FrameParams& fp, const uint3
     return 1;
 }
 
-int setup_rays(Context* c, const DScene& sc, const hxr_ray* rays, uint32_t n, const RayQueue& q)
+template <bool SHADOW> static void launch_setup(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint)
 {
-    LaunchScope ls(c, PROF_OTHER);
-    k_setup_rays<<<stage_grid(c, n), 128, 0, c->stream>>>(sc, rays, n, q);
+    const uint32_t blocks = stage_grid(c, n_hint);
+    // counting builds and scenes with CSG / heightfield / inline tree walks take the generic variant
+    if (cnt) k_setup<SHADOW, true, false><<<blocks, 128, 0, c->stream>>>(sc, geom, count, cap, cnt);
+    else if (sc.simple_inline) k_setup<SHADOW, false, true><<<blocks, 128, 0, c->stream>>>(sc, geom, count, cap, nullptr);
+    else k_setup<SHADOW, false, false><<<blocks, 128, 0, c->stream>>>(sc, geom, count, cap, nullptr);
+}
+int setup_closest(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint)
+{
+    if (sc.n_inline == 0 && !cnt) {
+        // nothing inline: only the depth guard, which the generator / shading never violate for queued rays... but explicit
+        // rays (test hooks) may: keep the launch (it is cheap) so that pre = -2 is always decided here
+    }
+    LaunchScope ls(c, PROF_SETUP);
+    launch_setup<false>(c, sc, geom, count, cap, cnt, n_hint);
     return 1;
 }
-int setup_segments(Context* c, const DScene& sc, const double* seg, uint32_t n, const ShadowQueue& q)
+int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint)
 {
-    LaunchScope ls(c, PROF_OTHER);
-    k_setup_segments<<<stage_grid(c, n), 128, 0, c->stream>>>(sc, seg, n, q);
+    if (sc.n_inline == 0 && sc.n_lights == 0) return 0;
+    LaunchScope ls(c, PROF_SETUP);
+    launch_setup<true>(c, sc, geom, count, cap, cnt, n_hint);
     return 1;
 }
 

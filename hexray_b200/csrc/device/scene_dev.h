@@ -120,9 +120,11 @@ struct DScene {
     // rounded outward (the walk kernel skips a mesh whose box the ray certainly misses before paying for the double transform)
     const int32_t* big_nodes;
     const float* big_box;
-    // per node: conservative world-space box of its geometry (min xyz, max xyz; +-1e300 when unbounded or unknown): the
-    // node loops skip a node whose box the ray misses before paying for the object-space transform and intersector
-    const double* node_box;
+    // inline nodes in scene order: inline_nodes[k] = node index; inline_box[6 * k] = conservative world-space box of its geometry
+    // as floats rounded outward (min xyz, max xyz; +-inf when unbounded or unknown): the node loops skip a node whose box
+    // the ray misses before paying for the object-space transform and intersector
+    const int32_t* inline_nodes;
+    const float* inline_box;
     // per node: 1 if nothing downstream reads u, v, dNdx, dNdy of a hit on it (no texture anywhere in its shader, no bump map):
     // finalize then skips the TriAttrUv gather and leaves those fields zero. full_attr = 1 overrides (the trace_closest hook).
     const int32_t* node_lean;

@@ -366,21 +366,28 @@ int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
                 b[3 + k] = mx[k] + pad;
             }
         }
-        m_scene.node_box = uploadArray(box.data(), box.size());
-        if (!m_scene.node_box) return oom();
         {
-            // float copies of the walked nodes' boxes, rounded outward (the walk kernel's pre-test)
-            std::vector<float> fb((size_t)std::max(1, m_nBig) * 6, 0.0f);
-            for (int sl = 0; sl < m_nBig; sl++)
-                for (int k = 0; k < 3; k++) {
-                    const double lo = box[(size_t)bigNodes[sl] * 6 + k], hi = box[(size_t)bigNodes[sl] * 6 + 3 + k];
-                    fb[(size_t)sl * 6 + k] = lo < -3e38 ? -INFINITY : std::nextafter((float)lo, -INFINITY);
-                    fb[(size_t)sl * 6 + 3 + k] = hi > 3e38 ? INFINITY : std::nextafter((float)hi, INFINITY);
-                }
-            m_scene.big_box = uploadArray(fb.data(), fb.size());
-            if (!m_scene.big_box) return oom();
+            // float copies of the boxes, rounded outward: the pre-test of the walk kernel (walked nodes) and of the inline node loops
+            std::vector<int32_t> inlineNodes;
+            for (int i = 0; i < s.n_nodes; i++)
+                if (slot[i] < 0) inlineNodes.push_back(i);
+            auto floatBoxes = [&](const std::vector<int32_t>& nodes) {
+                std::vector<float> fb(std::max<size_t>(1, nodes.size()) * 6, 0.0f);
+                for (size_t sl = 0; sl < nodes.size(); sl++)
+                    for (int k = 0; k < 3; k++) {
+                        const double lo = box[(size_t)nodes[sl] * 6 + k], hi = box[(size_t)nodes[sl] * 6 + 3 + k];
+                        fb[sl * 6 + k] = lo < -3e38 ? -INFINITY : std::nextafter((float)lo, -INFINITY);
+                        fb[sl * 6 + 3 + k] = hi > 3e38 ? INFINITY : std::nextafter((float)hi, INFINITY);
+                    }
+                return fb;
+            };
+            const std::vector<float> bb = floatBoxes(bigNodes), ib = floatBoxes(inlineNodes);
+            m_scene.big_box = uploadArray(bb.data(), bb.size());
+            m_scene.inline_box = uploadArray(ib.data(), ib.size());
+            m_scene.inline_nodes = uploadArray(inlineNodes.data(), inlineNodes.size());
+            if (!m_scene.big_box || !m_scene.inline_box || !m_scene.inline_nodes) return oom();
+            m_scene.n_inline = (int)inlineNodes.size();
         }
-        m_scene.n_inline = s.n_nodes - m_nBig;
         m_scene.use_node_box = getenv("HXR_NO_NODE_BOX") ? 0 : 1;
         m_scene.simple_inline = 1;
         for (int i = 0; i < s.n_nodes; i++) {
@@ -518,9 +525,10 @@ uint32_t Renderer::readCount(const uint32_t* dptr)
     return v;
 }
 
-// One bounce = walk(closest) -> shade -> walk(shadow) -> resolve(shadow). The counts stay on the device: the host
-// enqueues max_depth + 1 bounces (a ray's depth grows by one per bounce and the guard stops it at max_depth) with grids
-// sized from an upper bound of each level's population; levels that turn out empty cost four near-empty launches.
+// One bounce = [setup(closest)] -> walk(closest) -> shade -> setup(shadow) -> walk(shadow) -> resolve(shadow). The counts stay
+// on the device: the host enqueues max_depth + 1 bounces (a ray's depth grows by one per bounce and the guard stops it at
+// max_depth) with grids sized from an upper bound of each level's population; levels that turn out empty cost a few
+// near-empty launches.
 void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st)
 {
     int cur = 0;
@@ -534,6 +542,7 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
         const RayQueue q = queue(cur);
         dev::zero(m_dev, m_counters + (cur ? C_Q0 : C_Q1), sizeof(uint32_t));
         dev::zero(m_dev, m_counters + C_SHADOW, 3 * sizeof(uint32_t));  // shadow count + both walk cursors
+        if (level > 0) st.kernel_launches += dev::setup_closest(m_dev, m_scene, q.geom, q.count, q.cap, cnt, n);  // (level 0 arrives set up)
         st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.count, q.cap, m_cand, m_counters + C_HEAD_A, cnt, n);
         Sinks sk;
         sk.next = queue(1 - cur);
@@ -553,8 +562,9 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
             const uint32_t e = (uint32_t)std::min<uint64_t>(n, (uint64_t)b + chunk);
             if (b) dev::zero(m_dev, m_counters + C_SHADOW, 3 * sizeof(uint32_t));
             st.kernel_launches += dev::shade(m_dev, m_scene, fp, q, m_cand, b, e, sk, m_totals, cnt);
-            if (m_scene.n_big) {
+            {
                 const uint32_t ns = (uint32_t)std::min<uint64_t>(m_shadowCap, (uint64_t)(e - b) * perHit);
+                st.kernel_launches += dev::setup_shadow(m_dev, m_scene, m_sg, m_counters + C_SHADOW, m_shadowCap, cnt, ns);
                 st.kernel_launches += dev::walk(m_dev, m_scene, true, m_sg, m_counters + C_SHADOW, m_shadowCap, scand, m_counters + C_HEAD_B, cnt, ns);
                 st.kernel_launches += dev::resolve_shadow(m_dev, m_scene, sk.shadow, scand, accum, nullptr, m_totals, cnt, ns);
             }
@@ -786,6 +796,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
         st.trace_shadow_ms = ms[dev::PROF_WALK_SHADOW] + ms[dev::PROF_SHADOW_RESOLVE];
         st.shade_ms = ms[dev::PROF_SHADE];
         st.other_ms = ms[dev::PROF_OTHER] + ms[dev::PROF_GEN];
+        st.setup_ms = ms[dev::PROF_SETUP];
         st.trace_closest_launches = ln[dev::PROF_WALK_CLOSEST];
         st.trace_shadow_launches = ln[dev::PROF_WALK_SHADOW] + ln[dev::PROF_SHADOW_RESOLVE];
         st.walk_ms = ms[dev::PROF_WALK_CLOSEST] + ms[dev::PROF_WALK_SHADOW];
@@ -853,6 +864,25 @@ int Renderer::saveFrameExr(const void* d_rgb, int W, int H, const char* path)
 }
 
 // ------------------------------------------------------------------------------ test hooks
+// explicit rays as raw queue records (their inline part is decided on the device by setup_closest)
+static void rawRays(const hxr_ray* rays, uint32_t m, std::vector<RayGeom>& geoms, std::vector<RayAux>& auxs)
+{
+    geoms.resize(m);
+    auxs.resize(m);
+    for (uint32_t i = 0; i < m; i++) {
+        Ray ray;
+        ray.o = ld3(rays[i].start);
+        ray.d = ld3(rays[i].dir);
+        ray.depth = rays[i].depth;
+        ray.flags = rays[i].flags;
+        geoms[i] = raw_geom(ray);
+        auxs[i].w[0] = auxs[i].w[1] = auxs[i].w[2] = 1.0f;
+        auxs[i].pixel = i;
+        auxs[i].sample = 0;
+        auxs[i].stream = 1;
+    }
+}
+
 int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
 {
     if (!m_haveScene) return fail(HXR_ERR_INVALID, "trace: no scene");
@@ -862,16 +892,18 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
     if (!m_hits) return fail(HXR_ERR_CUDA, "trace_closest: out of device memory");
     dev::clear_error(m_dev);
     std::vector<HitRec> recs;
-    static_assert(sizeof(hxr_ray) <= sizeof(RayGeom), "the explicit rays are staged in the second ray queue");
+    std::vector<RayGeom> geoms;
+    std::vector<RayAux> auxs;
     for (size_t first = 0; first < n; first += m_cap) {
         const uint32_t m = (uint32_t)std::min<size_t>(m_cap, n - first);
         recs.resize(m);
-        hxr_ray* staged = (hxr_ray*)m_qg[1];
-        dev::upload(m_dev, staged, rays + first, (size_t)m * sizeof(hxr_ray));
+        rawRays(rays + first, m, geoms, auxs);
+        const RayQueue q = queue(0);
+        dev::upload(m_dev, q.geom, geoms.data(), (size_t)m * sizeof(RayGeom));
+        dev::upload(m_dev, q.count, &m, sizeof m);
         DScene full = m_scene;
         full.full_attr = 1;  // the hook reports u, v, dNdx, dNdy of every hit, whatever the node's shader reads
-        const RayQueue q = queue(0);
-        dev::setup_rays(m_dev, full, staged, m, q);
+        dev::setup_closest(m_dev, full, q.geom, q.count, q.cap, nullptr, m);
         dev::zero(m_dev, m_counters + C_HEAD_A, sizeof(uint32_t));
         dev::walk(m_dev, full, false, q.geom, q.count, q.cap, m_cand, m_counters + C_HEAD_A, nullptr, m);
         dev::hit_records(m_dev, full, q, m_cand, m_hits, m);
@@ -903,14 +935,21 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
     if (!m_visible) m_visible = (uint8_t*)dev::alloc(m_dev, (size_t)m_shadowCap);
     if (!m_visible) return fail(HXR_ERR_CUDA, "trace_visible: out of device memory");
     dev::clear_error(m_dev);
-    static_assert(6 * sizeof(double) <= sizeof(RayGeom), "the explicit segments are staged in a ray queue");
-    const uint32_t batchCap = std::min(m_shadowCap, m_cap);
+    const uint32_t batchCap = m_shadowCap;
+    std::vector<RayGeom> geoms;
     for (size_t first = 0; first < n; first += batchCap) {
         const uint32_t m = (uint32_t)std::min<size_t>(batchCap, n - first);
-        double* staged = (double*)m_qg[1];
-        dev::upload(m_dev, staged, seg + first * 6, (size_t)m * 6 * sizeof(double));
+        geoms.resize(m);
+        for (uint32_t i = 0; i < m; i++) {
+            double D;
+            const double* sg = seg + (first + i) * 6;
+            const Ray ray = shadow_ray(ld3(sg), ld3(sg + 3), D);
+            geoms[i] = shadow_geom(ray, D, false);
+        }
         const ShadowQueue q = shadowQueue();
-        dev::setup_segments(m_dev, m_scene, staged, m, q);
+        dev::upload(m_dev, q.geom, geoms.data(), (size_t)m * sizeof(RayGeom));
+        dev::upload(m_dev, q.count, &m, sizeof m);
+        dev::setup_shadow(m_dev, m_scene, q.geom, q.count, q.cap, nullptr, m);
         dev::zero(m_dev, m_counters + C_HEAD_B, sizeof(uint32_t));
         dev::walk(m_dev, m_scene, true, q.geom, q.count, q.cap, m_cand, m_counters + C_HEAD_B, nullptr, m);
         dev::resolve_shadow(m_dev, m_scene, q, m_cand, nullptr, m_visible, nullptr, nullptr, m);
@@ -936,6 +975,8 @@ int Renderer::traceColor(const hxr_ray* rays, size_t n, float* rgb)
     fp.sample_stride = 1;
     hxr_stats st;
     memset(&st, 0, sizeof st);
+    std::vector<RayGeom> geoms;
+    std::vector<RayAux> auxs;
     int rc = HXR_OK;
     m_countTraversal = false;
     m_allocFailed = false;
@@ -943,9 +984,12 @@ int Renderer::traceColor(const hxr_ray* rays, size_t n, float* rgb)
     for (size_t first = 0; first < n && rc == HXR_OK; first += batch) {
         const uint32_t m = (uint32_t)std::min<size_t>(batch, n - first);
         dev::zero(m_dev, acc, (size_t)batch * 3 * sizeof(float));
-        hxr_ray* staged = (hxr_ray*)m_qg[1];
-        dev::upload(m_dev, staged, rays + first, (size_t)m * sizeof(hxr_ray));
-        dev::setup_rays(m_dev, m_scene, staged, m, queue(0));  // pixel = index in the batch, weight 1
+        rawRays(rays + first, m, geoms, auxs);  // pixel = index in the batch, weight 1
+        const RayQueue q = queue(0);
+        dev::upload(m_dev, q.geom, geoms.data(), (size_t)m * sizeof(RayGeom));
+        dev::upload(m_dev, q.aux, auxs.data(), (size_t)m * sizeof(RayAux));
+        dev::upload(m_dev, q.count, &m, sizeof m);
+        dev::setup_closest(m_dev, m_scene, q.geom, q.count, q.cap, nullptr, m);
         drain(fp, acc, m, st);
         if (m_allocFailed) rc = HXR_ERR_CUDA;
         else if (readCount(m_counters + C_OVERFLOW)) rc = fail(HXR_ERR_OVERFLOW, "trace_color: queue overflow");

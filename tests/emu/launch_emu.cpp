@@ -101,35 +101,29 @@ int gen_primary(Context* c, const DScene& sc, const FrameParams& fp, const uint3
     return 1;
 }
 
-int setup_rays(Context* c, const DScene& sc, const hxr_ray* rays, uint32_t n, const RayQueue& q)
+int setup_closest(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t)
 {
+    const uint32_t n = std::min(*count, cap);
     parallel_for(c, n, [&](uint32_t i) {
-        const hxr_ray r = rays[i];
-        Ray ray;
-        ray.o = ld3(r.start);
-        ray.d = ld3(r.dir);
-        ray.depth = r.depth;
-        ray.flags = r.flags;
-        place_ray<false, false>(sc, q.geom, q.aux, i, ray, mkc(1, 1, 1), i, 0u, 1u, nullptr);
-    });
-    *q.count = n;
-    c->launches[PROF_OTHER]++;
+        if (cnt) setup_closest_geom<true, false>(sc, geom[i], cnt);
+        else if (sc.simple_inline) setup_closest_geom<false, true>(sc, geom[i], nullptr);
+        else setup_closest_geom<false, false>(sc, geom[i], nullptr);
+    }, cnt != nullptr);
+    c->launches[PROF_SETUP]++;
     return 1;
 }
 
-int setup_segments(Context* c, const DScene& sc, const double* seg, uint32_t n, const ShadowQueue& q)
+int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t)
 {
+    if (sc.n_inline == 0 && sc.n_lights == 0) return 0;
+    const uint32_t n = std::min(*count, cap);
     parallel_for(c, n, [&](uint32_t i) {
-        double D;
-        const Ray ray = shadow_ray(ld3(seg + 6 * (size_t)i), ld3(seg + 6 * (size_t)i + 3), D);
-        q.geom[i] = shadow_geom(ray, D, inline_blocked<false, false>(sc, ray, D, nullptr));
-        ShadowAux a;
-        a.c[0] = a.c[1] = a.c[2] = 0;
-        a.pixel = i;
-        q.aux[i] = a;
-    });
-    *q.count = n;
-    c->launches[PROF_OTHER]++;
+        if (geom[i].pre == -2) return;
+        if (cnt) setup_shadow_geom<true, false>(sc, geom[i], cnt);
+        else if (sc.simple_inline) setup_shadow_geom<false, true>(sc, geom[i], nullptr);
+        else setup_shadow_geom<false, false>(sc, geom[i], nullptr);
+    }, cnt != nullptr);
+    c->launches[PROF_SETUP]++;
     return 1;
 }
 
