@@ -47,7 +47,7 @@ void timer_stop(Context*, Timer*);
 double timer_ms(Context*, Timer*);     // blocks until the stop event has happened
 
 // per-category device time of the launches below (CUDA events around every launch when enabled)
-enum ProfCat { PROF_WALK_CLOSEST = 0, PROF_WALK_SHADOW = 1, PROF_SHADE = 2, PROF_SHADOW_RESOLVE = 3, PROF_GEN = 4, PROF_OTHER = 5, PROF_SETUP = 6, PROF_NCAT = 7 };
+enum ProfCat { PROF_WALK_CLOSEST = 0, PROF_WALK_SHADOW = 1, PROF_SHADE = 2, PROF_SHADOW_RESOLVE = 3, PROF_GEN = 4, PROF_OTHER = 5, PROF_SETUP = 6, PROF_EXACT = 7, PROF_NCAT = 8 };
 void prof_enable(Context*, bool on);
 void prof_reset(Context*);
 void prof_collect(Context*, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);  // blocks; launches are counted even when disabled
@@ -76,8 +76,16 @@ int gen_primary(Context*, const DScene& sc, const FrameParams& fp, const uint32_
 int setup_closest(Context*, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint);
 int setup_shadow(Context*, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint);
 
-// the KD walk of the big meshes for geom[0 .. *count): one candidate record per ray. head: work-fetch cursor (zeroed by the caller)
-int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+// the KD walk of the big meshes for geom[0 .. *count): one candidate record per ray (wb.head zeroed by the caller).
+// Rays whose record overflowed are appended to ovf_list (capacity cap, count *ovf_count, zeroed by the caller) and then
+// redone exactly by a second, small launch that replaces their records (exact_fix_item); totals->cand_overflow += their number.
+struct WalkBuffers {
+    CandRec* cand;
+    uint32_t* head;       // work-fetch cursor of the persistent kernel
+    uint32_t* ovf_list;
+    uint32_t* ovf_count;
+};
+int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb, FrameTotals* totals,
          TravCounters* cnt, uint32_t n_hint);
 
 // shade q[begin .. min(end, *q.count)): exact test of the candidates, winner, shading; pushes child rays and shadow rays

@@ -396,8 +396,9 @@ struct WalkShared {
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayGeom* __restrict__ geom, const uint32_t* __restrict__ count,
-                                                                              uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, TravCounters* cnt,
-                                                                              int walkSteps, int refillMin, int useMail, int branchFreePush)
+                                                                              uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, uint32_t* ovf_list,
+                                                                              uint32_t* ovf_count, TravCounters* cnt, int walkSteps, int refillMin, int useMail,
+                                                                              int branchFreePush)
 {
     __shared__ WalkShared<SSTACK> sh;
     constexpr int HXR_SSTACK = SSTACK;
@@ -447,7 +448,10 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         if (idle == FULL || __popc(idle) >= refillMin) {
             // rays that have tried all their meshes leave their candidate record
             if (!active && hasRay && slot >= nBig) {
-                reinterpret_cast<uint4*>(cand)[rayIdx] = make_uint4(sh.cand[0][tid], sh.cand[1][tid], sh.cand[2][tid], sh.meta[tid]);
+                const uint32_t meta = sh.meta[tid];
+                reinterpret_cast<uint4*>(cand)[rayIdx] = make_uint4(sh.cand[0][tid], sh.cand[1][tid], sh.cand[2][tid], meta);
+                // more candidates than the record holds (rare): listed for the exact walk (k_exact_fix)
+                if ((meta & 0xFFu) > HXR_CAND_MAX && (meta & 0xFFu) != HXR_CAND_BLOCKED) ovf_list[atomicAdd(ovf_count, 1u)] = rayIdx;
                 hasRay = false;
             }
             // empty lanes take new rays
@@ -671,6 +675,23 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     if (COUNT) flush_trav(cnt, local);
 }
 
+// the rays whose candidate record overflowed, redone with the exact double walk (dense: every lane is on the slow path)
+template <bool SHADOW, bool COUNT>
+__global__ void __launch_bounds__(128, 1) k_exact_fix(DScene sc, const RayGeom* __restrict__ geom, CandRec* cand, const uint32_t* __restrict__ ovf_list,
+                                                      const uint32_t* __restrict__ ovf_count, uint32_t cap, FrameTotals* totals, TravCounters* cnt)
+{
+    const uint32_t n = min(*ovf_count, cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TravCounters local = {0, 0, 0, 0};
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint32_t i = ovf_list[k];
+        const CandRec r = exact_fix_item<SHADOW, COUNT>(sc, load_geom(geom + i), COUNT ? &local : nullptr);
+        reinterpret_cast<uint4*>(cand)[i] = make_uint4(r.tri[0], r.tri[1], r.tri[2], r.meta);
+    }
+    if (totals && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&totals->cand_overflow, (unsigned long long)n);
+    if (COUNT) flush_trav(cnt, local);
+}
+
 // GI (one path vertex) and Whitted (shader tree with its stacks) are separate compilations, and so are scenes whose inline
 // nodes are only planes / spheres / cubes / quads (SIMPLE: no CSG, heightfield or inline tree-walk code, no stack frame)
 template <bool GI, bool COUNT, bool SIMPLE>
@@ -818,7 +839,7 @@ int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* co
 }
 
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
-static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
                           TravCounters* cnt, uint32_t n_hint)
 {
     int& full = c->walkGrid[SHADOW][COUNT][SSTACK == 9 ? 0 : (SSTACK == 12 ? 2 : 1)][PACKED];
@@ -831,33 +852,48 @@ static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, con
         if (c->walkBlocksPerSm > 0) full = std::min(full, c->sms * c->walkBlocksPerSm);
     }
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, ((uint64_t)n_hint + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, cand, head, cnt, c->walkSteps, c->refillMin, c->useMail, c->bfPush);
+    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, wb.cand, wb.head, wb.ovf_list, wb.ovf_count, cnt, c->walkSteps,
+                                                                                  c->refillMin, c->useMail, c->bfPush);
 }
 template <bool SHADOW, bool PACKED>
-static void launch_walk_p(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+static void launch_walk_p(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
                           TravCounters* cnt, uint32_t n_hint)
 {
-    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(c, sc, geom, count, cap, cand, head, cnt, n_hint); return; }
+    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(c, sc, geom, count, cap, wb, cnt, n_hint); return; }
     switch (c->sstack) {
-        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(c, sc, geom, count, cap, cand, head, nullptr, n_hint); break;
-        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(c, sc, geom, count, cap, cand, head, nullptr, n_hint); break;
-        default: launch_walk_s<SHADOW, false, 10, PACKED>(c, sc, geom, count, cap, cand, head, nullptr, n_hint); break;
+        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(c, sc, geom, count, cap, wb, nullptr, n_hint); break;
+        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(c, sc, geom, count, cap, wb, nullptr, n_hint); break;
+        default: launch_walk_s<SHADOW, false, 10, PACKED>(c, sc, geom, count, cap, wb, nullptr, n_hint); break;
     }
 }
 
-int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t* head,
+int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb, FrameTotals* totals,
          TravCounters* cnt, uint32_t n_hint)
 {
     if (sc.n_big == 0) return 0;
-    LaunchScope ls(c, shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST);
-    if (shadow) {
-        if (sc.walk_packed) launch_walk_p<true, true>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
-        else launch_walk_p<true, false>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
-    } else {
-        if (sc.walk_packed) launch_walk_p<false, true>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
-        else launch_walk_p<false, false>(c, sc, geom, count, cap, cand, head, cnt, n_hint);
+    {
+        LaunchScope ls(c, shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST);
+        if (shadow) {
+            if (sc.walk_packed) launch_walk_p<true, true>(c, sc, geom, count, cap, wb, cnt, n_hint);
+            else launch_walk_p<true, false>(c, sc, geom, count, cap, wb, cnt, n_hint);
+        } else {
+            if (sc.walk_packed) launch_walk_p<false, true>(c, sc, geom, count, cap, wb, cnt, n_hint);
+            else launch_walk_p<false, false>(c, sc, geom, count, cap, wb, cnt, n_hint);
+        }
     }
-    return 1;
+    {
+        LaunchScope ls(c, PROF_EXACT);
+        // a fraction of a percent of the rays: a small grid; it loops over whatever the list holds
+        const uint32_t blocks = stage_grid(c, std::max<uint32_t>(1, n_hint / 64), 4);
+        if (shadow) {
+            if (cnt) k_exact_fix<true, true><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, cnt);
+            else k_exact_fix<true, false><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, nullptr);
+        } else {
+            if (cnt) k_exact_fix<false, true><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, cnt);
+            else k_exact_fix<false, false><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, nullptr);
+        }
+    }
+    return 2;
 }
 
 int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,

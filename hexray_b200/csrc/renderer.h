@@ -61,6 +61,7 @@ private:
     int renderOnce(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, uint32_t primaryBatch, bool& overflow);
     uint32_t readCount(const uint32_t* dptr);
     RayQueue queue(int i) const;
+    dev::WalkBuffers walkBuffers(CandRec* cand, bool shadow) const;
     ShadowQueue shadowQueue() const;
 
     std::string m_err;
@@ -79,6 +80,7 @@ private:
     RayGeom* m_sg = nullptr;
     ShadowAux* m_sa = nullptr;
     CandRec* m_cand = nullptr;
+    uint32_t* m_ovfList = nullptr;   // rays whose candidate record overflowed in the current walk
     CandRec* m_scand = nullptr;      // shadow candidates of levels shaded in chunks (allocated on first use)
     bool m_allocFailed = false;
     HitRec* m_hits = nullptr;        // test hook only, allocated on first use

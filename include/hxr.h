@@ -267,7 +267,7 @@ typedef struct hxr_stats {
     double walk_ms;         /* device time of the KD-walk kernel launches (closest-hit + shadow) */
     uint64_t walk_launches;
     uint64_t cand_overflow; /* rays whose walk left more candidates than a record holds (redone with the exact double walk) */
-    double shadow_resolve_ms, gen_ms, setup_ms; /* with profiling on: the shadow-resolve, primary-ray and inline-setup kernels */
+    double shadow_resolve_ms, gen_ms, setup_ms, exact_ms; /* with profiling on: the shadow-resolve, primary-ray, inline-setup and exact-redo kernels */
 } hxr_stats;
 
 typedef struct hxr_ray {

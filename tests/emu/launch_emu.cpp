@@ -127,20 +127,31 @@ int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* co
     return 1;
 }
 
-int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, CandRec* cand, uint32_t*,
+static std::atomic<unsigned long long>* as_atomic(unsigned long long* p) { return reinterpret_cast<std::atomic<unsigned long long>*>(p); }
+
+int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb, FrameTotals* totals,
          TravCounters* cnt, uint32_t)
 {
     if (sc.n_big == 0) return 0;
     const uint32_t n = std::min(*count, cap);
+    CandRec* cand = wb.cand;
     parallel_for(c, n, [&](uint32_t i) {
         if (shadow) cand[i] = cnt ? walk_ray_item<true, true>(sc, geom[i], cnt) : walk_ray_item<true, false>(sc, geom[i], nullptr);
         else cand[i] = cnt ? walk_ray_item<false, true>(sc, geom[i], cnt) : walk_ray_item<false, false>(sc, geom[i], nullptr);
+        const uint32_t k = cand[i].meta & 0xFFu;
+        if (k > HXR_CAND_MAX && k != HXR_CAND_BLOCKED) wb.ovf_list[__atomic_fetch_add(wb.ovf_count, 1u, __ATOMIC_RELAXED)] = i;
     }, cnt != nullptr);
+    const uint32_t m = std::min(*wb.ovf_count, cap);
+    parallel_for(c, m, [&](uint32_t k) {
+        const uint32_t i = wb.ovf_list[k];
+        if (shadow) cand[i] = cnt ? exact_fix_item<true, true>(sc, geom[i], cnt) : exact_fix_item<true, false>(sc, geom[i], nullptr);
+        else cand[i] = cnt ? exact_fix_item<false, true>(sc, geom[i], cnt) : exact_fix_item<false, false>(sc, geom[i], nullptr);
+    }, cnt != nullptr);
+    if (totals && m) as_atomic(&totals->cand_overflow)->fetch_add(m);
     c->launches[shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST]++;
-    return 1;
+    c->launches[PROF_EXACT]++;
+    return 2;
 }
-
-static std::atomic<unsigned long long>* as_atomic(unsigned long long* p) { return reinterpret_cast<std::atomic<unsigned long long>*>(p); }
 
 int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,
           FrameTotals* totals, TravCounters* cnt)
