@@ -297,6 +297,7 @@ __device__ __forceinline__ void flush_trav(TravCounters* cnt, const TravCounters
     if (local.kd_leaves) atomicAdd(&cnt->kd_leaves, local.kd_leaves);
     if (local.tri_tests) atomicAdd(&cnt->tri_tests, local.tri_tests);
     if (local.mesh_queries) atomicAdd(&cnt->mesh_queries, local.mesh_queries);
+    if (local.cand_resolves) atomicAdd(&cnt->cand_resolves, local.cand_resolves);
 }
 
 // ---- kernels ----------------------------------------------------------------------------
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup(DS
 {
     const uint32_t n = min(*count, cap);
     const uint32_t stride = gridDim.x * blockDim.x;
-    TravCounters local = {0, 0, 0, 0};
+    TravCounters local = {0, 0, 0, 0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         RayGeom g = load_geom_rw(geom + i);
         if (SHADOW) {
@@ -396,9 +397,8 @@ struct WalkShared {
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayGeom* __restrict__ geom, const uint32_t* __restrict__ count,
-                                                                              uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, uint32_t* ovf_list,
-                                                                              uint32_t* ovf_count, TravCounters* cnt, int walkSteps, int refillMin, int useMail,
-                                                                              int branchFreePush)
+                                                                              uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, FrameTotals* totals,
+                                                                              TravCounters* cnt, int walkSteps, int refillMin, int useMail, int branchFreePush)
 {
     __shared__ WalkShared<SSTACK> sh;
     constexpr int HXR_SSTACK = SSTACK;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     int sp = 0;
     uint32_t rayIdx = 0;
     int slot = 0;  // next walked-mesh slot this ray has to try (the mesh being walked is slot - 1)
-    TravCounters local = {0, 0, 0, 0};
+    TravCounters local = {0, 0, 0, 0, 0};
 
     auto push = [&](const WalkEnt& e) {
         if (sp < HXR_SSTACK) {
@@ -448,10 +448,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         if (idle == FULL || __popc(idle) >= refillMin) {
             // rays that have tried all their meshes leave their candidate record
             if (!active && hasRay && slot >= nBig) {
-                const uint32_t meta = sh.meta[tid];
-                reinterpret_cast<uint4*>(cand)[rayIdx] = make_uint4(sh.cand[0][tid], sh.cand[1][tid], sh.cand[2][tid], meta);
-                // more candidates than the record holds (rare): listed for the exact walk (k_exact_fix)
-                if ((meta & 0xFFu) > HXR_CAND_MAX && (meta & 0xFFu) != HXR_CAND_BLOCKED) ovf_list[atomicAdd(ovf_count, 1u)] = rayIdx;
+                reinterpret_cast<uint4*>(cand)[rayIdx] = make_uint4(sh.cand[0][tid], sh.cand[1][tid], sh.cand[2][tid], sh.meta[tid]);
                 hasRay = false;
             }
             // empty lanes take new rays
@@ -642,7 +639,12 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 // a surviving pair becomes a candidate of its owner's ray: a slot in the owner's shared-memory record (lanes
                 // serving the same owner take different slots through the atomic; the count saturates far below its 8-bit field)
                 if (emit) {
-                    if ((sh.meta[ot] & 0xFFu) < 100u) {
+                    const uint32_t m0 = sh.meta[ot];
+                    const uint32_t n0 = min(m0 & 0xFFu, (uint32_t)HXR_CAND_MAX);
+                    bool dup = false;  // already recorded (from a neighbouring leaf, longer ago than the mailbox remembers)
+#pragma unroll
+                    for (uint32_t i = 0; i < HXR_CAND_MAX; i++) dup = dup || (i < n0 && sh.cand[i][ot] == ti && ((m0 >> (8u + 8u * i)) & 0xFFu) == (uint32_t)oSlot);
+                    if (!dup && (m0 & 0xFFu) < 100u) {
                         const uint32_t pos = atomicAdd(&sh.meta[ot], 1u) & 0xFFu;
                         if (pos < HXR_CAND_MAX) {
                             sh.cand[pos][ot] = ti;
@@ -659,36 +661,30 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         __syncwarp();
         if (hasLeaf) {
             if (COUNT) { local.kd_leaves++; local.tri_tests += leafCnt; }
+            uint32_t tb = sh.tb[tid];
+            if (!(SHADOW && tb == 0u) && (sh.meta[tid] & 0xFFu) > HXR_CAND_MAX) {
+                // the record is full (rare: distant grazing rays on which the float bounds decide nothing): settle it exactly,
+                // together with every triangle of this leaf - the candidates that did not fit all come from it
+                CandRec rec;
+                rec.tri[0] = sh.cand[0][tid]; rec.tri[1] = sh.cand[1][tid]; rec.tri[2] = sh.cand[2][tid];
+                rec.meta = sh.meta[tid];
+                float tbNow = __uint_as_float(tb);
+                resolve_overflow<SHADOW>(sc, geom + rayIdx, slot - 1, leafTris + (cur & ~HXR_KD_LEAF) + 1u, leafCnt, rec, tbNow, wcap);
+                sh.cand[0][tid] = rec.tri[0]; sh.cand[1][tid] = rec.tri[1]; sh.cand[2][tid] = rec.tri[2];
+                sh.meta[tid] = rec.meta;
+                tb = __float_as_uint(tbNow);
+                sh.tb[tid] = tb;
+                if (totals) atomicAdd(&totals->cand_overflow, 1ull);
+            }
             cur = HXR_POP;
-            const uint32_t tb = sh.tb[tid];
             tbest = __uint_as_float(tb);
             if (SHADOW && tb == 0u) {  // certainly blocked: the ray is finished
                 sh.meta[tid] = HXR_CAND_BLOCKED;
                 active = false;
                 slot = nBig;
-            } else if ((sh.meta[tid] & 0xFFu) > HXR_CAND_MAX) {  // the record overflowed: its consumer redoes this ray exactly, stop here
-                active = false;
-                slot = nBig;
             }
         }
     }
-    if (COUNT) flush_trav(cnt, local);
-}
-
-// the rays whose candidate record overflowed, redone with the exact double walk (dense: every lane is on the slow path)
-template <bool SHADOW, bool COUNT>
-__global__ void __launch_bounds__(128, 1) k_exact_fix(DScene sc, const RayGeom* __restrict__ geom, CandRec* cand, const uint32_t* __restrict__ ovf_list,
-                                                      const uint32_t* __restrict__ ovf_count, uint32_t cap, FrameTotals* totals, TravCounters* cnt)
-{
-    const uint32_t n = min(*ovf_count, cap);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    TravCounters local = {0, 0, 0, 0};
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        const uint32_t i = ovf_list[k];
-        const CandRec r = exact_fix_item<SHADOW, COUNT>(sc, load_geom(geom + i), COUNT ? &local : nullptr);
-        reinterpret_cast<uint4*>(cand)[i] = make_uint4(r.tri[0], r.tri[1], r.tri[2], r.meta);
-    }
-    if (totals && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&totals->cand_overflow, (unsigned long long)n);
     if (COUNT) flush_trav(cnt, local);
 }
 
@@ -702,7 +698,7 @@ __global__ void __launch_bounds__(128, SIMPLE ? (GI ? HXR_SHADE_GI_BLOCKS : HXR_
     const uint32_t e = min(end, min(*q.count, q.cap));
     const uint32_t stride = gridDim.x * blockDim.x;
     EmitCounters ec = {0, 0};
-    TravCounters local = {0, 0, 0, 0};
+    TravCounters local = {0, 0, 0, 0, 0};
     for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
         const RayGeom g = load_geom(q.geom + i);
         const RayAux a = load_aux(q.aux + i);
@@ -723,7 +719,7 @@ __global__ void __launch_bounds__(128, COUNT ? 1 : 4) k_resolve_shadow(DScene sc
     const uint32_t n = min(*q.count, q.cap);
     const uint32_t stride = gridDim.x * blockDim.x;
     EmitCounters ec = {0, 0};
-    TravCounters local = {0, 0, 0, 0};
+    TravCounters local = {0, 0, 0, 0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         CandRec cr;
         cr.meta = 0;
@@ -840,7 +836,7 @@ int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* co
 
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
 static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
-                          TravCounters* cnt, uint32_t n_hint)
+                          FrameTotals* totals, TravCounters* cnt, uint32_t n_hint)
 {
     int& full = c->walkGrid[SHADOW][COUNT][SSTACK == 9 ? 0 : (SSTACK == 12 ? 2 : 1)][PACKED];
     if (!full) {
@@ -852,18 +848,18 @@ static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, con
         if (c->walkBlocksPerSm > 0) full = std::min(full, c->sms * c->walkBlocksPerSm);
     }
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, ((uint64_t)n_hint + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, wb.cand, wb.head, wb.ovf_list, wb.ovf_count, cnt, c->walkSteps,
-                                                                                  c->refillMin, c->useMail, c->bfPush);
+    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, wb.cand, wb.head, totals, cnt, c->walkSteps, c->refillMin,
+                                                                                  c->useMail, c->bfPush);
 }
 template <bool SHADOW, bool PACKED>
 static void launch_walk_p(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
-                          TravCounters* cnt, uint32_t n_hint)
+                          FrameTotals* totals, TravCounters* cnt, uint32_t n_hint)
 {
-    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(c, sc, geom, count, cap, wb, cnt, n_hint); return; }
+    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(c, sc, geom, count, cap, wb, totals, cnt, n_hint); return; }
     switch (c->sstack) {
-        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(c, sc, geom, count, cap, wb, nullptr, n_hint); break;
-        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(c, sc, geom, count, cap, wb, nullptr, n_hint); break;
-        default: launch_walk_s<SHADOW, false, 10, PACKED>(c, sc, geom, count, cap, wb, nullptr, n_hint); break;
+        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(c, sc, geom, count, cap, wb, totals, nullptr, n_hint); break;
+        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(c, sc, geom, count, cap, wb, totals, nullptr, n_hint); break;
+        default: launch_walk_s<SHADOW, false, 10, PACKED>(c, sc, geom, count, cap, wb, totals, nullptr, n_hint); break;
     }
 }
 
@@ -874,26 +870,14 @@ int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const u
     {
         LaunchScope ls(c, shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST);
         if (shadow) {
-            if (sc.walk_packed) launch_walk_p<true, true>(c, sc, geom, count, cap, wb, cnt, n_hint);
-            else launch_walk_p<true, false>(c, sc, geom, count, cap, wb, cnt, n_hint);
+            if (sc.walk_packed) launch_walk_p<true, true>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
+            else launch_walk_p<true, false>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
         } else {
-            if (sc.walk_packed) launch_walk_p<false, true>(c, sc, geom, count, cap, wb, cnt, n_hint);
-            else launch_walk_p<false, false>(c, sc, geom, count, cap, wb, cnt, n_hint);
+            if (sc.walk_packed) launch_walk_p<false, true>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
+            else launch_walk_p<false, false>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
         }
     }
-    {
-        LaunchScope ls(c, PROF_EXACT);
-        // a fraction of a percent of the rays: a small grid; it loops over whatever the list holds
-        const uint32_t blocks = stage_grid(c, std::max<uint32_t>(1, n_hint / 64), 4);
-        if (shadow) {
-            if (cnt) k_exact_fix<true, true><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, cnt);
-            else k_exact_fix<true, false><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, nullptr);
-        } else {
-            if (cnt) k_exact_fix<false, true><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, cnt);
-            else k_exact_fix<false, false><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, nullptr);
-        }
-    }
-    return 2;
+    return 1;
 }
 
 int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,

@@ -144,6 +144,7 @@ struct DScene {
 // optional traversal counters (HXR_RENDER_COUNT_TRAVERSAL)
 struct TravCounters {
     unsigned long long kd_inner, kd_leaves, tri_tests, mesh_queries;
+    unsigned long long cand_resolves;  // candidate records that filled up and were settled exactly inside the walk
 };
 
 }  // namespace hxr

@@ -138,19 +138,10 @@ int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const u
     parallel_for(c, n, [&](uint32_t i) {
         if (shadow) cand[i] = cnt ? walk_ray_item<true, true>(sc, geom[i], cnt) : walk_ray_item<true, false>(sc, geom[i], nullptr);
         else cand[i] = cnt ? walk_ray_item<false, true>(sc, geom[i], cnt) : walk_ray_item<false, false>(sc, geom[i], nullptr);
-        const uint32_t k = cand[i].meta & 0xFFu;
-        if (k > HXR_CAND_MAX && k != HXR_CAND_BLOCKED) wb.ovf_list[__atomic_fetch_add(wb.ovf_count, 1u, __ATOMIC_RELAXED)] = i;
     }, cnt != nullptr);
-    const uint32_t m = std::min(*wb.ovf_count, cap);
-    parallel_for(c, m, [&](uint32_t k) {
-        const uint32_t i = wb.ovf_list[k];
-        if (shadow) cand[i] = cnt ? exact_fix_item<true, true>(sc, geom[i], cnt) : exact_fix_item<true, false>(sc, geom[i], nullptr);
-        else cand[i] = cnt ? exact_fix_item<false, true>(sc, geom[i], cnt) : exact_fix_item<false, false>(sc, geom[i], nullptr);
-    }, cnt != nullptr);
-    if (totals && m) as_atomic(&totals->cand_overflow)->fetch_add(m);
+    (void)totals;
     c->launches[shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST]++;
-    c->launches[PROF_EXACT]++;
-    return 2;
+    return 1;
 }
 
 int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,
