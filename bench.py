@@ -331,7 +331,7 @@ def ours(a):
     def run(n, to_host, first_seed):
         rays = np.zeros(2, dtype=np.float64)
         prof = {"trace_closest_ms": 0.0, "trace_shadow_ms": 0.0, "shade_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0, "walk_ms": 0.0,
-                "setup_ms": 0.0, "shadow_resolve_ms": 0.0, "gen_ms": 0.0, "cand_overflow": 0,
+                "setup_ms": 0.0, "shadow_resolve_ms": 0.0, "gen_ms": 0.0, "finish_ms": 0.0, "cand_overflow": 0,
                 "trace_closest_launches": 0, "trace_shadow_launches": 0, "walk_launches": 0, "kernel_launches": 0, "post_ms": 0.0}
         for i in range(n):
             st, post_ms = step(first_seed + i, to_host)
@@ -437,7 +437,7 @@ def ours(a):
                          "random_gather": gather,
                          "walk_share_of_step": walk_ms / max(1e-9, prof["render_ms"]),
                          "traversal_share_of_step": (prof["trace_closest_ms"] + prof["trace_shadow_ms"]) / max(1e-9, prof["render_ms"])},
-            "kernel_ms_per_step": {k: prof[k] / a.steps for k in ("trace_closest_ms", "trace_shadow_ms", "walk_ms", "setup_ms", "shade_ms", "shadow_resolve_ms", "gen_ms", "other_ms", "render_ms", "cand_overflow")},
+            "kernel_ms_per_step": {k: prof[k] / a.steps for k in ("trace_closest_ms", "trace_shadow_ms", "walk_ms", "setup_ms", "finish_ms", "shade_ms", "shadow_resolve_ms", "gen_ms", "other_ms", "render_ms", "cand_overflow")},
         }
         if world == 1 and not a.no_cpu_baseline:
             b = argparse.Namespace(**vars(a))

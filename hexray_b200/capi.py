@@ -117,7 +117,7 @@ class Stats(C.Structure):
                 ("trace_closest_ms", c_f64), ("trace_shadow_ms", c_f64), ("shade_ms", c_f64), ("other_ms", c_f64),
                 ("trace_closest_launches", c_u64), ("trace_shadow_launches", c_u64), ("spp_done", c_u32),
                 ("aa_pixels", c_u32), ("walk_ms", c_f64), ("walk_launches", c_u64), ("cand_overflow", c_u64),
-                ("shadow_resolve_ms", c_f64), ("gen_ms", c_f64), ("setup_ms", c_f64)]
+                ("shadow_resolve_ms", c_f64), ("gen_ms", c_f64), ("setup_ms", c_f64), ("finish_ms", c_f64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -47,7 +47,7 @@ void timer_stop(Context*, Timer*);
 double timer_ms(Context*, Timer*);     // blocks until the stop event has happened
 
 // per-category device time of the launches below (CUDA events around every launch when enabled)
-enum ProfCat { PROF_WALK_CLOSEST = 0, PROF_WALK_SHADOW = 1, PROF_SHADE = 2, PROF_SHADOW_RESOLVE = 3, PROF_GEN = 4, PROF_OTHER = 5, PROF_SETUP = 6, PROF_NCAT = 7 };
+enum ProfCat { PROF_WALK_CLOSEST = 0, PROF_WALK_SHADOW = 1, PROF_SHADE = 2, PROF_SHADOW_RESOLVE = 3, PROF_GEN = 4, PROF_OTHER = 5, PROF_SETUP = 6, PROF_FINISH = 7, PROF_NCAT = 8 };
 void prof_enable(Context*, bool on);
 void prof_reset(Context*);
 void prof_collect(Context*, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);  // blocks; launches are counted even when disabled
@@ -56,7 +56,7 @@ void prof_collect(Context*, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]);
 struct FrameTotals {
     unsigned long long rays_closest;   // closest-hit queries past the depth guard
     unsigned long long rays_shadow;    // visible() queries
-    unsigned long long cand_overflow;  // candidate records that filled up and were settled exactly inside the walk
+    unsigned long long cand_overflow;  // rays whose candidate record filled up (finished by the second, exact-on-the-spot walk)
     unsigned long long pad;
 };
 
@@ -77,10 +77,13 @@ int setup_closest(Context*, const DScene& sc, RayGeom* geom, const uint32_t* cou
 int setup_shadow(Context*, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint);
 
 // the KD walk of the big meshes for geom[0 .. *count): one candidate record per ray (wb.head zeroed by the caller).
-// A record that fills up is settled exactly inside the walk (resolve_overflow); totals->cand_overflow counts those events.
+// A ray whose record fills up stops there and is appended to ovf_list (capacity cap, count *ovf_count, zeroed by the caller);
+// a second, small launch finishes those rays (finish_overflowed_ray) and replaces their records. totals->cand_overflow += their number.
 struct WalkBuffers {
     CandRec* cand;
     uint32_t* head;       // work-fetch cursor of the persistent kernel
+    OverflowEntry* ovf_list;
+    uint32_t* ovf_count;
 };
 int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb, FrameTotals* totals,
          TravCounters* cnt, uint32_t n_hint);

@@ -297,7 +297,7 @@ __device__ __forceinline__ void flush_trav(TravCounters* cnt, const TravCounters
     if (local.kd_leaves) atomicAdd(&cnt->kd_leaves, local.kd_leaves);
     if (local.tri_tests) atomicAdd(&cnt->tri_tests, local.tri_tests);
     if (local.mesh_queries) atomicAdd(&cnt->mesh_queries, local.mesh_queries);
-    if (local.cand_resolves) atomicAdd(&cnt->cand_resolves, local.cand_resolves);
+
 }
 
 // ---- kernels ----------------------------------------------------------------------------
@@ -397,8 +397,9 @@ struct WalkShared {
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
 __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayGeom* __restrict__ geom, const uint32_t* __restrict__ count,
-                                                                              uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, FrameTotals* totals,
-                                                                              TravCounters* cnt, int walkSteps, int refillMin, int useMail, int branchFreePush)
+                                                                              uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, OverflowEntry* ovf_list,
+                                                                              uint32_t* ovf_count, TravCounters* cnt, int walkSteps, int refillMin, int useMail,
+                                                                              int branchFreePush)
 {
     __shared__ WalkShared<SSTACK> sh;
     constexpr int HXR_SSTACK = SSTACK;
@@ -661,20 +662,18 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
         __syncwarp();
         if (hasLeaf) {
             if (COUNT) { local.kd_leaves++; local.tri_tests += leafCnt; }
-            uint32_t tb = sh.tb[tid];
+            const uint32_t tb = sh.tb[tid];
             if (!(SHADOW && tb == 0u) && (sh.meta[tid] & 0xFFu) > HXR_CAND_MAX) {
-                // the record is full (rare: distant grazing rays on which the float bounds decide nothing): settle it exactly,
-                // together with every triangle of this leaf - the candidates that did not fit all come from it
-                CandRec rec;
-                rec.tri[0] = sh.cand[0][tid]; rec.tri[1] = sh.cand[1][tid]; rec.tri[2] = sh.cand[2][tid];
-                rec.meta = sh.meta[tid];
-                float tbNow = __uint_as_float(tb);
-                resolve_overflow<SHADOW>(sc, geom + rayIdx, slot - 1, leafTris + (cur & ~HXR_KD_LEAF) + 1u, leafCnt, rec, tbNow, wcap);
-                sh.cand[0][tid] = rec.tri[0]; sh.cand[1][tid] = rec.tri[1]; sh.cand[2][tid] = rec.tri[2];
-                sh.meta[tid] = rec.meta;
-                tb = __float_as_uint(tbNow);
-                sh.tb[tid] = tb;
-                if (totals) atomicAdd(&totals->cand_overflow, 1ull);
+                // the record is full (rare: distant grazing rays on which the float bounds decide nothing): the ray stops here and
+                // is listed for k_finish, which resumes at this leaf with exact tests on the spot
+                OverflowEntry oe;
+                oe.ray = rayIdx;
+                oe.slot = slot - 1;
+                oe.tstop = tmin;
+                oe.pad = 0;
+                ovf_list[atomicAdd(ovf_count, 1u)] = oe;
+                active = false;
+                slot = nBig;
             }
             cur = HXR_POP;
             tbest = __uint_as_float(tb);
@@ -685,6 +684,28 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             }
         }
     }
+    if (COUNT) flush_trav(cnt, local);
+}
+
+// the rays whose candidate record filled up: resumed where they stopped, exact tests on the spot (one ray per thread)
+template <bool SHADOW, bool COUNT>
+__global__ void __launch_bounds__(128, 2) k_finish(DScene sc, const RayGeom* __restrict__ geom, CandRec* cand, const OverflowEntry* __restrict__ ovf_list,
+                                                   const uint32_t* __restrict__ ovf_count, uint32_t cap, FrameTotals* totals, TravCounters* cnt)
+{
+    const uint32_t n = min(*ovf_count, cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TravCounters local = {0, 0, 0, 0, 0};
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(ovf_list + k));
+        OverflowEntry oe;
+        oe.ray = u.x; oe.slot = (int32_t)u.y; oe.tstop = __uint_as_float(u.z); oe.pad = 0;
+        const uint4 c = reinterpret_cast<const uint4*>(cand)[oe.ray];
+        CandRec rec;
+        rec.tri[0] = c.x; rec.tri[1] = c.y; rec.tri[2] = c.z; rec.meta = c.w;
+        const CandRec r = finish_overflowed_ray<SHADOW, COUNT>(sc, load_geom(geom + oe.ray), rec, oe, COUNT ? &local : nullptr);
+        reinterpret_cast<uint4*>(cand)[oe.ray] = make_uint4(r.tri[0], r.tri[1], r.tri[2], r.meta);
+    }
+    if (totals && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&totals->cand_overflow, (unsigned long long)n);
     if (COUNT) flush_trav(cnt, local);
 }
 
@@ -848,8 +869,8 @@ static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, con
         if (c->walkBlocksPerSm > 0) full = std::min(full, c->sms * c->walkBlocksPerSm);
     }
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, ((uint64_t)n_hint + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, wb.cand, wb.head, totals, cnt, c->walkSteps, c->refillMin,
-                                                                                  c->useMail, c->bfPush);
+    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, wb.cand, wb.head, wb.ovf_list, wb.ovf_count, cnt, c->walkSteps,
+                                                                                  c->refillMin, c->useMail, c->bfPush);
 }
 template <bool SHADOW, bool PACKED>
 static void launch_walk_p(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
@@ -877,7 +898,19 @@ int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const u
             else launch_walk_p<false, false>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
         }
     }
-    return 1;
+    {
+        LaunchScope ls(c, PROF_FINISH);
+        // a fraction of a percent of the rays: a small grid (it loops over whatever the list holds)
+        const uint32_t blocks = stage_grid(c, std::max<uint32_t>(1, n_hint / 32), 8);
+        if (shadow) {
+            if (cnt) k_finish<true, true><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, cnt);
+            else k_finish<true, false><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, nullptr);
+        } else {
+            if (cnt) k_finish<false, true><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, cnt);
+            else k_finish<false, false><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, nullptr);
+        }
+    }
+    return 2;
 }
 
 int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,

@@ -104,6 +104,10 @@ struct DImage {
 };
 
 struct DScene {
+    // this struct's copy in device memory (static tables only: made by hxr_upload_scene, it does not follow later camera or
+    // settings changes). For the rare non-inlined device functions: they take the scene by pointer, because a reference to
+    // the kernel parameter would make the compiler keep a copy of all of it in every thread's local memory.
+    const DScene* self;
     const hxr_node* nodes;
     const hxr_geometry* geoms;
     const DMesh* meshes;
@@ -144,7 +148,7 @@ struct DScene {
 // optional traversal counters (HXR_RENDER_COUNT_TRAVERSAL)
 struct TravCounters {
     unsigned long long kd_inner, kd_leaves, tri_tests, mesh_queries;
-    unsigned long long cand_resolves;  // candidate records that filled up and were settled exactly inside the walk
+    unsigned long long reserved;
 };
 
 }  // namespace hxr

@@ -13,7 +13,7 @@
 namespace hxr {
 
 // device counters (uint32): queue counts, the shadow queue's count, the work-fetch cursors of the two walks, flags
-enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_HEAD_A = 3, C_HEAD_B = 4, C_OVERFLOW = 5, C_AA = 6, C_NCOUNTERS = 16 };
+enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_HEAD_A = 3, C_HEAD_B = 4, C_OVF_A = 5, C_OVF_B = 6, C_OVERFLOW = 7, C_AA = 8, C_NCOUNTERS = 16 };
 
 Renderer::~Renderer()
 {
@@ -430,6 +430,13 @@ int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
         m_maxShadowPerHit = (int)std::max<long>(m_maxShadowPerHit, sh);
         m_maxChildrenPerHit = (int)std::max<long>(m_maxChildrenPerHit, ch);
     }
+    {
+        // the scene struct itself, in device memory (DScene::self)
+        DScene* d = (DScene*)keep(dev::alloc(m_dev, sizeof(DScene)));
+        if (!d) return oom();
+        m_scene.self = d;
+        if (!dev::upload(m_dev, d, &m_scene, sizeof(DScene))) return oom();
+    }
     m_haveScene = true;
     return HXR_OK;
 }
@@ -460,6 +467,7 @@ void Renderer::freeQueues()
     dev::free_(m_dev, m_sa); m_sa = nullptr;
     dev::free_(m_dev, m_cand); m_cand = nullptr;
     dev::free_(m_dev, m_scand); m_scand = nullptr;
+    dev::free_(m_dev, m_ovfList); m_ovfList = nullptr;
     dev::free_(m_dev, m_hits); m_hits = nullptr;
     dev::free_(m_dev, m_visible); m_visible = nullptr;
     m_cap = m_shadowCap = 0;
@@ -485,10 +493,11 @@ bool Renderer::ensureQueues()
     m_sg = (RayGeom*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(RayGeom));
     m_sa = (ShadowAux*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(ShadowAux));
     m_cand = (CandRec*)dev::alloc(m_dev, (size_t)std::max(cap, shadowCap) * sizeof(CandRec));
+    m_ovfList = (OverflowEntry*)dev::alloc(m_dev, (size_t)std::max(cap, shadowCap) * sizeof(OverflowEntry));
     if (!m_counters) m_counters = (uint32_t*)dev::alloc(m_dev, C_NCOUNTERS * sizeof(uint32_t));
     if (!m_totals) m_totals = (dev::FrameTotals*)dev::alloc(m_dev, sizeof(dev::FrameTotals));
     if (!m_trav) m_trav = (TravCounters*)dev::alloc(m_dev, sizeof(TravCounters));
-    if (!m_qg[0] || !m_qg[1] || !m_qa[0] || !m_qa[1] || !m_sg || !m_sa || !m_cand || !m_counters || !m_totals || !m_trav) {
+    if (!m_qg[0] || !m_qg[1] || !m_qa[0] || !m_qa[1] || !m_sg || !m_sa || !m_cand || !m_ovfList || !m_counters || !m_totals || !m_trav) {
         m_err = "queue allocation failed (out of device memory: lower hxr_config.queue_capacity)";
         freeQueues();
         return false;
@@ -504,6 +513,8 @@ dev::WalkBuffers Renderer::walkBuffers(CandRec* cand, bool shadow) const
     dev::WalkBuffers wb;
     wb.cand = cand;
     wb.head = m_counters + (shadow ? C_HEAD_B : C_HEAD_A);
+    wb.ovf_list = m_ovfList;
+    wb.ovf_count = m_counters + (shadow ? C_OVF_B : C_OVF_A);
     return wb;
 }
 RayQueue Renderer::queue(int i) const
@@ -548,7 +559,7 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
         const uint32_t n = (uint32_t)std::min<uint64_t>(hint, m_cap);
         const RayQueue q = queue(cur);
         dev::zero(m_dev, m_counters + (cur ? C_Q0 : C_Q1), sizeof(uint32_t));
-        dev::zero(m_dev, m_counters + C_SHADOW, 3 * sizeof(uint32_t));  // shadow count + both walk cursors
+        dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));  // shadow count + the walks' cursors and overflow-list counts
         if (level > 0) st.kernel_launches += dev::setup_closest(m_dev, m_scene, q.geom, q.count, q.cap, cnt, n);  // (level 0 arrives set up)
         st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.count, q.cap, walkBuffers(m_cand, false), m_totals, cnt, n);
         Sinks sk;
@@ -567,7 +578,7 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
         }
         for (uint32_t b = 0; b < n; b += chunk) {
             const uint32_t e = (uint32_t)std::min<uint64_t>(n, (uint64_t)b + chunk);
-            if (b) dev::zero(m_dev, m_counters + C_SHADOW, 3 * sizeof(uint32_t));
+            if (b) dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));
             st.kernel_launches += dev::shade(m_dev, m_scene, fp, q, m_cand, b, e, sk, m_totals, cnt);
             {
                 const uint32_t ns = (uint32_t)std::min<uint64_t>(m_shadowCap, (uint64_t)(e - b) * perHit);
@@ -804,6 +815,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
         st.shade_ms = ms[dev::PROF_SHADE];
         st.other_ms = ms[dev::PROF_OTHER] + ms[dev::PROF_GEN];
         st.setup_ms = ms[dev::PROF_SETUP];
+        st.finish_ms = ms[dev::PROF_FINISH];
         st.trace_closest_launches = ln[dev::PROF_WALK_CLOSEST];
         st.trace_shadow_launches = ln[dev::PROF_WALK_SHADOW] + ln[dev::PROF_SHADOW_RESOLVE];
         st.walk_ms = ms[dev::PROF_WALK_CLOSEST] + ms[dev::PROF_WALK_SHADOW];
@@ -911,7 +923,7 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
         DScene full = m_scene;
         full.full_attr = 1;  // the hook reports u, v, dNdx, dNdy of every hit, whatever the node's shader reads
         dev::setup_closest(m_dev, full, q.geom, q.count, q.cap, nullptr, m);
-        dev::zero(m_dev, m_counters + C_SHADOW, 3 * sizeof(uint32_t));
+        dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));
         dev::walk(m_dev, full, false, q.geom, q.count, q.cap, walkBuffers(m_cand, false), nullptr, nullptr, m);
         dev::hit_records(m_dev, full, q, m_cand, m_hits, m);
         if (!dev::download(m_dev, recs.data(), m_hits, (size_t)m * sizeof(HitRec)) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
@@ -957,7 +969,7 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
         dev::upload(m_dev, q.geom, geoms.data(), (size_t)m * sizeof(RayGeom));
         dev::upload(m_dev, q.count, &m, sizeof m);
         dev::setup_shadow(m_dev, m_scene, q.geom, q.count, q.cap, nullptr, m);
-        dev::zero(m_dev, m_counters + C_HEAD_A, 2 * sizeof(uint32_t));
+        dev::zero(m_dev, m_counters + C_HEAD_A, 4 * sizeof(uint32_t));
         dev::walk(m_dev, m_scene, true, q.geom, q.count, q.cap, walkBuffers(m_cand, true), nullptr, nullptr, m);
         dev::resolve_shadow(m_dev, m_scene, q, m_cand, nullptr, m_visible, nullptr, nullptr, m);
         if (!dev::download(m_dev, out + first, m_visible, m) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));

@@ -80,6 +80,7 @@ private:
     RayGeom* m_sg = nullptr;
     ShadowAux* m_sa = nullptr;
     CandRec* m_cand = nullptr;
+    OverflowEntry* m_ovfList = nullptr;  // rays whose candidate record filled up in the current walk
     CandRec* m_scand = nullptr;      // shadow candidates of levels shaded in chunks (allocated on first use)
     bool m_allocFailed = false;
     HitRec* m_hits = nullptr;        // test hook only, allocated on first use

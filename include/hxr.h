@@ -266,8 +266,8 @@ typedef struct hxr_stats {
     uint32_t aa_pixels;
     double walk_ms;         /* device time of the KD-walk kernel launches (closest-hit + shadow) */
     uint64_t walk_launches;
-    uint64_t cand_overflow; /* candidate records that filled up during the walk and were settled exactly on the spot */
-    double shadow_resolve_ms, gen_ms, setup_ms; /* with profiling on: the shadow-resolve, primary-ray and inline-setup kernels */
+    uint64_t cand_overflow; /* rays whose candidate record filled up during the walk (finished by a second, exact-on-the-spot walk) */
+    double shadow_resolve_ms, gen_ms, setup_ms, finish_ms; /* with profiling on: the shadow-resolve, primary-ray, inline-setup and overflow-finish kernels */
 } hxr_stats;
 
 typedef struct hxr_ray {

@@ -136,12 +136,26 @@ int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const u
     const uint32_t n = std::min(*count, cap);
     CandRec* cand = wb.cand;
     parallel_for(c, n, [&](uint32_t i) {
-        if (shadow) cand[i] = cnt ? walk_ray_item<true, true>(sc, geom[i], cnt) : walk_ray_item<true, false>(sc, geom[i], nullptr);
-        else cand[i] = cnt ? walk_ray_item<false, true>(sc, geom[i], cnt) : walk_ray_item<false, false>(sc, geom[i], nullptr);
+        OverflowEntry oe;
+        if (shadow) cand[i] = cnt ? walk_ray_item<true, true>(sc, geom[i], oe, cnt) : walk_ray_item<true, false>(sc, geom[i], oe, nullptr);
+        else cand[i] = cnt ? walk_ray_item<false, true>(sc, geom[i], oe, cnt) : walk_ray_item<false, false>(sc, geom[i], oe, nullptr);
+        if (oe.slot >= 0) {
+            oe.ray = i;
+            oe.pad = 0;
+            wb.ovf_list[__atomic_fetch_add(wb.ovf_count, 1u, __ATOMIC_RELAXED)] = oe;
+        }
     }, cnt != nullptr);
-    (void)totals;
+    const uint32_t m = std::min(*wb.ovf_count, cap);
+    parallel_for(c, m, [&](uint32_t k) {
+        const OverflowEntry oe = wb.ovf_list[k];
+        const uint32_t i = oe.ray;
+        if (shadow) cand[i] = cnt ? finish_overflowed_ray<true, true>(sc, geom[i], cand[i], oe, cnt) : finish_overflowed_ray<true, false>(sc, geom[i], cand[i], oe, nullptr);
+        else cand[i] = cnt ? finish_overflowed_ray<false, true>(sc, geom[i], cand[i], oe, cnt) : finish_overflowed_ray<false, false>(sc, geom[i], cand[i], oe, nullptr);
+    }, cnt != nullptr);
+    if (totals && m) as_atomic(&totals->cand_overflow)->fetch_add(m);
     c->launches[shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST]++;
-    return 1;
+    c->launches[PROF_FINISH]++;
+    return 2;
 }
 
 int shade(Context* c, const DScene& sc, const FrameParams& fp, const RayQueue& q, const CandRec* cand, uint32_t begin, uint32_t end, const Sinks& sinks,
