@@ -113,9 +113,9 @@ static int test_tri_filter(bool packed, size_t n, const double* rays, const doub
         const d3 N = cross(ld3(tt.AB), ld3(tt.AC));
         tt.N[0] = N.x; tt.N[1] = N.y; tt.N[2] = N.z;
         for (int k = 0; k < 3; k++) { tf.A[k] = (float)tt.A[k]; tf.AB[k] = (float)tt.AB[k]; tf.AC[k] = (float)tt.AC[k]; tf.N[k] = (float)tt.N[k]; }
-        // what push_walk_task puts into a WalkTask (pipeline.h): float ray, error bound from |o| and the mesh extent
-        const double mo = std::max(std::fabs(r[0]), std::max(std::fabs(r[1]), std::fabs(r[2])));
-        const float err = f32_above((mo + (double)std::nextafter((float)amax, INFINITY)) * (1.01 / 8388608.0));
+        // what enter_mesh hands the walk (pipeline.h): float ray, error bound from |o| and the mesh extent
+        const float mo = std::max(std::fabs((float)r[0]), std::max(std::fabs((float)r[1]), std::fabs((float)r[2])));
+        const float err = (mo * (1.0f + 1e-6f) + std::nextafter((float)amax, INFINITY)) * (1.02f / 8388608.0f);
         float ghi = 0;
         TriPacked tp;
         if (packed && !pack_tri(tt, tp)) { g_lastError = "hxr_test_tri_filter_packed: triangle does not fit the packed form"; return HXR_ERR_INVALID; }

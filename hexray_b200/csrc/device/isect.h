@@ -891,9 +891,10 @@ HXR_HD_NOINLINE bool geom_intersect(const DScene& sc, int gi, const Ray& ray, Hi
 template <bool COUNT, bool SIMPLE>
 HXR_HD bool node_intersect(const DScene& sc, const hxr_node& nd, const Ray& ray, Hit& info, double world_limit, TravCounters* cnt)
 {
+    const bool ident = (nd.pad & HXR_NODE_IDENT) != 0;  // v * I == v: skip the mat-vecs of an untransformed node
     Ray t;
-    t.o = mul_vm(ray.o - ld3(nd.T.offset), nd.T.inv);
-    const d3 dl = mul_vm(ray.d, nd.T.inv);
+    t.o = ident ? ray.o - ld3(nd.T.offset) : mul_vm(ray.o - ld3(nd.T.offset), nd.T.inv);
+    const d3 dl = ident ? ray.d : mul_vm(ray.d, nd.T.inv);
     t.d = normalize_f(dl);
     t.depth = ray.depth;
     t.flags = ray.flags;
@@ -907,7 +908,7 @@ HXR_HD bool node_intersect(const DScene& sc, const hxr_node& nd, const Ray& ray,
             const DMesh& M = sc.meshes[g.a];
             MeshBest best;
             double gamma_limit = HXR_INF;
-            if (world_limit < HXR_INF) gamma_limit = world_limit / length(mul_vm(t.d, nd.T.m)) * (1.0 + 1e-9) + 1e-9;  // prunes only
+            if (world_limit < HXR_INF) gamma_limit = world_limit / length(ident ? t.d : mul_vm(t.d, nd.T.m)) * (1.0 + 1e-9) + 1e-9;  // prunes only
             hit = mesh_bruteforce(M, t, gamma_limit, best);
             if (hit) mesh_fill_hit(M, nd.geom, t, best, info);
         }
@@ -915,14 +916,14 @@ HXR_HD bool node_intersect(const DScene& sc, const hxr_node& nd, const Ray& ray,
         double gamma_limit = HXR_INF;
         if (world_limit < HXR_INF) {
             // world distance of the object-space point o + g*d is g * |d * m|
-            const double k = length(mul_vm(t.d, nd.T.m));
+            const double k = length(ident ? t.d : mul_vm(t.d, nd.T.m));
             gamma_limit = world_limit / k * (1.0 + 1e-9) + 1e-9;
         }
         hit = geom_intersect<0, COUNT>(sc, nd.geom, t, info, gamma_limit, cnt);
     }
     if (!hit) return false;
-    info.ip = mul_vm(info.ip, nd.T.m) + ld3(nd.T.offset);
-    info.norm = normalize_m(mul_vm(info.norm, nd.T.inv_t));
+    info.ip = (ident ? info.ip : mul_vm(info.ip, nd.T.m)) + ld3(nd.T.offset);
+    info.norm = normalize_m(ident ? info.norm : mul_vm(info.norm, nd.T.inv_t));
     info.dist = distance3(ray.o, info.ip);
     return true;
 }

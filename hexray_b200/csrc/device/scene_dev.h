@@ -17,6 +17,10 @@
 #include "hd.h"
 #include "../../../include/hxr.h"
 
+/* hxr_node::pad in the DEVICE copy of the node table (set by hxr_upload_scene): bit 0 = m, inv and inv_t are exactly the identity
+ * (a node without rotate / scale): v * I == v bit for bit, so the three mat-vecs per transform are skipped */
+#define HXR_NODE_IDENT 1
+
 #define HXR_KD_MAX_DEPTH 60 /* the host build caps the tree depth here */
 #define HXR_KD_STACK 96     /* traversal stack entries: a block step (two levels) pushes at most three */
 
@@ -86,6 +90,7 @@ struct DMesh {
     int32_t n_tris;
     float abs_max;  // largest |coordinate| of the mesh box (error bound of the float filter)
     int32_t pad;
+    float fbmin[3], fbmax[3];  // the box inflated by 1e-6 (the slab test's tolerance, src/bbox.h) as floats rounded outward: the walk's entry test
     int32_t brute;  // test all triangles in index order (tiny meshes, or HXR_CFG_BRUTE_FORCE_MESHES) instead of walking the tree; 3: and skip the box gate
 };
 

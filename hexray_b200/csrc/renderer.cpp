@@ -243,6 +243,10 @@ int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
             amax = std::max(amax, std::max(std::fabs(m.bbox_min[k]), std::fabs(m.bbox_max[k])));
         }
         d.abs_max = std::nextafter((float)amax, INFINITY);
+        for (int k = 0; k < 3; k++) {
+            d.fbmin[k] = std::nextafter((float)(m.bbox_min[k] - 1e-6), -INFINITY);
+            d.fbmax[k] = std::nextafter((float)(m.bbox_max[k] + 1e-6), INFINITY);
+        }
         d.faceted = m.faceted;
         d.backface = m.backface_culling;
         d.n_tris = m.n_triangles;
@@ -285,7 +289,19 @@ int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
         if (n && !di[i].rgb) return oom();
     }
     memset(&m_scene, 0, sizeof m_scene);
-    m_scene.nodes = uploadArray(s.nodes, s.n_nodes);
+    {
+        // the device copy of the node table carries one derived flag: an untransformed node (HXR_NODE_IDENT)
+        std::vector<hxr_node> nodes(s.nodes, s.nodes + s.n_nodes);
+        for (hxr_node& nd : nodes) {
+            bool ident = !getenv("HXR_NO_IDENT");
+            for (int k = 0; k < 9 && ident; k++) {
+                const double want = (k % 4 == 0) ? 1.0 : 0.0;
+                ident = nd.T.m[k] == want && nd.T.inv[k] == want && nd.T.inv_t[k] == want;
+            }
+            nd.pad = ident ? HXR_NODE_IDENT : 0;
+        }
+        m_scene.nodes = uploadArray(nodes.data(), nodes.size());
+    }
     m_scene.geoms = uploadArray(s.geometries, s.n_geometries);
     m_scene.meshes = uploadArray(dm.data(), dm.size());
     m_scene.hfs = uploadArray(dh.data(), dh.size());
