@@ -69,14 +69,17 @@ struct FrameTotals {
 //             sample = fp.sample_base + (i % spp_pass) * fp.sample_stride
 // pixels_count (device, may be null): when given, only the first *pixels_count * spp_pass items exist
 int gen_primary(Context*, const DScene& sc, const FrameParams& fp, const uint32_t* pixels, const uint32_t* pixels_count, uint32_t first_pixel,
-                uint32_t n_items, uint32_t spp_pass, const RayQueue& q);
+                uint32_t n_items, uint32_t spp_pass, const RayQueue& q, CandRec* cand);
 
-// the inline part of queued rays, in place: geom[i].limit / .pre for closest-hit rays (every inline node in scene order: analytic
-// primitives, CSG, heightfields, quads, in double), geom[i].pre = -2 for shadow rays an inline node or a light blocks
-int setup_closest(Context*, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint);
-int setup_shadow(Context*, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint);
+// The inline part of queued rays, in place: geom[i].limit / .pre for closest-hit rays (every inline node in scene order: analytic
+// primitives, CSG, heightfields, quads, in double), geom[i].pre = -2 for shadow rays an inline node or a light blocks; and the
+// rays' slot-0 entry records for the walk (q.entry). Rays with nothing to walk get a dead entry and their candidate record
+// (cand[i]) here. accum (shadow rays, may be null): shadow rays that nothing can block add their colour right away.
+int setup_closest(Context*, const DScene& sc, const RayQueue& q, CandRec* cand, TravCounters* cnt, uint32_t n_hint);
+int setup_shadow(Context*, const DScene& sc, const ShadowQueue& q, CandRec* cand, float* accum, TravCounters* cnt, uint32_t n_hint);
 
-// the KD walk of the big meshes for geom[0 .. *count): one candidate record per ray (wb.head zeroed by the caller).
+// the KD walk of the big meshes for the rays geom[0 .. *count) with slot-0 entries entry[]: one candidate record per live ray
+// (wb.head zeroed by the caller).
 // A ray whose record fills up stops there and is appended to ovf_list (capacity cap, count *ovf_count, zeroed by the caller);
 // a second, small launch finishes those rays (finish_overflowed_ray) and replaces their records. totals->cand_overflow += their number.
 struct WalkBuffers {
@@ -85,8 +88,8 @@ struct WalkBuffers {
     OverflowEntry* ovf_list;
     uint32_t* ovf_count;
 };
-int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb, FrameTotals* totals,
-         TravCounters* cnt, uint32_t n_hint);
+int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const MeshEntry* entry, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
+         FrameTotals* totals, TravCounters* cnt, uint32_t n_hint);
 
 // shade q[begin .. min(end, *q.count)): exact test of the candidates, winner, shading; pushes child rays and shadow rays
 // (raw: their inline part is decided by setup_closest / setup_shadow).

@@ -43,7 +43,7 @@ struct Context {
     bool prof = false;
     // walk-loop tunables (uniform kernel arguments; environment overrides for A/B runs: HXR_WALK_STEPS, HXR_REFILL_MIN, HXR_SSTACK,
     // HXR_NO_MAILBOX, HXR_BRANCHY_PUSH, HXR_WALK_CARVEOUT, HXR_WALK_BLOCKS_PER_SM; measured optima are the defaults)
-    int walkSteps = 3, refillMin = 8, sstack = 10, useMail = 1, bfPush = 1, walkCarveout = -1, walkBlocksPerSm = 0;
+    int walkSteps = 4, refillMin = 8, sstack = 10, useMail = 1, bfPush = 1, walkCarveout = -1, walkBlocksPerSm = 0;
     uint64_t launches[PROF_NCAT] = {};
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPairs[PROF_NCAT];
@@ -322,35 +322,33 @@ __device__ __forceinline__ void flush_trav(TravCounters* cnt, const TravCounters
 template <bool SIMPLE>
 __global__ void __launch_bounds__(128, SIMPLE ? HXR_GEN_BLOCKS : 1) k_gen_primary(DScene sc, FrameParams fp, const uint32_t* __restrict__ pixels,
                                                                                   const uint32_t* __restrict__ pixels_count, uint32_t first_pixel,
-                                                                                  uint32_t n_items, uint32_t spp_pass, RayQueue q)
+                                                                                  uint32_t n_items, uint32_t spp_pass, RayQueue q, CandRec* cand)
 {
     if (pixels_count) n_items = min(n_items, *pixels_count * spp_pass);
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
         const uint32_t pi = i / spp_pass;
         const uint32_t pixel = pixels ? pixels[pi] : first_pixel + pi;
-        gen_primary_item<SIMPLE>(sc, fp, pixel, fp.sample_base + (i % spp_pass) * fp.sample_stride, q.geom, q.aux, i);
+        gen_primary_item<SIMPLE>(sc, fp, pixel, fp.sample_base + (i % spp_pass) * fp.sample_stride, q, cand, i);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *q.count = n_items;
 }
 
-// the inline part of queued rays, in place: reads the 64-byte record, writes back its last 16 bytes
+// the inline part of queued rays, in place (reads the 64-byte record, writes back its last 16 bytes), and their slot-0 entry
+// records for the walk
 template <bool SHADOW, bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup(DScene sc, RayGeom* geom, const uint32_t* __restrict__ count, uint32_t cap,
-                                                                              TravCounters* cnt)
+__global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup(DScene sc, RayGeom* geom, MeshEntry* entry, CandRec* cand, const ShadowAux* aux,
+                                                                              float* accum, const uint32_t* __restrict__ count, uint32_t cap, TravCounters* cnt)
 {
     const uint32_t n = min(*count, cap);
     const uint32_t stride = gridDim.x * blockDim.x;
     TravCounters local = {0, 0, 0, 0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         RayGeom g = load_geom_rw(geom + i);
-        if (SHADOW) {
-            if (g.pre == -2) continue;
-            setup_shadow_geom<COUNT, SIMPLE>(sc, g, COUNT ? &local : nullptr);
-            if (g.pre != -2) continue;  // not blocked: nothing to write
-        } else {
-            setup_closest_geom<COUNT, SIMPLE>(sc, g, COUNT ? &local : nullptr);
-        }
+        const int32_t pre0 = g.pre;
+        if (SHADOW) setup_shadow_geom<COUNT, SIMPLE>(sc, g, entry ? entry + i : nullptr, cand ? cand + i : nullptr, aux + i, accum, COUNT ? &local : nullptr);
+        else setup_closest_geom<COUNT, SIMPLE>(sc, g, entry ? entry + i : nullptr, cand ? cand + i : nullptr, COUNT ? &local : nullptr);
+        if (SHADOW && g.pre == pre0) continue;  // nothing to write back
         double2 tail;
         tail.x = g.limit;
         tail.y = __longlong_as_double((long long)(((unsigned long long)g.depth_flags << 32) | (unsigned long long)(uint32_t)g.pre));
@@ -396,7 +394,8 @@ struct WalkShared {
 
 // SSTACK = stack entries kept in shared memory: every entry costs 1.5 KB of the SM's 256 KB L1/shared array per block
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
-__global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayGeom* __restrict__ geom, const uint32_t* __restrict__ count,
+__global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DScene sc, const RayGeom* __restrict__ geom,
+                                                                              const MeshEntry* __restrict__ entry, const uint32_t* __restrict__ count,
                                                                               uint32_t cap, CandRec* __restrict__ cand, uint32_t* head, OverflowEntry* ovf_list,
                                                                               uint32_t* ovf_count, TravCounters* cnt, int walkSteps, int refillMin, int useMail,
                                                                               int branchFreePush)
@@ -419,6 +418,12 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
     wr.col = &sh.ray[0][tid];
     wr.par = 0;
     for (int r = 0; r < 9; r++) sh.ray[r][tid] = 0.0f;
+    // walked slot 0: what almost every ray walks (its entry arrives precomputed)
+    const int mesh0 = slot_mesh(sc, 0);
+    const KdBlock* const blocks0 = sc.meshes[mesh0].blocks;
+    const uint32_t* const leafTris0 = sc.meshes[mesh0].leaf_tris;
+    const void* const tris0 = PACKED ? (const void*)sc.meshes[mesh0].tri_pk : (const void*)sc.meshes[mesh0].tri_f32;
+    const bool backface0 = sc.meshes[mesh0].backface != 0;
     const KdBlock* blocks = nullptr;  // the current mesh
     const uint32_t* leafTris = nullptr;
     const void* tris = nullptr;  // TriPacked (32 B) or TriF32 (48 B) records of the current mesh
@@ -464,23 +469,50 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                 if (!active && !hasRay) {
                     const uint32_t k = base + __popc(empty & ((1u << lane) - 1u));
                     if (k < n) {
-                        const uint4 w3 = __ldg(reinterpret_cast<const uint4*>(geom + k) + 3);
-                        if ((int32_t)w3.z == -2) {  // past the depth guard / already blocked: nothing to walk
-                            reinterpret_cast<uint4*>(cand)[k] = make_uint4(0u, 0u, 0u, SHADOW ? HXR_CAND_BLOCKED : 0u);
-                        } else {
+                        // the ray's slot-0 entry record, computed by the kernel that set the ray up: three 128-bit loads
+                        const uint4* ep = reinterpret_cast<const uint4*>(entry + k);
+                        const uint4 w0 = __ldg(ep), w1 = __ldg(ep + 1), w2 = __ldg(ep + 2);
+                        if (__uint_as_float(w2.w) >= 0.0f) {  // (a dead ray has its candidate record already)
                             rayIdx = k;
                             hasRay = true;
-                            slot = 0;
-                            const double lim = __hiloint2double((int)w3.y, (int)w3.x);
-                            wcap = __double2float_ru(fmin(lim, 3e38));
+                            slot = 1;
+                            kup = __uint_as_float(w2.w);
+                            tbest = __uint_as_float(w2.x);
+                            wcap = tbest < 3e38f ? fminf(tbest * kup, 3.4e38f) : 3.4e38f;
                             sh.meta[tid] = 0u;
                             sh.cand[0][tid] = 0u; sh.cand[1][tid] = 0u; sh.cand[2][tid] = 0u;
+                            tmin = __uint_as_float(w1.z);
+                            tmax = __uint_as_float(w1.w);
+                            if (tmin <= tmax) {
+                                const float ox = __uint_as_float(w0.x), oy = __uint_as_float(w0.y), oz = __uint_as_float(w0.z);
+                                const float dx = __uint_as_float(w0.w), dy = __uint_as_float(w1.x), dz = __uint_as_float(w1.y);
+                                const WalkRay w = walk_ray_f(ox, oy, oz, dx, dy, dz);
+                                wr.par = w.par;
+                                sh.ray[0][tid] = ox; sh.ray[1][tid] = oy; sh.ray[2][tid] = oz;
+                                sh.ray[3][tid] = w.ix; sh.ray[4][tid] = w.iy; sh.ray[5][tid] = w.iz;
+                                sh.ray[6][tid] = dx; sh.ray[7][tid] = dy; sh.ray[8][tid] = dz;
+                                occ = __uint_as_float(w2.y);
+                                err = __uint_as_float(w2.z);
+                                meshIdx = mesh0;
+                                sh.tb[tid] = __float_as_uint(tbest);
+                                sh.mail[0][tid] = 0xFFFFFFFFu;
+                                sh.mail[1][tid] = 0xFFFFFFFFu;
+                                blocks = blocks0;
+                                leafTris = leafTris0;
+                                tris = tris0;
+                                backface = backface0;
+                                sp = 0;
+                                cur = 0;
+                                active = true;
+                                if (COUNT) local.mesh_queries++;
+                            }
                         }
                     }
                 }
             }
-            // lanes between two meshes: into the next mesh whose box the ray enters
-            if (!active && hasRay) {
+            // lanes between two meshes (scenes with several walked nodes): into the next mesh whose box the ray enters -
+            // the kernel's only double arithmetic (the reference's Node::intersect transform, rounded to float at the end)
+            if (nBig > 1 && !active && hasRay && slot < nBig) {
                 const RayGeom g = load_geom(geom + rayIdx);
                 {
                     const float of[3] = {(float)g.o[0], (float)g.o[1], (float)g.o[2]}, df[3] = {(float)g.d[0], (float)g.d[1], (float)g.d[2]};
@@ -505,7 +537,7 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                         occ = e.occ;
                         err = e.err;
                         kup = e.kup;
-                        meshIdx = e.mesh;
+                        meshIdx = slot_mesh(sc, slot);
                         sh.tb[tid] = __float_as_uint(tbest);
                         sh.mail[0][tid] = 0xFFFFFFFFu;
                         sh.mail[1][tid] = 0xFFFFFFFFu;
@@ -820,43 +852,42 @@ static uint32_t stage_grid(const Context* c, uint32_t n, int perSm = 16)
 }
 
 int gen_primary(Context* c, const DScene& sc, const FrameParams& fp, const uint32_t* pixels, const uint32_t* pixels_count, uint32_t first_pixel,
-                uint32_t n_items, uint32_t spp_pass, const RayQueue& q)
+                uint32_t n_items, uint32_t spp_pass, const RayQueue& q, CandRec* cand)
 {
     LaunchScope ls(c, PROF_GEN);
     const uint32_t blocks = stage_grid(c, n_items, 32);
-    if (sc.simple_inline) k_gen_primary<true><<<blocks, 128, 0, c->stream>>>(sc, fp, pixels, pixels_count, first_pixel, n_items, spp_pass, q);
-    else k_gen_primary<false><<<blocks, 128, 0, c->stream>>>(sc, fp, pixels, pixels_count, first_pixel, n_items, spp_pass, q);
+    RayQueue qq = q;
+    if (!sc.n_big) { qq.entry = nullptr; cand = nullptr; }
+    if (sc.simple_inline) k_gen_primary<true><<<blocks, 128, 0, c->stream>>>(sc, fp, pixels, pixels_count, first_pixel, n_items, spp_pass, qq, cand);
+    else k_gen_primary<false><<<blocks, 128, 0, c->stream>>>(sc, fp, pixels, pixels_count, first_pixel, n_items, spp_pass, qq, cand);
     return 1;
 }
 
-template <bool SHADOW> static void launch_setup(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint)
+template <bool SHADOW> static void launch_setup(Context* c, const DScene& sc, RayGeom* geom, MeshEntry* entry, CandRec* cand, const ShadowAux* aux, float* accum,
+                                                const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint)
 {
     const uint32_t blocks = stage_grid(c, n_hint);
+    if (!sc.n_big) { entry = nullptr; cand = nullptr; }
     // counting builds and scenes with CSG / heightfield / inline tree walks take the generic variant
-    if (cnt) k_setup<SHADOW, true, false><<<blocks, 128, 0, c->stream>>>(sc, geom, count, cap, cnt);
-    else if (sc.simple_inline) k_setup<SHADOW, false, true><<<blocks, 128, 0, c->stream>>>(sc, geom, count, cap, nullptr);
-    else k_setup<SHADOW, false, false><<<blocks, 128, 0, c->stream>>>(sc, geom, count, cap, nullptr);
+    if (cnt) k_setup<SHADOW, true, false><<<blocks, 128, 0, c->stream>>>(sc, geom, entry, cand, aux, accum, count, cap, cnt);
+    else if (sc.simple_inline) k_setup<SHADOW, false, true><<<blocks, 128, 0, c->stream>>>(sc, geom, entry, cand, aux, accum, count, cap, nullptr);
+    else k_setup<SHADOW, false, false><<<blocks, 128, 0, c->stream>>>(sc, geom, entry, cand, aux, accum, count, cap, nullptr);
 }
-int setup_closest(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint)
+int setup_closest(Context* c, const DScene& sc, const RayQueue& q, CandRec* cand, TravCounters* cnt, uint32_t n_hint)
 {
-    if (sc.n_inline == 0 && !cnt) {
-        // nothing inline: only the depth guard, which the generator / shading never violate for queued rays... but explicit
-        // rays (test hooks) may: keep the launch (it is cheap) so that pre = -2 is always decided here
-    }
     LaunchScope ls(c, PROF_SETUP);
-    launch_setup<false>(c, sc, geom, count, cap, cnt, n_hint);
+    launch_setup<false>(c, sc, q.geom, q.entry, cand, nullptr, nullptr, q.count, q.cap, cnt, n_hint);
     return 1;
 }
-int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t n_hint)
+int setup_shadow(Context* c, const DScene& sc, const ShadowQueue& q, CandRec* cand, float* accum, TravCounters* cnt, uint32_t n_hint)
 {
-    if (sc.n_inline == 0 && sc.n_lights == 0) return 0;
     LaunchScope ls(c, PROF_SETUP);
-    launch_setup<true>(c, sc, geom, count, cap, cnt, n_hint);
+    launch_setup<true>(c, sc, q.geom, q.entry, cand, q.aux, accum, q.count, q.cap, cnt, n_hint);
     return 1;
 }
 
 template <bool SHADOW, bool COUNT, int SSTACK, bool PACKED>
-static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
+static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, const MeshEntry* entry, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
                           FrameTotals* totals, TravCounters* cnt, uint32_t n_hint)
 {
     int& full = c->walkGrid[SHADOW][COUNT][SSTACK == 9 ? 0 : (SSTACK == 12 ? 2 : 1)][PACKED];
@@ -869,33 +900,33 @@ static void launch_walk_s(Context* c, const DScene& sc, const RayGeom* geom, con
         if (c->walkBlocksPerSm > 0) full = std::min(full, c->sms * c->walkBlocksPerSm);
     }
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)full, ((uint64_t)n_hint + HXR_WALK_BLOCK - 1) / HXR_WALK_BLOCK));
-    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, count, cap, wb.cand, wb.head, wb.ovf_list, wb.ovf_count, cnt, c->walkSteps,
+    k_walk<SHADOW, COUNT, SSTACK, PACKED><<<grid, HXR_WALK_BLOCK, 0, c->stream>>>(sc, geom, entry, count, cap, wb.cand, wb.head, wb.ovf_list, wb.ovf_count, cnt, c->walkSteps,
                                                                                   c->refillMin, c->useMail, c->bfPush);
 }
 template <bool SHADOW, bool PACKED>
-static void launch_walk_p(Context* c, const DScene& sc, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
+static void launch_walk_p(Context* c, const DScene& sc, const RayGeom* geom, const MeshEntry* entry, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
                           FrameTotals* totals, TravCounters* cnt, uint32_t n_hint)
 {
-    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(c, sc, geom, count, cap, wb, totals, cnt, n_hint); return; }
+    if (cnt) { launch_walk_s<SHADOW, true, 10, PACKED>(c, sc, geom, entry, count, cap, wb, totals, cnt, n_hint); return; }
     switch (c->sstack) {
-        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(c, sc, geom, count, cap, wb, totals, nullptr, n_hint); break;
-        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(c, sc, geom, count, cap, wb, totals, nullptr, n_hint); break;
-        default: launch_walk_s<SHADOW, false, 10, PACKED>(c, sc, geom, count, cap, wb, totals, nullptr, n_hint); break;
+        case 9: launch_walk_s<SHADOW, false, 9, PACKED>(c, sc, geom, entry, count, cap, wb, totals, nullptr, n_hint); break;
+        case 12: launch_walk_s<SHADOW, false, 12, PACKED>(c, sc, geom, entry, count, cap, wb, totals, nullptr, n_hint); break;
+        default: launch_walk_s<SHADOW, false, 10, PACKED>(c, sc, geom, entry, count, cap, wb, totals, nullptr, n_hint); break;
     }
 }
 
-int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb, FrameTotals* totals,
-         TravCounters* cnt, uint32_t n_hint)
+int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const MeshEntry* entry, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
+         FrameTotals* totals, TravCounters* cnt, uint32_t n_hint)
 {
     if (sc.n_big == 0) return 0;
     {
         LaunchScope ls(c, shadow ? PROF_WALK_SHADOW : PROF_WALK_CLOSEST);
         if (shadow) {
-            if (sc.walk_packed) launch_walk_p<true, true>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
-            else launch_walk_p<true, false>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
+            if (sc.walk_packed) launch_walk_p<true, true>(c, sc, geom, entry, count, cap, wb, totals, cnt, n_hint);
+            else launch_walk_p<true, false>(c, sc, geom, entry, count, cap, wb, totals, cnt, n_hint);
         } else {
-            if (sc.walk_packed) launch_walk_p<false, true>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
-            else launch_walk_p<false, false>(c, sc, geom, count, cap, wb, totals, cnt, n_hint);
+            if (sc.walk_packed) launch_walk_p<false, true>(c, sc, geom, entry, count, cap, wb, totals, cnt, n_hint);
+            else launch_walk_p<false, false>(c, sc, geom, entry, count, cap, wb, totals, cnt, n_hint);
         }
     }
     {

@@ -147,11 +147,13 @@ bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& ou
     out.build_ms = 0;
     size_t filterBytes = 0;
     for (int i = 0; i < s.n_meshes; i++) filterBytes += (size_t)s.meshes[i].n_triangles * sizeof(TriF32);
-    // the walk's 32-byte form of the triangles: one sector per test instead of 1.5-2, at ~35 more instructions per test.
-    // Measured (profiles/README.md): on terrain-10M (triangles >> L2, walk bound by memory) k_walk -2.7 %; on cornell_box (36
-    // triangles, walk bound by issue slots) k_walk +12 %. So: packed when the scene's filter triangles outgrow the L2
-    // (HXR_TRI_PACK=0/1 overrides). A mesh with an edge that does not fit the format keeps the scene on tri_f32.
-    const bool wantPack = getenv("HXR_TRI_PACK") ? atoi(getenv("HXR_TRI_PACK")) != 0 : filterBytes > ((size_t)64 << 20);
+    // The walk's optional 32-byte form of the triangles (TriPacked: one sector per test instead of 1.5-2, ~35 more instructions
+    // per test). Round 1's walk waited on memory and gained 2.7 % from it on terrain-10M; since round 2 the walk is bound by
+    // instruction issue (ncu: 70-78 % issue-active) and the 48-byte TriF32 records are 2.5 % FASTER there (profiles/README.md),
+    // as they always were on L2-resident scenes. So: off unless HXR_TRI_PACK=1 asks for it (kept for scenes that outgrow HBM
+    // bandwidth and for the layout-invariance test). A mesh with an edge that does not fit the format keeps the scene on TriF32.
+    const bool wantPack = getenv("HXR_TRI_PACK") ? atoi(getenv("HXR_TRI_PACK")) != 0 : false;
+    (void)filterBytes;
     for (int i = 0; i < s.n_meshes; i++) {
         const hxr_mesh& m = s.meshes[i];
         MeshTables& M = out.meshes[i];
@@ -483,6 +485,8 @@ void Renderer::freeQueues()
     dev::free_(m_dev, m_sa); m_sa = nullptr;
     dev::free_(m_dev, m_cand); m_cand = nullptr;
     dev::free_(m_dev, m_scand); m_scand = nullptr;
+    dev::free_(m_dev, m_entry); m_entry = nullptr;
+    dev::free_(m_dev, m_sentry); m_sentry = nullptr;
     dev::free_(m_dev, m_ovfList); m_ovfList = nullptr;
     dev::free_(m_dev, m_hits); m_hits = nullptr;
     dev::free_(m_dev, m_visible); m_visible = nullptr;
@@ -509,11 +513,13 @@ bool Renderer::ensureQueues()
     m_sg = (RayGeom*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(RayGeom));
     m_sa = (ShadowAux*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(ShadowAux));
     m_cand = (CandRec*)dev::alloc(m_dev, (size_t)std::max(cap, shadowCap) * sizeof(CandRec));
+    m_entry = (MeshEntry*)dev::alloc(m_dev, (size_t)cap * sizeof(MeshEntry));
+    m_sentry = (MeshEntry*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(MeshEntry));
     m_ovfList = (OverflowEntry*)dev::alloc(m_dev, (size_t)std::max(cap, shadowCap) * sizeof(OverflowEntry));
     if (!m_counters) m_counters = (uint32_t*)dev::alloc(m_dev, C_NCOUNTERS * sizeof(uint32_t));
     if (!m_totals) m_totals = (dev::FrameTotals*)dev::alloc(m_dev, sizeof(dev::FrameTotals));
     if (!m_trav) m_trav = (TravCounters*)dev::alloc(m_dev, sizeof(TravCounters));
-    if (!m_qg[0] || !m_qg[1] || !m_qa[0] || !m_qa[1] || !m_sg || !m_sa || !m_cand || !m_ovfList || !m_counters || !m_totals || !m_trav) {
+    if (!m_qg[0] || !m_qg[1] || !m_qa[0] || !m_qa[1] || !m_sg || !m_sa || !m_cand || !m_entry || !m_sentry || !m_ovfList || !m_counters || !m_totals || !m_trav) {
         m_err = "queue allocation failed (out of device memory: lower hxr_config.queue_capacity)";
         freeQueues();
         return false;
@@ -538,6 +544,7 @@ RayQueue Renderer::queue(int i) const
     RayQueue q;
     q.geom = m_qg[i];
     q.aux = m_qa[i];
+    q.entry = m_entry;
     q.count = m_counters + (i ? C_Q1 : C_Q0);
     q.cap = m_cap;
     return q;
@@ -547,6 +554,7 @@ ShadowQueue Renderer::shadowQueue() const
     ShadowQueue q;
     q.geom = m_sg;
     q.aux = m_sa;
+    q.entry = m_sentry;
     q.count = m_counters + C_SHADOW;
     q.cap = m_shadowCap;
     return q;
@@ -576,8 +584,8 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
         const RayQueue q = queue(cur);
         dev::zero(m_dev, m_counters + (cur ? C_Q0 : C_Q1), sizeof(uint32_t));
         dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));  // shadow count + the walks' cursors and overflow-list counts
-        if (level > 0) st.kernel_launches += dev::setup_closest(m_dev, m_scene, q.geom, q.count, q.cap, cnt, n);  // (level 0 arrives set up)
-        st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.count, q.cap, walkBuffers(m_cand, false), m_totals, cnt, n);
+        if (level > 0) st.kernel_launches += dev::setup_closest(m_dev, m_scene, q, m_cand, cnt, n);  // (level 0 arrives set up)
+        st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, false), m_totals, cnt, n);
         Sinks sk;
         sk.next = queue(1 - cur);
         sk.shadow = shadowQueue();
@@ -598,8 +606,8 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
             st.kernel_launches += dev::shade(m_dev, m_scene, fp, q, m_cand, b, e, sk, m_totals, cnt);
             {
                 const uint32_t ns = (uint32_t)std::min<uint64_t>(m_shadowCap, (uint64_t)(e - b) * perHit);
-                st.kernel_launches += dev::setup_shadow(m_dev, m_scene, m_sg, m_counters + C_SHADOW, m_shadowCap, cnt, ns);
-                st.kernel_launches += dev::walk(m_dev, m_scene, true, m_sg, m_counters + C_SHADOW, m_shadowCap, walkBuffers(scand, true), m_totals, cnt, ns);
+                st.kernel_launches += dev::setup_shadow(m_dev, m_scene, sk.shadow, scand, accum, cnt, ns);
+                st.kernel_launches += dev::walk(m_dev, m_scene, true, m_sg, m_sentry, m_counters + C_SHADOW, m_shadowCap, walkBuffers(scand, true), m_totals, cnt, ns);
                 st.kernel_launches += dev::resolve_shadow(m_dev, m_scene, sk.shadow, scand, accum, nullptr, m_totals, cnt, ns);
             }
         }
@@ -720,7 +728,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
                 const uint32_t items = (uint32_t)(nPix * k);
                 for (int e = 0; e < eyes; e++) {
                     setEye(e);
-                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, 0, items, k, queue(0));
+                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, 0, items, k, queue(0), m_cand);
                     drain(fp, eyeBuf[e], items, st);
                 }
             }
@@ -731,7 +739,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
                     const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, nPix - first);
                     for (int e = 0; e < eyes; e++) {
                         setEye(e);
-                        st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, (uint32_t)first, items, 1, queue(0));
+                        st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, (uint32_t)first, items, 1, queue(0), m_cand);
                         drain(fp, eyeBuf[e], items, st);
                     }
                 }
@@ -757,7 +765,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
                 const uint32_t items = (uint32_t)std::min<size_t>(primaryBatch, count - off);
                 for (int e = 0; e < eyes; e++) {
                     setEye(e);
-                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, (uint32_t)(first + off), items, 1, queue(0));
+                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, nullptr, nullptr, (uint32_t)(first + off), items, 1, queue(0), m_cand);
                     drain(fp, eyeBuf[e], items, st);
                 }
             }
@@ -783,7 +791,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
                 const uint32_t np = std::min(pixPerBatch, nAA - first);
                 for (int e = 0; e < eyes; e++) {
                     setEye(e);
-                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, m_aaList + first, nullptr, 0, np * 4, 4, queue(0));
+                    st.kernel_launches += dev::gen_primary(m_dev, m_scene, fp, m_aaList + first, nullptr, 0, np * 4, 4, queue(0), m_cand);
                     drain(fp, eyeBuf[e], np * 4, st);
                 }
             }
@@ -938,9 +946,9 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
         dev::upload(m_dev, q.count, &m, sizeof m);
         DScene full = m_scene;
         full.full_attr = 1;  // the hook reports u, v, dNdx, dNdy of every hit, whatever the node's shader reads
-        dev::setup_closest(m_dev, full, q.geom, q.count, q.cap, nullptr, m);
+        dev::setup_closest(m_dev, full, q, m_cand, nullptr, m);
         dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));
-        dev::walk(m_dev, full, false, q.geom, q.count, q.cap, walkBuffers(m_cand, false), nullptr, nullptr, m);
+        dev::walk(m_dev, full, false, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, false), nullptr, nullptr, m);
         dev::hit_records(m_dev, full, q, m_cand, m_hits, m);
         if (!dev::download(m_dev, recs.data(), m_hits, (size_t)m * sizeof(HitRec)) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
         for (uint32_t i = 0; i < m; i++) {
@@ -984,9 +992,9 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
         const ShadowQueue q = shadowQueue();
         dev::upload(m_dev, q.geom, geoms.data(), (size_t)m * sizeof(RayGeom));
         dev::upload(m_dev, q.count, &m, sizeof m);
-        dev::setup_shadow(m_dev, m_scene, q.geom, q.count, q.cap, nullptr, m);
+        dev::setup_shadow(m_dev, m_scene, q, m_cand, nullptr, nullptr, m);
         dev::zero(m_dev, m_counters + C_HEAD_A, 4 * sizeof(uint32_t));
-        dev::walk(m_dev, m_scene, true, q.geom, q.count, q.cap, walkBuffers(m_cand, true), nullptr, nullptr, m);
+        dev::walk(m_dev, m_scene, true, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, true), nullptr, nullptr, m);
         dev::resolve_shadow(m_dev, m_scene, q, m_cand, nullptr, m_visible, nullptr, nullptr, m);
         if (!dev::download(m_dev, out + first, m_visible, m) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
     }
@@ -1024,7 +1032,7 @@ int Renderer::traceColor(const hxr_ray* rays, size_t n, float* rgb)
         dev::upload(m_dev, q.geom, geoms.data(), (size_t)m * sizeof(RayGeom));
         dev::upload(m_dev, q.aux, auxs.data(), (size_t)m * sizeof(RayAux));
         dev::upload(m_dev, q.count, &m, sizeof m);
-        dev::setup_closest(m_dev, m_scene, q.geom, q.count, q.cap, nullptr, m);
+        dev::setup_closest(m_dev, m_scene, q, m_cand, nullptr, m);
         drain(fp, acc, m, st);
         if (m_allocFailed) rc = HXR_ERR_CUDA;
         else if (readCount(m_counters + C_OVERFLOW)) rc = fail(HXR_ERR_OVERFLOW, "trace_color: queue overflow");

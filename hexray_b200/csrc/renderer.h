@@ -80,6 +80,8 @@ private:
     RayGeom* m_sg = nullptr;
     ShadowAux* m_sa = nullptr;
     CandRec* m_cand = nullptr;
+    MeshEntry* m_entry = nullptr;    // slot-0 entry records of the closest-hit rays of the current level
+    MeshEntry* m_sentry = nullptr;   // ... of the shadow rays
     OverflowEntry* m_ovfList = nullptr;  // rays whose candidate record filled up in the current walk
     CandRec* m_scand = nullptr;      // shadow candidates of levels shaded in chunks (allocated on first use)
     bool m_allocFailed = false;

@@ -86,42 +86,50 @@ void prof_collect(Context* c, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT]
 }
 
 int gen_primary(Context* c, const DScene& sc, const FrameParams& fp, const uint32_t* pixels, const uint32_t* pixels_count, uint32_t first_pixel,
-                uint32_t n_items, uint32_t spp_pass, const RayQueue& q)
+                uint32_t n_items, uint32_t spp_pass, const RayQueue& q, CandRec* cand)
 {
+    RayQueue qq = q;
+    if (!sc.n_big) { qq.entry = nullptr; cand = nullptr; }
     if (pixels_count) n_items = std::min(n_items, *pixels_count * spp_pass);
     parallel_for(c, n_items, [&](uint32_t i) {
         const uint32_t pi = i / spp_pass;
         const uint32_t pixel = pixels ? pixels[pi] : first_pixel + pi;
         const uint32_t sample = fp.sample_base + (i % spp_pass) * fp.sample_stride;
-        if (sc.simple_inline) gen_primary_item<true>(sc, fp, pixel, sample, q.geom, q.aux, i);
-        else gen_primary_item<false>(sc, fp, pixel, sample, q.geom, q.aux, i);
+        if (sc.simple_inline) gen_primary_item<true>(sc, fp, pixel, sample, qq, cand, i);
+        else gen_primary_item<false>(sc, fp, pixel, sample, qq, cand, i);
     });
     *q.count = n_items;
     c->launches[PROF_GEN]++;
     return 1;
 }
 
-int setup_closest(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t)
+int setup_closest(Context* c, const DScene& sc, const RayQueue& q, CandRec* cand, TravCounters* cnt, uint32_t)
 {
-    const uint32_t n = std::min(*count, cap);
+    const uint32_t n = std::min(*q.count, q.cap);
+    RayGeom* geom = q.geom;
+    MeshEntry* entry = sc.n_big ? q.entry : nullptr;
     parallel_for(c, n, [&](uint32_t i) {
-        if (cnt) setup_closest_geom<true, false>(sc, geom[i], cnt);
-        else if (sc.simple_inline) setup_closest_geom<false, true>(sc, geom[i], nullptr);
-        else setup_closest_geom<false, false>(sc, geom[i], nullptr);
+        MeshEntry* e = entry ? entry + i : nullptr;
+        CandRec* cr = entry ? cand + i : nullptr;
+        if (cnt) setup_closest_geom<true, false>(sc, geom[i], e, cr, cnt);
+        else if (sc.simple_inline) setup_closest_geom<false, true>(sc, geom[i], e, cr, nullptr);
+        else setup_closest_geom<false, false>(sc, geom[i], e, cr, nullptr);
     }, cnt != nullptr);
     c->launches[PROF_SETUP]++;
     return 1;
 }
 
-int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* count, uint32_t cap, TravCounters* cnt, uint32_t)
+int setup_shadow(Context* c, const DScene& sc, const ShadowQueue& q, CandRec* cand, float* accum, TravCounters* cnt, uint32_t)
 {
-    if (sc.n_inline == 0 && sc.n_lights == 0) return 0;
-    const uint32_t n = std::min(*count, cap);
+    const uint32_t n = std::min(*q.count, q.cap);
+    RayGeom* geom = q.geom;
+    MeshEntry* entry = sc.n_big ? q.entry : nullptr;
     parallel_for(c, n, [&](uint32_t i) {
-        if (geom[i].pre == -2) return;
-        if (cnt) setup_shadow_geom<true, false>(sc, geom[i], cnt);
-        else if (sc.simple_inline) setup_shadow_geom<false, true>(sc, geom[i], nullptr);
-        else setup_shadow_geom<false, false>(sc, geom[i], nullptr);
+        MeshEntry* e = entry ? entry + i : nullptr;
+        CandRec* cr = entry ? cand + i : nullptr;
+        if (cnt) setup_shadow_geom<true, false>(sc, geom[i], e, cr, q.aux + i, accum, cnt);
+        else if (sc.simple_inline) setup_shadow_geom<false, true>(sc, geom[i], e, cr, q.aux + i, accum, nullptr);
+        else setup_shadow_geom<false, false>(sc, geom[i], e, cr, q.aux + i, accum, nullptr);
     }, cnt != nullptr);
     c->launches[PROF_SETUP]++;
     return 1;
@@ -129,16 +137,17 @@ int setup_shadow(Context* c, const DScene& sc, RayGeom* geom, const uint32_t* co
 
 static std::atomic<unsigned long long>* as_atomic(unsigned long long* p) { return reinterpret_cast<std::atomic<unsigned long long>*>(p); }
 
-int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const uint32_t* count, uint32_t cap, const WalkBuffers& wb, FrameTotals* totals,
-         TravCounters* cnt, uint32_t)
+int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const MeshEntry* entry, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
+         FrameTotals* totals, TravCounters* cnt, uint32_t)
 {
     if (sc.n_big == 0) return 0;
     const uint32_t n = std::min(*count, cap);
     CandRec* cand = wb.cand;
     parallel_for(c, n, [&](uint32_t i) {
         OverflowEntry oe;
-        if (shadow) cand[i] = cnt ? walk_ray_item<true, true>(sc, geom[i], oe, cnt) : walk_ray_item<true, false>(sc, geom[i], oe, nullptr);
-        else cand[i] = cnt ? walk_ray_item<false, true>(sc, geom[i], oe, cnt) : walk_ray_item<false, false>(sc, geom[i], oe, nullptr);
+        if (entry[i].kup < 0.0f) return;  // dead: its candidate record was written by the setup kernel
+        if (shadow) cand[i] = cnt ? walk_ray_item<true, true>(sc, geom[i], entry[i], oe, cnt) : walk_ray_item<true, false>(sc, geom[i], entry[i], oe, nullptr);
+        else cand[i] = cnt ? walk_ray_item<false, true>(sc, geom[i], entry[i], oe, cnt) : walk_ray_item<false, false>(sc, geom[i], entry[i], oe, nullptr);
         if (oe.slot >= 0) {
             oe.ray = i;
             oe.pad = 0;
