@@ -90,7 +90,9 @@ HXR_HD d3 hemisphere_sample(Rng& rng, const d3& normal)
     double theta = 2 * HXR_PI * u;
     double cosPhi = 2 * v - 1;
     double sinPhi = sqrt(1 - cosPhi * cosPhi);
-    d3 vec = mk3(cos(theta) * sinPhi, cosPhi, sin(theta) * sinPhi);
+    double st, ct;
+    sincos(theta, &st, &ct);  // one argument reduction for both
+    d3 vec = mk3(ct * sinPhi, cosPhi, st * sinPhi);
     if (dot(vec, normal) < 0) vec = -vec;
     return vec;
 }

@@ -122,6 +122,9 @@ struct DScene {
     const hxr_texture* textures;
     const DImage* images;
     const hxr_light* lights;
+    // per light: conservative float world box of what a ray can hit of it (rect lights; an empty box for point lights):
+    // raycast's light loop skips the double transform of a light whose box the ray certainly misses
+    const float* light_box;
     // per node: slot of its traversal results if its geometry is a "big" mesh (walked by the persistent
     // traversal kernel), -1 otherwise (analytic primitives, CSG, heightfields, meshes <= HXR_SMALL_MESH)
     const int32_t* node_slot;

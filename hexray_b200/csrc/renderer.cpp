@@ -312,6 +312,32 @@ int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
     m_scene.textures = uploadArray(s.textures, s.n_textures);
     m_scene.images = uploadArray(di.data(), di.size());
     m_scene.lights = uploadArray(s.lights, s.n_lights);
+    {
+        // world boxes of the rect lights (unit square in local xz, src/lights.cpp:53-73), padded; point lights cannot be hit
+        std::vector<float> lb((size_t)std::max(1, s.n_lights) * 6, 0.0f);
+        for (int i = 0; i < s.n_lights; i++) {
+            float* b = &lb[(size_t)i * 6];
+            if (s.lights[i].type != HXR_LIGHT_RECT) { for (int k = 0; k < 3; k++) { b[k] = INFINITY; b[3 + k] = -INFINITY; } continue; }
+            const hxr_transform& T = s.lights[i].T;
+            double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+            for (int c = 0; c < 4; c++) {
+                const double p[3] = {(c & 1) ? 0.5 : -0.5, 0.0, (c & 2) ? 0.5 : -0.5};
+                for (int k = 0; k < 3; k++) {
+                    const double w = p[0] * T.m[k] + p[1] * T.m[3 + k] + p[2] * T.m[6 + k] + T.offset[k];
+                    mn[k] = std::min(mn[k], w);
+                    mx[k] = std::max(mx[k], w);
+                }
+            }
+            for (int k = 0; k < 3; k++) {
+                const double pad = 1e-4 * (1.0 + std::max(std::fabs(mn[k]), std::fabs(mx[k])));
+                const bool ok = std::isfinite(mn[k]) && std::isfinite(mx[k]) && std::fabs(mn[k]) < 1e30 && std::fabs(mx[k]) < 1e30;
+                b[k] = ok ? std::nextafter((float)(mn[k] - pad), -INFINITY) : -INFINITY;
+                b[3 + k] = ok ? std::nextafter((float)(mx[k] + pad), INFINITY) : INFINITY;
+            }
+        }
+        m_scene.light_box = uploadArray(lb.data(), lb.size());
+        if (!m_scene.light_box) return oom();
+    }
     if (!m_scene.nodes || !m_scene.geoms || !m_scene.meshes || !m_scene.hfs || !m_scene.shaders || !m_scene.layers ||
         !m_scene.textures || !m_scene.images || !m_scene.lights)
         return oom();
