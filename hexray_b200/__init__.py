@@ -91,10 +91,16 @@ class SceneFile:
 class Renderer:
     """One GPU context (one process per GPU)."""
 
-    def __init__(self, device=0, queue_capacity=0, api_=None, flags=0):
+    def __init__(self, device=0, queue_capacity=0, api_=None, flags=0, devices=None):
+        """devices: a list of CUDA ordinals for ONE context over several GPUs (the library shards every frame over them and
+        sums the partial frames itself); default: the single GPU `device`."""
         self.api = api_ or api()
         self.ctx = C.c_void_p()
-        cfg = capi.Config(device, flags, queue_capacity)
+        if devices:
+            self._devs = (C.c_int32 * len(devices))(*devices)
+            cfg = capi.Config(device, flags, queue_capacity, len(devices), 0, self._devs)
+        else:
+            cfg = capi.Config(device, flags, queue_capacity, 0, 0, None)
         st = self.api.lib.hxr_create(C.byref(cfg), C.byref(self.ctx))
         if st != capi.HXR_OK:
             raise HxrError(st, self.api.last_error(None))
@@ -180,6 +186,9 @@ class Renderer:
     def save_frame_exr(self, path, dptr=None, width=0, height=0):
         """Bitmap::saveEXR of the last rendered frame (or the device frame at `dptr`): float -> half on the GPU."""
         self._check(self.api.lib.hxr_save_frame_exr(self.ctx, C.c_void_p(dptr) if dptr else None, width, height, path.encode()))
+
+    def reduce_backend(self):
+        return self.api.lib.hxr_reduce_backend(self.ctx).decode()
 
     def set_profiling(self, on):
         self._check(self.api.lib.hxr_set_profiling(self.ctx, 1 if on else 0))

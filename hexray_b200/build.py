@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libhexray_b200.so")
 OBJ = os.path.join(HERE, "build")
 
-HOST_SOURCES = ["abi.cpp", "renderer.cpp", "host/scene.cpp", "host/mesh.cpp", "host/flatten.cpp",
+HOST_SOURCES = ["abi.cpp", "renderer.cpp", "multi.cpp", "host/scene.cpp", "host/mesh.cpp", "host/flatten.cpp",
                 "host/bitmap.cpp", "host/kdtree.cpp"]
 CUDA_SOURCES = ["device/launch_cuda.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -73,7 +73,7 @@ def build(force=False, verbose=False, out=None, defines=()):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    link = [nvcc, "-shared", "-o", OUT] + objs + ["-lz", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a"]
+    link = [nvcc, "-shared", "-o", OUT] + objs + ["-lz", "-ldl", "-lpthread", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)

@@ -102,7 +102,8 @@ class Camera(C.Structure):
 
 
 class Config(C.Structure):
-    _fields_ = [("device", c_i32), ("flags", c_i32), ("queue_capacity", c_u64)]
+    _fields_ = [("device", c_i32), ("flags", c_i32), ("queue_capacity", c_u64), ("n_devices", c_i32), ("reserved", c_i32),
+                ("devices", C.POINTER(c_i32))]
 
 
 class RenderParams(C.Structure):
@@ -117,7 +118,7 @@ class Stats(C.Structure):
                 ("trace_closest_ms", c_f64), ("trace_shadow_ms", c_f64), ("shade_ms", c_f64), ("other_ms", c_f64),
                 ("trace_closest_launches", c_u64), ("trace_shadow_launches", c_u64), ("spp_done", c_u32),
                 ("aa_pixels", c_u32), ("walk_ms", c_f64), ("walk_launches", c_u64), ("cand_overflow", c_u64),
-                ("shadow_resolve_ms", c_f64), ("gen_ms", c_f64), ("setup_ms", c_f64), ("finish_ms", c_f64)]
+                ("shadow_resolve_ms", c_f64), ("gen_ms", c_f64), ("setup_ms", c_f64), ("finish_ms", c_f64), ("reduce_ms", c_f64), ("n_devices", c_u32), ("reserved", c_u32)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -141,7 +142,7 @@ SYMBOLS = ["hxr_create", "hxr_destroy", "hxr_last_error", "hxr_upload_scene", "h
            "hxr_render_device", "hxr_resolve_device", "hxr_trace_closest", "hxr_trace_visible", "hxr_trace_color",
            "hxr_get_accel_info", "hxr_set_profiling", "hxr_scene_load", "hxr_scene_file_scene", "hxr_scene_file_camera",
            "hxr_scene_file_set_synthetic_mesh", "hxr_scene_file_write_obj", "hxr_scene_file_free", "hxr_save_image", "hxr_load_image",
-           "hxr_test_tri_filter", "hxr_test_tri_filter_packed", "hxr_save_frame_bmp", "hxr_save_frame_exr"]
+           "hxr_test_tri_filter", "hxr_test_tri_filter_packed", "hxr_save_frame_bmp", "hxr_save_frame_exr", "hxr_device_count", "hxr_reduce_backend"]
 
 
 class Api:
@@ -180,6 +181,9 @@ class Api:
         L.hxr_save_image.argtypes = [C.c_char_p, C.POINTER(c_f32), c_i32, c_i32]
         L.hxr_save_frame_bmp.argtypes = [vp, vp, c_i32, c_i32, C.c_char_p]
         L.hxr_save_frame_exr.argtypes = [vp, vp, c_i32, c_i32, C.c_char_p]
+        L.hxr_device_count.argtypes = []
+        L.hxr_reduce_backend.argtypes = [vp]
+        L.hxr_reduce_backend.restype = C.c_char_p
         L.hxr_test_tri_filter.argtypes = [C.c_size_t, vp, vp, vp, c_i32, vp, vp, vp, vp]
         L.hxr_test_tri_filter_packed.argtypes = [C.c_size_t, vp, vp, vp, c_i32, vp, vp, vp, vp]
         L.hxr_load_image.argtypes = [C.c_char_p, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_f32), C.c_size_t]

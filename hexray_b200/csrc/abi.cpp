@@ -4,11 +4,11 @@
 #include <string>
 #include "../../include/hxr.h"
 #include "host/scene.h"
-#include "renderer.h"
+#include "multi.h"
 #include "device/isect.h"
 
 struct hxr_ctx {
-    hxr::Renderer r;
+    hxr::MultiRenderer m;  // one or several GPUs
     std::string err;
 };
 
@@ -44,8 +44,8 @@ int hxr_create(const hxr_config* cfg, hxr_ctx** out)
     memset(&c, 0, sizeof c);
     if (cfg) c = *cfg;
     std::unique_ptr<hxr_ctx> ctx(new hxr_ctx);
-    int rc = ctx->r.create(c, c.device);
-    if (rc != HXR_OK) { g_lastError = ctx->r.error(); return rc; }
+    int rc = ctx->m.create(c);
+    if (rc != HXR_OK) { g_lastError = ctx->m.error(); return rc; }
     *out = ctx.release();
     return HXR_OK;
     HXR_GUARD_END(g_lastError)
@@ -59,7 +59,7 @@ void hxr_destroy(hxr_ctx* ctx)
 const char* hxr_last_error(const hxr_ctx* ctx)
 {
     if (!ctx) return g_lastError.c_str();
-    return ctx->err.empty() ? ctx->r.error().c_str() : ctx->err.c_str();
+    return ctx->err.empty() ? ctx->m.error().c_str() : ctx->err.c_str();
 }
 
 #define HXR_CTX_CALL(expr)                                   \
@@ -69,29 +69,32 @@ const char* hxr_last_error(const hxr_ctx* ctx)
     return (expr);                                           \
     HXR_GUARD_END(ctx->err)
 
-int hxr_upload_scene(hxr_ctx* ctx, const hxr_scene* scene) { HXR_CTX_CALL(ctx->r.uploadScene(scene)) }
-int hxr_set_camera(hxr_ctx* ctx, const hxr_camera* cam) { HXR_CTX_CALL(ctx->r.setCamera(cam)) }
+int hxr_device_count(void) { return hxr::dev::device_count(); }
+const char* hxr_reduce_backend(const hxr_ctx* ctx) { return ctx ? ctx->m.reduceName() : "none"; }
+
+int hxr_upload_scene(hxr_ctx* ctx, const hxr_scene* scene) { HXR_CTX_CALL(ctx->m.uploadScene(scene)) }
+int hxr_set_camera(hxr_ctx* ctx, const hxr_camera* cam) { HXR_CTX_CALL(ctx->m.setCamera(cam)) }
 
 int hxr_render(hxr_ctx* ctx, const hxr_render_params* p, float* rgb_out, hxr_stats* stats)
 {
     if (ctx && !p) { ctx->err = "null render params"; return HXR_ERR_INVALID; }
     if (ctx && !rgb_out) { ctx->err = "null output buffer"; return HXR_ERR_INVALID; }
-    HXR_CTX_CALL(ctx->r.render(*p, rgb_out, nullptr, stats))
+    HXR_CTX_CALL(ctx->m.render(*p, rgb_out, nullptr, stats))
 }
 int hxr_render_device(hxr_ctx* ctx, const hxr_render_params* p, void* d_rgb, hxr_stats* stats)
 {
     if (ctx && !p) { ctx->err = "null render params"; return HXR_ERR_INVALID; }
     if (ctx && !d_rgb) { ctx->err = "null output buffer"; return HXR_ERR_INVALID; }
-    HXR_CTX_CALL(ctx->r.render(*p, nullptr, d_rgb, stats))
+    HXR_CTX_CALL(ctx->m.render(*p, nullptr, d_rgb, stats))
 }
-int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t w, int32_t h, int32_t spp) { HXR_CTX_CALL(ctx->r.resolveDevice(d_rgb, w, h, spp)) }
-int hxr_set_profiling(hxr_ctx* ctx, int32_t on) { HXR_CTX_CALL((ctx->r.setProfiling(on != 0), HXR_OK)) }
-int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits) { HXR_CTX_CALL(ctx->r.traceClosest(rays, n, hits)) }
-int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->r.traceVisible(seg, n, vis)) }
-int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { HXR_CTX_CALL(ctx->r.traceColor(rays, n, rgb)) }
-int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out) { HXR_CTX_CALL(ctx->r.accelInfo(mesh, out)) }
-int hxr_save_frame_bmp(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->r.saveFrameBmp(d_rgb, w, h, path)) }
-int hxr_save_frame_exr(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->r.saveFrameExr(d_rgb, w, h, path)) }
+int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t w, int32_t h, int32_t spp) { HXR_CTX_CALL(ctx->m.primary().resolveDevice(d_rgb, w, h, spp)) }
+int hxr_set_profiling(hxr_ctx* ctx, int32_t on) { HXR_CTX_CALL((ctx->m.setProfiling(on != 0), HXR_OK)) }
+int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits) { HXR_CTX_CALL(ctx->m.primary().traceClosest(rays, n, hits)) }
+int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->m.primary().traceVisible(seg, n, vis)) }
+int hxr_trace_color(hxr_ctx* ctx, const hxr_ray* rays, size_t n, float* rgb) { HXR_CTX_CALL(ctx->m.primary().traceColor(rays, n, rgb)) }
+int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out) { HXR_CTX_CALL(ctx->m.primary().accelInfo(mesh, out)) }
+int hxr_save_frame_bmp(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->m.primary().saveFrameBmp(d_rgb, w, h, path)) }
+int hxr_save_frame_exr(hxr_ctx* ctx, const void* d_rgb, int32_t w, int32_t h, const char* path) { HXR_CTX_CALL(ctx->m.primary().saveFrameExr(d_rgb, w, h, path)) }
 
 static int test_tri_filter(bool packed, size_t n, const double* rays, const double* tris, const double* tbest, int32_t backface, int32_t* cls_out,
                            float* ghi_out, int32_t* exact_out, double* gamma_out)

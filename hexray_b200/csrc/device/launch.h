@@ -121,5 +121,19 @@ int to_exr_rows(Context*, const float* rgb, int W, int H, uint16_t* out);
 // anaglyph mix of the two eyes' images into out (n_pixels RGB pixels)
 int stereo_mix(Context*, float* out, const float* left, const float* right, size_t n_pixels);
 
+// ---- several devices in one process (multi.cpp: one Renderer per device, one host thread each) ----------------------
+// Can kernels of `a` read `b`'s device memory directly (NVLink / PCIe peer access, enabled here)? The same device: yes.
+bool enable_peer(Context* a, Context* b);
+// dst = (dst + srcs[0] + ... + srcs[n_src - 1]) * scale over n floats, ONE kernel on a's device that reads the other
+// devices' buffers in place over NVLink: the per-GPU partial frames are summed and resolved (1 / spp) in the same pass
+#define HXR_MAX_PEERS 15
+int reduce_peers(Context* a, float* dst, const float* const* srcs, int n_src, size_t n, float scale);
+// An NCCL communicator over the contexts (ncclCommInitAll; libnccl is loaded at run time, nullptr + err if it is missing or
+// refuses, e.g. the same device twice). comm_reduce_sum: ncclReduce(sum) of bufs[i] (on ctxs[i]) into bufs[0] on the contexts' streams.
+struct Comm;
+Comm* comm_create(Context* const* ctxs, int n, char* err, size_t errlen);
+void comm_destroy(Comm*);
+bool comm_reduce_sum(Comm*, float* const* bufs, size_t n);
+
 }  // namespace dev
 }  // namespace hxr

@@ -25,6 +25,7 @@
 // kernels are grid-stride loops over device-side counts, sized by a host-side upper bound of the count: the host never
 // reads a count back between bounces.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -1026,5 +1027,112 @@ int stereo_mix(Context* c, float* out, const float* left, const float* right, si
     k_stereo_mix<<<c->sms * 8, 256, 0, c->stream>>>(out, left, right, n_pixels);
     return 1;
 }
+// ---- several devices ---------------------------------------------------------------------------------------------
+bool enable_peer(Context* a, Context* b)
+{
+    if (a->device == b->device) return true;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, a->device, b->device) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+    if (cudaSetDevice(a->device) != cudaSuccess) return false;
+    const cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+    cudaGetLastError();
+    return true;
+}
+
+struct PeerPtrs { const float* p[HXR_MAX_PEERS]; };
+// the partial frames of the other GPUs, read where they lie (peer memory over NVLink), summed into this GPU's and resolved
+__global__ void __launch_bounds__(256) k_reduce_peers(float* __restrict__ dst, PeerPtrs srcs, int n_src, size_t n, float scale)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 a = reinterpret_cast<const float4*>(dst)[i];
+        for (int k = 0; k < n_src; k++) {
+            const float4 b = reinterpret_cast<const float4*>(srcs.p[k])[i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+        reinterpret_cast<float4*>(dst)[i] = a;
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float a = dst[i];
+        for (int k = 0; k < n_src; k++) a += srcs.p[k][i];
+        dst[i] = a * scale;
+    }
+}
+int reduce_peers(Context* c, float* dst, const float* const* srcs, int n_src, size_t n, float scale)
+{
+    if (n_src > HXR_MAX_PEERS) return 0;
+    LaunchScope ls(c, PROF_OTHER);
+    PeerPtrs pp;
+    for (int k = 0; k < HXR_MAX_PEERS; k++) pp.p[k] = k < n_src ? srcs[k] : nullptr;
+    k_reduce_peers<<<c->sms * 8, 256, 0, c->stream>>>(dst, pp, n_src, n, scale);
+    return 1;
+}
+
+// NCCL, bound at run time: the library must load (and render on one GPU) where libnccl is absent
+struct Comm {
+    void* lib = nullptr;
+    int n = 0;
+    std::vector<void*> comms;  // ncclComm_t
+    std::vector<Context*> ctxs;
+    int (*groupStart)() = nullptr;
+    int (*groupEnd)() = nullptr;
+    int (*reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*commDestroy)(void*) = nullptr;
+    const char* (*errString)(int) = nullptr;
+};
+Comm* comm_create(Context* const* ctxs, int n, char* err, size_t errlen)
+{
+    auto fail = [&](const std::string& m) -> Comm* { snprintf(err, errlen, "%s", m.c_str()); return nullptr; };
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail("libnccl.so.2 not found");
+    Comm* c = new Comm;
+    c->lib = lib;
+    c->n = n;
+    auto initAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
+    c->groupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+    c->groupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+    c->reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(lib, "ncclReduce");
+    c->commDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    c->errString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!initAll || !c->groupStart || !c->groupEnd || !c->reduce || !c->commDestroy) { delete c; return fail("libnccl lacks the expected symbols"); }
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) {
+        devs[i] = ctxs[i]->device;
+        for (int j = 0; j < i; j++)
+            if (devs[j] == devs[i]) { delete c; return fail("NCCL needs distinct devices"); }
+        c->ctxs.push_back(ctxs[i]);
+    }
+    c->comms.resize(n, nullptr);
+    const int rc = initAll(c->comms.data(), n, devs.data());
+    if (rc != 0) {
+        const std::string m = std::string("ncclCommInitAll: ") + (c->errString ? c->errString(rc) : "failed");
+        delete c;
+        return fail(m);
+    }
+    return c;
+}
+void comm_destroy(Comm* c)
+{
+    if (!c) return;
+    for (void* m : c->comms)
+        if (m) c->commDestroy(m);
+    delete c;
+}
+bool comm_reduce_sum(Comm* c, float* const* bufs, size_t n)
+{
+    // ncclFloat = 7, ncclSum = 0 (nccl.h); one group: every rank of this process enqueues its part on its own stream
+    bool ok = c->groupStart() == 0;
+    for (int i = 0; i < c->n && ok; i++) {
+        cudaSetDevice(c->ctxs[i]->device);
+        ok = c->reduce(bufs[i], bufs[i], n, 7, 0, 0, c->comms[i], c->ctxs[i]->stream) == 0;
+    }
+    ok = (c->groupEnd() == 0) && ok;
+    return ok;
+}
+
 }  // namespace dev
 }  // namespace hxr

@@ -643,10 +643,23 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
 }
 
 // ------------------------------------------------------------------------------ frames
-int Renderer::render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats)
+void Renderer::framePlan(const hxr_render_params& p, bool& mc, int& spp) const
+{
+    // what render() would pick (src/main.cpp:421-425)
+    int raysPerPixel = 0;
+    if (m_scene.cam.dof) raysPerPixel = m_scene.cam.num_samples;
+    if (m_scene.settings.gi) raysPerPixel = std::max(raysPerPixel, m_scene.settings.num_paths);
+    mc = raysPerPixel > 0;
+    if (p.mode == HXR_MODE_WHITTED) mc = false;
+    if (p.mode == HXR_MODE_MONTECARLO) mc = true;
+    spp = p.spp > 0 ? p.spp : std::max(raysPerPixel, 1);
+}
+
+int Renderer::render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, bool noOutput)
 {
     if (!m_haveScene || !m_haveCamera) return fail(HXR_ERR_INVALID, "render: scene and camera must be set first");
-    if (!hostOut && !devOut) return fail(HXR_ERR_INVALID, "render: no output buffer");
+    if (!hostOut && !devOut && !noOutput) return fail(HXR_ERR_INVALID, "render: no output buffer");
+    m_noOutput = noOutput;
     if (!ensureQueues()) return HXR_ERR_CUDA;
     uint32_t batch = m_maxChildrenPerHit > 1 ? m_cap / 4 : m_cap;
     for (int attempt = 0; attempt < 6; attempt++) {
@@ -667,14 +680,9 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
     const int H = p.height > 0 ? p.height : m_scene.settings.frame_height;
     if (W <= 0 || H <= 0 || (uint64_t)W * H > (1ull << 31)) return fail(HXR_ERR_INVALID, "bad frame size");
     const size_t nPix = (size_t)W * H;
-    // what render() would pick (src/main.cpp:421-425)
-    int raysPerPixel = 0;
-    if (m_scene.cam.dof) raysPerPixel = m_scene.cam.num_samples;
-    if (m_scene.settings.gi) raysPerPixel = std::max(raysPerPixel, m_scene.settings.num_paths);
-    bool mc = raysPerPixel > 0;
-    if (p.mode == HXR_MODE_WHITTED) mc = false;
-    if (p.mode == HXR_MODE_MONTECARLO) mc = true;
-    int spp = p.spp > 0 ? p.spp : std::max(raysPerPixel, 1);
+    bool mc;
+    int spp;
+    framePlan(p, mc, spp);
     const int shardCount = p.shard_count > 1 ? p.shard_count : 1;
     const int shardIndex = shardCount > 1 ? p.shard_index : 0;
     if (shardIndex < 0 || shardIndex >= shardCount) return fail(HXR_ERR_INVALID, "bad shard index");

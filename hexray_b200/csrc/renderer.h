@@ -34,7 +34,10 @@ public:
     int uploadScene(const hxr_scene* sc);                          // builds the tables itself
     int uploadScene(const hxr_scene& sc, const SceneTables& tab);  // tables built by the caller (shared across devices)
     int setCamera(const hxr_camera* cam);
-    int render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats);
+    // noOutput: leave the (partial) frame in frame() and copy it nowhere (multi.cpp sums the shards itself)
+    int render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, bool noOutput = false);
+    // what render() will do with these parameters: Monte-Carlo or Whitted, and the samples per pixel of the WHOLE frame
+    void framePlan(const hxr_render_params& p, bool& mc, int& spp) const;
     int resolveDevice(void* d_rgb, int W, int H, int spp);
     int saveFrameBmp(const void* d_rgb, int W, int H, const char* path);
     int saveFrameExr(const void* d_rgb, int W, int H, const char* path);
@@ -59,6 +62,7 @@ private:
     // run the wavefront on the rays in queue 0 until the ray tree is exhausted (no host read-back between bounces)
     void drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st);
     int renderOnce(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, uint32_t primaryBatch, bool& overflow);
+    bool m_noOutput = false;
     uint32_t readCount(const uint32_t* dptr);
     RayQueue queue(int i) const;
     dev::WalkBuffers walkBuffers(CandRec* cand, bool shadow) const;

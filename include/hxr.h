@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define HXR_ABI_VERSION 1
+#define HXR_ABI_VERSION 2
 
 typedef enum hxr_status {
     HXR_OK = 0,
@@ -222,10 +222,18 @@ typedef struct hxr_camera { /* results of Camera::beginFrame (src/camera.cpp:30-
  * `useKDTree false` path (src/mesh.cpp:255-262); results are identical, only (much) slower */
 #define HXR_CFG_BRUTE_FORCE_MESHES 1
 
+/* One context = one or several GPUs of the box, all owned by the library (reference: the ThreadPool of src/threading.cpp:54-97
+ * that main() creates at src/main.cpp:546). With n_devices > 1 hxr_render shards every frame over the GPUs (Monte-Carlo:
+ * sample passes; Whitted: row bands), sums the partial frames on the first GPU - one kernel reading the peers' buffers over
+ * NVLink, or an NCCL reduce on a communicator the library creates with ncclCommInitAll (HXR_REDUCE=nccl) - resolves and
+ * returns the finished frame; the scene is uploaded to every GPU, its KD-trees are built once. */
 typedef struct hxr_config {
-    int32_t device;           /* CUDA device ordinal */
+    int32_t device;           /* CUDA device ordinal (used when n_devices == 0) */
     int32_t flags;            /* HXR_CFG_* */
-    uint64_t queue_capacity;  /* ray-queue capacity in rays; 0 = default */
+    uint64_t queue_capacity;  /* ray-queue capacity in rays per GPU; 0 = default */
+    int32_t n_devices;        /* 0 / 1: one GPU (`device`); > 1: that many GPUs */
+    int32_t reserved;
+    const int32_t* devices;   /* n_devices ordinals, or NULL for 0 .. n_devices - 1 */
 } hxr_config;
 
 typedef enum hxr_render_mode {
@@ -268,6 +276,9 @@ typedef struct hxr_stats {
     uint64_t walk_launches;
     uint64_t cand_overflow; /* rays whose candidate record filled up during the walk (finished by a second, exact-on-the-spot walk) */
     double shadow_resolve_ms, gen_ms, setup_ms, finish_ms; /* with profiling on: the shadow-resolve, primary-ray, inline-setup and overflow-finish kernels */
+    double reduce_ms;       /* multi-GPU contexts: summing + resolving the partial frames on the first GPU (inside render_ms) */
+    uint32_t n_devices;     /* GPUs that rendered this frame */
+    uint32_t reserved;
 } hxr_stats;
 
 typedef struct hxr_ray {
@@ -296,6 +307,11 @@ int hxr_create(const hxr_config* cfg, hxr_ctx** out);
 void hxr_destroy(hxr_ctx* ctx);
 /* message of the last failed call on this context (ctx == NULL: last failed hxr_create / loader call) */
 const char* hxr_last_error(const hxr_ctx* ctx);
+
+/* number of usable CUDA devices in this process (0: none) */
+int hxr_device_count(void);
+/* how a multi-GPU context sums its partial frames: "peer", "nccl", "host" ("none" for one GPU) */
+const char* hxr_reduce_backend(const hxr_ctx* ctx);
 
 int hxr_upload_scene(hxr_ctx* ctx, const hxr_scene* scene);
 int hxr_set_camera(hxr_ctx* ctx, const hxr_camera* cam);

@@ -289,5 +289,21 @@ int stereo_mix(Context* c, float* out, const float* left, const float* right, si
     c->launches[PROF_OTHER]++;
     return 1;
 }
+bool enable_peer(Context*, Context*) { return true; }
+int reduce_peers(Context* c, float* dst, const float* const* srcs, int n_src, size_t n, float scale)
+{
+    for (size_t i = 0; i < n; i++) {
+        float a = dst[i];
+        for (int k = 0; k < n_src; k++) a += srcs[k][i];
+        dst[i] = a * scale;
+    }
+    c->launches[PROF_OTHER]++;
+    return 1;
+}
+struct Comm { int n; };
+Comm* comm_create(Context* const*, int, char* err, size_t errlen) { snprintf(err, errlen, "no NCCL in the host emulation"); return nullptr; }
+void comm_destroy(Comm* c) { delete c; }
+bool comm_reduce_sum(Comm*, float* const*, size_t) { return false; }
+
 }  // namespace dev
 }  // namespace hxr

@@ -28,7 +28,7 @@ def test_struct_sizes_match_header(gpu_api):
     assert C.sizeof(capi.Transform) == 240 and C.sizeof(capi.Geometry) == 64 and C.sizeof(capi.Triangle) == 184
     assert C.sizeof(capi.Node) == 256 and C.sizeof(capi.Shader) == 56 and C.sizeof(capi.Layer) == 20
     assert C.sizeof(capi.Texture) == 56 and C.sizeof(capi.Light) == 304 and C.sizeof(capi.Camera) == 208
-    assert C.sizeof(capi.RenderParams) == 48 and C.sizeof(capi.Stats) == 176 and C.sizeof(capi.Config) == 16
+    assert C.sizeof(capi.RenderParams) == 48 and C.sizeof(capi.Stats) == 192 and C.sizeof(capi.Config) == 32
 
 
 def test_no_cpu_fallback(gpu_api):

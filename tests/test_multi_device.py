@@ -1,0 +1,81 @@
+"""One context over several devices (hxr_config.devices): the library shards the frame, sums the partial frames and resolves.
+CPU tier: the host emulation's two fake devices through ctypes and through the C++ host program; GPU tier: the product."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hexray_b200 as hx
+import hxr_testlib as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_cpp(lib, out):
+    subprocess.run([os.path.join(ROOT, "tests", "cpp", "build.sh"), lib, out], check=True)
+    return os.path.join(ROOT, "tests", "cpp", out, "test_multi_gpu")
+
+
+def check_multi(api, devices, spp, size):
+    out = {}
+    for scene, kw in (("cornell_box", dict(spp=spp, seed=5)), ("kdtree_test", {})):
+        sf = hx.SceneFile(T.scene_path(scene), api_=api)
+        imgs = []
+        for devs in (None, devices):
+            r = hx.Renderer(api_=api, queue_capacity=1 << 20, devices=devs).load(sf)
+            img, st = r.render(width=size, height=size, **kw)
+            imgs.append((img.copy(), st))
+            if devs:
+                assert st["n_devices"] == len(devs) and r.reduce_backend() in ("peer", "nccl", "host")
+            r.close()
+        sf.close()
+        (a, sa), (b, sb) = imgs
+        if scene == "cornell_box":
+            assert sa["rays_closest"] == sb["rays_closest"]  # sample passes: exactly the same rays, dealt over the devices
+        else:
+            assert sb["rays_closest"] >= sa["rays_closest"]  # row bands: plus one halo row per band for the AA detector
+        assert float(a.mean()) > 0.01
+        assert np.abs(a - b).max() < 2e-4 * max(1.0, float(a.max())), scene
+        out[scene] = sb
+    return out
+
+
+def test_two_emulated_devices(emu_api):
+    check_multi(emu_api, [0, 1], 8, 64)
+
+
+def test_cpp_host_on_the_emulation(emu_api):
+    exe = build_cpp(os.path.join(ROOT, "tests", "emu", "libhxr_emu.so"), "bin_emu")
+    p = subprocess.run([exe, T.scene_path("cornell_box"), "0,1", "8", "64"], capture_output=True, text=True, cwd=os.path.dirname(hx.data_root()))
+    assert p.returncode == 0 and "OK" in p.stdout, p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+def test_multi_context_on_the_gpu(gpu_api):
+    # two contexts' worth of GPU state even on a one-GPU box (the same ordinal twice): the sharded render, the peer reduce
+    # kernel and the resolve are all exercised; on a multi-GPU box the second device is a different GPU
+    n = gpu_api.lib.hxr_device_count()
+    assert n >= 1
+    check_multi(gpu_api, [0, 1 % n], 64, 256)
+
+
+@pytest.mark.gpu
+def test_cpp_host_renders_on_several_gpus(gpu_api):
+    exe = build_cpp(gpu_api.path, "bin")
+    n = gpu_api.lib.hxr_device_count()
+    devs = ",".join(str(i % n) for i in range(max(2, min(n, 8))))
+    p = subprocess.run([exe, T.scene_path("cornell_box"), devs, "64", "256"], capture_output=True, text=True, cwd=os.path.dirname(hx.data_root()))
+    assert p.returncode == 0 and "OK" in p.stdout, p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+def test_nccl_reduce_when_several_gpus(gpu_api):
+    if gpu_api.lib.hxr_device_count() < 2:
+        pytest.skip("one GPU: NCCL refuses the same device twice")
+    os.environ["HXR_REDUCE"] = "nccl"
+    try:
+        st = check_multi(gpu_api, [0, 1], 64, 256)
+    finally:
+        del os.environ["HXR_REDUCE"]
+    assert st["cornell_box"]["n_devices"] == 2
