@@ -5,9 +5,14 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU renderer (oracle/_ref), rank 0 only
 
 Workload (BASELINE.json configs[4]): the synthetic 10 M-triangle terrain inside a
-five-wall Lambert box under one 4x4 RectLight, path traced (gi on, depth 8) at 1920x1080, a fixed
-number of samples per pixel per GPU per step; sample passes are sharded across ranks and the
-per-rank sums are reduced with NCCL (weak scaling: total spp = spp_per_gpu x N).
+five-wall Lambert box under one 4x4 RectLight, path traced (gi on, depth 8) at 1920x1080 x 1024 samples
+per pixel: ONE FIXED FRAME whatever the GPU count (strong scaling). Its sample passes are dealt over the
+GPUs (GPU g renders the samples s % N == g of every pixel) and the per-GPU sums are reduced once per frame:
+  * under torchrun (one process per GPU, the driver's launch): torch.distributed NCCL reduce
+    (hexray_b200.distributed.render_frame, the function the tests exercise);
+  * in one process (`python bench.py --gpus N` without torchrun): the library's own multi-GPU context
+    (hxr_config.devices: one kernel on GPU 0 sums the peers' frames over NVLink).
+`--spp S` instead renders S samples per pixel PER GPU per step (weak scaling; quick A/B runs).
 
 A step = one frame: ray generation -> closest hit -> shading -> shadow rays -> ... -> accumulate
 (-> reduce -> resolve). metric = Mrays/s, rays = closest-hit queries past the depth guard +
@@ -97,6 +102,11 @@ Node front {{
 # algorithmic bytes per ray of the traversal roofline: 64 B ray+hit record,
 # 32 B per inner node visited, 48 B per triangle tested, 16 B per leaf entered
 B_RECORD, B_INNER, B_TRI, B_LEAF = 64, 32, 48, 16
+# what the walk kernel actually reads and writes per ray: 48 B entry record + 16 B candidate record,
+# 32 B per block step (two tree levels), 48 B triangle + 4 B index per test, 4 B leaf count per leaf
+F_RECORD, F_INNER, F_TRI, F_LEAF = 64, 32, 52, 4
+
+DATA = os.path.join(ROOT, "assets", "data")  # the reference's scene assets, staged by __graft_entry__.build()
 
 
 def parse_args():
@@ -108,15 +118,17 @@ def parse_args():
     ap.add_argument("--workload", default="terrain", choices=["terrain", "soup", "cornell_box", "kdtree_test", "smallpt"])
     ap.add_argument("--soup-triangles", type=int, default=10000000, help="soup workload: random triangles in [-500,500]^3 (SURVEY.md 8d, worst-case incoherence)")
     ap.add_argument("--grid-side", type=int, default=2237, help="terrain vertices per side (2237 -> 9 999 392 triangles)")
-    ap.add_argument("--spp", type=int, default=32, help="samples per pixel per GPU per step")
+    ap.add_argument("--spp-total", type=int, default=1024, help="samples per pixel of the WHOLE frame, dealt over the GPUs (strong scaling; BASELINE config 5)")
+    ap.add_argument("--spp", type=int, default=0, help="if > 0: samples per pixel PER GPU per step instead (weak scaling, quick runs)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--ref-width", type=int, default=384, help="reference arm: bounded sample resolution")
     ap.add_argument("--ref-height", type=int, default=216)
     ap.add_argument("--ref-spp", type=int, default=8, help="reference arm: samples per pixel of the bounded sample (the cpu_baseline leg of our arm uses 4x)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the bundled-scene block (configs C1-C4) of the N=1 line")
     ap.add_argument("--queue-capacity", type=int, default=64 << 20,
-                    help="rays per wave of the wavefront renderer: 64 Mi holds one whole 1080p x 32 spp pass (measured: 1475 -> 1542 Mrays/s against 16 Mi; ~45 GB of the 180 GB HBM)")
+                    help="rays per wave of the wavefront renderer: 64 Mi holds one whole 1080p x 32 spp pass (~19 GB of queues out of 180 GB HBM)")
     return ap.parse_args()
 
 
@@ -137,6 +149,19 @@ def synthetic_mesh_name(a):
     if getattr(a, "workload", "terrain") == "soup":
         return "synthetic:soup:%d:0x5EEE" % a.soup_triangles
     return "synthetic:terrain:%d:0x5EED" % a.grid_side
+
+
+def frame_spp(a, world):
+    """(samples per pixel of the whole frame, scaling label)"""
+    if a.spp > 0:
+        return a.spp * world, "weak"
+    return a.spp_total, "strong"
+
+
+def base_config(a, world):
+    spp_total, scaling = frame_spp(a, world)
+    return {"workload": workload_name(a), "width": a.width, "height": a.height, "spp_total": spp_total,
+            "spp_per_gpu": spp_total / world, "integrator": "path tracing (gi), maxTraceDepth 8"}, scaling
 
 
 def measured_peaks():
@@ -188,33 +213,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def run_reference_sample(a, workdir, threads=0, repeat=1):
-    """Time the reference's own CPU renderer (oracle/_ref/hexray_ref: the unmodified reference sources behind a
-    headless shim) on a bounded sample of the workload. Returns (Mrays/s best, info dict)."""
+# (this arm never loads libhexray_b200.so: the procedural mesh is written by tools/bin/hxr_objgen, a host-only program)
+def reference_binary():
     ref = os.path.join(ROOT, "oracle", "_ref", "hexray_ref_count")
-    if not os.path.exists(ref):
+    return ref if os.path.exists(ref) else None
+
+
+def run_reference(scene, cwd, width, height, spp, threads=0, repeat=1):
+    ref = reference_binary()
+    if ref is None:
         return None, {"unavailable": "oracle/_ref/hexray_ref_count not built (run `make -C oracle` where /root/reference exists)"}
-    import hexray_b200 as hx
-    if a.workload in ("terrain", "soup"):
-        size = a.grid_side if a.workload == "terrain" else a.soup_triangles
-        obj = os.path.join(workdir, "%s_%d.obj" % (a.workload, size))
-        scene = os.path.join(workdir, "%s_ref_%d.hexray" % (a.workload, size))
-        if not os.path.exists(obj):
-            # the procedural mesh is produced by the host front-end (pure host code) and handed to the reference as an OBJ
-            gen = os.path.join(workdir, "%s_gen_%d.hexray" % (a.workload, size))
-            with open(gen, "w") as f:
-                f.write(scene_text(a, synthetic_mesh_name(a), a.ref_width, a.ref_height, a.ref_spp))
-            sf = hx.SceneFile(gen)
-            sf.write_obj(0, obj + ".tmp")
-            sf.close()
-            os.replace(obj + ".tmp", obj)
-        with open(scene, "w") as f:
-            f.write(scene_text(a, os.path.basename(obj), a.ref_width, a.ref_height, a.ref_spp))
-        cwd = workdir
-    else:
-        scene = os.path.join(hx.data_root(), a.workload + ".hexray")
-        cwd = os.path.dirname(hx.data_root())
-    cmd = [ref, "render", scene, "--width", str(a.ref_width), "--height", str(a.ref_height), "--spp", str(a.ref_spp), "--repeat", str(repeat)]
+    cmd = [ref, "render", scene, "--width", str(width), "--height", str(height), "--repeat", str(repeat)]
+    if spp:
+        cmd += ["--spp", str(spp)]
     if threads:
         cmd += ["--threads", str(threads)]
     t0 = time.time()
@@ -223,22 +234,47 @@ def run_reference_sample(a, workdir, threads=0, repeat=1):
         return None, {"unavailable": "reference run failed: " + p.stderr[-300:]}
     info = json.loads(p.stdout.strip().splitlines()[-1])
     info["wall_s"] = time.time() - t0
-    rays = info["rays_closest"] + info["rays_shadow"]
-    info["rays"] = rays
-    return rays / info["best_ms"] / 1e3, info
+    info["rays"] = info["rays_closest"] + info["rays_shadow"]
+    return info["rays"] / info["best_ms"] / 1e3, info
+
+
+def run_reference_sample(a, workdir, threads=0, repeat=1):
+    """Time the reference's own CPU renderer (oracle/_ref/hexray_ref_count: the unmodified reference sources behind a
+    headless shim) on a bounded sample of the workload. Returns (Mrays/s best, info dict)."""
+    if a.workload in ("terrain", "soup"):
+        size = a.grid_side if a.workload == "terrain" else a.soup_triangles
+        obj = os.path.join(workdir, "%s_%d.obj" % (a.workload, size))
+        scene = os.path.join(workdir, "%s_ref_%d.hexray" % (a.workload, size))
+        if not os.path.exists(obj):
+            gen = os.path.join(ROOT, "tools", "bin", "hxr_objgen")
+            if not os.path.exists(gen):
+                return None, {"unavailable": "tools/bin/hxr_objgen not built (python -c 'import __graft_entry__ as g; g.build()')"}
+            seed = "0x5EED" if a.workload == "terrain" else "0x5EEE"
+            p = subprocess.run([gen, a.workload, str(size), seed, obj + ".tmp"], capture_output=True, text=True)
+            if p.returncode != 0:
+                return None, {"unavailable": "hxr_objgen failed: " + p.stderr[-200:]}
+            os.replace(obj + ".tmp", obj)
+        with open(scene, "w") as f:
+            f.write(scene_text(a, os.path.basename(obj), a.ref_width, a.ref_height, a.ref_spp))
+        cwd = workdir
+    else:
+        scene = os.path.join(DATA, a.workload + ".hexray")
+        cwd = os.path.dirname(DATA)
+    return run_reference(scene, cwd, a.ref_width, a.ref_height, a.ref_spp, threads, repeat)
 
 
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     workdir = os.path.join(tempfile.gettempdir(), "hexray_b200_bench")
     os.makedirs(workdir, exist_ok=True)
     total = a.steps + a.warmup
     mr, info = run_reference_sample(a, workdir, repeat=total)
+    cfg, scaling = base_config(a, max(world, a.gpus))
     line = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "width": a.width, "height": a.height, "spp_per_gpu": a.spp}}
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg}
     if mr is None:
         line["unavailable"] = info["unavailable"]
         print(json.dumps(line))
@@ -254,22 +290,75 @@ def reference_arm(a):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ bundled scenes (configs C1-C4)
+EXTRA_SCENES = [
+    # (scene, config tag, GPU spp override, CPU spp for the bounded sample (0 = the scene's own), also at 1080p on the GPU)
+    ("simple", "C1", 0, 0, True),
+    ("meshes", "C2", 0, 0, True),
+    ("kdtree_test", "C2/C4", 0, 0, True),
+    ("heightfield", "C4", 0, 0, True),
+    ("beer", "C4", 0, 0, True),
+    ("cornell_box", "C3", 256, 16, False),
+]
+
+
+def extra_scenes(hx, device, want_cpu):
+    """Mrays/s and ms/frame of the bundled scenes on one GPU (median of 3 frames after 2 warm-up frames, CUDA-event time of
+    hxr_render), at their own resolution and - Whitted scenes - at 1920x1080, next to the reference on this box's host cores."""
+    import numpy as np
+    out = []
+    for scene, tag, spp, cpu_spp, hd in EXTRA_SCENES:
+        path = os.path.join(DATA, scene + ".hexray")
+        if not os.path.exists(path):
+            continue
+        sf = hx.SceneFile(path)
+        r = hx.Renderer(device=device)
+        r.load(sf)
+        W0, H0 = r.frame_size()
+        rec = {"scene": "data/%s.hexray" % scene, "config": tag}
+        sizes = [(W0, H0, "own")] + ([(1920, int(round(1920 * H0 / W0)), "1080p-class")] if hd else [])
+        for W, H, label in sizes:
+            ms, rays = [], 0
+            for i in range(5):
+                _, st = r.render(width=W, height=H, spp=spp, seed=i)
+                if i >= 2:
+                    ms.append(st["render_ms"])
+                    rays = st["rays_closest"] + st["rays_shadow"]
+            m = float(np.median(ms))
+            rec[label] = {"width": W, "height": H, "spp": spp or None, "rays": rays, "ms_per_frame": m, "mrays_per_s": rays / m / 1e3,
+                          "kernel_launches": st["kernel_launches"]}
+        r.close()
+        sf.close()
+        if want_cpu and reference_binary():
+            mr, info = run_reference(path, os.path.dirname(DATA), W0, H0, cpu_spp, repeat=2)
+            if mr is not None:
+                rec["cpu_reference"] = {"mrays_per_s": mr, "ms_per_frame": info["best_ms"], "cores": info["threads"], "rays": info["rays"],
+                                        "sample": "%dx%d%s" % (W0, H0, " x %d spp (bounded sample of the 256-spp frame)" % cpu_spp if cpu_spp else "")}
+        out.append(rec)
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def ours(a):
     import numpy as np
     import torch
-    import torch.distributed as dist
     import hexray_b200 as hx
 
+    os.environ.setdefault("HEXRAY_DATA", DATA)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
     if world > 1:
+        import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # one process that owns several GPUs (no torchrun): the library's multi-GPU context
+    in_library = world == 1 and a.gpus > 1
+    n_gpus = a.gpus if in_library else world
     dev = torch.device("cuda", local)
     W, H = a.width, a.height
-    spp_total = a.spp * world
+    spp_total, scaling = frame_spp(a, n_gpus)
 
     workdir = os.path.join(tempfile.gettempdir(), "hexray_b200_bench")
     os.makedirs(workdir, exist_ok=True)
@@ -278,10 +367,10 @@ def ours(a):
         with open(path, "w") as f:
             f.write(scene_text(a, synthetic_mesh_name(a), W, H, spp_total))
     else:
-        path = os.path.join(hx.data_root(), a.workload + ".hexray")
+        path = os.path.join(DATA, a.workload + ".hexray")
     t0 = time.time()
     sf = hx.SceneFile(path)
-    r = hx.Renderer(device=local, queue_capacity=a.queue_capacity)
+    r = hx.Renderer(device=local, queue_capacity=a.queue_capacity, devices=list(range(a.gpus)) if in_library else None)
     r.load(sf)
     setup_s = time.time() - t0
     accel = r.accel_info(0) if sf.pod.contents.n_meshes > 0 else {}
@@ -304,35 +393,37 @@ def ours(a):
     from hexray_b200 import distributed
 
     def step(i, to_host):
-        """one frame: this rank's sample passes -> (NCCL reduce) -> resolve [-> host]. Returns (stats, device ms of the
-        part that runs on torch's stream: reduce + resolve + copy)."""
+        """one frame: this rank's sample passes -> reduce -> resolve [-> host]. Returns (stats, device ms of the part that
+        runs on torch's stream: reduce + resolve + copy)."""
         if flush is not None:
             flush.zero_()
             torch.cuda.synchronize(dev)
         if to_host:
             r.set_camera(cam)  # the per-frame input of the C ABI (hxr_set_camera), host -> device
-        if world == 1 and to_host:
-            _, st = r.render(width=W, height=H, mode=mode, spp=spp_total, seed=i, out=host.numpy().reshape(H, W, 3))
+        if world == 1:
+            # one GPU, or the library's multi-GPU context: ONE call; the reduce + resolve are inside (stats: reduce_ms)
+            if to_host:
+                _, st = r.render(width=W, height=H, mode=mode, spp=spp_total, seed=i, out=host.numpy().reshape(H, W, 3))
+            else:
+                st = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=spp_total, seed=i)
             return st, 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        st = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=spp_total, seed=i, shard=(rank, world))
         e0.record()
-        if world > 1:
-            dist.reduce(acc, dst=0)
-            torch.cuda.synchronize(dev)  # NCCL runs on torch's stream, the resolve kernel on the library's
-            if rank == 0:
-                r.resolve_device(acc.data_ptr(), W, H, spp_total)
+        st = distributed.render_frame(r, acc, W, H, spp_total=spp_total, seed=i, rank=rank, world=world, mode=mode, dist=dist,
+                                      sync=lambda: torch.cuda.synchronize(dev), on_rendered=e0.record)
         if to_host and rank == 0:
             host.copy_(acc, non_blocking=False)
         e1.record()
         torch.cuda.synchronize(dev)
         return st, e0.elapsed_time(e1)
 
+    KEYS = ("trace_closest_ms", "trace_shadow_ms", "walk_ms", "setup_ms", "finish_ms", "shade_ms", "shadow_resolve_ms", "gen_ms", "other_ms",
+            "render_ms", "reduce_ms")
+
     def run(n, to_host, first_seed):
         rays = np.zeros(2, dtype=np.float64)
-        prof = {"trace_closest_ms": 0.0, "trace_shadow_ms": 0.0, "shade_ms": 0.0, "other_ms": 0.0, "render_ms": 0.0, "walk_ms": 0.0,
-                "setup_ms": 0.0, "shadow_resolve_ms": 0.0, "gen_ms": 0.0, "finish_ms": 0.0, "cand_overflow": 0,
-                "trace_closest_launches": 0, "trace_shadow_launches": 0, "walk_launches": 0, "kernel_launches": 0, "post_ms": 0.0}
+        prof = {k: 0.0 for k in KEYS}
+        prof.update({"walk_launches": 0, "kernel_launches": 0, "post_ms": 0.0, "cand_overflow": 0})
         for i in range(n):
             st, post_ms = step(first_seed + i, to_host)
             rays += (st["rays_closest"], st["rays_shadow"])
@@ -340,8 +431,8 @@ def ours(a):
                 prof[k] += post_ms if k == "post_ms" else st[k]
         return rays, prof
 
-    # ---- device-resident throughput ("value"): CUDA-event time of the frames (render on the library's stream +
-    # reduce/resolve on torch's), max over ranks; the wall clock around the same region is reported beside it
+    # ---- device-resident throughput ("value"): CUDA-event time of the frames (render on the library's stream(s) +
+    # reduce/resolve), max over ranks; the wall clock around the same region is reported beside it
     r.set_profiling(True)
     run(a.warmup, False, 1000)
     barrier()
@@ -379,8 +470,11 @@ def ours(a):
     dt_wall = allmax(dt_wall)
     dt_e = allmax(dt_e)
 
-    # ---- traversal counters (a separate, un-timed counting pass of the same workload at 1 spp per rank)
-    cst = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=world, seed=0, shard=(rank, world), flags=hx.RENDER_COUNT_TRAVERSAL)
+    # ---- traversal counters (a separate, un-timed counting pass of the same workload at 1 spp per GPU)
+    if world == 1:
+        cst = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=n_gpus, seed=0, flags=hx.RENDER_COUNT_TRAVERSAL)
+    else:
+        cst = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=world, seed=0, shard=(rank, world), flags=hx.RENDER_COUNT_TRAVERSAL)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -390,14 +484,15 @@ def ours(a):
         per_ray = {"inner": cst["kd_inner"] / max(1, n_rays_cnt), "tri": cst["tri_tests"] / max(1, n_rays_cnt),
                    "leaf": cst["kd_leaves"] / max(1, n_rays_cnt), "mesh_queries": cst["mesh_queries"] / max(1, n_rays_cnt)}
         b_ray = B_RECORD + B_INNER * per_ray["inner"] + B_TRI * per_ray["tri"] + B_LEAF * per_ray["leaf"]
-        walk_ms = prof["walk_ms"]
-        walk_launches = prof["walk_launches"]
-        my_rays = total_rays / world  # rank 0's share (shards are equal)
+        f_ray = F_RECORD + F_INNER * per_ray["inner"] + F_TRI * per_ray["tri"] + F_LEAF * per_ray["leaf"]
+        walk_ms = prof["walk_ms"]  # this GPU's k_walk launches (in-library multi-GPU: the slowest GPU's)
+        walk_launches = prof["walk_launches"] / (n_gpus if in_library else 1)
+        my_rays = total_rays / n_gpus  # one GPU's share (shards are equal)
         achieved = my_rays * b_ray / (walk_ms * 1e-3) / 1e9 if walk_ms > 0 else None
         hbm_bound = geometry_bytes > (126 << 20)
         peak = peaks["hbm_gbs"] if hbm_bound else 23149.0
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "walk_traffic.json")  # written by tools/ncu_traffic.py from an `ncu --set full` capture
+        tp = os.path.join(ROOT, "profiles", "walk_traffic_r2.json")  # written by tools/ncu_traffic.py from an ncu pass over the timed-size k_walk launches
         if os.path.exists(tp) and a.workload == "terrain" and a.grid_side == 2237:
             with open(tp) as f:
                 traffic = json.load(f)
@@ -414,32 +509,38 @@ def ours(a):
                     gather["walk_dram_gbs"] = traffic["dram_bytes_per_launch"] / (walk_ms / max(1, walk_launches) * 1e-3) / 1e9
             except Exception:
                 gather = None
+        cfg, _ = base_config(a, n_gpus)
+        cfg.update({"sharding": "sample passes s % N == gpu; " + ("torch.distributed NCCL reduce of the sum buffers (one process per GPU)" if world > 1 else
+                                                                  ("library-owned multi-GPU context, reduce: " + r.reduce_backend() if in_library else "one GPU")),
+                    "l2": "geometry %.2f GB >> 126 MB L2" % (geometry_bytes / 1e9) if flush is None else "512 MB buffer written between timed iterations",
+                    "rays_per_step": total_rays / a.steps, "setup_s": setup_s, "kd": accel, "queue_capacity_rays": a.queue_capacity})
+        path_peak = peak * 1e9 / b_ray / 1e6  # Mrays/s one GPU could do if the whole path ran at the traversal roofline
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 walk + f64 exact tests", "data": "synthetic",
-            "config": {"workload": workload_name(a), "width": W, "height": H, "spp_per_gpu": a.spp, "spp_total": spp_total,
-                       "integrator": "path tracing (gi), maxTraceDepth 8", "sharding": "sample passes s %% N == rank, NCCL reduce of the sum buffer",
-                       "l2": "geometry %.2f GB >> 126 MB L2" % (geometry_bytes / 1e9) if flush is None else "512 MB buffer written between timed iterations",
-                       "rays_per_step": total_rays / a.steps, "setup_s": setup_s, "kd": accel},
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f32 walk + f64 exact tests", "data": "synthetic", "config": cfg,
             "ms_per_frame": dt / a.steps * 1e3, "wall_ms_per_step": dt_wall / a.steps * 1e3,
-            "timing": "CUDA events (render on the library's stream + reduce/resolve on torch's), max over ranks; wall clock beside it",
+            "timing": "CUDA events (render on the library's stream + reduce/resolve), max over ranks; wall clock beside it",
             "e2e": {"value": float(rays_e.sum()) / dt_e / 1e6, "unit": "Mrays/s", "ms_per_step": dt_e / a.steps * 1e3,
                     "h2d_bytes_per_step": 256, "d2h_bytes_per_step": W * H * 12},
             "gpu_launches": int(prof["kernel_launches"]),
             "clocks": clk.summary(),
+            "N_inner": per_ray["inner"], "N_tri": per_ray["tri"], "N_leaf": per_ray["leaf"],
             "roofline": {"bound": "hbm" if hbm_bound else "l2", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_source": traffic,
                          "kernel": "k_walk (KD-tree walk: closest-hit + shadow launches)", "peak_source": peak_src if hbm_bound else "tools/microbench L2 read (profiles/microbench_r1.json)",
-                         "bytes_per_ray": b_ray, "bytes_per_launch": my_rays * b_ray / max(1, walk_launches), "per_ray": per_ray,
+                         "bytes_per_ray": b_ray, "bytes_per_ray_fetched": f_ray,
+                         "frac_fetched": (my_rays * f_ray / (walk_ms * 1e-3) / 1e9 / peak) if walk_ms > 0 else None,
+                         "path_frac": (value / n_gpus) / path_peak, "path_peak_mrays_per_gpu": path_peak,
+                         "bytes_per_launch": my_rays * b_ray / max(1, walk_launches), "per_ray": per_ray,
                          "launches": int(walk_launches), "avg_launch_ms": walk_ms / max(1, walk_launches),
                          "random_gather": gather,
-                         "walk_share_of_step": walk_ms / max(1e-9, prof["render_ms"]),
-                         "traversal_share_of_step": (prof["trace_closest_ms"] + prof["trace_shadow_ms"]) / max(1e-9, prof["render_ms"])},
-            "kernel_ms_per_step": {k: prof[k] / a.steps for k in ("trace_closest_ms", "trace_shadow_ms", "walk_ms", "setup_ms", "finish_ms", "shade_ms", "shadow_resolve_ms", "gen_ms", "other_ms", "render_ms", "cand_overflow")},
+                         "walk_share_of_step": walk_ms / max(1e-9, prof["render_ms"])},
+            "kernel_ms_per_step": {k: prof[k] / a.steps for k in KEYS},
+            "cand_overflow_per_step": prof["cand_overflow"] / a.steps,
         }
-        if world == 1 and not a.no_cpu_baseline:
+        if n_gpus == 1 and not a.no_cpu_baseline:
             b = argparse.Namespace(**vars(a))
             b.ref_spp = a.ref_spp * 4  # ~10 s of CPU rendering on the 1 M-triangle variant
             note = ""
@@ -455,6 +556,9 @@ def ours(a):
             else:
                 line["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": info["threads"], "kind": "reference",
                                         "sample": "%dx%d x %d spp, %d rays, %.1f s wall incl. load%s" % (b.ref_width, b.ref_height, b.ref_spp, info["rays"], info["wall_s"], note)}
+        if n_gpus == 1 and not a.no_extra:
+            r.close()
+            line["extra"] = {"scenes": extra_scenes(hx, local, not a.no_cpu_baseline)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -34,13 +34,13 @@ def api():
 
 
 def data_root():
-    """Directory holding the scene assets (`data/` of the reference). HEXRAY_DATA overrides; otherwise the
-    copy staged next to the compiled reference (oracle/_ref/data), else the reference checkout itself."""
+    """Directory holding the scene assets (`data/` of the reference: scenes, meshes, textures, cubemaps). HEXRAY_DATA
+    overrides; otherwise the copy staged at <repo>/assets/data (by __graft_entry__.build()), else the reference checkout."""
     env = os.environ.get("HEXRAY_DATA")
     if env:
         return env
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for cand in (os.path.join(here, "oracle", "_ref", "data"), "/root/reference/data"):
+    for cand in (os.path.join(here, "assets", "data"), "/root/reference/data"):
         if os.path.isdir(cand):
             return cand
     raise FileNotFoundError("scene assets not found: set HEXRAY_DATA to the reference's data/ directory")

@@ -19,7 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.path.join(ROOT, "oracle", "_ref", "hexray_ref")
-DATA = os.path.join(ROOT, "oracle", "_ref", "data")
+DATA = os.path.join(ROOT, "assets", "data")  # the reference's data/ staged by __graft_entry__.build()
 
 WHITTED = {  # scene -> (W, H)
     "simple": (320, 180), "meshes": (320, 240), "kdtree_test": (320, 240), "heightfield": (320, 240),
@@ -189,6 +189,20 @@ def stereo():
         print("stereo", name, img.shape, float(img.mean()), img.reshape(-1, 3).mean(0))
 
 
+def output():
+    """What the reference WRITES (a27): takeScreenshot -> Bitmap::saveImage (src/sdl.cpp:103-116, src/bitmap.cpp:202-288) of a
+    small frame whose row size needs BMP padding: the float frame (exactly, float32), the BMP file bytes and the EXR file bytes."""
+    tmp, bmp, exr = "/tmp/hxr_golden.bin", "/tmp/hxr_golden.bmp", "/tmp/hxr_golden.exr"
+    W, H = 203, 77
+    args = ["render", scene_path("simple"), "--width", str(W), "--height", str(H), "--out", tmp, "--bmp", bmp, "--exr", exr]
+    info = run(args)
+    vfb = np.fromfile(tmp, dtype=np.float32).reshape(H, W, 3)
+    np.savez_compressed(os.path.join(HERE, "output_simple.npz"), vfb=vfb, bmp=np.frombuffer(open(bmp, "rb").read(), dtype=np.uint8),
+                        exr=np.frombuffer(open(exr, "rb").read(), dtype=np.uint8),
+                        cmd="hexray_ref render data/simple.hexray --width %d --height %d --out vfb.f32 --bmp out.bmp --exr out.exr" % (W, H), info=json.dumps(info))
+    print("output", vfb.shape, float(vfb.mean()), os.path.getsize(bmp), os.path.getsize(exr))
+
+
 def features():
     """Scenes written for this repo that exercise what no bundled scene does (tests/hxr_testlib.py: FEATURES_*)."""
     sys.path.insert(0, ROOT)
@@ -213,6 +227,9 @@ def features():
     print("features stochastic", float(img.mean()))
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "output":
+    output()
+    sys.exit(0)
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "features":
         features()

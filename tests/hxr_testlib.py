@@ -15,10 +15,13 @@ WHITTED_SCENES = ["simple", "meshes", "kdtree_test", "heightfield", "bumpmap", "
 MC_SCENES = ["cornell_box", "smallpt", "hw12/sphtri", "zaphod", "hw10/bokeh"]
 PRIMARY_SCENES = ["kdtree_test", "meshes", "heightfield", "smallpt", "simple", "hw10/bokeh", "boxed"]
 
-# Parity tolerances (BASELINE.json north_star):
+# Parity tolerances (BASELINE.json north_star, SURVEY.md 8d):
 #   deterministic scenes: |clamp(ours) - clamp(reference)| <= 1/255 per channel on >= 99.9 % of pixels
-#   stochastic scenes   : RMSE(ours@N, converged reference) <= 1.25 * RMSE(ours@N seed A, ours@N seed B)/sqrt(2) + 0.004
-#                         and per-channel mean |delta| <= 0.004 (clamped images)
+#   stochastic scenes   : with own = RMSE(ours@N seed A, ours@N seed B) / sqrt(2), the noise of ONE N-spp frame, and
+#                         Nref the sample count of the converged reference fixture (its noise: own * sqrt(N / Nref)),
+#                           RMSE(ours@N, reference@Nref) <= 1.2 * own * sqrt(1 + N / Nref) + 3e-4   (3e-4: the fixture is fp16)
+#                           per-channel mean |delta| <= 0.002, and the same RMSE bound on 8x8 box-filtered images
+#                         (GPU tier, live oracle: RMSE(ours@N, oracle@N) <= 1.2 * r0, r0 = RMSE of two oracle runs at N)
 PIXEL_TOL = 1.0 / 255.0
 PIXEL_FRACTION = 0.999
 
@@ -32,7 +35,28 @@ def golden(kind, scene):
 
 
 def scene_path(scene):
+    if os.path.isabs(scene):
+        return scene
     return os.path.join(hx.data_root(), scene + ".hexray")
+
+
+_SCRATCH = None
+
+
+def scratch_scene(name, text):
+    """Write a test-made scene where its asset paths resolve WITHOUT touching the data root: a scratch directory whose
+    entries are symlinks to the data root's (scene files resolve assets relative to their own directory)."""
+    global _SCRATCH
+    if _SCRATCH is None:
+        import tempfile
+        _SCRATCH = tempfile.mkdtemp(prefix="hxr_scratch_")
+        root = hx.data_root()
+        for e in os.listdir(root):
+            os.symlink(os.path.join(root, e), os.path.join(_SCRATCH, e))
+    path = os.path.join(_SCRATCH, name + ".hexray")
+    with open(path, "w") as f:
+        f.write(text)
+    return path
 
 
 def have_oracle():
@@ -50,17 +74,12 @@ def oracle_render(scene, W, H, spp=0, extra=()):
 
 
 def stereo_scene(scene, separation):
-    """A copy of a bundled scene with `stereoSeparation` set on its camera (anaglyph frames, src/main.cpp:234-248),
-    written next to the original so that its asset paths keep resolving."""
-    src = scene_path(scene)
-    dst = os.path.join(os.path.dirname(src), "_stereo_%s.hexray" % os.path.basename(scene))
-    text = open(src).read()
+    """A copy of a bundled scene with `stereoSeparation` set on its camera (anaglyph frames, src/main.cpp:234-248)."""
+    text = open(scene_path(scene)).read()
     i = text.index("Camera")
     j = text.index("{", i)
     text = text[:j + 1] + "\n\tstereoSeparation %g" % separation + text[j + 1:]
-    with open(dst, "w") as f:
-        f.write(text)
-    return os.path.relpath(dst, hx.data_root())[:-len(".hexray")]
+    return scratch_scene("_stereo_%s" % os.path.basename(scene), text)
 
 
 STEREO = {"kdtree_test": 12.0, "cornell_box": 40.0}  # scene -> stereoSeparation used by the fixtures
@@ -115,6 +134,30 @@ def rmse(a, b):
     return float(np.sqrt(((clamp01(a) - clamp01(b)) ** 2).mean()))
 
 
+def box_filter(img, k=8):
+    H, W = img.shape[:2]
+    H2, W2 = H // k * k, W // k * k
+    return clamp01(img)[:H2, :W2].reshape(H2 // k, k, W2 // k, k, 3).mean(axis=(1, 3))
+
+
+MC_REF_SPP = {"cornell_box": 4096, "smallpt": 4096, "hw12/sphtri": 2048, "zaphod": 2048, "hw10/bokeh": 1024}  # tests/golden/make_golden.py
+
+
+def mc_bounds(a, b, ref, n, n_ref, what):
+    """The stochastic-parity assertion (see the header): a, b = two of our N-spp frames, ref = the converged reference."""
+    out = {}
+    for label, f in (("pixels", clamp01), ("8x8 boxes", box_filter)):
+        fa, fb, fr = f(a), f(b), f(ref)
+        own = float(np.sqrt(((fa - fb) ** 2).mean())) / np.sqrt(2.0)  # noise of ONE render against the truth
+        err = float(np.sqrt(((fa - fr) ** 2).mean()))
+        bound = 1.2 * own * np.sqrt(1.0 + n / float(n_ref)) + 3e-4
+        assert err <= bound, "%s (%s): rmse vs converged reference %.5f > bound %.5f (own noise %.5f, N %d, Nref %d)" % (what, label, err, bound, own, n, n_ref)
+        out[label] = (err, own, bound)
+    mean_delta = np.abs(clamp01(a).mean(axis=(0, 1)) - clamp01(ref).mean(axis=(0, 1)))
+    assert mean_delta.max() <= 0.002, "%s: per-channel mean delta %s > 0.002" % (what, mean_delta)
+    return out
+
+
 def check_mc(sess, scene, spp):
     g = golden("mc", scene)
     ref = g["img"].astype(np.float32)
@@ -122,12 +165,25 @@ def check_mc(sess, scene, spp):
     r = sess.renderer(scene)
     a, st = r.render(width=W, height=H, spp=spp, seed=11)
     b, _ = r.render(width=W, height=H, spp=spp, seed=22)
-    own = rmse(a, b) / np.sqrt(2.0)  # noise of ONE render against the truth
-    err = rmse(a, ref)
-    mean_delta = np.abs(clamp01(a).mean(axis=(0, 1)) - clamp01(ref).mean(axis=(0, 1)))
-    assert err <= 1.25 * own + 0.004, "%s: rmse vs converged reference %.4f, own noise %.4f" % (scene, err, own)
-    assert mean_delta.max() <= 0.004, "%s: mean delta %s" % (scene, mean_delta)
+    res = mc_bounds(a, b, ref, spp, MC_REF_SPP[scene], scene)
+    err, own, _ = res["pixels"]
     return err, own, st
+
+
+def check_mc_live(sess, scene, spp, W, H):
+    """Against the compiled reference run HERE at the same N: r0 = RMSE between two oracle runs (different thread counts:
+    its default-seeded per-thread mt19937 streams land on different buckets), then RMSE(ours@N, oracle@N) <= 1.2 r0 and
+    per-channel mean |delta| <= 0.002."""
+    o1, _ = oracle_render(scene, W, H, spp=spp, extra=("--threads", "7"))
+    o2, _ = oracle_render(scene, W, H, spp=spp, extra=("--threads", "5"))
+    img, st = sess.renderer(scene).render(width=W, height=H, spp=spp, seed=31)
+    r0 = rmse(o1, o2)
+    err = 0.5 * (rmse(img, o1) + rmse(img, o2))
+    mean_delta = np.abs(clamp01(img).mean(axis=(0, 1)) - 0.5 * (clamp01(o1).mean(axis=(0, 1)) + clamp01(o2).mean(axis=(0, 1))))
+    assert r0 > 0, "the two oracle runs are identical: no noise floor to compare with"
+    assert err <= 1.2 * r0, "%s @%d spp: rmse(ours, oracle) %.5f > 1.2 * r0 (r0 = %.5f)" % (scene, spp, err, r0)
+    assert mean_delta.max() <= 0.002, "%s: per-channel mean delta %s > 0.002" % (scene, mean_delta)
+    return err, r0, mean_delta
 
 
 def check_primary(sess, scene):
@@ -235,11 +291,8 @@ def check_terrain(api, queue_capacity=1 << 20, spp=64):
         refimg = g["img"].astype(np.float32)
         a, st = r.render(width=W, height=H, spp=spp, seed=3)
         b, _ = r.render(width=W, height=H, spp=spp, seed=4)
-        own = rmse(a, b) / np.sqrt(2.0)
-        err = rmse(a, refimg)
-        mean_delta = np.abs(clamp01(a).mean(axis=(0, 1)) - clamp01(refimg).mean(axis=(0, 1)))
-        assert err <= 1.25 * own + 0.006, "terrain GI: rmse vs converged reference %.4f, own noise %.4f" % (err, own)
-        assert mean_delta.max() <= 0.006, "terrain GI: mean delta %s" % mean_delta
+        res = mc_bounds(a, b, refimg, spp, 1024, "terrain GI")
+        err, own, _ = res["pixels"]
         return err, own, st
     finally:
         r.close()
@@ -290,17 +343,12 @@ def check_stereo(sess, scene, spp=0):
         return frac
     a, st = r.render(width=W, height=H, spp=spp, seed=11)
     b, _ = r.render(width=W, height=H, spp=spp, seed=22)
-    own = rmse(a, b) / np.sqrt(2.0)
-    err = rmse(a, ref)
-    mean_delta = np.abs(clamp01(a).mean(axis=(0, 1)) - clamp01(ref).mean(axis=(0, 1)))
-    assert err <= 1.25 * own + 0.004, "stereo %s: rmse vs converged reference %.4f, own noise %.4f" % (scene, err, own)
-    assert mean_delta.max() <= 0.004, "stereo %s: mean delta %s" % (scene, mean_delta)
-    return err
+    res = mc_bounds(a, b, ref, spp, 4096, "stereo " + scene)
+    return res["pixels"][0]
 
 
 def many_meshes_scene(n_side=6):
     """n_side^2 instanced little meshes (44-triangle dice, a 10-triangle box) over a floor: many big-mesh nodes per scene."""
-    path = os.path.join(hx.data_root(), "_many_meshes.hexray")
     lines = ["GlobalSettings {\n\tframeWidth 160\n\tframeHeight 120\n\tambientLight (0.2, 0.2, 0.2)\n\tmaxTraceDepth 4\n}",
              "Camera camera {\n\tpos (0, 60, -140)\n\taspectRatio 1.33333\n\tpitch -22\n\tfov 90\n}",
              "PointLight l1 {\n\tpos (-60, 160, -80)\n\tcolor (1, 1, 1)\n\tpower 40000\n}",
@@ -316,9 +364,7 @@ def many_meshes_scene(n_side=6):
             lines.append("Node n%d {\n\tgeometry %s\n\tshader %s\n\tscale (%g, %g, %g)\n\trotate (%d, %d, 0)\n\ttranslate (%g, %g, %g)\n}" % (
                 k, geom, shader, scale, scale, scale, 17 * k % 360, 29 * k % 90, (i - n_side / 2) * 28.0, 10.0, (j - n_side / 2) * 28.0))
             k += 1
-    with open(path, "w") as f:
-        f.write("\n".join(lines) + "\n")
-    return "_many_meshes"
+    return scratch_scene("_many_meshes", "\n".join(lines) + "\n")
 
 
 def check_many_meshes(api):
@@ -541,11 +587,7 @@ Node nBox {
 
 
 def feature_scene(kind):
-    text = FEATURES_WHITTED if kind == "whitted" else FEATURES_STOCHASTIC
-    path = os.path.join(hx.data_root(), "_features_%s.hexray" % kind)
-    with open(path, "w") as f:
-        f.write(text)
-    return "_features_%s" % kind
+    return scratch_scene("_features_%s" % kind, FEATURES_WHITTED if kind == "whitted" else FEATURES_STOCHASTIC)
 
 
 def check_features(sess, frames=24):

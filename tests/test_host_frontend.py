@@ -190,3 +190,40 @@ def test_obj_round_trip(gpu_api, tmp_path):
     assert np.array_equal(va, vb)
     sf.close()
     sg.close()
+
+
+def T_payload(data, shape, ext):
+    """Every byte of the file that the reference DEFINES. BMP: Bitmap::saveBMP (src/bitmap.cpp:231-238) fwrite()s rowsz
+    bytes of a stack buffer of which it has filled only width * 3, so the 0-3 padding bytes of each row are uninitialised
+    stack in the reference's file (zero in ours, as its own comment and the format ask): they are left out. EXR: all of it."""
+    if ext != ".bmp":
+        return data
+    H, W = shape[:2]
+    rowsz = (W * 3 + 3) // 4 * 4
+    body = data[54:].reshape(H, rowsz)[:, :W * 3]
+    return np.concatenate([data[:54], body.reshape(-1)])
+
+
+def test_saved_files_equal_the_reference_bytes(emu_api, tmp_path):
+    """a27, byte for byte: the reference's own screenshot of a frame (takeScreenshot -> Bitmap::saveBMP / saveEXR,
+    src/sdl.cpp:103-116, src/bitmap.cpp:202-288; fixture written by the compiled reference, tests/golden/make_golden.py
+    output) against hxr_save_image of the SAME float frame - pure host code, so this runs on the CPU tier."""
+    import hexray_b200 as hx
+    g = np.load(os.path.join(ROOT, "tests", "golden", "output_simple.npz"))
+    vfb = g["vfb"]
+    for ext, key in ((".bmp", "bmp"), (".exr", "exr")):
+        p = str(tmp_path / ("ours" + ext))
+        hx.save_image(p, vfb, api_=emu_api)
+        ours = np.frombuffer(open(p, "rb").read(), dtype=np.uint8)
+        ref = g[key]
+        assert len(ours) == len(ref)
+        assert np.array_equal(T_payload(ours, vfb.shape, ext), T_payload(ref, vfb.shape, ext)), "%s differs from the reference's file" % ext
+    # the EXR pixels against an independent float -> half (numpy, IEEE round to nearest even): exact
+    H, W = vfb.shape[:2]
+    exr = g["exr"]
+    body = exr[len(exr) - H * (8 + W * 8):].reshape(H, 8 + W * 8)[:, 8:].copy().view(np.uint16).reshape(H, 4, W)
+    want = vfb.astype(np.float16).view(np.uint16)
+    assert np.array_equal(body[:, 3, :], want[:, :, 0]) and np.array_equal(body[:, 2, :], want[:, :, 1]) and np.array_equal(body[:, 1, :], want[:, :, 2])
+    assert (body[:, 0, :] == 0x3C00).all()  # alpha 1
+    back = hx.load_image(str(tmp_path / "ours.exr"), api_=emu_api)
+    assert np.array_equal(back, vfb.astype(np.float16).astype(np.float32))
