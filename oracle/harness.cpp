@@ -164,6 +164,12 @@ static void dump_hit(FILE* f, const Ray& ray, int mode /*0 raycast, 1 raytrace*/
     fwrite(rec, sizeof(double), 24, f);
 }
 
+#ifdef HXR_WITH_BRIDGE
+struct hxr_stats;
+bool renderOnGPU(hxr_stats* stats, unsigned long long seed);  // oracle/gpu_bridge.cpp
+void shutdownGPU();
+#endif
+
 int main(int argc, char** argv)
 {
     Args a = parse_args(argc, argv);
@@ -171,11 +177,19 @@ int main(int argc, char** argv)
     if (!setup(a, parse_ms, br_ms)) return 1;
     const int W = frameWidth(), H = frameHeight();
 
-    if (a.cmd == "render") {
+    if (a.cmd == "render" || a.cmd == "gpurender") {
         std::string times = "[";
         double best = 1e300;
         for (int r = 0; r < a.repeat; r++) {
             double t0 = now_ms();
+#ifdef HXR_WITH_BRIDGE
+            // the reference-side binding (oracle/gpu_bridge.cpp): the live scene graph -> include/hxr.h -> libhexray_b200.so -> vfb
+            if (a.cmd == "gpurender") {
+                if (!renderOnGPU(nullptr, 17)) return 1;
+            } else
+#else
+            if (a.cmd == "gpurender") { fprintf(stderr, "this binary was built without the GPU bridge\n"); return 2; }
+#endif
             render(false);
             double dt = now_ms() - t0;
             best = dt < best ? dt : best;

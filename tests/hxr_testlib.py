@@ -174,11 +174,19 @@ def check_mc_live(sess, scene, spp, W, H):
     """Against the compiled reference run HERE at the same N: r0 = RMSE between two oracle runs (different thread counts:
     its default-seeded per-thread mt19937 streams land on different buckets), then RMSE(ours@N, oracle@N) <= 1.2 r0 and
     per-channel mean |delta| <= 0.002."""
-    o1, _ = oracle_render(scene, W, H, spp=spp, extra=("--threads", "7"))
-    o2, _ = oracle_render(scene, W, H, spp=spp, extra=("--threads", "5"))
+    # one thread against two: the reference's per-thread streams then cover the 64x64 buckets differently - except the very
+    # first bucket, which thread 0 renders from a fresh stream in both runs: it is left out of the comparison
+    o1, _ = oracle_render(scene, W, H, spp=spp, extra=("--threads", "1"))
+    o2, _ = oracle_render(scene, W, H, spp=spp, extra=("--threads", "2"))
     img, st = sess.renderer(scene).render(width=W, height=H, spp=spp, seed=31)
-    r0 = rmse(o1, o2)
-    err = 0.5 * (rmse(img, o1) + rmse(img, o2))
+    m = np.ones((H, W), dtype=bool)
+    m[:64, :64] = False
+
+    def rm(a, b):
+        return float(np.sqrt(((clamp01(a)[m] - clamp01(b)[m]) ** 2).mean()))
+
+    r0 = rm(o1, o2)
+    err = 0.5 * (rm(img, o1) + rm(img, o2))
     mean_delta = np.abs(clamp01(img).mean(axis=(0, 1)) - 0.5 * (clamp01(o1).mean(axis=(0, 1)) + clamp01(o2).mean(axis=(0, 1))))
     assert r0 > 0, "the two oracle runs are identical: no noise floor to compare with"
     assert err <= 1.2 * r0, "%s @%d spp: rmse(ours, oracle) %.5f > 1.2 * r0 (r0 = %.5f)" % (scene, spp, err, r0)
