@@ -13,7 +13,7 @@ OUT = os.path.join(HERE, "libhexray_b200.so")
 OBJ = os.path.join(HERE, "build")
 
 HOST_SOURCES = ["abi.cpp", "renderer.cpp", "multi.cpp", "host/scene.cpp", "host/mesh.cpp", "host/flatten.cpp",
-                "host/bitmap.cpp", "host/kdtree.cpp"]
+                "host/bitmap.cpp", "host/kdtree.cpp", "host/cache.cpp"]
 CUDA_SOURCES = ["device/launch_cuda.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

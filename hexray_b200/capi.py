@@ -126,7 +126,7 @@ class Stats(C.Structure):
 
 class AccelInfo(C.Structure):
     _fields_ = [("nodes", c_u64), ("leaves", c_u64), ("tri_refs", c_u64), ("bytes_nodes", c_u64), ("bytes_tris", c_u64),
-                ("max_depth", c_u32), ("n_triangles", c_u32), ("build_ms", c_f64)]
+                ("max_depth", c_u32), ("n_triangles", c_u32), ("build_ms", c_f64), ("from_cache", c_u32), ("reserved", c_u32)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -6,6 +6,7 @@
 //                      reference's median-split KD build is replaced by the library's SAH build
 //                      at upload time (csrc/host/kdtree.cpp)
 #include <algorithm>
+#include "cache.h"
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -55,6 +56,30 @@ static void parseCorner(const char* b, const char* e, int& v, int& t, int& n)
 
 bool Mesh::loadFromOBJ(const char* filename)
 {
+    // a big file parsed before comes back from its binary cache (host/cache.h): O(read) instead of O(tokens)
+    {
+        ObjArrays a;
+        if (loadObjCache(filename, a)) {
+            auto fill = [](std::vector<Vec3>& dst, const std::vector<double>& src) {
+                dst.resize(src.size() / 3);
+                for (size_t i = 0; i < dst.size(); i++) dst[i] = Vec3(src[3 * i], src[3 * i + 1], src[3 * i + 2]);
+            };
+            fill(vertices, a.vertices);
+            fill(normals, a.normals);
+            fill(uvs, a.uvs);
+            triangles.resize(a.tris.size() / 9);
+            for (size_t t = 0; t < triangles.size(); t++) {
+                memset(&triangles[t], 0, sizeof(hxr_triangle));
+                for (int k = 0; k < 3; k++) {
+                    triangles[t].v[k] = a.tris[9 * t + k];
+                    triangles[t].n[k] = a.tris[9 * t + 3 + k];
+                    triangles[t].t[k] = a.tris[9 * t + 6 + k];
+                }
+            }
+            prepareTriangles();
+            return true;
+        }
+    }
     FILE* f = fopen(filename, "rt");
     if (!f) return false;
     vertices.assign(1, Vec3(0, 0, 0));
@@ -100,6 +125,24 @@ bool Mesh::loadFromOBJ(const char* filename)
             if (T.v[k] < 0 || T.v[k] >= (int)vertices.size() || T.n[k] < 0 || T.n[k] >= (int)normals.size() ||
                 T.t[k] < 0 || T.t[k] >= (int)uvs.size())
                 return false;
+    if (triangles.size() >= 50000 && cacheEnabled()) {  // (small files parse in milliseconds)
+        ObjArrays a;
+        auto flat = [](std::vector<double>& dst, const std::vector<Vec3>& src) {
+            dst.resize(src.size() * 3);
+            for (size_t i = 0; i < src.size(); i++) { dst[3 * i] = src[i].x; dst[3 * i + 1] = src[i].y; dst[3 * i + 2] = src[i].z; }
+        };
+        flat(a.vertices, vertices);
+        flat(a.normals, normals);
+        flat(a.uvs, uvs);
+        a.tris.resize(triangles.size() * 9);
+        for (size_t t = 0; t < triangles.size(); t++)
+            for (int k = 0; k < 3; k++) {
+                a.tris[9 * t + k] = triangles[t].v[k];
+                a.tris[9 * t + 3 + k] = triangles[t].n[k];
+                a.tris[9 * t + 6 + k] = triangles[t].t[k];
+            }
+        storeObjCache(filename, a);
+    }
     prepareTriangles();
     return true;
 }

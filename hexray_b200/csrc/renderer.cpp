@@ -8,6 +8,7 @@
 #include <functional>
 #include <thread>
 #include "host/bitmap.h"
+#include "host/cache.h"
 #include "host/exr_codec.h"
 
 namespace hxr {
@@ -157,8 +158,12 @@ bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& ou
     for (int i = 0; i < s.n_meshes; i++) {
         const hxr_mesh& m = s.meshes[i];
         MeshTables& M = out.meshes[i];
-        host::buildKdTree(m, host::KdBuildParams(), M.kd);
-        out.build_ms += M.kd.buildMs;
+        // through the cache (host/cache.h): a big tree built before - or being built right now by another process of this
+        // box, e.g. the other ranks of a torchrun job - is loaded instead of built again
+        const char* how = "built";
+        host::cachedKdTree(m, host::KdBuildParams(), M.kd, &how);
+        M.kdSource = how;
+        if (!strcmp(how, "built")) out.build_ms += M.kd.buildMs;
         const size_t nt = (size_t)m.n_triangles;
         M.tt.resize(nt);
         M.ta.resize(nt);
@@ -264,6 +269,7 @@ int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
         ai.max_depth = M.kd.maxDepth;
         ai.n_triangles = (uint32_t)m.n_triangles;
         ai.build_ms = M.kd.buildMs;
+        ai.from_cache = strcmp(M.kdSource, "built") != 0;
     }
     std::vector<DHeightfield> dh(s.n_heightfields);
     for (int i = 0; i < s.n_heightfields; i++) {

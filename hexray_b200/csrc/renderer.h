@@ -19,6 +19,7 @@ struct MeshTables {
     std::vector<TriAttrUv> tu;
     std::vector<TriF32> tf;
     std::vector<TriPacked> tp;  // empty: the scene walks tri_f32
+    const char* kdSource = "built";  // "built" here, or "cache" / "waited" (host/cache.h)
 };
 struct SceneTables {
     std::vector<MeshTables> meshes;

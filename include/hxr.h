@@ -351,7 +351,9 @@ typedef struct hxr_accel_info {
     uint64_t nodes, leaves, tri_refs, bytes_nodes, bytes_tris;
     uint32_t max_depth;
     uint32_t n_triangles;
-    double build_ms;
+    double build_ms;        /* of the build that produced the tree (possibly in an earlier process: see from_cache) */
+    uint32_t from_cache;    /* 1: the tree came from the on-disk cache, or from another process that was building it */
+    uint32_t reserved;
 } hxr_accel_info;
 int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out);
 

@@ -7,5 +7,5 @@ cd "$(dirname "$0")"
 SRC=../../hexray_b200/csrc
 g++ -std=c++17 -O2 -fPIC -shared -DHXR_EMU -Wall -Wno-unused-function \
     $SRC/abi.cpp $SRC/renderer.cpp $SRC/multi.cpp $SRC/host/scene.cpp $SRC/host/mesh.cpp $SRC/host/flatten.cpp \
-    $SRC/host/bitmap.cpp $SRC/host/kdtree.cpp launch_emu.cpp \
+    $SRC/host/bitmap.cpp $SRC/host/kdtree.cpp $SRC/host/cache.cpp launch_emu.cpp \
     -o libhxr_emu.so -lz -lpthread
