@@ -187,6 +187,17 @@ class Renderer:
         """Bitmap::saveEXR of the last rendered frame (or the device frame at `dptr`): float -> half on the GPU."""
         self._check(self.api.lib.hxr_save_frame_exr(self.ctx, C.c_void_p(dptr) if dptr else None, width, height, path.encode()))
 
+    def progressive(self, n_passes, width=0, height=0, spp=0, seed=0, max_depth=-1):
+        """Refine one Monte-Carlo frame pass by pass (hxr_progressive_*): yields (estimate [H, W, 3], stats) after every pass."""
+        W, H = self.frame_size(width, height)
+        p = self._params(width, height, MODE_MONTECARLO, spp, -1, max_depth, seed, (0, 0), 0)
+        self._check(self.api.lib.hxr_progressive_begin(self.ctx, C.byref(p), n_passes))
+        out = np.empty((H, W, 3), dtype=np.float32)
+        for _ in range(n_passes):
+            st = capi.Stats()
+            self._check(self.api.lib.hxr_progressive_pass(self.ctx, out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st)))
+            yield out, st.as_dict()
+
     def reduce_backend(self):
         return self.api.lib.hxr_reduce_backend(self.ctx).decode()
 

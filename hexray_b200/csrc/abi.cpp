@@ -88,6 +88,13 @@ int hxr_render_device(hxr_ctx* ctx, const hxr_render_params* p, void* d_rgb, hxr
     HXR_CTX_CALL(ctx->m.render(*p, nullptr, d_rgb, stats))
 }
 int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t w, int32_t h, int32_t spp) { HXR_CTX_CALL(ctx->m.primary().resolveDevice(d_rgb, w, h, spp)) }
+int hxr_progressive_begin(hxr_ctx* ctx, const hxr_render_params* p, int32_t n_passes)
+{
+    if (ctx && !p) { ctx->err = "null render params"; return HXR_ERR_INVALID; }
+    HXR_CTX_CALL(ctx->m.progressiveBegin(*p, n_passes))
+}
+int hxr_progressive_pass(hxr_ctx* ctx, float* rgb_out, hxr_stats* stats) { HXR_CTX_CALL(ctx->m.progressivePass(rgb_out, stats)) }
+int hxr_progressive_state(hxr_ctx* ctx, float* sum_out, int32_t* passes_done, int32_t* spp_done) { HXR_CTX_CALL(ctx->m.progressiveState(sum_out, passes_done, spp_done)) }
 int hxr_set_profiling(hxr_ctx* ctx, int32_t on) { HXR_CTX_CALL((ctx->m.setProfiling(on != 0), HXR_OK)) }
 int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits) { HXR_CTX_CALL(ctx->m.primary().traceClosest(rays, n, hits)) }
 int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->m.primary().traceVisible(seg, n, vis)) }

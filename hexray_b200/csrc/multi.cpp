@@ -8,6 +8,10 @@ namespace hxr {
 
 MultiRenderer::~MultiRenderer()
 {
+    if (!m_r.empty()) {
+        dev::free_(m_r[0]->device(), m_sum);
+        dev::free_(m_r[0]->device(), m_estimate);
+    }
     dev::comm_destroy(m_comm);
 }
 
@@ -80,6 +84,151 @@ int MultiRenderer::setCamera(const hxr_camera* cam)
     return HXR_OK;
 }
 
+int MultiRenderer::reduceShards(float scale, double& reduceMs)
+{
+    const int N = (int)m_r.size();
+    Renderer& r0 = *m_r[0];
+    dev::Context* d0 = r0.device();
+    const size_t n = (size_t)r0.frameWidth() * r0.frameHeight() * 3;
+    dev::Timer* tm = dev::timer_create(d0);
+    dev::timer_start(d0, tm);
+    bool ok = true;
+    if (N == 1) {
+        if (scale != 1.0f) dev::scale_all(d0, r0.frame(), n, scale);
+    } else if (m_comm) {
+        std::vector<float*> bufs;
+        for (auto& r : m_r) bufs.push_back(r->frame());
+        ok = dev::comm_reduce_sum(m_comm, bufs.data(), n);
+        if (ok && scale != 1.0f) dev::scale_all(d0, r0.frame(), n, scale);
+    } else if (m_peer) {
+        std::vector<const float*> srcs;
+        for (int i = 1; i < N; i++) srcs.push_back(m_r[i]->frame());
+        dev::reduce_peers(d0, r0.frame(), srcs.data(), N - 1, n, scale);
+    } else {
+        m_stage.resize(n);
+        std::vector<float> sum(n, 0.0f);
+        for (int i = 0; i < N && ok; i++) {
+            ok = dev::download(m_r[i]->device(), m_stage.data(), m_r[i]->frame(), n * sizeof(float));
+            for (size_t k = 0; k < n; k++) sum[k] += m_stage[k];
+        }
+        for (size_t k = 0; k < n; k++) sum[k] *= scale;
+        ok = ok && dev::upload(d0, r0.frame(), sum.data(), n * sizeof(float));
+    }
+    dev::timer_stop(d0, tm);
+    reduceMs = dev::timer_ms(d0, tm);
+    dev::timer_destroy(d0, tm);
+    for (auto& r : m_r) ok = dev::sync(r->device()) && ok;
+    if (!ok || dev::failed(d0)) return fail(HXR_ERR_CUDA, std::string("multi-GPU reduce failed: ") + dev::last_error(d0));
+    return HXR_OK;
+}
+
+static void mergeStats(std::vector<hxr_stats>& st, double reduceMs, hxr_stats& s)
+{
+    s = st[0];
+    for (size_t i = 1; i < st.size(); i++) {
+        s.rays_closest += st[i].rays_closest;
+        s.rays_shadow += st[i].rays_shadow;
+        s.kd_inner += st[i].kd_inner;
+        s.kd_leaves += st[i].kd_leaves;
+        s.tri_tests += st[i].tri_tests;
+        s.mesh_queries += st[i].mesh_queries;
+        s.kernel_launches += st[i].kernel_launches;
+        s.cand_overflow += st[i].cand_overflow;
+        s.spp_done += st[i].spp_done;
+        s.aa_pixels += st[i].aa_pixels;
+        s.walk_launches += st[i].walk_launches;
+        s.render_ms = std::max(s.render_ms, st[i].render_ms);  // the GPUs run side by side: the frame takes as long as the slowest
+        s.walk_ms = std::max(s.walk_ms, st[i].walk_ms);
+    }
+    s.reduce_ms = reduceMs;
+    s.render_ms += reduceMs;
+    s.n_devices = (uint32_t)st.size();
+}
+
+// ---- progressive frames: pass k of P on GPU g of N renders the sample passes s % (P * N) == k * N + g
+int MultiRenderer::progressiveBegin(const hxr_render_params& p, int nPasses)
+{
+    m_err.clear();
+    if (nPasses < 1) return fail(HXR_ERR_INVALID, "progressive: n_passes must be >= 1");
+    if (p.shard_count > 1) return fail(HXR_ERR_INVALID, "progressive: the passes are the shards; leave shard_count at 0");
+    bool mc;
+    int spp;
+    m_r[0]->framePlan(p, mc, spp);
+    if (!mc) return fail(HXR_ERR_INVALID, "progressive rendering refines Monte-Carlo frames (gi or dof scenes, or mode = HXR_MODE_MONTECARLO)");
+    m_pp = p;
+    m_pp.mode = HXR_MODE_MONTECARLO;
+    m_pp.spp = spp;
+    m_passes = nPasses;
+    m_passNext = 0;
+    m_sppSoFar = 0;
+    m_sppTotal = spp;
+    return HXR_OK;
+}
+
+int MultiRenderer::progressivePass(float* hostOut, hxr_stats* stats)
+{
+    m_err.clear();
+    if (m_passes <= 0) return fail(HXR_ERR_INVALID, "progressive: call hxr_progressive_begin first");
+    if (m_passNext >= m_passes) return fail(HXR_ERR_INVALID, "progressive: all passes are done");
+    const int N = (int)m_r.size(), P = m_passes, k = m_passNext;
+    std::vector<int> rc(N, HXR_OK);
+    std::vector<hxr_stats> st(N);
+    std::vector<std::thread> th;
+    for (int g = 0; g < N; g++)
+        th.emplace_back([&, g] {
+            hxr_render_params q = m_pp;
+            q.shard_index = k * N + g;
+            q.shard_count = P * N;
+            rc[g] = m_r[g]->render(q, nullptr, nullptr, &st[g], true);
+        });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < N; g++)
+        if (rc[g] != HXR_OK) return fail(rc[g], m_r[g]->error());
+    double reduceMs = 0;
+    const int rrc = reduceShards(1.0f, reduceMs);  // ONE reduce per pass; the sum stays un-normalised
+    if (rrc != HXR_OK) return rrc;
+    Renderer& r0 = *m_r[0];
+    dev::Context* d0 = r0.device();
+    const size_t n = (size_t)r0.frameWidth() * r0.frameHeight() * 3;
+    if (k == 0 || m_sumFloats != n) {
+        if (m_sumFloats != n) {
+            dev::free_(d0, m_sum);
+            dev::free_(d0, m_estimate);
+            m_sum = (float*)dev::alloc(d0, n * sizeof(float));
+            m_estimate = (float*)dev::alloc(d0, n * sizeof(float));
+            m_sumFloats = (m_sum && m_estimate) ? n : 0;
+            if (!m_sumFloats) return fail(HXR_ERR_CUDA, "progressive: out of device memory");
+        }
+        dev::zero(d0, m_sum, n * sizeof(float));
+    }
+    dev::add_into(d0, m_sum, r0.frame(), n);
+    for (int g = 0; g < N; g++) m_sppSoFar += (int)st[g].spp_done;
+    m_passNext++;
+    if (hostOut) {
+        dev::copy_d2d(d0, m_estimate, m_sum, n * sizeof(float));
+        dev::scale_all(d0, m_estimate, n, 1.0f / (float)std::max(1, m_sppSoFar));
+        if (!dev::download(d0, hostOut, m_estimate, n * sizeof(float))) return fail(HXR_ERR_CUDA, dev::last_error(d0));
+    } else if (!dev::sync(d0)) {
+        return fail(HXR_ERR_CUDA, dev::last_error(d0));
+    }
+    if (stats) {
+        mergeStats(st, reduceMs, *stats);
+        stats->spp_done = (uint32_t)m_sppSoFar;
+    }
+    return HXR_OK;
+}
+
+int MultiRenderer::progressiveState(float* sumOut, int* passesDone, int* sppDone)
+{
+    if (passesDone) *passesDone = m_passNext;
+    if (sppDone) *sppDone = m_sppSoFar;
+    if (sumOut) {
+        if (!m_sum || m_passNext == 0) return fail(HXR_ERR_INVALID, "progressive: no pass rendered yet");
+        if (!dev::download(m_r[0]->device(), sumOut, m_sum, m_sumFloats * sizeof(float))) return fail(HXR_ERR_CUDA, dev::last_error(m_r[0]->device()));
+    }
+    return HXR_OK;
+}
+
 int MultiRenderer::render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats)
 {
     m_err.clear();
@@ -104,64 +253,18 @@ int MultiRenderer::render(const hxr_render_params& p, float* hostOut, void* devO
     // the frames meet on the first GPU: sum, and for Monte-Carlo frames the division by the sample count, in one pass
     Renderer& r0 = *m_r[0];
     dev::Context* d0 = r0.device();
-    const int W = r0.frameWidth(), H = r0.frameHeight();
-    const size_t n = (size_t)W * H * 3;
+    const size_t n = (size_t)r0.frameWidth() * r0.frameHeight() * 3;
     bool mc;
     int spp;
     r0.framePlan(p, mc, spp);
-    const float scale = mc ? 1.0f / (float)spp : 1.0f;
-    dev::Timer* tm = dev::timer_create(d0);
-    dev::timer_start(d0, tm);
+    double reduceMs = 0;
+    const int rrc = reduceShards(mc ? 1.0f / (float)spp : 1.0f, reduceMs);
+    if (rrc != HXR_OK) return rrc;
     bool ok = true;
-    if (m_comm) {
-        std::vector<float*> bufs;
-        for (auto& r : m_r) bufs.push_back(r->frame());
-        ok = dev::comm_reduce_sum(m_comm, bufs.data(), n);
-        if (ok && scale != 1.0f) dev::scale_all(d0, r0.frame(), n, scale);
-    } else if (m_peer) {
-        std::vector<const float*> srcs;
-        for (int i = 1; i < N; i++) srcs.push_back(m_r[i]->frame());
-        dev::reduce_peers(d0, r0.frame(), srcs.data(), N - 1, n, scale);
-    } else {
-        m_stage.resize(n);
-        std::vector<float> sum(n, 0.0f);
-        for (int i = 0; i < N && ok; i++) {
-            ok = dev::download(m_r[i]->device(), m_stage.data(), m_r[i]->frame(), n * sizeof(float));
-            for (size_t k = 0; k < n; k++) sum[k] += m_stage[k];
-        }
-        for (size_t k = 0; k < n; k++) sum[k] *= scale;
-        ok = ok && dev::upload(d0, r0.frame(), sum.data(), n * sizeof(float));
-    }
-    dev::timer_stop(d0, tm);
-    const double reduceMs = dev::timer_ms(d0, tm);
-    dev::timer_destroy(d0, tm);
-    for (auto& r : m_r) ok = dev::sync(r->device()) && ok;
-    if (!ok || dev::failed(d0)) return fail(HXR_ERR_CUDA, std::string("multi-GPU reduce failed: ") + dev::last_error(d0));
     if (devOut) ok = dev::copy_d2d(d0, devOut, r0.frame(), n * sizeof(float)) && dev::sync(d0);
     if (hostOut) ok = ok && dev::download(d0, hostOut, r0.frame(), n * sizeof(float));
     if (!ok) return fail(HXR_ERR_CUDA, std::string("result copy failed: ") + dev::last_error(d0));
-    if (stats) {
-        hxr_stats s = st[0];
-        for (int i = 1; i < N; i++) {
-            s.rays_closest += st[i].rays_closest;
-            s.rays_shadow += st[i].rays_shadow;
-            s.kd_inner += st[i].kd_inner;
-            s.kd_leaves += st[i].kd_leaves;
-            s.tri_tests += st[i].tri_tests;
-            s.mesh_queries += st[i].mesh_queries;
-            s.kernel_launches += st[i].kernel_launches;
-            s.cand_overflow += st[i].cand_overflow;
-            s.spp_done += st[i].spp_done;
-            s.aa_pixels += st[i].aa_pixels;
-            s.walk_launches += st[i].walk_launches;
-            s.render_ms = std::max(s.render_ms, st[i].render_ms);  // the GPUs run side by side: the frame takes as long as the slowest
-            s.walk_ms = std::max(s.walk_ms, st[i].walk_ms);
-        }
-        s.reduce_ms = reduceMs;
-        s.render_ms += reduceMs;
-        s.n_devices = (uint32_t)N;
-        *stats = s;
-    }
+    if (stats) mergeStats(st, reduceMs, *stats);
     return HXR_OK;
 }
 

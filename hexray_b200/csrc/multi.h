@@ -20,6 +20,10 @@ public:
     int uploadScene(const hxr_scene* sc);
     int setCamera(const hxr_camera* cam);
     int render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats);
+    // progressive Monte-Carlo frames: see include/hxr.h
+    int progressiveBegin(const hxr_render_params& p, int nPasses);
+    int progressivePass(float* hostOut, hxr_stats* stats);
+    int progressiveState(float* sumOut, int* passesDone, int* sppDone);
     int deviceCount() const { return (int)m_r.size(); }
     Renderer& primary() { return *m_r[0]; }
     const std::string& error() const { return m_err.empty() ? m_r[0]->error() : m_err; }
@@ -35,6 +39,13 @@ private:
     bool m_peer = false;       // the first GPU can read every other GPU's memory
     const char* m_reduceName = "none";
     std::vector<float> m_stage;  // host staging of the last-resort reduce
+    int reduceShards(float scale, double& reduceMs);  // the GPUs' partial frames -> the first GPU's frame, times scale
+    // progressive state: the running sum lives on the first GPU
+    hxr_render_params m_pp{};
+    int m_passes = 0, m_passNext = 0, m_sppSoFar = 0, m_sppTotal = 0;
+    float* m_sum = nullptr;
+    float* m_estimate = nullptr;
+    size_t m_sumFloats = 0;
 };
 
 }  // namespace hxr

@@ -325,6 +325,19 @@ int hxr_render_device(hxr_ctx* ctx, const hxr_render_params* p, void* d_rgb, hxr
 /* scale a reduced device sum buffer by 1/spp in place (Monte-Carlo resolve, src/main.cpp:376). */
 int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t width, int32_t height, int32_t spp);
 
+/* ---- progressive rendering (reference: the interactive loop of src/main.cpp:387-414, 443-504 - gameloop / coarseRender -
+ * that shows a coarse frame first and refines it; here refinement = more sample passes of the same Monte-Carlo frame).
+ * hxr_progressive_begin fixes the frame (size, total spp, seed) and the number of passes; every hxr_progressive_pass renders
+ * the next pass (the samples s with (s / n_gpus) % n_passes == pass, dealt over the context's GPUs as usual), reduces it
+ * across the GPUs (ONE reduce per pass), adds it to the running per-pixel sum on the first GPU and returns the current
+ * estimate sum / samples_so_far in rgb_out (host, width*height*3 floats; may be NULL to skip the read-back). After the last
+ * pass the estimate equals what hxr_render returns for the same parameters (up to FP32 summation order). A camera change
+ * between frames is hxr_set_camera + hxr_progressive_begin. hxr_progressive_state exports the checkpoint (sum, samples):
+ * sum_out may be NULL; returns the number of passes done through *passes_done and the samples per pixel so far through *spp_done. */
+int hxr_progressive_begin(hxr_ctx* ctx, const hxr_render_params* p, int32_t n_passes);
+int hxr_progressive_pass(hxr_ctx* ctx, float* rgb_out, hxr_stats* stats);
+int hxr_progressive_state(hxr_ctx* ctx, float* sum_out, int32_t* passes_done, int32_t* spp_done);
+
 /* when on, every kernel launch of this context is bracketed by CUDA events and hxr_stats carries the
  * per-kernel-class device times (trace_closest_ms, trace_shadow_ms, shade_ms, other_ms) */
 int hxr_set_profiling(hxr_ctx* ctx, int32_t on);

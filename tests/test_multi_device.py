@@ -79,3 +79,31 @@ def test_nccl_reduce_when_several_gpus(gpu_api):
     finally:
         del os.environ["HXR_REDUCE"]
     assert st["cornell_box"]["n_devices"] == 2
+
+
+def check_progressive(api, devices):
+    """Pass-by-pass refinement (hxr_progressive_*): the estimate after the last pass is the frame hxr_render returns, the
+    estimates in between are proper (unbiased, noisier) frames, one reduce per pass."""
+    sf = hx.SceneFile(T.scene_path("cornell_box"), api_=api)
+    r = hx.Renderer(api_=api, queue_capacity=1 << 20, devices=devices).load(sf)
+    full, st = r.render(width=64, height=64, spp=16, seed=9)
+    errs, spps = [], []
+    for est, pst in r.progressive(4, width=64, height=64, spp=16, seed=9):
+        errs.append(float(np.abs(est - full).mean()))
+        spps.append(pst["spp_done"])
+        assert float(est.mean()) > 0.01
+    assert spps == [4, 8, 12, 16]
+    assert errs[-1] < 2e-5 * max(1.0, float(full.max())) and errs[0] > errs[-1]
+    r.close()
+    sf.close()
+
+
+def test_progressive_on_the_emulation(emu_api):
+    check_progressive(emu_api, None)
+    check_progressive(emu_api, [0, 1])
+
+
+@pytest.mark.gpu
+def test_progressive_on_the_gpu(gpu_api):
+    check_progressive(gpu_api, None)
+    check_progressive(gpu_api, [0, 1 % gpu_api.lib.hxr_device_count()])
