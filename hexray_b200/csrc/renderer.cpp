@@ -643,7 +643,9 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
                 st.kernel_launches += dev::resolve_shadow(m_dev, m_scene, sk.shadow, scand, accum, nullptr, m_totals, cnt, ns);
             }
         }
-        hint = std::min<uint64_t>(hint * fan, m_cap);
+        // (the hint only sizes grids - every kernel loops over the device-side count - so it need not be the worst case:
+        // ray trees die much faster than maxChildrenPerHit ^ level grows)
+        hint = std::min<uint64_t>(std::min<uint64_t>(hint * fan, (uint64_t)nPrimary * 2), m_cap);
         cur = 1 - cur;
     }
 }

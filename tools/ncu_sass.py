@@ -10,6 +10,7 @@ import sys
 def main():
     rep = sys.argv[1]
     which = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 0
+    want = next((a[7:] for a in sys.argv if a.startswith("--name=")), None)  # --name=substring: the first kernel whose name contains it
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     kernels, cur = [], None
     for r in csv.reader(io.StringIO(out)):
@@ -18,7 +19,14 @@ def main():
             kernels.append((r[1], cur))
         elif cur is not None:
             cur.append(r)
-    name, rs = kernels[which]
+    if want:
+        sel = [k for k in kernels if want in k[0]]
+        if not sel:
+            print("no kernel matching", want)
+            return
+        name, rs = sel[which if which < len(sel) else 0]
+    else:
+        name, rs = kernels[which]
     hdr, body = rs[0], rs[1:]
     iE, iT, iS, iSrc = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
     rows = [(int(r[iE]), int(r[iT]), int(r[iS]), r[iSrc].strip()) for r in body]
