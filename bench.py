@@ -392,7 +392,7 @@ def ours(a):
 
     from hexray_b200 import distributed
 
-    def step(i, to_host):
+    def step(i, to_host, flags=0):
         """one frame: this rank's sample passes -> reduce -> resolve [-> host]. Returns (stats, device ms of the part that
         runs on torch's stream: reduce + resolve + copy)."""
         if flush is not None:
@@ -405,12 +405,12 @@ def ours(a):
             if to_host:
                 _, st = r.render(width=W, height=H, mode=mode, spp=spp_total, seed=i, out=host.numpy().reshape(H, W, 3))
             else:
-                st = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=spp_total, seed=i)
+                st = r.render_device(acc.data_ptr(), width=W, height=H, mode=mode, spp=spp_total, seed=i, flags=flags)
             return st, 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         st = distributed.render_frame(r, acc, W, H, spp_total=spp_total, seed=i, rank=rank, world=world, mode=mode, dist=dist,
-                                      sync=lambda: torch.cuda.synchronize(dev), on_rendered=e0.record)
+                                      sync=lambda: torch.cuda.synchronize(dev), on_rendered=e0.record, flags=flags)
         if to_host and rank == 0:
             host.copy_(acc, non_blocking=False)
         e1.record()
@@ -420,12 +420,12 @@ def ours(a):
     KEYS = ("trace_closest_ms", "trace_shadow_ms", "walk_ms", "setup_ms", "finish_ms", "shade_ms", "shadow_resolve_ms", "gen_ms", "other_ms",
             "render_ms", "reduce_ms")
 
-    def run(n, to_host, first_seed):
+    def run(n, to_host, first_seed, flags=0):
         rays = np.zeros(2, dtype=np.float64)
         prof = {k: 0.0 for k in KEYS}
         prof.update({"walk_launches": 0, "kernel_launches": 0, "post_ms": 0.0, "cand_overflow": 0})
         for i in range(n):
-            st, post_ms = step(first_seed + i, to_host)
+            st, post_ms = step(first_seed + i, to_host, flags)
             rays += (st["rays_closest"], st["rays_shadow"])
             for k in prof:
                 prof[k] += post_ms if k == "post_ms" else st[k]
@@ -433,15 +433,21 @@ def ours(a):
 
     # ---- device-resident throughput ("value"): CUDA-event time of the frames (render on the library's stream(s) +
     # reduce/resolve), max over ranks; the wall clock around the same region is reported beside it
-    r.set_profiling(True)
     run(a.warmup, False, 1000)
     barrier()
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
-        rays, prof = run(a.steps, False, 0)
+        rays, timed = run(a.steps, False, 0)
         barrier()
         dt_wall = time.perf_counter() - t0
-    dt = (prof["render_ms"] + prof["post_ms"]) * 1e-3
+    dt = (timed["render_ms"] + timed["post_ms"]) * 1e-3
+    # ---- per-kernel device times (the roofline's denominator): the same K steps once more with every kernel on ONE stream
+    # (HXR_RENDER_ONE_LANE) -- in the timed region above the shadow chain of a bounce runs beside the next bounce's closest-hit
+    # chain on a second stream, so event pairs around a launch there would also count its neighbour
+    r.set_profiling(True)
+    _, prof = run(a.steps, False, 0, hx.RENDER_ONE_LANE)
+    r.set_profiling(False)
+    barrier()
     # ---- end to end through the C ABI with host buffers ("e2e"): wall clock around blocking calls that end with the
     # frame in host memory
     run(min(a.warmup, 1), True, 2000)
@@ -450,7 +456,6 @@ def ours(a):
     rays_e, _ = run(a.steps, True, 0)
     barrier()
     dt_e = time.perf_counter() - t0
-    r.set_profiling(False)
 
     def allsum(x):
         t = torch.tensor(x, dtype=torch.float64, device=dev)
@@ -523,7 +528,7 @@ def ours(a):
             "timing": "CUDA events (render on the library's stream + reduce/resolve), max over ranks; wall clock beside it",
             "e2e": {"value": float(rays_e.sum()) / dt_e / 1e6, "unit": "Mrays/s", "ms_per_step": dt_e / a.steps * 1e3,
                     "h2d_bytes_per_step": 256, "d2h_bytes_per_step": W * H * 12},
-            "gpu_launches": int(prof["kernel_launches"]),
+            "gpu_launches": int(timed["kernel_launches"]),
             "clocks": clk.summary(),
             "N_inner": per_ray["inner"], "N_tri": per_ray["tri"], "N_leaf": per_ray["leaf"],
             "roofline": {"bound": "hbm" if hbm_bound else "l2", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -538,6 +543,8 @@ def ours(a):
                          "random_gather": gather,
                          "walk_share_of_step": walk_ms / max(1e-9, prof["render_ms"])},
             "kernel_ms_per_step": {k: prof[k] / a.steps for k in KEYS},
+            "kernel_ms_source": "the same K steps repeated after the timed region with every kernel on ONE stream (HXR_RENDER_ONE_LANE, CUDA events "
+                                "around each launch); render_ms there is the one-lane step, ms_per_step above the two-lane one",
             "cand_overflow_per_step": prof["cand_overflow"] / a.steps,
         }
         if n_gpus == 1 and not a.no_cpu_baseline:

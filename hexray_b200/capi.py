@@ -17,6 +17,7 @@ STATUS_NAMES = {0: "HXR_OK", -1: "HXR_ERR_INVALID", -2: "HXR_ERR_NO_DEVICE", -3:
                 -4: "HXR_ERR_PARSE", -5: "HXR_ERR_IO", -6: "HXR_ERR_OVERFLOW"}
 MODE_AUTO, MODE_WHITTED, MODE_MONTECARLO = 0, 1, 2
 RENDER_COUNT_TRAVERSAL = 1
+RENDER_ONE_LANE = 2
 CFG_BRUTE_FORCE_MESHES = 1
 
 

@@ -31,7 +31,14 @@ bool download(Context*, void* dst, const void* src, size_t bytes);       // bloc
 bool download_async(Context*, void* dst, const void* src, size_t bytes); // stream ordered; dst should be pinned
 bool zero(Context*, void* p, size_t bytes);
 bool copy_d2d(Context*, void* dst, const void* src, size_t bytes);
-bool sync(Context*);
+bool sync(Context*);  // both lanes
+// Two stream-ordered lanes per context: lane 0 (main) and lane 1 (aux). Every launch, memset and copy below goes to the lane
+// selected by lane(); fork makes the aux lane wait for everything queued on the main lane so far, join makes the main lane
+// wait for the aux lane. The frame driver runs the shadow chain of one bounce on the aux lane while the closest-hit chain of
+// the next bounce runs on the main lane (they share no buffers): small frames, whose launches do not fill the GPU, overlap.
+void lane(Context*, int which);
+void fork(Context*);
+void join(Context*);
 // text of the first failed call or kernel launch since the last clear_error ("" if none): launches are asynchronous, so
 // the frame driver checks this once per frame instead of after every launch
 const char* last_error(const Context*);

@@ -39,7 +39,9 @@ namespace dev {
 struct Context {
     int device = -1;
     int sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // the CURRENT lane's stream (lane()): what every launch below uses
+    cudaStream_t lanes[2] = {nullptr, nullptr};
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::string err;  // first failure since clear_error
     bool prof = false;
     // walk-loop tunables (uniform kernel arguments; environment overrides for A/B runs: HXR_WALK_STEPS, HXR_REFILL_MIN, HXR_SSTACK,
@@ -92,25 +94,31 @@ Context* create(int device, char* err, size_t errlen)
     if (const char* v = getenv("HXR_WALK_CARVEOUT")) c->walkCarveout = std::min(100, std::max(0, atoi(v)));
     if (const char* v = getenv("HXR_WALK_BLOCKS_PER_SM")) c->walkBlocksPerSm = std::max(1, atoi(v));
     if (const char* v = getenv("HXR_REFILL_MIN")) c->refillMin = std::min(32, std::max(1, atoi(v)));
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&c->lanes[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->lanes[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return fail("cudaStreamCreate failed");
     }
+    c->stream = c->lanes[0];
     return c;
 }
 void destroy(Context* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->lanes[0]);
+    cudaStreamSynchronize(c->lanes[1]);
     for (int k = 0; k < PROF_NCAT; k++)
         for (auto& pr : c->evPairs[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
+    cudaEventDestroy(c->evFork);
+    cudaEventDestroy(c->evJoin);
+    cudaStreamDestroy(c->lanes[0]);
+    cudaStreamDestroy(c->lanes[1]);
     delete c;
 }
 int device_of(const Context* c) { return c->device; }
-void* stream_of(const Context* c) { return (void*)c->stream; }
+void* stream_of(const Context* c) { return (void*)c->lanes[0]; }
 const char* backend_name() { return "cuda sm_100a"; }
 const char* last_error(const Context* c) { return c->err.c_str(); }
 bool failed(const Context* c) { return !c->err.empty(); }
@@ -156,7 +164,20 @@ bool download(Context* c, void* d, const void* s, size_t n)
 bool download_async(Context* c, void* d, const void* s, size_t n) { return use(c) && ck(c, cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, c->stream), "D2H copy"); }
 bool zero(Context* c, void* p, size_t n) { return use(c) && ck(c, cudaMemsetAsync(p, 0, n, c->stream), "memset"); }
 bool copy_d2d(Context* c, void* d, const void* s, size_t n) { return use(c) && ck(c, cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream), "D2D copy"); }
-bool sync(Context* c) { return use(c) && ck(c, cudaStreamSynchronize(c->stream), "stream sync"); }
+bool sync(Context* c) { return use(c) && ck(c, cudaStreamSynchronize(c->lanes[1]), "stream sync") && ck(c, cudaStreamSynchronize(c->lanes[0]), "stream sync"); }
+void lane(Context* c, int which) { c->stream = c->lanes[which ? 1 : 0]; }
+void fork(Context* c)
+{
+    use(c);
+    ck(c, cudaEventRecord(c->evFork, c->lanes[0]), "fork");
+    ck(c, cudaStreamWaitEvent(c->lanes[1], c->evFork, 0), "fork");
+}
+void join(Context* c)
+{
+    use(c);
+    ck(c, cudaEventRecord(c->evJoin, c->lanes[1]), "join");
+    ck(c, cudaStreamWaitEvent(c->lanes[0], c->evJoin, 0), "join");
+}
 
 struct Timer { cudaEvent_t a, b; };
 Timer* timer_create(Context* c)
@@ -206,7 +227,8 @@ void prof_reset(Context* c)
 void prof_collect(Context* c, double ms[PROF_NCAT], uint64_t launches[PROF_NCAT])
 {
     use(c);
-    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->lanes[0]);
+    cudaStreamSynchronize(c->lanes[1]);
     for (int k = 0; k < PROF_NCAT; k++) {
         double s = 0;
         for (auto& pr : c->evPairs[k]) {

@@ -14,7 +14,7 @@
 namespace hxr {
 
 // device counters (uint32): queue counts, the shadow queue's count, the work-fetch cursors of the two walks, flags
-enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_HEAD_A = 3, C_HEAD_B = 4, C_OVF_A = 5, C_OVF_B = 6, C_OVERFLOW = 7, C_AA = 8, C_NCOUNTERS = 16 };
+enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_HEAD_A = 3, C_OVF_A = 4, C_HEAD_B = 5, C_OVF_B = 6, C_OVERFLOW = 7, C_AA = 8, C_NCOUNTERS = 16 };
 
 Renderer::~Renderer()
 {
@@ -520,6 +520,7 @@ void Renderer::freeQueues()
     dev::free_(m_dev, m_entry); m_entry = nullptr;
     dev::free_(m_dev, m_sentry); m_sentry = nullptr;
     dev::free_(m_dev, m_ovfList); m_ovfList = nullptr;
+    dev::free_(m_dev, m_ovfListS); m_ovfListS = nullptr;
     dev::free_(m_dev, m_hits); m_hits = nullptr;
     dev::free_(m_dev, m_visible); m_visible = nullptr;
     m_cap = m_shadowCap = 0;
@@ -548,6 +549,13 @@ bool Renderer::ensureQueues()
     m_entry = (MeshEntry*)dev::alloc(m_dev, (size_t)cap * sizeof(MeshEntry));
     m_sentry = (MeshEntry*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(MeshEntry));
     m_ovfList = (OverflowEntry*)dev::alloc(m_dev, (size_t)std::max(cap, shadowCap) * sizeof(OverflowEntry));
+    // the two lanes of drain(): the shadow chain needs its own candidate records and overflow list (HXR_NO_OVERLAP=1: one lane)
+    m_overlap = !getenv("HXR_NO_OVERLAP");
+    if (m_overlap) {
+        m_scand = (CandRec*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(CandRec));
+        m_ovfListS = (OverflowEntry*)dev::alloc(m_dev, (size_t)shadowCap * sizeof(OverflowEntry));
+        if (!m_scand || !m_ovfListS) m_overlap = false;  // (short of memory: one lane, shared buffers)
+    }
     if (!m_counters) m_counters = (uint32_t*)dev::alloc(m_dev, C_NCOUNTERS * sizeof(uint32_t));
     if (!m_totals) m_totals = (dev::FrameTotals*)dev::alloc(m_dev, sizeof(dev::FrameTotals));
     if (!m_trav) m_trav = (TravCounters*)dev::alloc(m_dev, sizeof(TravCounters));
@@ -567,7 +575,7 @@ dev::WalkBuffers Renderer::walkBuffers(CandRec* cand, bool shadow) const
     dev::WalkBuffers wb;
     wb.cand = cand;
     wb.head = m_counters + (shadow ? C_HEAD_B : C_HEAD_A);
-    wb.ovf_list = m_ovfList;
+    wb.ovf_list = shadow && m_ovfListS ? m_ovfListS : m_ovfList;
     wb.ovf_count = m_counters + (shadow ? C_OVF_B : C_OVF_A);
     return wb;
 }
@@ -601,8 +609,12 @@ uint32_t Renderer::readCount(const uint32_t* dptr)
 
 // One bounce = [setup(closest)] -> walk(closest) -> shade -> setup(shadow) -> walk(shadow) -> resolve(shadow). The counts stay
 // on the device: the host enqueues max_depth + 1 bounces (a ray's depth grows by one per bounce and the guard stops it at
-// max_depth) with grids sized from an upper bound of each level's population; levels that turn out empty cost a few
-// near-empty launches.
+// max_depth); levels that turn out empty cost a few near-empty launches. Two bounds per level: `bound`, a true upper bound of
+// the level's population (what the shade launches must cover), and `grid`, a realistic one that only sizes grids (every kernel
+// loops over the device-side count; ray trees die much faster than maxChildrenPerHit ^ level grows).
+// Two lanes: the shadow chain of bounce L (aux lane) shares no buffer with the closest-hit chain of bounce L + 1 (main lane),
+// so they are queued side by side; the main lane waits for the aux lane only before the next shade launch, which refills the
+// shadow queue. Big waves fill the GPU either way; small frames, whose launches are latency-bound, overlap.
 void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr_stats& st)
 {
     int cur = 0;
@@ -610,44 +622,48 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
     const uint32_t chunk = std::max<uint32_t>(1, m_shadowCap / perHit);
     const uint64_t fan = fp.gi ? 1u : (uint64_t)std::max(1, m_maxChildrenPerHit);
     TravCounters* cnt = m_countTraversal ? m_trav : nullptr;
-    uint64_t hint = nPrimary;
-    for (int level = 0; level <= fp.max_depth && hint > 0; level++) {
-        const uint32_t n = (uint32_t)std::min<uint64_t>(hint, m_cap);
+    const bool overlap = m_overlap && !m_oneLane && m_scand && m_ovfListS;
+    bool auxBusy = false;
+    uint64_t bound = nPrimary;
+    for (int level = 0; level <= fp.max_depth && bound > 0; level++) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(bound, m_cap);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n, (uint64_t)nPrimary * 2);
         const RayQueue q = queue(cur);
         dev::zero(m_dev, m_counters + (cur ? C_Q0 : C_Q1), sizeof(uint32_t));
-        dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));  // shadow count + the walks' cursors and overflow-list counts
-        if (level > 0) st.kernel_launches += dev::setup_closest(m_dev, m_scene, q, m_cand, cnt, n);  // (level 0 arrives set up)
-        st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, false), m_totals, cnt, n);
+        dev::zero(m_dev, m_counters + C_HEAD_A, 2 * sizeof(uint32_t));  // the closest-hit walk's cursor and overflow-list count
+        if (level > 0) st.kernel_launches += dev::setup_closest(m_dev, m_scene, q, m_cand, cnt, grid);  // (level 0 arrives set up)
+        st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, false), m_totals, cnt, grid);
         Sinks sk;
         sk.next = queue(1 - cur);
         sk.shadow = shadowQueue();
         sk.accum = accum;
         sk.overflow = m_counters + C_OVERFLOW;
-        // The candidate buffer serves both walks when the whole level is shaded by one launch (path tracing: always): every
-        // closest-hit record has been consumed before the shadow walk writes its own. A level shaded in chunks (Whitted
-        // hits with many light samples) needs the shadow records elsewhere.
-        CandRec* scand = m_cand;
-        if (n > chunk && m_scene.n_big) {
+        // The shadow walk has its own candidate buffer when it may run beside the next closest-hit walk, or when the level is
+        // shaded in chunks (Whitted hits with many light samples: later chunks still need their closest-hit records).
+        CandRec* scand = overlap ? m_scand : m_cand;
+        if (!overlap && n > chunk && m_scene.n_big) {
             if (!m_scand) m_scand = (CandRec*)dev::alloc(m_dev, (size_t)m_shadowCap * sizeof(CandRec));
             if (!m_scand) { m_err = "shadow candidate buffer allocation failed"; m_allocFailed = true; return; }
             scand = m_scand;
         }
+        const bool side = overlap && n <= chunk;  // one shade launch covers the level: its shadow chain goes to the aux lane
         for (uint32_t b = 0; b < n; b += chunk) {
             const uint32_t e = (uint32_t)std::min<uint64_t>(n, (uint64_t)b + chunk);
-            if (b) dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));
+            if (auxBusy) { dev::join(m_dev); auxBusy = false; }  // the previous shadow chain is done with the shadow queue
+            dev::zero(m_dev, m_counters + C_SHADOW, sizeof(uint32_t));
             st.kernel_launches += dev::shade(m_dev, m_scene, fp, q, m_cand, b, e, sk, m_totals, cnt);
-            {
-                const uint32_t ns = (uint32_t)std::min<uint64_t>(m_shadowCap, (uint64_t)(e - b) * perHit);
-                st.kernel_launches += dev::setup_shadow(m_dev, m_scene, sk.shadow, scand, accum, cnt, ns);
-                st.kernel_launches += dev::walk(m_dev, m_scene, true, m_sg, m_sentry, m_counters + C_SHADOW, m_shadowCap, walkBuffers(scand, true), m_totals, cnt, ns);
-                st.kernel_launches += dev::resolve_shadow(m_dev, m_scene, sk.shadow, scand, accum, nullptr, m_totals, cnt, ns);
-            }
+            const uint32_t ns = (uint32_t)std::min<uint64_t>(m_shadowCap, (uint64_t)std::min<uint64_t>(e - b, grid) * perHit);
+            if (side) { dev::fork(m_dev); dev::lane(m_dev, 1); }
+            dev::zero(m_dev, m_counters + C_HEAD_B, 2 * sizeof(uint32_t));
+            st.kernel_launches += dev::setup_shadow(m_dev, m_scene, sk.shadow, scand, accum, cnt, ns);
+            st.kernel_launches += dev::walk(m_dev, m_scene, true, m_sg, m_sentry, m_counters + C_SHADOW, m_shadowCap, walkBuffers(scand, true), m_totals, cnt, ns);
+            st.kernel_launches += dev::resolve_shadow(m_dev, m_scene, sk.shadow, scand, accum, nullptr, m_totals, cnt, ns);
+            if (side) { dev::lane(m_dev, 0); auxBusy = true; }
         }
-        // (the hint only sizes grids - every kernel loops over the device-side count - so it need not be the worst case:
-        // ray trees die much faster than maxChildrenPerHit ^ level grows)
-        hint = std::min<uint64_t>(std::min<uint64_t>(hint * fan, (uint64_t)nPrimary * 2), m_cap);
+        bound = std::min<uint64_t>(bound * fan, m_cap);
         cur = 1 - cur;
     }
+    if (auxBusy) dev::join(m_dev);
 }
 
 // ------------------------------------------------------------------------------ frames
@@ -698,6 +714,7 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
     const hxr_settings savedSettings = m_scene.settings;
     if (p.max_depth >= 0) m_scene.settings.max_trace_depth = p.max_depth;
     m_countTraversal = (p.flags & HXR_RENDER_COUNT_TRAVERSAL) != 0;
+    m_oneLane = (p.flags & HXR_RENDER_ONE_LANE) != 0;
     dev::clear_error(m_dev);
     m_allocFailed = false;
 

@@ -88,6 +88,8 @@ private:
     MeshEntry* m_entry = nullptr;    // slot-0 entry records of the closest-hit rays of the current level
     MeshEntry* m_sentry = nullptr;   // ... of the shadow rays
     OverflowEntry* m_ovfList = nullptr;  // rays whose candidate record filled up in the current walk
+    OverflowEntry* m_ovfListS = nullptr; // ... of the shadow walk, when it runs on its own lane
+    bool m_overlap = false;
     CandRec* m_scand = nullptr;      // shadow candidates of levels shaded in chunks (allocated on first use)
     bool m_allocFailed = false;
     HitRec* m_hits = nullptr;        // test hook only, allocated on first use
@@ -106,6 +108,7 @@ private:
     size_t m_accumPixels = 0;
     size_t m_aaCap = 0;
     bool m_countTraversal = false;
+    bool m_oneLane = false;
 };
 
 }  // namespace hxr

@@ -20,14 +20,14 @@ from . import MODE_AUTO
 
 
 def render_frame(renderer, acc, width, height, spp_total=0, seed=0, rank=0, world=1, mode=MODE_AUTO, dist=None, sync=None,
-                 on_rendered=None):
+                 on_rendered=None, flags=0):
     """Render one frame into `acc` (a float32 tensor of width*height*3 elements in the memory the renderer writes:
     CUDA for the product). After the call rank 0 holds the finished frame; other ranks hold their partial sums.
     `dist` is torch.distributed (initialised) when world > 1. `sync()` must make the collective's result visible to the
     library's own stream (e.g. torch.cuda.synchronize); when it is None the tensor's device is synchronised.
     `on_rendered()` is called once this rank's shard is rendered, before the reduce. Returns the render stats of this rank."""
     st = renderer.render_device(acc.data_ptr(), width=width, height=height, mode=mode, spp=spp_total, seed=seed,
-                                shard=(rank, world))
+                                shard=(rank, world), flags=flags)
     if on_rendered is not None:
         on_rendered()
     if world > 1:

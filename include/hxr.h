@@ -260,6 +260,9 @@ typedef struct hxr_render_params {
 } hxr_render_params;
 
 #define HXR_RENDER_COUNT_TRAVERSAL 1 /* also count KD inner-node visits / triangle tests (slower) */
+#define HXR_RENDER_ONE_LANE 2        /* queue every kernel of the frame on ONE stream (default: the shadow chain of a bounce runs on a
+                                      * second stream beside the next bounce's closest-hit chain); the per-kernel times of hxr_stats
+                                      * are exclusive only in this mode */
 
 typedef struct hxr_stats {
     uint64_t rays_closest;  /* closest-hit queries past the depth guard (src/main.cpp:65) */

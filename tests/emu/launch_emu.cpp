@@ -67,6 +67,9 @@ bool download_async(Context*, void* d, const void* s, size_t n) { memcpy(d, s, n
 bool zero(Context*, void* p, size_t n) { memset(p, 0, n); return true; }
 bool copy_d2d(Context*, void* d, const void* s, size_t n) { memcpy(d, s, n); return true; }
 bool sync(Context*) { return true; }
+void lane(Context*, int) {}
+void fork(Context*) {}
+void join(Context*) {}
 const char* last_error(const Context*) { return ""; }
 bool failed(const Context*) { return false; }
 void clear_error(Context*) {}
