@@ -769,7 +769,29 @@ __global__ void __launch_bounds__(128, 2) k_finish(DScene sc, const RayGeom* __r
 }
 
 // GI (one path vertex) and Whitted (shader tree with its stacks) are separate compilations, and so are scenes whose inline
-// nodes are only planes / spheres / cubes / quads (SIMPLE: no CSG, heightfield or inline tree-walk code, no stack frame)
+// nodes are only planes / spheres / cubes / quads (SIMPLE: no CSG, heightfield or inline tree-walk code, no stack frame).
+//
+// Material-sorted shading (the reference dispatches per hit through Shader::computeColor virtuals, src/shading.cpp:67-343,
+// src/main.cpp:105-113). SORT variants work on 128 queued rays per block at a time, in two phases:
+//   1. every thread resolves its own ray (exact tests, winner across nodes); rays that end here (miss, light, depth guard) add
+//      their colour and drop out;
+//   2. if some warp holds hits of more than one material, the surviving hits are ranked by the shader of the node they hit,
+//      through shared memory (the IntersectionInfo travels as 15 doubles, one column per ray: conflict-free), and thread t
+//      shades the hit of rank t; otherwise every thread shades its own hit straight from registers.
+// So a warp of phase 2 runs ONE material's code (Lambert + its light loop, Phong, the Layered tree of one object, Refl, Refr)
+// unless a material's run straddles it, and the lanes freed by the dropped rays are compacted into whole idle warps. No extra
+// pass over DRAM and no extra launch: the sort key only exists once the hit is resolved, and it stays on chip.
+#ifndef HXR_SHADE_SORT
+#define HXR_SHADE_SORT 1  // bit 0: Whitted, bit 1: GI
+#endif
+struct ShadeSortShared {
+    double hit[16][128];  // dist, ip, norm, dNdx, dNdy, u, v of each resolved hit
+    int32_t node[128];
+    uint32_t ray[128];    // queue index of the ray
+    int32_t key[128];     // shader index of the node hit, or -1
+    uint16_t order[128];
+};
+
 template <bool GI, bool COUNT, bool SIMPLE>
 __global__ void __launch_bounds__(128, SIMPLE ? (GI ? HXR_SHADE_GI_BLOCKS : HXR_SHADE_WH_BLOCKS) : 1)
     k_shade(DScene sc, FrameParams fp, RayQueue q, const CandRec* __restrict__ cand, uint32_t begin, uint32_t end, Sinks sinks, FrameTotals* totals,
@@ -779,13 +801,82 @@ __global__ void __launch_bounds__(128, SIMPLE ? (GI ? HXR_SHADE_GI_BLOCKS : HXR_
     const uint32_t stride = gridDim.x * blockDim.x;
     EmitCounters ec = {0, 0};
     TravCounters local = {0, 0, 0, 0, 0};
-    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
-        const RayGeom g = load_geom(q.geom + i);
-        const RayAux a = load_aux(q.aux + i);
-        CandRec cr;
-        cr.meta = 0;
-        if (sc.n_big) cr = load_cand(cand + i);
-        shade_item<GI, COUNT, SIMPLE>(sc, fp, g, a, cr, sinks, ec, COUNT ? &local : nullptr);
+    if ((HXR_SHADE_SORT >> (GI ? 1 : 0)) & 1) {
+        __shared__ ShadeSortShared sh;
+        const uint32_t t = threadIdx.x;
+        for (uint32_t base = begin + blockIdx.x * blockDim.x; base < e; base += stride) {  // (block-uniform trip count)
+            const uint32_t i = base + t;
+            int key = -1;
+            PathState p;
+            Hit info;
+            int node = -1;
+            if (i < e) {
+                const RayGeom g = load_geom(q.geom + i);
+                const RayAux a = load_aux(q.aux + i);
+                CandRec cr;
+                cr.meta = 0;
+                if (sc.n_big) cr = load_cand(cand + i);
+                p = path_state(g, a);
+                f3 early;
+                if (!resolve_closest<COUNT, SIMPLE>(sc, p.ray, g.limit, g.pre, cr, info, node, early, ec, COUNT ? &local : nullptr)) accum_pixel(sinks.accum, p.pixel, p.w * early);
+                else key = sc.nodes[node].shader;
+            }
+            // a warp whose hits already share one material has nothing to gain; the block only permutes when some warp is mixed
+            const unsigned hits = __ballot_sync(0xffffffffu, key >= 0);
+            const int first = __shfl_sync(0xffffffffu, key, hits ? __ffs(hits) - 1 : 0);
+            sh.key[t] = key;
+            if (__syncthreads_or(key >= 0 && key != first)) {
+                if (key >= 0) {
+                    sh.hit[0][t] = info.dist;
+                    sh.hit[1][t] = info.ip.x; sh.hit[2][t] = info.ip.y; sh.hit[3][t] = info.ip.z;
+                    sh.hit[4][t] = info.norm.x; sh.hit[5][t] = info.norm.y; sh.hit[6][t] = info.norm.z;
+                    sh.hit[7][t] = info.dNdx.x; sh.hit[8][t] = info.dNdx.y; sh.hit[9][t] = info.dNdx.z;
+                    sh.hit[10][t] = info.dNdy.x; sh.hit[11][t] = info.dNdy.y; sh.hit[12][t] = info.dNdy.z;
+                    sh.hit[13][t] = info.u; sh.hit[14][t] = info.v;
+                    sh.node[t] = node;
+                    sh.ray[t] = i;
+                    // rank among the hits: by key, ties by thread (128 broadcast reads)
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < 128; j++) {
+                        const int kj = sh.key[j];
+                        rank += (kj >= 0 && (kj < key || (kj == key && j < t))) ? 1u : 0u;
+                    }
+                    sh.order[rank] = (uint16_t)t;
+                }
+                const uint32_t nHits = (uint32_t)__syncthreads_count(key >= 0);
+                key = -1;
+                if (t < nHits) {
+                    const uint32_t s = sh.order[t];
+                    const uint32_t ri = sh.ray[s];
+                    p = path_state(load_geom(q.geom + ri), load_aux(q.aux + ri));
+                    info.dist = sh.hit[0][s];
+                    info.ip = mk3(sh.hit[1][s], sh.hit[2][s], sh.hit[3][s]);
+                    info.norm = mk3(sh.hit[4][s], sh.hit[5][s], sh.hit[6][s]);
+                    info.dNdx = mk3(sh.hit[7][s], sh.hit[8][s], sh.hit[9][s]);
+                    info.dNdy = mk3(sh.hit[10][s], sh.hit[11][s], sh.hit[12][s]);
+                    info.u = sh.hit[13][s];
+                    info.v = sh.hit[14][s];
+                    node = sh.node[s];
+                    key = 0;
+                }
+            }
+            if (key >= 0) {
+                info.geom = -1;
+                if (GI) shade_gi_item<COUNT, SIMPLE>(sc, fp, p, info, node, sinks, ec, COUNT ? &local : nullptr);
+                else shade_whitted_item<COUNT, SIMPLE>(sc, fp, p, info, node, sinks, ec, COUNT ? &local : nullptr);
+            }
+            // (no barrier here: sh.key is last read before the count barrier above, the columns and sh.order before this thread
+            // reaches the next batch's first barrier)
+        }
+    } else {
+        for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
+            const RayGeom g = load_geom(q.geom + i);
+            const RayAux a = load_aux(q.aux + i);
+            CandRec cr;
+            cr.meta = 0;
+            if (sc.n_big) cr = load_cand(cand + i);
+            shade_item<GI, COUNT, SIMPLE>(sc, fp, g, a, cr, sinks, ec, COUNT ? &local : nullptr);
+        }
     }
     flush_totals(totals, ec);
     if (totals && blockIdx.x == 0 && threadIdx.x == 0 && e > begin) atomicAdd(&totals->rays_closest, (unsigned long long)(e - begin));
