@@ -18,6 +18,8 @@ def pytest_configure(config):
 def emu_api():
     """tests/emu/libhxr_emu.so: host build of the per-ray functions (test infrastructure, not the product)."""
     from hexray_b200 import capi
+    if os.environ.get("HXR_EMU_LIB"):  # e.g. the sanitizer build (tests/emu/build_emu.sh asan)
+        return capi.Api(os.path.abspath(os.environ["HXR_EMU_LIB"]))
     so = os.path.join(ROOT, "tests", "emu", "libhxr_emu.so")
     src_dirs = [os.path.join(ROOT, "hexray_b200", "csrc"), os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "include")]
     newest = 0

@@ -5,4 +5,6 @@ cd "$(dirname "$0")"
 LIB=${1:-../../hexray_b200/libhexray_b200.so}
 OUT=${2:-bin}
 mkdir -p "$OUT"
-g++ -std=c++17 -O2 -Wall test_multi_gpu.cpp -o "$OUT/test_multi_gpu" "$LIB" -Wl,-rpath,"$(dirname "$(realpath "$LIB")")"
+DIR="$(dirname "$(realpath "$LIB")")"
+# (-l: keeps the bare file name in DT_NEEDED, so the binary runs from any directory through its rpath)
+g++ -std=c++17 -O2 -Wall test_multi_gpu.cpp -o "$OUT/test_multi_gpu" -L"$DIR" -l:"$(basename "$LIB")" -Wl,-rpath,"$DIR"

@@ -1,14 +1,21 @@
 #!/bin/bash
-# multi-GPU check: our arm under torchrun on N GPUs of one box (as the driver launches it)
-N=${1:-2}; TAG=${2:-scale}
+# scaling evidence on N GPUs of one box: gpu_scale.sh N [tests]
+#   torchrun bench (one process per GPU, NCCL reduce) and the library-owned multi-GPU context (one process, peer-memory reduce)
+N=$1
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${TAG}_smi.txt
-python bench.py --gpus 1 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_n1.json 2> gpurun_out/${TAG}_n1.err; echo "n1 rc=$?"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 2 --warmup 3 > gpurun_out/${TAG}_n$N.json 2> gpurun_out/${TAG}_n$N.err; echo "n$N rc=$?"
-tail -3 gpurun_out/${TAG}_n$N.err
-python -c "
+if [ "$2" = "tests" ]; then
+  ( timeout 1200 python -m pytest tests/test_multi_device.py -m gpu -x -q ) > gpurun_out/scale_n${N}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/scale_n${N}_pytest.log
+  ( tests/cpp/build.sh && cd assets && ../tests/cpp/bin/test_multi_gpu data/cornell_box.hexray $(seq -s, 0 $((N-1))) 64 256 ) > gpurun_out/scale_n${N}_cpp.log 2>&1; echo "cpp rc=$?"; tail -5 gpurun_out/scale_n${N}_cpp.log
+fi
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu-baseline > gpurun_out/scale_r2_torchrun_n${N}.json 2> gpurun_out/scale_r2_torchrun_n${N}.err; echo "torchrun rc=$?"
+python bench.py --gpus $N --no-cpu-baseline > gpurun_out/scale_r2_library_n${N}.json 2> gpurun_out/scale_r2_library_n${N}.err; echo "library rc=$?"
+HXR_REDUCE=nccl python bench.py --gpus $N --no-cpu-baseline --steps 2 > gpurun_out/scale_r2_library_nccl_n${N}.json 2> gpurun_out/scale_r2_library_nccl_n${N}.err; echo "library nccl rc=$?"
+python - <<PY
 import json
-for n in (1,$N):
-    j=json.loads(open('gpurun_out/${TAG}_n%d.json'%n).read().strip().splitlines()[-1])
-    print(n, round(j['value'],1), round(j['ms_per_step'],1), round(j['wall_ms_per_step'],1), round(j['e2e']['value'],1), j['config']['spp_total'])
-"
+for f in ("torchrun", "library", "library_nccl"):
+    try:
+        j = json.loads(open("gpurun_out/scale_r2_%s_n$N.json" % f).read().strip().splitlines()[-1])
+        print(f, j["n_gpus"], round(j["value"], 1), "e2e", round(j["e2e"]["value"], 1), "ms/step", round(j["ms_per_step"], 1), "reduce_ms", j["kernel_ms_per_step"].get("reduce_ms"), "setup_s", round(j["config"]["setup_s"], 1), j["config"]["sharding"])
+    except Exception as e:
+        print(f, "failed", e)
+PY

@@ -16,7 +16,8 @@ r = hx.Renderer().load(sf)
 for prof in (False, True):
     r.set_profiling(prof)
     for i in range(4):
-        img, st = r.render(width=W, height=H, spp=spp, seed=i)
+        # per-kernel times: every kernel on one stream (the two-lane frame's event pairs overlap)
+        img, st = r.render(width=W, height=H, spp=spp, seed=i, flags=hx.RENDER_ONE_LANE if prof else 0)
     rays = st["rays_closest"] + st["rays_shadow"]
     keys = ("render_ms", "walk_ms", "setup_ms", "finish_ms", "shade_ms", "shadow_resolve_ms", "gen_ms", "other_ms", "kernel_launches", "aa_pixels", "cand_overflow")
     print(json.dumps({"scene": scene, "profiling": prof, "rays": rays, "mrays_s": rays / st["render_ms"] / 1e3, **{k: round(st[k], 3) if isinstance(st[k], float) else st[k] for k in keys}}))
