@@ -566,6 +566,16 @@ def ours(a):
         if n_gpus == 1 and not a.no_extra:
             r.close()
             line["extra"] = {"scenes": extra_scenes(hx, local, not a.no_cpu_baseline)}
+            if sf.pod.contents.n_meshes > 0:
+                # the same mesh's KD-tree built on the GPU (HXR_CFG_DEVICE_KD_BUILD) next to the host build above
+                t0 = time.time()
+                rd = hx.Renderer(device=local, queue_capacity=1 << 20, flags=hx.CFG_DEVICE_KD_BUILD)
+                rd.load(sf)
+                ai = rd.accel_info(0)
+                line["extra"]["device_kd_build"] = {"build_ms": ai["build_ms"], "device_passes_ms": ai["device_ms"], "upload_scene_s": time.time() - t0,
+                                                    "nodes": ai["nodes"], "leaves": ai["leaves"], "tri_refs": ai["tri_refs"], "max_depth": ai["max_depth"],
+                                                    "host_build_ms": accel.get("build_ms"), "host_tree_from_cache": accel.get("from_cache")}
+                rd.close()
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

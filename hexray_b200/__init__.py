@@ -19,7 +19,7 @@ import numpy as np
 
 from . import capi
 from .capi import (HxrError, MODE_AUTO, MODE_MONTECARLO, MODE_WHITTED, RENDER_COUNT_TRAVERSAL, RENDER_ONE_LANE,  # noqa: F401
-                   CFG_BRUTE_FORCE_MESHES)
+                   CFG_BRUTE_FORCE_MESHES, CFG_DEVICE_KD_BUILD)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhexray_b200.so")
 _api = None

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libhexray_b200.so")
 OBJ = os.path.join(HERE, "build")
 
-HOST_SOURCES = ["abi.cpp", "renderer.cpp", "multi.cpp", "host/scene.cpp", "host/mesh.cpp", "host/flatten.cpp",
+HOST_SOURCES = ["abi.cpp", "renderer.cpp", "multi.cpp", "kd_device_build.cpp", "host/scene.cpp", "host/mesh.cpp", "host/flatten.cpp",
                 "host/bitmap.cpp", "host/kdtree.cpp", "host/cache.cpp"]
 CUDA_SOURCES = ["device/launch_cuda.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -19,6 +19,7 @@ MODE_AUTO, MODE_WHITTED, MODE_MONTECARLO = 0, 1, 2
 RENDER_COUNT_TRAVERSAL = 1
 RENDER_ONE_LANE = 2
 CFG_BRUTE_FORCE_MESHES = 1
+CFG_DEVICE_KD_BUILD = 2
 
 
 class HxrError(RuntimeError):
@@ -127,7 +128,7 @@ class Stats(C.Structure):
 
 class AccelInfo(C.Structure):
     _fields_ = [("nodes", c_u64), ("leaves", c_u64), ("tri_refs", c_u64), ("bytes_nodes", c_u64), ("bytes_tris", c_u64),
-                ("max_depth", c_u32), ("n_triangles", c_u32), ("build_ms", c_f64), ("from_cache", c_u32), ("reserved", c_u32)]
+                ("max_depth", c_u32), ("n_triangles", c_u32), ("build_ms", c_f64), ("from_cache", c_u32), ("device_build", c_u32), ("device_ms", c_f64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -8,6 +8,7 @@
 // multi.cpp drives one per device from one host thread each); there is no process-wide device state.
 #pragma once
 #include "pipeline.h"
+#include "kdbuild.h"
 
 namespace hxr {
 namespace dev {
@@ -111,6 +112,28 @@ int resolve_shadow(Context*, const DScene& sc, const ShadowQueue& q, const CandR
 
 // raycast() records for q[0 .. *q.count) (test hook)
 int hit_records(Context*, const DScene& sc, const RayQueue& q, const CandRec* cand, HitRec* hits, uint32_t n_hint);
+
+// ---- device KD-tree build: one level of the whole tree per round of these passes (kdbuild.h; driver: csrc/kdbuild.cpp).
+// All pointers are device memory of the context. tb = triangle bounds, SoA [6][nTris].
+int kd_bounds(Context*, const double* vertices, const int32_t* triV, uint32_t nTris, double* tb);
+int kd_iota(Context*, uint32_t* refTri, uint32_t* refNode, uint32_t n);  // refTri[i] = i, refNode[i] = 0
+// start / end histograms ([nNodes][3][2][HXR_KDB_BINS], zeroed by the caller) of the nodes with more than P.binnedAbove references
+int kd_bin(Context*, const kdb::Params& P, const kdb::NodeWork* work, const uint32_t* refTri, const uint32_t* refNode, uint32_t nRefs, const double* tb,
+           uint32_t nTris, uint32_t* hist);
+// hist may be null when no node of the level is binned
+int kd_choose(Context*, const kdb::Params& P, const kdb::NodeWork* work, uint32_t nNodes, int depth, const uint32_t* hist, const uint32_t* refTri,
+              const double* tb, uint32_t nTris, kdb::Decision* dec);
+int kd_classify(Context*, const uint32_t* refTri, const uint32_t* refNode, uint32_t nRefs, const kdb::Decision* dec, const double* tb, uint32_t nTris,
+                uint32_t* flagL, uint32_t* flagR);  // also flagL[nRefs] = flagR[nRefs] = 0
+int scan_u32(Context*, uint32_t* data, uint32_t n);  // exclusive prefix sum, in place
+// childRefs / isSplit / leafRefs [nNodes + 1] (last = 0); *levelMax = the largest child (zeroed by the caller)
+int kd_plan(Context*, const kdb::NodeWork* work, uint32_t nNodes, kdb::Decision* dec, const uint32_t* scanL, const uint32_t* scanR, uint32_t* childRefs,
+            uint32_t* isSplit, uint32_t* leafRefs, uint32_t* levelMax);
+int kd_emit(Context*, const kdb::NodeWork* work, uint32_t nNodes, const kdb::Decision* dec, const uint32_t* childRefs, const uint32_t* isSplit,
+            const uint32_t* leafRefs, uint32_t outCount, uint32_t leafBase, kdb::OutNode* out, kdb::NodeWork* next);
+int kd_scatter(Context*, const uint32_t* refTri, const uint32_t* refNode, uint32_t nRefs, const kdb::NodeWork* work, const kdb::Decision* dec,
+               const uint32_t* scanL, const uint32_t* scanR, const uint32_t* childRefs, const uint32_t* isSplit, const uint32_t* leafRefs,
+               uint32_t leafBase, uint32_t* nextTri, uint32_t* nextNode, uint32_t* leafOut);
 
 // needsAA flags -> compacted pixel list (order unspecified) ; *n_out = number of flagged pixels
 // rows restricted to y with ((y / HXR_ROW_BAND) % shard_count) == shard_index

@@ -25,6 +25,7 @@
 // kernels are grid-stride loops over device-side counts, sized by a host-side upper bound of the count: the host never
 // reads a count back between bounces.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
 #include <algorithm>
 #include <cstdio>
@@ -51,6 +52,8 @@ struct Context {
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPairs[PROF_NCAT];
     int walkGrid[2][2][3][2] = {};  // cached occupancy-derived grid per k_walk instantiation
+    void* scanTmp = nullptr;  // scratch of the prefix sums of the device KD build
+    size_t scanTmpBytes = 0;
 };
 
 static bool ck(Context* c, cudaError_t e, const char* what)
@@ -111,6 +114,7 @@ void destroy(Context* c)
     for (int k = 0; k < PROF_NCAT; k++)
         for (auto& pr : c->evPairs[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
+    if (c->scanTmp) cudaFree(c->scanTmp);
     cudaEventDestroy(c->evFork);
     cudaEventDestroy(c->evJoin);
     cudaStreamDestroy(c->lanes[0]);
@@ -1250,6 +1254,8 @@ bool comm_reduce_sum(Comm* c, float* const* bufs, size_t n)
     ok = (c->groupEnd() == 0) && ok;
     return ok;
 }
+
+#include "kdbuild_kernels.inl"
 
 }  // namespace dev
 }  // namespace hxr

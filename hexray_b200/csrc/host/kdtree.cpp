@@ -22,6 +22,25 @@
 namespace hxr {
 namespace host {
 
+void resolveKdParams(const hxr_mesh& mesh, KdBuildParams& P)
+{
+    // experiment knobs (defaults in kdtree.h)
+    if (const char* e = getenv("HXR_KD_INTERSECT_COST")) P.intersectCost = (float)atof(e);
+    if (const char* e = getenv("HXR_KD_MAX_LEAF")) P.maxLeafSize = atoi(e);
+    if (const char* e = getenv("HXR_KD_EMPTY_BONUS")) P.emptyBonus = (float)atof(e);
+    if (P.maxDepth < 0) P.maxDepth = (int)std::lround(8 + 1.3 * std::log2((double)std::max(1, mesh.n_triangles)));
+    P.maxDepth = std::min(P.maxDepth, HXR_KD_MAX_DEPTH);
+}
+
+void kdRootBox(const hxr_mesh& mesh, double mn[3], double mx[3])
+{
+    for (int a = 0; a < 3; a++) {
+        // float-rounded outward so that float splits compare consistently with the triangle bounds
+        mn[a] = std::nextafter((float)mesh.bbox_min[a], -INFINITY);
+        mx[a] = std::nextafter((float)mesh.bbox_max[a], +INFINITY);
+    }
+}
+
 namespace {
 
 struct Box {
@@ -45,10 +64,7 @@ struct Builder {
 
     explicit Builder(const hxr_mesh& m, const KdBuildParams& p) : mesh(m), P(p)
     {
-        // experiment knobs (defaults in kdtree.h)
-        if (const char* e = getenv("HXR_KD_INTERSECT_COST")) P.intersectCost = (float)atof(e);
-        if (const char* e = getenv("HXR_KD_MAX_LEAF")) P.maxLeafSize = atoi(e);
-        if (const char* e = getenv("HXR_KD_EMPTY_BONUS")) P.emptyBonus = (float)atof(e);
+        resolveKdParams(m, P);
         const int n = m.n_triangles;
         tb.resize(n);
         for (int i = 0; i < n; i++) {
@@ -66,8 +82,7 @@ struct Builder {
                 tb[i].mx[a] = mx[a];
             }
         }
-        maxDepth = P.maxDepth >= 0 ? P.maxDepth : (int)std::lround(8 + 1.3 * std::log2((double)std::max(1, n)));
-        maxDepth = std::min(maxDepth, HXR_KD_MAX_DEPTH);
+        maxDepth = P.maxDepth;
     }
 
     static bool goesLeft(const TriBounds& b, int axis, float split)
@@ -288,17 +303,19 @@ void makeBlocks(KdTree& t, const hxr_mesh& mesh)
 
 }  // namespace
 
+void packKdTree(KdTree& tree, const hxr_mesh& mesh)
+{
+    if (tree.nodes.empty()) tree.nodes.push_back(KdNode{0, 3, 0, 0});
+    makeBlocks(tree, mesh);
+}
+
 void buildKdTree(const hxr_mesh& mesh, const KdBuildParams& params, KdTree& out)
 {
     const auto t0 = std::chrono::steady_clock::now();
     Builder B(mesh, params);
     const int n = mesh.n_triangles;
     Box root;
-    for (int a = 0; a < 3; a++) {
-        // float-rounded outward so that float splits compare consistently with the triangle bounds
-        root.mn[a] = std::nextafter((float)mesh.bbox_min[a], -INFINITY);
-        root.mx[a] = std::nextafter((float)mesh.bbox_max[a], +INFINITY);
-    }
+    kdRootBox(mesh, root.mn, root.mx);
     std::vector<uint32_t> all(n);
     for (int i = 0; i < n; i++) all[i] = (uint32_t)i;
 

@@ -17,6 +17,7 @@ struct KdTree {
     uint32_t maxDepth = 0;
     uint64_t leaves = 0;
     double buildMs = 0;
+    double deviceMs = 0;  // device-built trees: the part of buildMs spent on the GPU passes (the rest packs the blocks on the host)
 };
 
 struct KdBuildParams {
@@ -30,6 +31,13 @@ struct KdBuildParams {
 };
 
 void buildKdTree(const hxr_mesh& mesh, const KdBuildParams& params, KdTree& out);
+
+// The two ends of a build somebody else does (the device build, csrc/kdbuild.cpp): the parameters with the environment knobs
+// and the depth limit resolved, the root box (float-rounded outward), and the packing of a finished binary tree
+// (out.nodes / out.leafTris raw lists / maxDepth / leaves) into the blocks and leaf lists the device walks.
+void resolveKdParams(const hxr_mesh& mesh, KdBuildParams& params);
+void kdRootBox(const hxr_mesh& mesh, double mn[3], double mx[3]);
+void packKdTree(KdTree& tree, const hxr_mesh& mesh);
 
 }  // namespace host
 }  // namespace hxr

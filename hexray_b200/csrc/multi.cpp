@@ -65,7 +65,7 @@ int MultiRenderer::uploadScene(const hxr_scene* sc)
     // the KD-trees and triangle records once, for every GPU
     SceneTables tab;
     std::string why;
-    if (!buildSceneTables(*sc, m_cfg, tab, why)) return fail(HXR_ERR_INVALID, "invalid scene: " + why);
+    if (!buildSceneTables(*sc, m_cfg, tab, why, m_r[0]->device())) return fail(HXR_ERR_INVALID, "invalid scene: " + why);
     std::vector<int> rc(m_r.size(), HXR_OK);
     std::vector<std::thread> th;
     for (size_t i = 0; i < m_r.size(); i++) th.emplace_back([&, i] { rc[i] = m_r[i]->uploadScene(*sc, tab); });

@@ -1,6 +1,7 @@
 // renderer.cpp — see renderer.h. Host logic only: validation, KD build, uploads, and the
 // wavefront schedule. Everything per-ray runs in the kernels behind device/launch.h.
 #include "renderer.h"
+#include "kd_device_build.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -139,9 +140,8 @@ static bool validateScene(const hxr_scene& s, std::string& why)
 
 
 // ---- the device-independent part of a scene upload: KD-trees and flattened triangle records
-bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& out, std::string& why)
+bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& out, std::string& why, dev::Context* buildOn)
 {
-    (void)cfg;
     if (!validateScene(s, why)) return false;
     out.meshes.clear();
     out.meshes.resize(s.n_meshes);
@@ -161,9 +161,18 @@ bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& ou
         // through the cache (host/cache.h): a big tree built before - or being built right now by another process of this
         // box, e.g. the other ranks of a torchrun job - is loaded instead of built again
         const char* how = "built";
-        host::cachedKdTree(m, host::KdBuildParams(), M.kd, &how);
+        const char* envBuild = getenv("HXR_KD_BUILD");
+        const bool onDevice = buildOn && m.n_triangles > 1 && (envBuild ? !strcmp(envBuild, "device") : (cfg.flags & HXR_CFG_DEVICE_KD_BUILD) != 0);
+        if (onDevice) {
+            // the tree is built by the GPU, level by level (kd_device_build.cpp); nothing is read from or written to the cache
+            std::string err;
+            if (!buildKdTreeOnDevice(buildOn, m, host::KdBuildParams(), M.kd, err)) { why = err; return false; }
+            how = "device";
+        } else {
+            host::cachedKdTree(m, host::KdBuildParams(), M.kd, &how);
+        }
         M.kdSource = how;
-        if (!strcmp(how, "built")) out.build_ms += M.kd.buildMs;
+        if (!strcmp(how, "built") || !strcmp(how, "device")) out.build_ms += M.kd.buildMs;
         const size_t nt = (size_t)m.n_triangles;
         M.tt.resize(nt);
         M.ta.resize(nt);
@@ -214,7 +223,7 @@ int Renderer::uploadScene(const hxr_scene* sp)
     if (!sp) return fail(HXR_ERR_INVALID, "null scene");
     SceneTables tab;
     std::string why;
-    if (!buildSceneTables(*sp, m_cfg, tab, why)) return fail(HXR_ERR_INVALID, "invalid scene: " + why);
+    if (!buildSceneTables(*sp, m_cfg, tab, why, m_dev)) return fail(HXR_ERR_INVALID, "invalid scene: " + why);
     return uploadScene(*sp, tab);
 }
 
@@ -269,7 +278,9 @@ int Renderer::uploadScene(const hxr_scene& s, const SceneTables& tab)
         ai.max_depth = M.kd.maxDepth;
         ai.n_triangles = (uint32_t)m.n_triangles;
         ai.build_ms = M.kd.buildMs;
-        ai.from_cache = strcmp(M.kdSource, "built") != 0;
+        ai.from_cache = strcmp(M.kdSource, "built") != 0 && strcmp(M.kdSource, "device") != 0;
+        ai.device_build = !strcmp(M.kdSource, "device");
+        ai.device_ms = M.kd.deviceMs;
     }
     std::vector<DHeightfield> dh(s.n_heightfields);
     for (int i = 0; i < s.n_heightfields; i++) {

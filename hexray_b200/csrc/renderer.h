@@ -19,14 +19,15 @@ struct MeshTables {
     std::vector<TriAttrUv> tu;
     std::vector<TriF32> tf;
     std::vector<TriPacked> tp;  // empty: the scene walks tri_f32
-    const char* kdSource = "built";  // "built" here, or "cache" / "waited" (host/cache.h)
+    const char* kdSource = "built";  // "built" here (host), "device" (built on the GPU), or "cache" / "waited" (host/cache.h)
 };
 struct SceneTables {
     std::vector<MeshTables> meshes;
     double build_ms = 0;
 };
 // validates the scene and builds its host tables (KD-trees with all host threads); false + why on an invalid scene
-bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& out, std::string& why);
+// buildOn: the context whose GPU builds the KD-trees when the configuration asks for the device build (HXR_CFG_DEVICE_KD_BUILD)
+bool buildSceneTables(const hxr_scene& s, const hxr_config& cfg, SceneTables& out, std::string& why, dev::Context* buildOn = nullptr);
 
 class Renderer {
 public:

@@ -221,6 +221,8 @@ typedef struct hxr_camera { /* results of Camera::beginFrame (src/camera.cpp:30-
 /* test hook: test every triangle of every mesh in index order instead of walking the KD-tree — the reference's
  * `useKDTree false` path (src/mesh.cpp:255-262); results are identical, only (much) slower */
 #define HXR_CFG_BRUTE_FORCE_MESHES 1
+#define HXR_CFG_DEVICE_KD_BUILD 2 /* build the meshes' KD-trees on the GPU (level-synchronous SAH build) instead of on the host cores;
+                                    * the environment variable HXR_KD_BUILD=device|host overrides the flag */
 
 /* One context = one or several GPUs of the box, all owned by the library (reference: the ThreadPool of src/threading.cpp:54-97
  * that main() creates at src/main.cpp:546). With n_devices > 1 hxr_render shards every frame over the GPUs (Monte-Carlo:
@@ -369,7 +371,8 @@ typedef struct hxr_accel_info {
     uint32_t n_triangles;
     double build_ms;        /* of the build that produced the tree (possibly in an earlier process: see from_cache) */
     uint32_t from_cache;    /* 1: the tree came from the on-disk cache, or from another process that was building it */
-    uint32_t reserved;
+    uint32_t device_build;  /* 1: the tree was built on the GPU (HXR_CFG_DEVICE_KD_BUILD) */
+    double device_ms;       /* device-built trees: the part of build_ms spent in the GPU passes (the rest packs the blocks on the host) */
 } hxr_accel_info;
 int hxr_get_accel_info(hxr_ctx* ctx, int32_t mesh, hxr_accel_info* out);
 

@@ -12,6 +12,6 @@ OUT=libhxr_emu.so
 OPT="-O2"
 if [ "$1" = "asan" ]; then OUT=libhxr_emu_asan.so; OPT="-O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer"; fi
 g++ -std=c++17 $OPT -fPIC -shared -DHXR_EMU -Wall -Wno-unused-function \
-    $SRC/abi.cpp $SRC/renderer.cpp $SRC/multi.cpp $SRC/host/scene.cpp $SRC/host/mesh.cpp $SRC/host/flatten.cpp \
+    $SRC/abi.cpp $SRC/renderer.cpp $SRC/multi.cpp $SRC/kd_device_build.cpp $SRC/host/scene.cpp $SRC/host/mesh.cpp $SRC/host/flatten.cpp \
     $SRC/host/bitmap.cpp $SRC/host/kdtree.cpp $SRC/host/cache.cpp launch_emu.cpp \
     -o $OUT -lz -lpthread

@@ -308,5 +308,79 @@ Comm* comm_create(Context* const*, int, char* err, size_t errlen) { snprintf(err
 void comm_destroy(Comm* c) { delete c; }
 bool comm_reduce_sum(Comm*, float* const*, size_t) { return false; }
 
+// ---- device KD-tree build: the passes of kdbuild.h as loops
+int kd_bounds(Context*, const double* vertices, const int32_t* triV, uint32_t nTris, double* tb)
+{
+    for (uint32_t t = 0; t < nTris; t++) kdb::bounds_item(t, vertices, triV, tb, nTris);
+    return 1;
+}
+int kd_iota(Context*, uint32_t* refTri, uint32_t* refNode, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; i++) { refTri[i] = i; refNode[i] = 0; }
+    return 1;
+}
+int kd_bin(Context*, const kdb::Params& P, const kdb::NodeWork* work, const uint32_t* refTri, const uint32_t* refNode, uint32_t nRefs, const double* tb,
+           uint32_t nTris, uint32_t* hist)
+{
+    for (uint32_t i = 0; i < nRefs; i++) {
+        const uint32_t node = refNode[i];
+        const kdb::NodeWork& w = work[node];
+        if ((int)w.count <= P.binnedAbove) continue;
+        const uint32_t t = refTri[i];
+        for (int a = 0; a < 3; a++) {
+            if (!(w.mx[a] - w.mn[a] > 0)) continue;
+            int b0, b1;
+            kdb::bin_range(tb[(size_t)a * nTris + t], tb[(size_t)(3 + a) * nTris + t], w.mn[a], w.mx[a], b0, b1);
+            hist[((size_t)node * 3 + a) * 2 * HXR_KDB_BINS + b0]++;
+            hist[((size_t)node * 3 + a) * 2 * HXR_KDB_BINS + HXR_KDB_BINS + b1]++;
+        }
+    }
+    return 1;
+}
+int kd_choose(Context*, const kdb::Params& P, const kdb::NodeWork* work, uint32_t nNodes, int depth, const uint32_t* hist, const uint32_t* refTri,
+              const double* tb, uint32_t nTris, kdb::Decision* dec)
+{
+    for (uint32_t n = 0; n < nNodes; n++)
+        kdb::choose_serial(P, work[n], depth, hist ? hist + (size_t)n * 3 * 2 * HXR_KDB_BINS : nullptr, refTri, tb, nTris, dec[n]);
+    return 1;
+}
+int kd_classify(Context*, const uint32_t* refTri, const uint32_t* refNode, uint32_t nRefs, const kdb::Decision* dec, const double* tb, uint32_t nTris,
+                uint32_t* flagL, uint32_t* flagR)
+{
+    for (uint32_t i = 0; i < nRefs; i++) kdb::classify_item(i, refTri, refNode, dec, tb, nTris, flagL, flagR);
+    flagL[nRefs] = flagR[nRefs] = 0;
+    return 1;
+}
+int scan_u32(Context*, uint32_t* data, uint32_t n)
+{
+    uint32_t run = 0;
+    for (uint32_t i = 0; i < n; i++) { const uint32_t v = data[i]; data[i] = run; run += v; }
+    return 1;
+}
+int kd_plan(Context*, const kdb::NodeWork* work, uint32_t nNodes, kdb::Decision* dec, const uint32_t* scanL, const uint32_t* scanR, uint32_t* childRefs,
+            uint32_t* isSplit, uint32_t* leafRefs, uint32_t* levelMax)
+{
+    for (uint32_t n = 0; n < nNodes; n++) {
+        kdb::plan_item(n, work, dec, scanL, scanR, childRefs, isSplit, leafRefs);
+        if (isSplit[n]) *levelMax = std::max(*levelMax, std::max(dec[n].nl, childRefs[n] - dec[n].nl));
+    }
+    childRefs[nNodes] = isSplit[nNodes] = leafRefs[nNodes] = 0;
+    return 1;
+}
+int kd_emit(Context*, const kdb::NodeWork* work, uint32_t nNodes, const kdb::Decision* dec, const uint32_t* childRefs, const uint32_t* isSplit,
+            const uint32_t* leafRefs, uint32_t outCount, uint32_t leafBase, kdb::OutNode* out, kdb::NodeWork* next)
+{
+    for (uint32_t n = 0; n < nNodes; n++) kdb::emit_item(n, work, dec, childRefs, isSplit, leafRefs, outCount, leafBase, out, next);
+    return 1;
+}
+int kd_scatter(Context*, const uint32_t* refTri, const uint32_t* refNode, uint32_t nRefs, const kdb::NodeWork* work, const kdb::Decision* dec,
+               const uint32_t* scanL, const uint32_t* scanR, const uint32_t* childRefs, const uint32_t* isSplit, const uint32_t* leafRefs,
+               uint32_t leafBase, uint32_t* nextTri, uint32_t* nextNode, uint32_t* leafOut)
+{
+    for (uint32_t i = 0; i < nRefs; i++)
+        kdb::scatter_item(i, refTri, refNode, work, dec, scanL, scanR, childRefs, isSplit, leafRefs, leafBase, nextTri, nextNode, leafOut);
+    return 1;
+}
+
 }  // namespace dev
 }  // namespace hxr

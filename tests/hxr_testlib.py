@@ -632,3 +632,41 @@ def check_small_queue(api):
         r.close()
         sf.close()
     assert np.abs(out[0] - out[1]).max() < 1e-4
+
+
+def check_device_kd_build(api, kind, size, n_rays):
+    """the KD-tree built ON THE DEVICE (level-synchronous SAH build, csrc/device/kdbuild.h) must serve the walk
+    exactly like the host-built one: explicit rays through the device-built tree equal testing every triangle in index order (the
+    reference's useKDTree=false path, src/mesh.cpp:255-262) bit for bit, and the tree is of the same quality as the host's."""
+    rng = np.random.default_rng(size)
+    if kind == "terrain":
+        sf = terrain_scene_file(api, size)
+        o = np.concatenate([np.tile([[0.0, 150.0, -600.0]], (n_rays // 2, 1)),
+                            np.stack([rng.uniform(-500, 500, n_rays // 2), rng.uniform(-30, 200, n_rays // 2), rng.uniform(-500, 500, n_rays // 2)], 1)])
+        d = np.concatenate([np.stack([rng.uniform(-0.7, 0.7, n_rays // 2), rng.uniform(-0.6, 0.05, n_rays // 2), np.ones(n_rays // 2)], 1),
+                            rng.normal(size=(n_rays // 2, 3))])
+    else:
+        sf = soup_scene_file(api, size)
+        o = rng.uniform(-480, 480, (n_rays, 3))
+        d = rng.normal(size=(n_rays, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.zeros((n_rays, 2))], axis=1)
+    hits, info = {}, {}
+    for name, flags in (("host", 0), ("device", hx.CFG_DEVICE_KD_BUILD), ("brute", hx.CFG_BRUTE_FORCE_MESHES)):
+        r = hx.Renderer(api_=api, queue_capacity=1 << 20, flags=flags).load(sf)
+        hits[name] = r.trace_closest(rays).copy()
+        info[name] = r.accel_info(0)
+        r.close()
+    sf.close()
+    assert info["device"]["device_build"] == 1 and info["host"]["device_build"] == 0 and info["device"]["from_cache"] == 0
+    assert info["device"]["n_triangles"] == info["host"]["n_triangles"]
+    for k in ("tri_refs", "leaves", "nodes"):
+        assert abs(info["device"][k] / max(1, info["host"][k]) - 1) < 0.15, (k, info["device"][k], info["host"][k])
+    assert info["device"]["max_depth"] <= info["host"]["max_depth"] + 2
+    for name in ("device", "host"):
+        a, b = hits[name], hits["brute"]
+        assert (a["node"] == b["node"]).all() and (a["status"] == b["status"]).all(), name
+        m = a["status"] == 0
+        assert np.array_equal(a["dist"][m], b["dist"][m]) and np.array_equal(a["ip"][m], b["ip"][m]) and np.array_equal(a["norm"][m], b["norm"][m]), name
+    assert (hits["brute"]["node"] >= 0).sum() > n_rays // 8
+    return info

@@ -19,3 +19,19 @@ for f in ("torchrun", "library", "library_nccl"):
     except Exception as e:
         print(f, "failed", e)
 PY
+# tile-sharded Whitted frame (16-row bands + one-row halo) at 1080p on 1 and N GPUs of this box
+HEXRAY_DATA=assets/data python - <<PY | tee gpurun_out/scale_r2_whitted_n${N}.txt
+import numpy as np, hexray_b200 as hx, os
+sf = hx.SceneFile(os.path.join(hx.data_root(), "kdtree_test.hexray"))
+out = {}
+for devs in ([0], list(range($N))):
+    r = hx.Renderer(devices=devs).load(sf)
+    ms = []
+    for i in range(6):
+        img, st = r.render(width=1920, height=1080)
+        if i >= 2: ms.append(st["render_ms"])
+    out[len(devs)] = (img, float(np.median(ms)), st["rays_closest"] + st["rays_shadow"], st.get("reduce_ms", 0.0))
+    r.close()
+a, b = out[1], out[$N]
+print("kdtree_test 1920x1080 Whitted+AA: 1 GPU %.3f ms (%d rays) | $N GPUs %.3f ms (%d rays incl. halo rows, reduce %.3f ms) | speed-up %.2f | max |diff| %.2e" % (a[1], a[2], b[1], b[2], b[3], a[1] / b[1], float(np.abs(a[0] - b[0]).max())))
+PY
