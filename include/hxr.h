@@ -81,7 +81,8 @@ typedef struct hxr_triangle {
 
 /* reference Mesh after beginRender (src/mesh.cpp:49-87): slot 0 of vertices/normals/uvs
  * is the OBJ sentinel (src/mesh.cpp:307-310). The KD-tree is NOT part of the ABI: the
- * library builds its own on the host during hxr_upload_scene. */
+ * library builds its own during hxr_upload_scene - on the host cores, or on the GPU
+ * with HXR_CFG_DEVICE_KD_BUILD. */
 typedef struct hxr_mesh {
     int32_t n_vertices, n_normals, n_uvs, n_triangles;
     const double* vertices; /* 3 per entry */
