@@ -95,6 +95,7 @@ struct WalkBuffers {
     uint32_t* head;       // work-fetch cursor of the persistent kernel
     OverflowEntry* ovf_list;
     uint32_t* ovf_count;
+    uint32_t* fetch;      // work-fetch cursor of the kernel that finishes the listed rays (zero when the walk is queued)
 };
 int walk(Context*, const DScene& sc, bool shadow, const RayGeom* geom, const MeshEntry* entry, const uint32_t* count, uint32_t cap, const WalkBuffers& wb,
          FrameTotals* totals, TravCounters* cnt, uint32_t n_hint);

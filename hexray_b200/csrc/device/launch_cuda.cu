@@ -34,6 +34,10 @@
 #include <vector>
 #include "launch.h"
 
+#ifndef HXR_FINISH_WARP
+#define HXR_FINISH_WARP 1 /* overflowed rays are finished by one WARP each (k_finish_warp); 0: one thread each (k_finish). HXR_FINISH_WARP in the environment overrides */
+#endif
+
 namespace hxr {
 namespace dev {
 
@@ -48,6 +52,7 @@ struct Context {
     // walk-loop tunables (uniform kernel arguments; environment overrides for A/B runs: HXR_WALK_STEPS, HXR_REFILL_MIN, HXR_SSTACK,
     // HXR_NO_MAILBOX, HXR_BRANCHY_PUSH, HXR_WALK_CARVEOUT, HXR_WALK_BLOCKS_PER_SM; measured optima are the defaults)
     int walkSteps = 4, refillMin = 8, sstack = 10, useMail = 1, bfPush = 1, walkCarveout = -1, walkBlocksPerSm = 0;
+    int finishWarp = HXR_FINISH_WARP;  // overflowed rays: one warp per ray (k_finish_warp) or one thread per ray (k_finish)
     uint64_t launches[PROF_NCAT] = {};
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evPairs[PROF_NCAT];
@@ -97,6 +102,7 @@ Context* create(int device, char* err, size_t errlen)
     if (const char* v = getenv("HXR_WALK_CARVEOUT")) c->walkCarveout = std::min(100, std::max(0, atoi(v)));
     if (const char* v = getenv("HXR_WALK_BLOCKS_PER_SM")) c->walkBlocksPerSm = std::max(1, atoi(v));
     if (const char* v = getenv("HXR_REFILL_MIN")) c->refillMin = std::min(32, std::max(1, atoi(v)));
+    if (const char* v = getenv("HXR_FINISH_WARP")) c->finishWarp = atoi(v) != 0;
     if (cudaStreamCreateWithFlags(&c->lanes[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->lanes[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
@@ -406,6 +412,9 @@ __global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup(DS
 // lane filters a certain hit), the candidate slots (3 x 4 B + count/slot word), a two-entry mailbox and the first HXR_SSTACK
 // stack entries (12 B each); deeper entries overflow to local memory (rare: the stack is shallow for almost all rays).
 #define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
+#ifndef HXR_LEAF_BREAK
+#define HXR_LEAF_BREAK 0 /* > 0: phase 1 ends early once this many lanes of the warp hold a leaf */
+#endif
 
 template <int SSTACK>
 struct WalkShared {
@@ -605,7 +614,9 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
                     WalkEnt e;
                     if (sp < HXR_SSTACK) { e.ref = sh.stRef[sp][tid]; e.lo = sh.stMin[sp][tid]; e.hi = sh.stMax[sp][tid]; }
                     else { e.ref = ovRef[sp - HXR_SSTACK]; e.lo = ovMin[sp - HXR_SSTACK]; e.hi = ovMax[sp - HXR_SSTACK]; }
-                    if (e.lo <= tbest) { cur = e.ref; tmin = e.lo; tmax = e.hi; }  // else it cannot hold a closer hit: keep popping
+                    // else it cannot hold a closer hit: keep popping. (One pop per step: draining such entries in a loop right here
+                    // was A/B-ed - 1.35 failing pops per closest-hit ray on the terrain - and lost: walk 143.1 -> 145.0 ms, r2p.)
+                    if (e.lo <= tbest) { cur = e.ref; tmin = e.lo; tmax = e.hi; }
                 }
             }
             __syncwarp();  // lanes that popped and lanes that did not take the block step together
@@ -648,6 +659,10 @@ __global__ void __launch_bounds__(HXR_WALK_BLOCK, HXR_WALK_MIN_BLOCKS) k_walk(DS
             }
             if (stepping && active && (cur >> 31)) leafCnt = __ldg(leafTris + (cur & ~HXR_KD_LEAF));  // in flight while the others keep stepping
             __syncwarp();
+#if HXR_LEAF_BREAK
+            // enough lanes wait at a leaf to fill the cooperative rounds of phase 2: do not let them idle through the remaining steps
+            if (__popc(__ballot_sync(FULL, active && (cur >> 31))) >= HXR_LEAF_BREAK) break;
+#endif
         }
         // ---- phase 2: all (ray, triangle) pairs of the leaves held by this warp, dealt out over its 32 lanes
         const bool hasLeaf = active && (cur >> 31);
@@ -772,6 +787,208 @@ __global__ void __launch_bounds__(128, 2) k_finish(DScene sc, const RayGeom* __r
     if (COUNT) flush_trav(cnt, local);
 }
 
+// The same, ONE WARP per overflowed ray (HXR_FINISH_WARP, the default). The rays that arrive here are the long grazing ones on
+// which the float bounds decide nothing: they cross hundreds of leaves and every triangle of every leaf needs the exact double
+// test, i.e. a dependent chain of index -> filter record -> 96-byte exact record per TRIANGLE when one thread does it. ncu on the
+// one-thread form (profiles/r2/ncu_deep_bounce_r2_v1.txt): 2.97 lanes per instruction, 4.5 % warps active, the launch lasts as
+// long as its longest ray (0.78 ms for 41 k rays). Here the 32 lanes walk the tree together (the block steps are uniform: the
+// same loads, broadcast) and split each leaf's triangles among them, so a leaf costs one such chain, not one per triangle;
+// the leaf's winner is found with a shuffle reduction under the rule of tri_core (smallest parameter, then highest index), which
+// does not depend on the order of the tests - the verdict equals finish_overflowed_ray's (tests/test_gpu_parity.py:
+// test_finish_forms_agree). Rays are fetched one at a time through an atomic cursor: the long ones do not pile up on one warp.
+template <bool SHADOW, bool COUNT>
+__device__ __forceinline__ CandRec finish_overflowed_ray_warp(const DScene& sc, const RayGeom& g, const CandRec& rec, const OverflowEntry& ov, TravCounters* cnt,
+                                                              unsigned lane, uint32_t* stRef, float* stLo, float* stHi)
+{
+    const unsigned FULL = 0xffffffffu;
+    CandRec out;
+    out.tri[0] = out.tri[1] = out.tri[2] = 0;
+    out.meta = 0;
+    const Ray ray = geom_ray(g);
+    double bestDist = g.limit;  // closest: inline winner so far; shadow: |AB|
+    int bestNode = SHADOW ? 0x7FFFFFFF : g.pre;
+    MeshWinner win;
+    win.node = -1;
+    win.mb.tri = -1;
+    // true: the hit just recorded in mb blocks a shadow ray
+    auto blocks = [&](const hxr_node& nd, const Ray& t, const MeshBest& mb) -> bool {
+        const d3 ipw = node_mul_m(nd, t.o + mb.gamma * t.d) + ld3(nd.T.offset);
+        return distance3(ray.o, ipw) < g.limit;
+    };
+    // the recorded candidates (at most three): every lane runs them, uniformly - see finish_overflowed_ray for the grouping
+    MeshBest cur;
+    bool haveCur = false;
+    cur.tri = -1;
+    cur.gamma = 0;
+    cur.l2 = cur.l3 = 0;
+    {
+        int gs = -1;
+        MeshBest mb;
+        mb.tri = -1;
+        mb.gamma = 0;
+        mb.l2 = mb.l3 = 0;
+        Ray t = ray;
+        for (uint32_t i = 0; i <= HXR_CAND_MAX; i++) {
+            const int s = i < HXR_CAND_MAX ? (int)((rec.meta >> (8u + 8u * i)) & 0xFFu) : -2;
+            if (s != gs) {
+                if (gs >= 0) {
+                    if (gs == ov.slot) { cur = mb; haveCur = true; }
+                    else if (!SHADOW) fold_mesh_hit(sc.nodes[sc.big_nodes[gs]], sc.big_nodes[gs], ray, t, mb, bestDist, bestNode, win);
+                }
+                if (s < 0) break;
+                gs = s;
+                const hxr_node& nd = sc.nodes[sc.big_nodes[s]];
+                t = object_ray(nd, ray);
+                mb.gamma = gamma_limit_for(nd, t, g.limit);
+                mb.tri = -1;
+                mb.l2 = mb.l3 = 0;
+            }
+            const hxr_node& nd = sc.nodes[sc.big_nodes[s]];
+            const DMesh& M = node_mesh(sc, nd);
+            if (tri_test(M.tri_test, M.backface != 0, t, rec.tri[i], mb) && SHADOW && blocks(nd, t, mb)) {
+                out.meta = HXR_CAND_BLOCKED;
+                return out;
+            }
+        }
+    }
+    float wcap = f32_cap(bestDist);
+    const float of[3] = {(float)g.o[0], (float)g.o[1], (float)g.o[2]}, df[3] = {(float)g.d[0], (float)g.d[1], (float)g.d[2]};
+    for (int slot = ov.slot; slot < sc.n_big; slot++) {
+        const int node = sc.big_nodes[slot];
+        const hxr_node& nd = sc.nodes[node];
+        MeshBest mb;
+        mb.tri = -1;
+        mb.l2 = mb.l3 = 0;
+        bool walked = false;
+        MeshEntry e;
+        if ((slot == ov.slot || !box_certainly_missed(sc.big_box + 6 * slot, of, df, wcap)) && enter_mesh<SHADOW>(sc, slot, ray, fmin(g.limit, (double)wcap), e)) {
+            walked = true;
+            const DMesh& M = sc.meshes[slot_mesh(sc, slot)];
+            const Ray t = object_ray(nd, ray);
+            mb.gamma = gamma_limit_for(nd, t, fmin(g.limit, (double)wcap));
+            if (slot == ov.slot && haveCur) mb = cur;
+            if (COUNT && cnt) cnt->mesh_queries++;
+            const WalkRay w = walk_ray_f(e.ox, e.oy, e.oz, e.dx, e.dy, e.dz);
+            const bool bf = M.backface != 0;
+            // (segments that end before the stop point were examined by the first walk)
+            const float tskip = slot == ov.slot ? ov.tstop * (ov.tstop > 0 ? 1.0f - 1e-6f : 1.0f + 1e-6f) - 1e-30f : -INFINITY;
+            float tmin = e.tmin, tmax = e.tmax, tbest = fminf(e.tlimit, f32_above(mb.gamma));
+            int sp = 0;
+            uint32_t curRef = 0;
+            for (;;) {
+                if (curRef & HXR_KD_LEAF) {
+                    const uint32_t* list = M.leaf_tris + (curRef & ~HXR_KD_LEAF);
+                    const uint32_t nT = __ldg(list);
+                    if (COUNT && cnt) { cnt->tri_tests += nT; cnt->kd_leaves++; }
+                    for (uint32_t base = 0; base < nT; base += 32u) {
+                        // lane L: triangle base + L of the leaf, filtered in float, then the exact test against the leaf's starting best
+                        bool hit = false;
+                        double gm = 0, l2 = 0, l3 = 0;
+                        uint32_t ti = 0;
+                        if (base + lane < nT) {
+                            ti = __ldg(list + 1u + base + lane);
+                            float ghi;
+                            const int cls = sc.walk_packed ? tri_filter_packed(M.tri_pk + ti, bf, e.ox, e.oy, e.oz, e.dx, e.dy, e.dz, e.err, tbest, ghi)
+                                                           : tri_filter(M.tri_f32 + ti, bf, e.ox, e.oy, e.oz, e.dx, e.dy, e.dz, e.err, tbest, ghi);
+                            if (cls != HXR_TF_MISS) hit = tri_core(M.tri_test, bf, t, ti, mb.gamma, mb.tri, gm, l2, l3);
+                        }
+                        if (__ballot_sync(FULL, hit) == 0u) continue;
+                        // the winner among the lanes' hits: smallest parameter, then highest index (tri_core's own rule, so the
+                        // result is what testing them one after the other leaves in mb)
+                        bool bv = hit;
+                        double bg = gm;
+                        uint32_t bt = ti;
+                        unsigned bl = lane;
+#pragma unroll
+                        for (int d = 16; d >= 1; d >>= 1) {
+                            const bool ov_ = __shfl_xor_sync(FULL, (int)bv, d) != 0;
+                            const double og = __shfl_xor_sync(FULL, bg, d);
+                            const uint32_t ot = __shfl_xor_sync(FULL, bt, d);
+                            const unsigned ol = __shfl_xor_sync(FULL, bl, d);
+                            if (ov_ && (!bv || og < bg || (og == bg && ot > bt))) { bv = true; bg = og; bt = ot; bl = ol; }
+                        }
+                        mb.gamma = bg;
+                        mb.tri = (int)bt;
+                        mb.l2 = __shfl_sync(FULL, l2, bl);
+                        mb.l3 = __shfl_sync(FULL, l3, bl);
+                        if (SHADOW && blocks(nd, t, mb)) {
+                            out.meta = HXR_CAND_BLOCKED;
+                            return out;
+                        }
+                        tbest = fminf(tbest, f32_above(mb.gamma));
+                    }
+                } else {
+                    if (COUNT && cnt) cnt->kd_inner++;
+                    WalkEnt en[4];
+                    block_step(load_block(M.blocks + curRef), w, tmin, tmax, tbest, en[0], en[1], en[2], en[3]);
+                    bool have = false;
+                    WalkEnt c;
+                    c.ref = 0; c.lo = c.hi = 0;
+#pragma unroll
+                    for (int k = 3; k >= 0; k--) {
+                        if (!ent_valid(en[k]) || en[k].hi < tskip) continue;
+                        if (have && sp < HXR_KD_STACK) { stRef[sp] = c.ref; stLo[sp] = c.lo; stHi[sp] = c.hi; sp++; }  // (every lane writes the same entry)
+                        c = en[k];
+                        have = true;
+                    }
+                    if (have) { curRef = c.ref; tmin = c.lo; tmax = c.hi; continue; }
+                }
+                bool found = false;
+                while (sp > 0) {
+                    sp--;
+                    if (stLo[sp] <= tbest) { curRef = stRef[sp]; tmin = stLo[sp]; tmax = stHi[sp]; found = true; break; }
+                }
+                if (!found) break;
+            }
+        } else if (slot == ov.slot && haveCur) {
+            mb = cur;  // (cannot happen: the first walk entered this mesh)
+            walked = true;
+        }
+        if (walked && !SHADOW) {
+            const Ray t = object_ray(nd, ray);
+            fold_mesh_hit(nd, node, ray, t, mb, bestDist, bestNode, win);
+            wcap = fminf(wcap, f32_cap(bestDist));
+        }
+    }
+    if (SHADOW) return out;
+    if (win.node >= 0 && bestNode == win.node) {
+        out.tri[0] = (uint32_t)win.mb.tri;
+        out.meta = 1u | ((uint32_t)sc.node_slot[win.node] << 8);
+    }
+    return out;
+}
+
+template <bool SHADOW, bool COUNT>
+__global__ void __launch_bounds__(128, 4) k_finish_warp(DScene sc, const RayGeom* __restrict__ geom, CandRec* cand, const OverflowEntry* __restrict__ ovf_list,
+                                                        const uint32_t* __restrict__ ovf_count, uint32_t* fetch, uint32_t cap, FrameTotals* totals,
+                                                        TravCounters* cnt)
+{
+    __shared__ uint32_t sRef[4][HXR_KD_STACK];  // one traversal stack per warp
+    __shared__ float sLo[4][HXR_KD_STACK], sHi[4][HXR_KD_STACK];
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t n = min(*ovf_count, cap);
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    TravCounters local = {0, 0, 0, 0, 0};
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(fetch, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n) break;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(ovf_list + k));
+        OverflowEntry oe;
+        oe.ray = u.x; oe.slot = (int32_t)u.y; oe.tstop = __uint_as_float(u.z); oe.pad = 0;
+        const uint4 c = reinterpret_cast<const uint4*>(cand)[oe.ray];
+        CandRec rec;
+        rec.tri[0] = c.x; rec.tri[1] = c.y; rec.tri[2] = c.z; rec.meta = c.w;
+        __syncwarp();  // (the previous ray's stack is dead before this one's first push)
+        const CandRec r = finish_overflowed_ray_warp<SHADOW, COUNT>(sc, load_geom(geom + oe.ray), rec, oe, COUNT && lane == 0 ? &local : nullptr, lane, sRef[wib],
+                                                                    sLo[wib], sHi[wib]);
+        if (lane == 0) reinterpret_cast<uint4*>(cand)[oe.ray] = make_uint4(r.tri[0], r.tri[1], r.tri[2], r.meta);
+    }
+    if (totals && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&totals->cand_overflow, (unsigned long long)n);
+    if (COUNT) flush_trav(cnt, local);
+}
+
 // GI (one path vertex) and Whitted (shader tree with its stacks) are separate compilations, and so are scenes whose inline
 // nodes are only planes / spheres / cubes / quads (SIMPLE: no CSG, heightfield or inline tree-walk code, no stack frame).
 //
@@ -879,6 +1096,8 @@ __global__ void __launch_bounds__(128, SIMPLE ? (GI ? HXR_SHADE_GI_BLOCKS : HXR_
             CandRec cr;
             cr.meta = 0;
             if (sc.n_big) cr = load_cand(cand + i);
+            // (A/B-ed and dropped, r2r: requesting the thread's next candidate record here and prefetching the exact records and
+            // attributes it names into L2 - shade 45.5 -> 48.0 ms; the kernel is bound by issue and code size, not by the chain)
             shade_item<GI, COUNT, SIMPLE>(sc, fp, g, a, cr, sinks, ec, COUNT ? &local : nullptr);
         }
     }
@@ -1055,7 +1274,17 @@ int walk(Context* c, const DScene& sc, bool shadow, const RayGeom* geom, const M
         LaunchScope ls(c, PROF_FINISH);
         // a fraction of a percent of the rays: a small grid (it loops over whatever the list holds)
         const uint32_t blocks = stage_grid(c, std::max<uint32_t>(1, n_hint / 32), 8);
-        if (shadow) {
+        if (c->finishWarp) {
+            // one warp per listed ray, fetched through wb.fetch (zeroed together with the walk's cursor)
+            const uint32_t wblocks = stage_grid(c, std::max<uint32_t>(1, n_hint / 32) * 8, 4);
+            if (shadow) {
+                if (cnt) k_finish_warp<true, true><<<wblocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, wb.fetch, cap, totals, cnt);
+                else k_finish_warp<true, false><<<wblocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, wb.fetch, cap, totals, nullptr);
+            } else {
+                if (cnt) k_finish_warp<false, true><<<wblocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, wb.fetch, cap, totals, cnt);
+                else k_finish_warp<false, false><<<wblocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, wb.fetch, cap, totals, nullptr);
+            }
+        } else if (shadow) {
             if (cnt) k_finish<true, true><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, cnt);
             else k_finish<true, false><<<blocks, 128, 0, c->stream>>>(sc, geom, wb.cand, wb.ovf_list, wb.ovf_count, cap, totals, nullptr);
         } else {

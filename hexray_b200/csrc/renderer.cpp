@@ -15,7 +15,9 @@
 namespace hxr {
 
 // device counters (uint32): queue counts, the shadow queue's count, the work-fetch cursors of the two walks, flags
-enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_HEAD_A = 3, C_OVF_A = 4, C_HEAD_B = 5, C_OVF_B = 6, C_OVERFLOW = 7, C_AA = 8, C_NCOUNTERS = 16 };
+// (HEAD / OVF / FETCH of a walk are consecutive: one clear before the walk is queued)
+enum { C_Q0 = 0, C_Q1 = 1, C_SHADOW = 2, C_HEAD_A = 3, C_OVF_A = 4, C_FETCH_A = 5, C_HEAD_B = 6, C_OVF_B = 7, C_FETCH_B = 8, C_OVERFLOW = 9, C_AA = 10,
+       C_NCOUNTERS = 16 };
 
 Renderer::~Renderer()
 {
@@ -588,6 +590,7 @@ dev::WalkBuffers Renderer::walkBuffers(CandRec* cand, bool shadow) const
     wb.head = m_counters + (shadow ? C_HEAD_B : C_HEAD_A);
     wb.ovf_list = shadow && m_ovfListS ? m_ovfListS : m_ovfList;
     wb.ovf_count = m_counters + (shadow ? C_OVF_B : C_OVF_A);
+    wb.fetch = m_counters + (shadow ? C_FETCH_B : C_FETCH_A);
     return wb;
 }
 RayQueue Renderer::queue(int i) const
@@ -646,7 +649,7 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
         const uint32_t grid = (uint32_t)std::min<uint64_t>(n, (uint64_t)nPrimary * 2);
         const RayQueue q = queue(cur);
         dev::zero(m_dev, m_counters + (cur ? C_Q0 : C_Q1), sizeof(uint32_t));
-        dev::zero(m_dev, m_counters + C_HEAD_A, 2 * sizeof(uint32_t));  // the closest-hit walk's cursor and overflow-list count
+        dev::zero(m_dev, m_counters + C_HEAD_A, 3 * sizeof(uint32_t));  // the closest-hit walk's cursor, its overflow-list count and k_finish's cursor
         if (level > 0) st.kernel_launches += dev::setup_closest(m_dev, m_scene, q, m_cand, cnt, grid);  // (level 0 arrives set up)
         st.kernel_launches += dev::walk(m_dev, m_scene, false, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, false), m_totals, cnt, grid);
         Sinks sk;
@@ -670,7 +673,7 @@ void Renderer::drain(const FrameParams& fp, float* accum, uint32_t nPrimary, hxr
             st.kernel_launches += dev::shade(m_dev, m_scene, fp, q, m_cand, b, e, sk, m_totals, cnt);
             const uint32_t ns = (uint32_t)std::min<uint64_t>(m_shadowCap, (uint64_t)std::min<uint64_t>(e - b, grid) * perHit);
             if (side) { dev::fork(m_dev); dev::lane(m_dev, 1); }
-            dev::zero(m_dev, m_counters + C_HEAD_B, 2 * sizeof(uint32_t));
+            dev::zero(m_dev, m_counters + C_HEAD_B, 3 * sizeof(uint32_t));
             st.kernel_launches += dev::setup_shadow(m_dev, m_scene, sk.shadow, scand, accum, cnt, ns);
             st.kernel_launches += dev::walk(m_dev, m_scene, true, m_sg, m_sentry, m_counters + C_SHADOW, m_shadowCap, walkBuffers(scand, true), m_totals, cnt, ns);
             st.kernel_launches += dev::resolve_shadow(m_dev, m_scene, sk.shadow, scand, accum, nullptr, m_totals, cnt, ns);
@@ -1028,7 +1031,7 @@ int Renderer::traceClosest(const hxr_ray* rays, size_t n, hxr_hit* hits)
         DScene full = m_scene;
         full.full_attr = 1;  // the hook reports u, v, dNdx, dNdy of every hit, whatever the node's shader reads
         dev::setup_closest(m_dev, full, q, m_cand, nullptr, m);
-        dev::zero(m_dev, m_counters + C_SHADOW, 5 * sizeof(uint32_t));
+        dev::zero(m_dev, m_counters + C_SHADOW, (C_FETCH_B - C_SHADOW + 1) * sizeof(uint32_t));
         dev::walk(m_dev, full, false, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, false), nullptr, nullptr, m);
         dev::hit_records(m_dev, full, q, m_cand, m_hits, m);
         if (!dev::download(m_dev, recs.data(), m_hits, (size_t)m * sizeof(HitRec)) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));
@@ -1074,7 +1077,7 @@ int Renderer::traceVisible(const double* seg, size_t n, uint8_t* out)
         dev::upload(m_dev, q.geom, geoms.data(), (size_t)m * sizeof(RayGeom));
         dev::upload(m_dev, q.count, &m, sizeof m);
         dev::setup_shadow(m_dev, m_scene, q, m_cand, nullptr, nullptr, m);
-        dev::zero(m_dev, m_counters + C_HEAD_A, 4 * sizeof(uint32_t));
+        dev::zero(m_dev, m_counters + C_HEAD_A, (C_FETCH_B - C_HEAD_A + 1) * sizeof(uint32_t));
         dev::walk(m_dev, m_scene, true, q.geom, q.entry, q.count, q.cap, walkBuffers(m_cand, true), nullptr, nullptr, m);
         dev::resolve_shadow(m_dev, m_scene, q, m_cand, nullptr, m_visible, nullptr, nullptr, m);
         if (!dev::download(m_dev, out + first, m_visible, m) || dev::failed(m_dev)) return fail(HXR_ERR_CUDA, dev::last_error(m_dev));

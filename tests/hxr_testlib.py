@@ -337,6 +337,58 @@ def check_layout_switches(api, side=320, queue_capacity=1 << 20):
         assert np.allclose(img, out[0][2], rtol=2e-5, atol=1e-6), float(np.abs(img - out[0][2]).max())
 
 
+def grazing_rays(renderer, n, seed=7):
+    """Rays that leave the terrain surface almost tangentially (what deep GI bounces produce): the float bounds of the walk
+    decide little on them, so 1-2 % fill their candidate record and are finished by the overflow kernel."""
+    rng = np.random.default_rng(seed)
+    o = np.stack([rng.uniform(-480, 480, n), np.full(n, 300.0), rng.uniform(-480, 480, n)], axis=1)
+    d = np.tile([0.0, -1.0, 0.0], (n, 1))
+    h = renderer.trace_closest(np.concatenate([o, d, np.zeros((n, 2))], axis=1))
+    m = (h["status"] == 0) & (h["node"] == 0)
+    ip, nr = h["ip"][m], h["norm"][m]
+    az = rng.uniform(0, 2 * np.pi, len(ip))
+    d2 = np.stack([np.cos(az), rng.uniform(-0.02, 0.1, len(ip)), np.sin(az)], axis=1)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    o2 = ip + nr * 1e-6
+    rays = np.concatenate([o2, d2, np.zeros((len(ip), 2))], axis=1)
+    seg = np.concatenate([o2, o2 + d2 * rng.uniform(20, 900, (len(ip), 1))], axis=1)
+    return rays, seg
+
+
+def check_finish_forms(api, side=708, n=30000, queue_capacity=1 << 20):
+    """Rays whose candidate record overflows are finished by one warp each (k_finish_warp: the lanes share a leaf's exact
+    tests, the winner comes from a shuffle reduction) or by one thread each (k_finish, HXR_FINISH_WARP=0). Both must return
+    what testing every triangle in index order returns (the reference's useKDTree=false path), bit for bit."""
+    out = []
+    rays = seg = None
+    for env, flags in (({}, 0), ({"HXR_FINISH_WARP": "0"}, 0), ({}, hx.CFG_BRUTE_FORCE_MESHES)):
+        os.environ.update(env)
+        try:
+            sf = terrain_scene_file(api, side)
+            r = hx.Renderer(api_=api, queue_capacity=queue_capacity, flags=flags).load(sf)
+        finally:
+            for k in env:
+                del os.environ[k]
+        if rays is None:
+            rays, seg = grazing_rays(r, n)
+            assert len(rays) > n // 2
+        hits = r.trace_closest(rays).copy()
+        vis = r.trace_visible(seg).copy()
+        overflow = 0
+        if flags == 0:  # a GI frame of the same scene: its stats say that the overflow path is really taken
+            _, st = r.render(width=96, height=54, spp=8, seed=5)
+            overflow = st["cand_overflow"]
+        out.append((hits, vis, overflow))
+        r.close()
+        sf.close()
+    assert out[0][2] > 0 and out[1][2] > 0, "no ray overflowed its candidate record: the test does not reach the finish kernels"
+    for hits, vis, _ in out[1:]:
+        for f in ("status", "node", "dist", "ip", "norm", "u", "v"):
+            assert np.array_equal(hits[f], out[0][0][f]), f
+        assert np.array_equal(vis, out[0][1])
+    return out[0][2]
+
+
 def check_stereo(sess, scene, spp=0):
     """Anaglyph frame of a bundled scene with stereoSeparation added, against the compiled reference's frame."""
     g = golden("stereo", scene)

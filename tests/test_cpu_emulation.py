@@ -41,6 +41,11 @@ def test_soup_walk_equals_brute_force(emu_api):
     T.check_soup_walk_equals_brute_force(emu_api, 100000, 1500)
 
 
+def test_grazing_rays_equal_brute_force(emu_api):
+    # rays leaving the terrain almost tangentially: 1-2 % overflow their candidate record and go through finish_overflowed_ray
+    assert T.check_finish_forms(emu_api, side=320, n=1500) > 0
+
+
 def test_layout_switches_do_not_change_results(emu_api):
     T.check_layout_switches(emu_api)
 

@@ -176,6 +176,11 @@ def test_layout_switches_do_not_change_results(gpu_api):
     T.check_layout_switches(gpu_api)
 
 
+def test_finish_forms_agree(gpu_api):
+    # overflowed candidate records: warp-per-ray finish == thread-per-ray finish == brute force, on grazing rays (1 M triangles)
+    T.check_finish_forms(gpu_api)
+
+
 def test_stereo_anaglyph(sess):
     # src/main.cpp:234-248: two traces per sample mixed into an anaglyph; Whitted + AA (deterministic) and GI
     T.check_stereo(sess, "kdtree_test")
