@@ -413,7 +413,11 @@ __global__ void __launch_bounds__(128, SIMPLE ? HXR_SETUP_BLOCKS : 1) k_setup(DS
 // stack entries (12 B each); deeper entries overflow to local memory (rare: the stack is shallow for almost all rays).
 #define HXR_POP 0x7FFFFFFFu /* cursor value: take the next entry from the stack */
 #ifndef HXR_LEAF_BREAK
-#define HXR_LEAF_BREAK 0 /* > 0: phase 1 ends early once this many lanes of the warp hold a leaf */
+// phase 1 ends early once this many lanes of the warp hold a leaf (0: always walkSteps steps). A/B on B200 (profiles/r2/ab/r2w_*,
+// r2x_*, r2p_*): 12 against 0 - terrain walk 143.1 -> 141.7 ms per 32-spp wave (1856 -> 1868 Mrays/s), beer / meshes / kdtree_test
+// at 1080p-class +1.8 / +1.6 / +1.9 %; 8 and 10 the same within noise, 16 and 20 half of it. The opposite rule - extra steps
+// while fewer than 4 / 8 lanes hold a leaf - loses (walk 142.2 / 143.1 ms)
+#define HXR_LEAF_BREAK 12
 #endif
 
 template <int SSTACK>
