@@ -1,7 +1,8 @@
 // launch_cuda.cu — the sm_100a kernels of the render hot path and their launchers
 // (implements device/launch.h; the only translation unit compiled by nvcc).
 //
-// One bounce of the wavefront is SIX launches; a ray lives in a 64-byte geometry record + a 24-byte payload between them:
+// One bounce of the wavefront is SIX launches + a small one after each walk; a ray lives in a 64-byte geometry record + a 24-byte
+// payload between them:
 //   k_setup<closest>     the inline part of raycast(), in place on the queue: depth guard + every inline node (analytic
 //                        primitives, CSG, heightfields, quads) in scene order, in double; reads 64 B, writes back 16 B
 //   k_walk<closest>      the KD-tree walk, FP32 only: PERSISTENT warps; a lane owns one RAY and walks, one after the other,
@@ -11,6 +12,8 @@
 //                        levels) alternates with a warp-cooperative phase that filters the triangles of all leaves held
 //                        by the warp, 32 (ray, triangle) pairs at a time; pairs the filter cannot rule out are collected
 //                        in the owner's shared-memory slots and leave the kernel as ONE 16-byte candidate record per ray
+//   k_finish_warp        the few rays whose candidate record filled up (a 4th candidate): the walk resumed where it stopped, ONE WARP
+//                        per ray, exact double tests on the spot (a leaf's triangles split over the lanes, shuffle argmin)
 //   k_shade<GI>          per ray: exact (double) test of its candidates, winner across inline nodes and meshes,
 //                        IntersectionInfo, lights, environment, bump, then the Whitted shader tree or the path-tracing vertex;
 //                        pushes child rays and shadow rays; radiance lands with RED.ADD.F32

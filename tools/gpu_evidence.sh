@@ -13,7 +13,7 @@ for part in "early 10 9" "deep 46 8"; do
   set -- $part
   ncu --set full --clock-control none --import-source on -k regex:"k_walk|k_shade|k_setup|k_resolve|k_finish|k_gen" -s $2 -c $3 -o /tmp/${TAG}_$1 $CMD > gpurun_out/${TAG}_ncu_$1.log 2>&1; echo "$1 rc=$?"
   python tools/ncu_summary.py /tmp/${TAG}_$1.ncu-rep > gpurun_out/${TAG}_$1_summary.txt 2>&1
-  for k in "k_walk<(bool)0" "k_walk<(bool)1" "k_shade" "k_setup<(bool)0" "k_setup<(bool)1" "k_resolve_shadow" "k_finish<(bool)0"; do
+  for k in "k_walk<(bool)0" "k_walk<(bool)1" "k_shade" "k_setup<(bool)0" "k_setup<(bool)1" "k_resolve_shadow" "k_finish_warp<(bool)0"; do
     n=$(echo "$k" | tr -c 'a-z0-9_' '_')
     python tools/ncu_sass.py /tmp/${TAG}_$1.ncu-rep "--name=$k" > gpurun_out/${TAG}_$1_sass_$n.txt 2>/dev/null
   done
