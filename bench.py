@@ -584,12 +584,41 @@ def ours(a):
     sf.close()
 
 
+class JsonOnlyStdout:
+    """The contract is ONE JSON line on stdout. Libraries write there too, from C (NCCL prints its version line at the first
+    collective when the box sets NCCL_DEBUG=VERSION): file descriptor 1 points at stderr while the bench runs, and only
+    print()s of this module reach the real stdout."""
+
+    def __enter__(self):
+        import builtins
+        sys.stdout.flush()
+        self.real = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        self.print = builtins.print
+
+        def to_real(*args, **kw):
+            if kw.get("file") is None:
+                kw["file"] = self.real
+            self.print(*args, **kw)
+            kw["file"].flush()
+        globals()["print"] = to_real
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        self.real.flush()
+        os.dup2(self.real.fileno(), 1)
+        del globals()["print"]
+        return False
+
+
 def main():
     a = parse_args()
-    if a.impl == "reference":
-        reference_arm(a)
-    else:
-        ours(a)
+    with JsonOnlyStdout():
+        if a.impl == "reference":
+            reference_arm(a)
+        else:
+            ours(a)
 
 
 if __name__ == "__main__":
