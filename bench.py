@@ -302,7 +302,48 @@ EXTRA_SCENES = [
 ]
 
 
-def extra_scenes(hx, device, want_cpu):
+def measured_l2_gbs():
+    """L2 read bandwidth of this GPU model as measured by tools/microbench.cu (profiles/microbench_r1.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "microbench_r1.json")) as f:
+            return float(json.load(f)["l2_read_gbs"]), "profiles/microbench_r1.json (tools/microbench.cu)"
+    except Exception:
+        return 23000.0, "fallback"
+
+
+def scene_traversal_roofline(hx, r, sf, W, H, spp, mrays, sm_ghz, sms=148):
+    """SURVEY 8d for a scene whose geometry sits in L2: T_ray = max(T_issue, T_mem) with
+    B_ray = 64 + 32 N_inner + 48 N_tri + 16 N_leaf bytes at the measured L2 bandwidth and
+    I_ray = 30 per node tested + analytic primitives (plane 10, sphere 25, cube 60, rect light 35) + 10 N_inner + 30 N_tri
+    FP32-pipe instructions at SMs x 128 lanes x clock. N_* come from a counting render of the same frame (per ray, rays =
+    closest-hit + visible() queries)."""
+    _, st = r.render(width=W, height=H, spp=min(spp, 16) if spp else 0, seed=0, flags=hx.RENDER_COUNT_TRAVERSAL)
+    rays = max(1, st["rays_closest"] + st["rays_shadow"])
+    n_inner, n_tri, n_leaf = st["kd_inner"] / rays, st["tri_tests"] / rays, st["kd_leaves"] / rays
+    pod = sf.pod.contents
+    prim = {0: 10.0, 1: 25.0, 2: 60.0}  # hxr_geometry_type: plane, sphere, cube
+
+    def geom_cost(gi, depth=0):
+        g = pod.geometries[gi]
+        if g.type == 3 and depth < 8:  # CSG: both children
+            return geom_cost(g.b, depth + 1) + geom_cost(g.c, depth + 1)
+        return prim.get(g.type, 0.0)  # meshes are counted through N_inner / N_tri; the heightfield DDA has no constant in 8d
+    inst = sum(30.0 + geom_cost(pod.nodes[i].geom) for i in range(pod.n_nodes))
+    inst += 35.0 * sum(1 for i in range(pod.n_lights) if pod.lights[i].type == 1)
+    inst += 10.0 * n_inner + 30.0 * n_tri
+    b_ray = 64.0 + 32.0 * n_inner + 48.0 * n_tri + 16.0 * n_leaf
+    l2, l2_src = measured_l2_gbs()
+    t_issue = inst / (sms * 128 * sm_ghz * 1e9)
+    t_mem = b_ray / (l2 * 1e9)
+    peak = 1e-6 / max(t_issue, t_mem)
+    note = "texture / shading bytes and instructions are excluded (traversal roofline)"
+    if pod.n_heightfields:
+        note += "; the heightfield DDA has no constant in SURVEY 8d: only its node transform is counted"
+    return {"note": note, "bound": "l2" if t_mem >= t_issue else "fp32 issue", "bytes_per_ray": b_ray, "inst_per_ray": inst, "N_inner": n_inner, "N_tri": n_tri,
+            "N_leaf": n_leaf, "l2_gbs": l2, "l2_source": l2_src, "sm_ghz": sm_ghz, "peak_mrays_per_s": peak, "frac": mrays / peak}
+
+
+def extra_scenes(hx, device, want_cpu, sm_ghz=1.965):
     """Mrays/s and ms/frame of the bundled scenes on one GPU (median of 3 frames after 2 warm-up frames, CUDA-event time of
     hxr_render), at their own resolution and - Whitted scenes - at 1920x1080, next to the reference on this box's host cores."""
     import numpy as np
@@ -327,6 +368,10 @@ def extra_scenes(hx, device, want_cpu):
             m = float(np.median(ms))
             rec[label] = {"width": W, "height": H, "spp": spp or None, "rays": rays, "ms_per_frame": m, "mrays_per_s": rays / m / 1e3,
                           "kernel_launches": st["kernel_launches"]}
+            try:  # the scene as a fraction of its traversal roofline (reporting only: never fails the bench)
+                rec[label]["roofline"] = scene_traversal_roofline(hx, r, sf, W, H, spp, rays / m / 1e3, sm_ghz)
+            except Exception as e:
+                rec[label]["roofline"] = {"error": str(e)[:200]}
         r.close()
         sf.close()
         if want_cpu and reference_binary():
@@ -565,7 +610,7 @@ def ours(a):
                                         "sample": "%dx%d x %d spp, %d rays, %.1f s wall incl. load%s" % (b.ref_width, b.ref_height, b.ref_spp, info["rays"], info["wall_s"], note)}
         if n_gpus == 1 and not a.no_extra:
             r.close()
-            line["extra"] = {"scenes": extra_scenes(hx, local, not a.no_cpu_baseline)}
+            line["extra"] = {"scenes": extra_scenes(hx, local, not a.no_cpu_baseline, sm_ghz=(line["clocks"].get("sm_mhz") or 1965.0) / 1e3)}
             if sf.pod.contents.n_meshes > 0:
                 # the same mesh's KD-tree built on the GPU (HXR_CFG_DEVICE_KD_BUILD) next to the host build above
                 t0 = time.time()
