@@ -187,16 +187,33 @@ class Renderer:
         """Bitmap::saveEXR of the last rendered frame (or the device frame at `dptr`): float -> half on the GPU."""
         self._check(self.api.lib.hxr_save_frame_exr(self.ctx, C.c_void_p(dptr) if dptr else None, width, height, path.encode()))
 
-    def progressive(self, n_passes, width=0, height=0, spp=0, seed=0, max_depth=-1):
-        """Refine one Monte-Carlo frame pass by pass (hxr_progressive_*): yields (estimate [H, W, 3], stats) after every pass."""
+    def progressive(self, n_passes, width=0, height=0, spp=0, seed=0, max_depth=-1, checkpoint=None):
+        """Refine one Monte-Carlo frame pass by pass (hxr_progressive_*): yields (estimate [H, W, 3], stats) after every pass.
+        checkpoint = (sum [H, W, 3] float32, passes_done, spp_done) from progressive_state() of an interrupted run of the same
+        frame: the passes already done are not rendered again (hxr_progressive_resume)."""
         W, H = self.frame_size(width, height)
         p = self._params(width, height, MODE_MONTECARLO, spp, -1, max_depth, seed, (0, 0), 0)
-        self._check(self.api.lib.hxr_progressive_begin(self.ctx, C.byref(p), n_passes))
+        first = 0
+        if checkpoint is None:
+            self._check(self.api.lib.hxr_progressive_begin(self.ctx, C.byref(p), n_passes))
+        else:
+            s, first, spp_done = checkpoint
+            s = np.ascontiguousarray(s, dtype=np.float32)
+            assert s.size == W * H * 3
+            self._check(self.api.lib.hxr_progressive_resume(self.ctx, C.byref(p), n_passes, s.ctypes.data_as(C.POINTER(C.c_float)), int(first), int(spp_done)))
         out = np.empty((H, W, 3), dtype=np.float32)
-        for _ in range(n_passes):
+        for _ in range(first, n_passes):
             st = capi.Stats()
             self._check(self.api.lib.hxr_progressive_pass(self.ctx, out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(st)))
             yield out, st.as_dict()
+
+    def progressive_state(self, width=0, height=0):
+        """The checkpoint of the progressive frame in flight: (un-normalised sum [H, W, 3], passes done, samples per pixel so far)."""
+        W, H = self.frame_size(width, height)
+        s = np.empty((H, W, 3), dtype=np.float32)
+        passes, spp = C.c_int32(0), C.c_int32(0)
+        self._check(self.api.lib.hxr_progressive_state(self.ctx, s.ctypes.data_as(C.POINTER(C.c_float)), C.byref(passes), C.byref(spp)))
+        return s, passes.value, spp.value
 
     def reduce_backend(self):
         return self.api.lib.hxr_reduce_backend(self.ctx).decode()

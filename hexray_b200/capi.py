@@ -145,7 +145,7 @@ SYMBOLS = ["hxr_create", "hxr_destroy", "hxr_last_error", "hxr_upload_scene", "h
            "hxr_get_accel_info", "hxr_set_profiling", "hxr_scene_load", "hxr_scene_file_scene", "hxr_scene_file_camera",
            "hxr_scene_file_set_synthetic_mesh", "hxr_scene_file_write_obj", "hxr_scene_file_free", "hxr_save_image", "hxr_load_image",
            "hxr_test_tri_filter", "hxr_test_tri_filter_packed", "hxr_save_frame_bmp", "hxr_save_frame_exr", "hxr_device_count", "hxr_reduce_backend",
-           "hxr_progressive_begin", "hxr_progressive_pass", "hxr_progressive_state"]
+           "hxr_progressive_begin", "hxr_progressive_pass", "hxr_progressive_state", "hxr_progressive_resume"]
 
 
 class Api:
@@ -187,6 +187,7 @@ class Api:
         L.hxr_progressive_begin.argtypes = [vp, C.POINTER(RenderParams), c_i32]
         L.hxr_progressive_pass.argtypes = [vp, C.POINTER(c_f32), C.POINTER(Stats)]
         L.hxr_progressive_state.argtypes = [vp, C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32)]
+        L.hxr_progressive_resume.argtypes = [vp, C.POINTER(RenderParams), c_i32, C.POINTER(c_f32), c_i32, c_i32]
         L.hxr_device_count.argtypes = []
         L.hxr_reduce_backend.argtypes = [vp]
         L.hxr_reduce_backend.restype = C.c_char_p

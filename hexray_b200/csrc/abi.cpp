@@ -95,6 +95,11 @@ int hxr_progressive_begin(hxr_ctx* ctx, const hxr_render_params* p, int32_t n_pa
 }
 int hxr_progressive_pass(hxr_ctx* ctx, float* rgb_out, hxr_stats* stats) { HXR_CTX_CALL(ctx->m.progressivePass(rgb_out, stats)) }
 int hxr_progressive_state(hxr_ctx* ctx, float* sum_out, int32_t* passes_done, int32_t* spp_done) { HXR_CTX_CALL(ctx->m.progressiveState(sum_out, passes_done, spp_done)) }
+int hxr_progressive_resume(hxr_ctx* ctx, const hxr_render_params* p, int32_t n_passes, const float* sum, int32_t passes_done, int32_t spp_done)
+{
+    if (ctx && !p) { ctx->err = "null render params"; return HXR_ERR_INVALID; }
+    HXR_CTX_CALL(ctx->m.progressiveResume(*p, n_passes, sum, passes_done, spp_done))
+}
 int hxr_set_profiling(hxr_ctx* ctx, int32_t on) { HXR_CTX_CALL((ctx->m.setProfiling(on != 0), HXR_OK)) }
 int hxr_trace_closest(hxr_ctx* ctx, const hxr_ray* rays, size_t n, hxr_hit* hits) { HXR_CTX_CALL(ctx->m.primary().traceClosest(rays, n, hits)) }
 int hxr_trace_visible(hxr_ctx* ctx, const double* seg, size_t n, uint8_t* vis) { HXR_CTX_CALL(ctx->m.primary().traceVisible(seg, n, vis)) }

@@ -191,14 +191,7 @@ int MultiRenderer::progressivePass(float* hostOut, hxr_stats* stats)
     dev::Context* d0 = r0.device();
     const size_t n = (size_t)r0.frameWidth() * r0.frameHeight() * 3;
     if (k == 0 || m_sumFloats != n) {
-        if (m_sumFloats != n) {
-            dev::free_(d0, m_sum);
-            dev::free_(d0, m_estimate);
-            m_sum = (float*)dev::alloc(d0, n * sizeof(float));
-            m_estimate = (float*)dev::alloc(d0, n * sizeof(float));
-            m_sumFloats = (m_sum && m_estimate) ? n : 0;
-            if (!m_sumFloats) return fail(HXR_ERR_CUDA, "progressive: out of device memory");
-        }
+        if (!ensureSum(n)) return fail(HXR_ERR_CUDA, "progressive: out of device memory");
         dev::zero(d0, m_sum, n * sizeof(float));
     }
     dev::add_into(d0, m_sum, r0.frame(), n);
@@ -215,6 +208,42 @@ int MultiRenderer::progressivePass(float* hostOut, hxr_stats* stats)
         mergeStats(st, reduceMs, *stats);
         stats->spp_done = (uint32_t)m_sppSoFar;
     }
+    return HXR_OK;
+}
+
+bool MultiRenderer::ensureSum(size_t n)
+{
+    if (m_sumFloats == n) return true;
+    dev::Context* d0 = m_r[0]->device();
+    dev::free_(d0, m_sum);
+    dev::free_(d0, m_estimate);
+    m_sum = (float*)dev::alloc(d0, n * sizeof(float));
+    m_estimate = (float*)dev::alloc(d0, n * sizeof(float));
+    m_sumFloats = (m_sum && m_estimate) ? n : 0;
+    return m_sumFloats != 0;
+}
+
+// A frame interrupted after passesDone passes goes on from its checkpoint (hxr_progressive_state of the run that wrote it).
+int MultiRenderer::progressiveResume(const hxr_render_params& p, int nPasses, const float* sum, int passesDone, int sppDone)
+{
+    const int rc = progressiveBegin(p, nPasses);
+    if (rc != HXR_OK) return rc;
+    const int N = (int)m_r.size();
+    // the samples the first passesDone passes of THIS plan cover: s in [0, spp) with s % (P * N) < passesDone * N
+    const long long period = (long long)nPasses * N, done = (long long)passesDone * N;
+    const long long expect = passesDone >= 0 && passesDone <= nPasses ? (m_sppTotal / period) * done + std::min<long long>(m_sppTotal % period, done) : -1;
+    if (!sum || passesDone < 1 || passesDone > nPasses || sppDone != expect) {
+        m_passes = 0;  // (no frame is open)
+        return fail(HXR_ERR_INVALID, "progressive resume: the checkpoint does not belong to this frame plan (passes, samples per pixel or GPU count differ)");
+    }
+    int W = 0, H = 0;
+    m_r[0]->frameSize(p, W, H);
+    const size_t n = (size_t)W * H * 3;
+    if (n == 0 || !ensureSum(n)) { m_passes = 0; return fail(HXR_ERR_CUDA, "progressive: out of device memory"); }
+    dev::Context* d0 = m_r[0]->device();
+    if (!dev::upload(d0, m_sum, sum, n * sizeof(float)) || !dev::sync(d0)) { m_passes = 0; return fail(HXR_ERR_CUDA, dev::last_error(d0)); }
+    m_passNext = passesDone;
+    m_sppSoFar = sppDone;
     return HXR_OK;
 }
 

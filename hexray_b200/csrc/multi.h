@@ -24,6 +24,7 @@ public:
     int progressiveBegin(const hxr_render_params& p, int nPasses);
     int progressivePass(float* hostOut, hxr_stats* stats);
     int progressiveState(float* sumOut, int* passesDone, int* sppDone);
+    int progressiveResume(const hxr_render_params& p, int nPasses, const float* sum, int passesDone, int sppDone);
     int deviceCount() const { return (int)m_r.size(); }
     Renderer& primary() { return *m_r[0]; }
     const std::string& error() const { return m_err.empty() ? m_r[0]->error() : m_err; }
@@ -46,6 +47,7 @@ private:
     float* m_sum = nullptr;
     float* m_estimate = nullptr;
     size_t m_sumFloats = 0;
+    bool ensureSum(size_t n);  // the running sum and the estimate buffer on the first GPU, n floats each
 };
 
 }  // namespace hxr

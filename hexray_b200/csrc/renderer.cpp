@@ -704,6 +704,12 @@ void Renderer::framePlan(const hxr_render_params& p, bool& mc, int& spp) const
     spp = p.spp > 0 ? p.spp : std::max(raysPerPixel, 1);
 }
 
+void Renderer::frameSize(const hxr_render_params& p, int& W, int& H) const
+{
+    W = p.width > 0 ? p.width : m_scene.settings.frame_width;
+    H = p.height > 0 ? p.height : m_scene.settings.frame_height;
+}
+
 int Renderer::render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, bool noOutput)
 {
     if (!m_haveScene || !m_haveCamera) return fail(HXR_ERR_INVALID, "render: scene and camera must be set first");
@@ -725,8 +731,8 @@ int Renderer::renderOnce(const hxr_render_params& p, float* hostOut, void* devOu
 {
     hxr_stats st;
     memset(&st, 0, sizeof st);
-    const int W = p.width > 0 ? p.width : m_scene.settings.frame_width;
-    const int H = p.height > 0 ? p.height : m_scene.settings.frame_height;
+    int W, H;
+    frameSize(p, W, H);
     if (W <= 0 || H <= 0 || (uint64_t)W * H > (1ull << 31)) return fail(HXR_ERR_INVALID, "bad frame size");
     const size_t nPix = (size_t)W * H;
     bool mc;

@@ -40,6 +40,7 @@ public:
     int render(const hxr_render_params& p, float* hostOut, void* devOut, hxr_stats* stats, bool noOutput = false);
     // what render() will do with these parameters: Monte-Carlo or Whitted, and the samples per pixel of the WHOLE frame
     void framePlan(const hxr_render_params& p, bool& mc, int& spp) const;
+    void frameSize(const hxr_render_params& p, int& W, int& H) const;  // the frame these parameters render (0 = the scene's own size)
     int resolveDevice(void* d_rgb, int W, int H, int spp);
     int saveFrameBmp(const void* d_rgb, int W, int H, const char* path);
     int saveFrameExr(const void* d_rgb, int W, int H, const char* path);

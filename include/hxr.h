@@ -339,10 +339,15 @@ int hxr_resolve_device(hxr_ctx* ctx, void* d_rgb, int32_t width, int32_t height,
  * estimate sum / samples_so_far in rgb_out (host, width*height*3 floats; may be NULL to skip the read-back). After the last
  * pass the estimate equals what hxr_render returns for the same parameters (up to FP32 summation order). A camera change
  * between frames is hxr_set_camera + hxr_progressive_begin. hxr_progressive_state exports the checkpoint (sum, samples):
- * sum_out may be NULL; returns the number of passes done through *passes_done and the samples per pixel so far through *spp_done. */
+ * sum_out may be NULL; returns the number of passes done through *passes_done and the samples per pixel so far through *spp_done.
+ * hxr_progressive_resume is hxr_progressive_begin continued from such a checkpoint (a frame interrupted after passes_done
+ * passes, possibly by another process): same scene, camera, parameters, n_passes and number of GPUs as the run that wrote it -
+ * spp_done is checked against the plan, a checkpoint of another plan is refused with HXR_ERR_INVALID; the next
+ * hxr_progressive_pass renders pass number passes_done. */
 int hxr_progressive_begin(hxr_ctx* ctx, const hxr_render_params* p, int32_t n_passes);
 int hxr_progressive_pass(hxr_ctx* ctx, float* rgb_out, hxr_stats* stats);
 int hxr_progressive_state(hxr_ctx* ctx, float* sum_out, int32_t* passes_done, int32_t* spp_done);
+int hxr_progressive_resume(hxr_ctx* ctx, const hxr_render_params* p, int32_t n_passes, const float* sum, int32_t passes_done, int32_t spp_done);
 
 /* when on, every kernel launch of this context is bracketed by CUDA events and hxr_stats carries the
  * per-kernel-class device times (trace_closest_ms, trace_shadow_ms, shade_ms, other_ms) */

@@ -98,6 +98,36 @@ def check_progressive(api, devices):
     sf.close()
 
 
+def check_progressive_resume(api, devices):
+    """A progressive frame interrupted after two of four passes goes on from its checkpoint (hxr_progressive_state ->
+    hxr_progressive_resume) in a NEW context and ends in the same estimates; a checkpoint of another plan is refused."""
+    sf = hx.SceneFile(T.scene_path("cornell_box"), api_=api)
+    kw = dict(width=64, height=64, spp=16, seed=9)
+    r = hx.Renderer(api_=api, queue_capacity=1 << 20, devices=devices).load(sf)
+    straight = [est.copy() for est, _ in r.progressive(4, **kw)]
+    gen = r.progressive(4, **kw)
+    next(gen)
+    next(gen)
+    ck = r.progressive_state(64, 64)
+    assert ck[1] == 2 and ck[2] == 8 and float(ck[0].mean()) > 0.01
+    r.close()
+    r2 = hx.Renderer(api_=api, queue_capacity=1 << 20, devices=devices).load(sf)
+    rest = [(est.copy(), st["spp_done"]) for est, st in r2.progressive(4, checkpoint=ck, **kw)]
+    assert [s for _, s in rest] == [12, 16]
+    for (est, _), ref in zip(rest, straight[2:]):
+        assert np.allclose(est, ref, rtol=2e-5, atol=1e-6), float(np.abs(est - ref).max())
+    for bad in (dict(n=8, ck=ck), dict(n=4, ck=(ck[0], 3, ck[2])), dict(n=4, ck=(ck[0], 2, 9))):
+        with pytest.raises(hx.HxrError):
+            list(r2.progressive(bad["n"], checkpoint=bad["ck"], **kw))
+    r2.close()
+    sf.close()
+
+
+def test_progressive_resume_on_the_emulation(emu_api):
+    check_progressive_resume(emu_api, None)
+    check_progressive_resume(emu_api, [0, 1])
+
+
 def test_progressive_on_the_emulation(emu_api):
     check_progressive(emu_api, None)
     check_progressive(emu_api, [0, 1])
