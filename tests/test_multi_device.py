@@ -128,6 +128,12 @@ def test_progressive_resume_on_the_emulation(emu_api):
     check_progressive_resume(emu_api, [0, 1])
 
 
+@pytest.mark.gpu
+def test_progressive_resume_on_the_gpu(gpu_api):
+    check_progressive_resume(gpu_api, None)
+    check_progressive_resume(gpu_api, [0, 1 % gpu_api.lib.hxr_device_count()])
+
+
 def test_progressive_on_the_emulation(emu_api):
     check_progressive(emu_api, None)
     check_progressive(emu_api, [0, 1])
