@@ -1,6 +1,8 @@
 // cache.cpp — see cache.h.
 #include "cache.h"
+#include <cerrno>
 #include <chrono>
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,8 +60,15 @@ struct KdHeader {
     uint64_t n_blocks, n_leaf_tris, leaves;
     uint32_t max_depth, pad;
     double build_ms;
+    uint64_t content;  // hashBytes over the blocks, then the leaf lists: a damaged file is rebuilt, not walked
 };
-const uint32_t KD_VERSION = 3;
+const uint32_t KD_VERSION = 4;
+
+uint64_t kdContentHash(const KdTree& kd)
+{
+    uint64_t h = hashBytes(kd.blocks.data(), kd.blocks.size() * sizeof(KdBlock), 0x4B444331ull);
+    return hashBytes(kd.leafTris.data(), kd.leafTris.size() * sizeof(uint32_t), h);
+}
 
 std::string kdPath(uint64_t key)
 {
@@ -123,8 +132,13 @@ bool loadKdTree(uint64_t key, const hxr_mesh& mesh, KdTree& out)
         out.maxDepth = h.max_depth;
         out.leaves = h.leaves;
         out.buildMs = h.build_ms;
+        ok = ok && kdContentHash(out) == h.content;
     }
     fclose(f);
+    if (!ok) {
+        out.blocks.clear();
+        out.leafTris.clear();
+    }
     return ok;
 }
 
@@ -143,6 +157,7 @@ void storeKdTree(uint64_t key, const hxr_mesh& mesh, const KdTree& kd)
     h.leaves = kd.leaves;
     h.max_depth = kd.maxDepth;
     h.build_ms = kd.buildMs;
+    h.content = kdContentHash(kd);
     writeAtomically(path, {{&h, sizeof h}, {kd.blocks.data(), kd.blocks.size() * sizeof(KdBlock)}, {kd.leafTris.data(), kd.leafTris.size() * sizeof(uint32_t)}});
 }
 
@@ -159,25 +174,52 @@ void cachedKdTree(const hxr_mesh& mesh, const KdBuildParams& params, KdTree& out
     const uint64_t key = meshContentKey(mesh, params);
     if (loadKdTree(key, mesh, out)) { *how = "cache"; return; }
     // build it, unless another process of this box is at it already: then wait for its file
+    // The lock file names its builder (pid): a lock whose process no longer exists - a run killed in the middle of its build -
+    // is stale, and is taken over instead of being waited for.
     const std::string lock = kdPath(key) + ".lock";
-    const int fd = open(lock.c_str(), O_CREAT | O_EXCL | O_WRONLY, 0666);
-    if (fd < 0) {
+    auto deadLockOwner = [&]() -> long {  // the pid the lock names if that process no longer exists, else 0
+        FILE* f = fopen(lock.c_str(), "r");
+        if (!f) return 0;
+        long pid = 0;
+        const int got = fscanf(f, "%ld", &pid);
+        fclose(f);
+        if (got != 1 || pid <= 0) return 0;  // (being written this instant, or a lock without a pid: the time-out below covers it)
+        return (kill((pid_t)pid, 0) != 0 && errno == ESRCH) ? pid : 0;
+    };
+    auto takeLock = [&]() -> bool {
+        const int fd = open(lock.c_str(), O_CREAT | O_EXCL | O_WRONLY, 0666);
+        if (fd < 0) return false;
+        char b[32];
+        const int n = snprintf(b, sizeof b, "%ld\n", (long)getpid());
+        if (write(fd, b, (size_t)n) != n) { /* an empty lock still excludes; its owner just cannot be probed */ }
+        close(fd);
+        return true;
+    };
+    bool mine = takeLock();
+    if (!mine) {
         const auto t0 = std::chrono::steady_clock::now();
         for (;;) {
             std::this_thread::sleep_for(std::chrono::milliseconds(50));
             if (loadKdTree(key, mesh, out)) { *how = "waited"; return; }
             struct stat st;
             const bool lockGone = stat(lock.c_str(), &st) != 0;
+            if (lockGone) {
+                if (loadKdTree(key, mesh, out)) { *how = "waited"; return; }
+                mine = takeLock();  // the builder left without publishing: build it here (unless somebody else was quicker)
+                if (mine) break;
+                continue;
+            }
             const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            // the builder vanished without publishing (or takes implausibly long): build it here
-            if ((lockGone && !loadKdTree(key, mesh, out)) || waited > 300.0) break;
-            if (lockGone) { *how = "waited"; return; }
+            const long dead = deadLockOwner();
+            if (dead || waited > 300.0) {
+                // stale (or implausibly slow): whoever removes the lock and takes a new one builds. The second look keeps a
+                // waiter from removing the fresh lock of another waiter that was quicker (the worst case is a tree built twice)
+                if (waited > 300.0 || deadLockOwner() == dead) unlink(lock.c_str());
+                mine = takeLock();
+                if (mine) break;
+            }
         }
-        buildKdTree(mesh, params, out);
-        *how = "built";
-        return;
     }
-    close(fd);
     buildKdTree(mesh, params, out);
     storeKdTree(key, mesh, out);
     unlink(lock.c_str());
@@ -190,8 +232,17 @@ struct ObjHeader {
     char magic[8];  // "HXROBJ\0\0"
     uint32_t version, pad;
     uint64_t key, n_vertices, n_normals, n_uvs, n_tris;
+    uint64_t content;  // hashBytes over the four arrays in file order
 };
-const uint32_t OBJ_VERSION = 1;
+const uint32_t OBJ_VERSION = 2;
+
+uint64_t objContentHash(const ObjArrays& a)
+{
+    uint64_t h = hashBytes(a.vertices.data(), a.vertices.size() * 8, 0x4F424A32ull);
+    h = hashBytes(a.normals.data(), a.normals.size() * 8, h);
+    h = hashBytes(a.uvs.data(), a.uvs.size() * 8, h);
+    return hashBytes(a.tris.data(), a.tris.size() * 4, h);
+}
 
 bool objKey(const char* objPath, uint64_t& key, std::string& path)
 {
@@ -228,8 +279,10 @@ bool loadObjCache(const char* objPath, ObjArrays& out)
         auto rd = [&](void* p, size_t bytes) { return bytes == 0 || fread(p, 1, bytes, f) == bytes; };
         ok = rd(out.vertices.data(), out.vertices.size() * 8) && rd(out.normals.data(), out.normals.size() * 8) && rd(out.uvs.data(), out.uvs.size() * 8) &&
              rd(out.tris.data(), out.tris.size() * 4);
+        ok = ok && objContentHash(out) == h.content;
     }
     fclose(f);
+    if (!ok) out = ObjArrays();
     return ok;
 }
 
@@ -247,6 +300,7 @@ void storeObjCache(const char* objPath, const ObjArrays& a)
     h.n_normals = a.normals.size() / 3;
     h.n_uvs = a.uvs.size() / 3;
     h.n_tris = a.tris.size() / 9;
+    h.content = objContentHash(a);
     writeAtomically(path, {{&h, sizeof h}, {a.vertices.data(), a.vertices.size() * 8}, {a.normals.data(), a.normals.size() * 8},
                            {a.uvs.data(), a.uvs.size() * 8}, {a.tris.data(), a.tris.size() * 4}});
 }

@@ -7,8 +7,9 @@
 //     while it is being built (the other ranks of a torchrun job: one process per GPU, the same scene) WAIT for that file
 //     instead of building the same tree again - the tree is built once per box, not once per GPU.
 // Files live in $HXR_CACHE_DIR (default /tmp/hexray_b200_cache); HXR_CACHE=0 turns both caches off. Every file is written to a
-// temporary name and renamed into place, and carries a magic, a version, its key and its element counts: a stale, foreign
-// or truncated file is ignored and rebuilt.
+// temporary name and renamed into place, and carries a magic, a version, its key, its element counts and a hash of its
+// payload: a stale, foreign, truncated or damaged file is ignored and rebuilt. The lock file of a tree being built names its
+// builder's pid; a lock whose process is gone (a run killed mid-build) is taken over, not waited for.
 #pragma once
 #include <cstdint>
 #include <string>

@@ -74,3 +74,47 @@ def test_a_tree_being_built_elsewhere_is_waited_for(emu_api, tmp_path, monkeypat
         infos.append(json.loads(o.strip().splitlines()[-1]))
     assert sum(1 for i in infos if i["from_cache"] == 0) == 1, infos
     assert len({(i["nodes"], i["tri_refs"]) for i in infos}) == 1
+
+
+def _load_terrain(emu_api, side):
+    sf = T.terrain_scene_file(emu_api, side)
+    r = hx.Renderer(api_=emu_api, queue_capacity=1 << 16).load(sf)
+    info = r.accel_info(0)
+    r.close()
+    sf.close()
+    return info
+
+
+def test_a_damaged_tree_file_is_rebuilt(emu_api, tmp_path, monkeypatch):
+    # the files carry a hash of their payload: a flipped byte in the middle of the tree must not reach the walk
+    monkeypatch.setenv("HXR_CACHE_DIR", str(tmp_path / "cache"))
+    first = _load_terrain(emu_api, 330)
+    assert first["from_cache"] == 0
+    kd = [f for f in os.listdir(tmp_path / "cache") if f.startswith("kd_") and f.endswith(".bin")]
+    assert len(kd) == 1
+    assert _load_terrain(emu_api, 330)["from_cache"] == 1
+    path = tmp_path / "cache" / kd[0]
+    blob = bytearray(path.read_bytes())
+    blob[len(blob) // 2] ^= 0x40
+    path.write_bytes(bytes(blob))
+    again = _load_terrain(emu_api, 330)
+    assert again["from_cache"] == 0 and again["nodes"] == first["nodes"] and again["tri_refs"] == first["tri_refs"]
+    assert _load_terrain(emu_api, 330)["from_cache"] == 1  # (the rebuilt tree replaced the damaged file)
+
+
+def test_a_stale_lock_is_taken_over(emu_api, tmp_path, monkeypatch):
+    # a run killed in the middle of its build leaves its lock file behind: the next run must not wait for it
+    monkeypatch.setenv("HXR_CACHE_DIR", str(tmp_path / "cache"))
+    first = _load_terrain(emu_api, 335)
+    kd = [f for f in os.listdir(tmp_path / "cache") if f.startswith("kd_") and f.endswith(".bin")]
+    assert len(kd) == 1
+    path = tmp_path / "cache" / kd[0]
+    p = subprocess.Popen(["true"])
+    p.wait()  # a pid that no longer exists
+    os.remove(path)
+    (tmp_path / "cache" / (kd[0] + ".lock")).write_text("%d\n" % p.pid)
+    t0 = time.time()
+    again = _load_terrain(emu_api, 335)
+    assert time.time() - t0 < 60
+    assert again["from_cache"] == 0 and again["nodes"] == first["nodes"]
+    assert not os.path.exists(tmp_path / "cache" / (kd[0] + ".lock")) and os.path.exists(path)
